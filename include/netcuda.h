@@ -1,0 +1,187 @@
+/* netcuda.h -- C ABI of the B200 (sm_100a) backend for VIT-FPGA's net forward path.
+ *
+ * This is the drop-in boundary as a shared library (libnetcuda.so): plain pointers and sizes,
+ * an opaque handle, `int` status codes.  No C++ or torch types cross it.  Every entry point
+ * replaces one step of the OpenCL life cycle in the reference's src/netFPGA.cpp (cited per
+ * function, `file:line` relative to the reference tree); INTEGRATION.md shows the C++ class
+ * (include/netCUDA.h) and a ctypes stub bound on top of it.
+ *
+ * Conventions
+ *   - every function returns NETCUDA_OK (0) or a NETCUDA_ERR_* code and never calls exit()
+ *     (the reference's AOCLUtils checkError prints + exit()s, e.g. src/netFPGA.cpp:274);
+ *   - netcuda_last_error() returns a thread-local, human readable description of the last
+ *     failure on the calling thread (role of aocl_utils::printError);
+ *   - host buffers are borrowed for the duration of the call; device pointers must live on the
+ *     handle's device; `stream` arguments are `cudaStream_t` passed as `void*` (NULL = the
+ *     handle's own stream);
+ *   - all weight matrices are row-major W[out][in], the reference's flat layout
+ *     (src/netFPGA.cpp:91-106).
+ */
+#ifndef NETCUDA_H
+#define NETCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NETCUDA_ABI_VERSION 1
+
+/* status codes */
+#define NETCUDA_OK 0
+#define NETCUDA_ERR_INVALID 1     /* bad argument / shape / state            */
+#define NETCUDA_ERR_CUDA 2        /* a CUDA runtime or driver call failed    */
+#define NETCUDA_ERR_UNSUPPORTED 3 /* valid request this build cannot serve   */
+#define NETCUDA_ERR_NO_DEVICE 4   /* no sm_100 device visible                */
+#define NETCUDA_ERR_KERNEL 5      /* a kernel reported a pipeline time-out   */
+
+/* net kinds */
+#define NETCUDA_KIND_MLP 0 /* what net::net_data describes (def/defines.h:14-23) */
+#define NETCUDA_KIND_VIT 1 /* vision transformer; no reference counterpart       */
+
+/* arithmetic */
+#define NETCUDA_PREC_FP32 0 /* CUDA-core fp32, k-ascending fmaf: bit-equal to the oracle   */
+#define NETCUDA_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate (MLP only)               */
+#define NETCUDA_PREC_BF16 2 /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate           */
+#define NETCUDA_PREC_INT8 3 /* tcgen05 kind::i8, Q1.7 operands, int32 accumulate (MLP only) */
+
+/* MLP activation placement.  The reference hints at a single net-wide "RELU2"
+ * (src/netFPGA.cpp:79) that never reaches the device; see DESIGN.md for the choice. */
+#define NETCUDA_ACT_RELU_HIDDEN 0 /* max(0,.) on every layer but the last (default) */
+#define NETCUDA_ACT_RELU_ALL 1    /* max(0,.) on every layer                        */
+#define NETCUDA_ACT_NONE 2        /* purely linear                                  */
+
+typedef struct netcuda_net netcuda_t; /* opaque */
+
+/* Describes the net to build.  Unused fields for a kind must be 0. */
+typedef struct netcuda_desc
+{
+    int32_t kind;       /* NETCUDA_KIND_*                                            */
+    int32_t precision;  /* NETCUDA_PREC_*                                            */
+    int32_t device;     /* CUDA ordinal                                              */
+    int32_t activation; /* NETCUDA_ACT_* (MLP)                                       */
+    int32_t max_batch;  /* samples processed per internal pass (0 = library default) */
+    /* MLP: mirrors net_fpga's n_ins / n_layers / n_p_l (include/netFPGA.h:22-26) */
+    int32_t n_ins;
+    int32_t n_layers;
+    const int32_t *n_p_l; /* n_layers entries, borrowed during netcuda_create only */
+    /* ViT */
+    int32_t image_size; /* square input, e.g. 224   */
+    int32_t patch_size; /* e.g. 16                  */
+    int32_t dim;        /* embedding width D        */
+    int32_t depth;      /* encoder blocks L         */
+    int32_t heads;      /* D / heads must be 64     */
+    int32_t mlp_dim;    /* hidden width of the MLP  */
+    int32_t n_classes;  /* head outputs             */
+} netcuda_desc;
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+
+/* Number of usable CUDA devices.  Replaces platform/device discovery,
+ * src/netFPGA.cpp:372-377 (clGetPlatformIDs / clGetDeviceIDs). */
+int netcuda_device_count(int *count);
+
+/* Create context, stream set, device arenas and pinned staging for `desc`.
+ * Replaces _init_program + _init_kernel, src/netFPGA.cpp:367-441. */
+int netcuda_create(const netcuda_desc *desc, netcuda_t **out);
+
+/* Release everything owned by the handle.  Replaces cleanup(), src/netFPGA.cpp:639-651. */
+int netcuda_destroy(netcuda_t *h);
+
+/* ---- weights ---------------------------------------------------------------------------- */
+
+/* Upload an MLP in the reference's flat layout: `w_flat` = all layers' W[out][in] matrices back
+ * to back, `b_flat` = all biases back to back (src/netFPGA.cpp:91-106).  Converted on upload to
+ * the handle's precision (INT8: q = clamp(rint(w*128)), bias rint(b*16384), see oracle/).
+ * Replaces _load_params, src/netFPGA.cpp:484-515. */
+int netcuda_upload_mlp(netcuda_t *h, const float *w_flat, const float *b_flat);
+
+/* INT8 handles only: upload already-quantised Q1.7 weights and Q2.14 int32 biases. */
+int netcuda_upload_mlp_i8(netcuda_t *h, const int8_t *w_flat, const int32_t *b_flat);
+
+/* Number of floats netcuda_upload_vit expects for `desc` (layout documented in DESIGN.md):
+ * patch_w[D][3PP] patch_b[D] cls[D] pos[N][D] { ln1_g ln1_b qkv_w[3D][D] qkv_b proj_w[D][D]
+ * proj_b ln2_g ln2_b fc1_w[F][D] fc1_b fc2_w[D][F] fc2_b } x depth, lnf_g lnf_b head_w[C][D] head_b. */
+int netcuda_vit_param_count(const netcuda_desc *desc, size_t *count);
+
+/* Upload a ViT from that flat fp32 layout. */
+int netcuda_upload_vit(netcuda_t *h, const float *flat, size_t count);
+
+/* ---- forward ---------------------------------------------------------------------------- */
+
+/* Host-to-host forward: `in` holds batch*n_in floats, `out` receives batch*n_out floats.
+ * Synchronous like the reference (blocking read at src/netFPGA.cpp:277) but batched; inputs are
+ * staged through pinned memory (or DMA'd in place when `in` is already page-locked) in
+ * max_batch-sized passes, with the copy of pass i+1 overlapping the compute of pass i.
+ * Replaces the H2D / task / D2H triple at src/netFPGA.cpp:266-277. */
+int netcuda_forward(netcuda_t *h, const float *in, size_t batch, float *out);
+
+/* Device-resident forward on `stream` (asynchronous; no host copies): the roofline path.
+ * d_in: fp32 [batch][n_in], d_out: fp32 [batch][n_out]. */
+int netcuda_forward_device(netcuda_t *h, const void *d_in, size_t batch, void *d_out, void *stream);
+
+/* INT8 handles: raw quantised forward, int8 [batch][n_in] -> int32 [batch][n_out]
+ * (accumulator of the last layer, Q2.14).  Used for the bit-exactness tests. */
+int netcuda_forward_device_i8(netcuda_t *h, const int8_t *d_in, size_t batch, int32_t *d_out, void *stream);
+int netcuda_forward_i8(netcuda_t *h, const int8_t *in, size_t batch, int32_t *out);
+
+/* ---- introspection ---------------------------------------------------------------------- */
+
+int netcuda_n_in(const netcuda_t *h, size_t *n);  /* floats per input sample  */
+int netcuda_n_out(const netcuda_t *h, size_t *n); /* floats per output sample */
+
+/* Wall-clock microseconds of the last netcuda_forward call, transfers included.
+ * Replaces get_forward_performance, src/netFPGA.cpp:603-611 (stopwatch at :262-284). */
+int netcuda_last_forward_us(const netcuda_t *h, int64_t *us);
+
+/* Kernels launched by this handle since creation (bench.py reports the per-step delta). */
+int netcuda_launch_count(const netcuda_t *h, uint64_t *count);
+
+/* Algorithmic multiply-accumulate FLOPs (2*MACs of the dense contractions) per sample. */
+int netcuda_flops_per_sample(const netcuda_t *h, double *flops);
+
+/* Select a debugging/measurement variant of the dense kernel for this handle:
+ * 0 = default (tcgen05), 1 = CUDA-core reference GEMM with the same operand rounding. */
+int netcuda_set_gemm_variant(netcuda_t *h, int variant);
+
+const char *netcuda_last_error(void);
+int netcuda_abi_version(void);
+
+/* ---- single-kernel entry points (tests/, profiles/) -------------------------------------- *
+ * Each launches exactly one hot-path kernel on device pointers so that it can be checked
+ * against the oracle in isolation.  `device` selects the GPU; stream NULL = legacy default. */
+
+#define NETCUDA_OUT_F32 0
+#define NETCUDA_OUT_BF16 1
+#define NETCUDA_OUT_S8 2
+#define NETCUDA_OUT_S32 3
+
+#define NETCUDA_EPI_NONE 0
+#define NETCUDA_EPI_RELU 1
+#define NETCUDA_EPI_GELU 2     /* exact (erf) GELU                                    */
+#define NETCUDA_EPI_RESIDUAL 3 /* out(fp32) = out + acc + bias (in-place residual add) */
+#define NETCUDA_EPI_REQUANT 4  /* INT8: q = min(127, max(0,acc+bias) >> 7)            */
+
+/* out[M][N] = epi(A[M][K] . W[N][K]^T + bias[N]).  precision selects operand type
+ * (BF16: bf16, TF32: fp32, INT8: int8, FP32: fp32 on CUDA cores); lda/ldw/ldc in elements. */
+int netcuda_op_gemm(int device, int precision, int variant,
+                    const void *d_a, int lda, const void *d_w, int ldw, const void *d_bias,
+                    void *d_out, int ldc, int out_type, int epilogue, int m, int n, int k, void *stream);
+
+/* y[r][:] = (x[r][:] - mean) * rstd * gamma + beta ; x fp32 (row stride ldx), y bf16 (row stride ldy). */
+int netcuda_op_layernorm(int device, const float *d_x, int ldx, const float *d_gamma, const float *d_beta,
+                         void *d_y, int ldy, int rows, int dim, float eps, void *stream);
+
+/* Multi-head attention core on packed qkv: d_qkv bf16 [batch*tokens][3*heads*64] (q|k|v blocks,
+ * head-major inside each), d_out bf16 [batch*tokens][heads*64] = softmax(q k^T / 8) v per head. */
+int netcuda_op_attention(int device, const void *d_qkv, void *d_out, int batch, int tokens, int heads, void *stream);
+
+/* fp32 NCHW images -> bf16 patch matrix [batch*np][3*p*p] (column = c*p*p + py*p + px). */
+int netcuda_op_patchify(int device, const float *d_img, void *d_patches, int batch, int image_size, int patch_size, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NETCUDA_H */
