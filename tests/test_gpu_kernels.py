@@ -1,0 +1,217 @@
+"""GPU parity tests, one hot-path kernel at a time, through the C ABI's single-kernel entry points
+(include/netcuda.h, netcuda_op_*).  The CPU oracle is the checker; nothing here is a fallback.
+
+Tolerances (written where they are used):
+  * integer paths: bit-exact;
+  * fp32-accumulating tensor-core GEMM with fp32 output, operands pre-rounded to the operand type on
+    both sides: 1e-4 of max|ref| (accumulation-order noise only);
+  * bf16 outputs: 2^-8 relative rounding on top -> 6e-3 of max|ref|.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16_round(torch, a):
+    return torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+
+
+def _tf32_trunc(a):
+    return (a.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def _max_rel(a, ref):
+    return float(np.abs(a.astype(np.float64) - ref.astype(np.float64)).max() / max(np.abs(ref).max(), 1e-30))
+
+
+GEMM_SHAPES = [
+    # (M, N, K) -- K in elements
+    (128, 128, 64),     # one tile, one k-block (bf16)
+    (128, 256, 64),     # BN = 256 path
+    (256, 384, 256),    # several tiles and k-blocks
+    (300, 200, 136),    # ragged in every dimension (K = 136: partial k-block, TMA zero fill)
+    (64, 10, 64),       # C1 last layer shape: tiny N
+    (64, 128, 784),     # C1 first layer
+    (1000, 1000, 192),  # more tiles than a wave of 148 would need at BN=256? no: exercises n tail
+    (20000, 768, 768),  # > 148 tiles: persistent loop + both accumulator stages + phase wrap
+]
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+@pytest.mark.parametrize("out_bf16", [False, True])
+def test_gemm_bf16_vs_oracle(netcuda, oracle, torch_cuda, m, n, k, out_bf16):
+    torch = torch_cuda
+    rng = np.random.default_rng(m * 7 + n * 3 + k)
+    a = _bf16_round(torch, rng.uniform(-1, 1, (m, k)).astype(np.float32))
+    w = _bf16_round(torch, rng.uniform(-1, 1, (n, k)).astype(np.float32))
+    bias = rng.uniform(-1, 1, n).astype(np.float32)
+    ldk = (k + 7) // 8 * 8
+    da = torch.zeros((m, ldk), dtype=torch.bfloat16, device="cuda")
+    dw = torch.zeros((n, ldk), dtype=torch.bfloat16, device="cuda")
+    da[:, :k] = torch.from_numpy(a).cuda().to(torch.bfloat16)
+    dw[:, :k] = torch.from_numpy(w).cuda().to(torch.bfloat16)
+    db = torch.from_numpy(bias).cuda()
+    ldc = n + 3  # odd pitch: the epilogue must not assume alignment of rows
+    if out_bf16:
+        ldc = n + 2
+    out = torch.full((m, ldc), -77.0, dtype=torch.bfloat16 if out_bf16 else torch.float32, device="cuda")
+    netcuda.op_gemm(da, dw, db, out, netcuda.PREC_BF16, netcuda.OUT_BF16 if out_bf16 else netcuda.OUT_F32,
+                    m=m, n=n, k=k, lda=ldk, ldw=ldk, ldc=ldc)
+    torch.cuda.synchronize()
+    got = out.float().cpu().numpy()
+    want = oracle.linear(a, w, bias)
+    assert _max_rel(got[:, :n], want) <= (6e-3 if out_bf16 else 1e-4)
+    assert (got[:, n:] == -77.0).all()  # nothing written past N
+
+
+@pytest.mark.parametrize("epi", ["relu", "gelu", "residual"])
+def test_gemm_bf16_epilogues(netcuda, oracle, torch_cuda, epi):
+    torch = torch_cuda
+    m, n, k = 333, 320, 192
+    rng = np.random.default_rng(5)
+    a = _bf16_round(torch, rng.standard_normal((m, k)).astype(np.float32))
+    w = _bf16_round(torch, (rng.standard_normal((n, k)) * 0.1).astype(np.float32))
+    bias = rng.standard_normal(n).astype(np.float32)
+    lin = oracle.linear(a, w, bias)
+    da, dw, db = (torch.from_numpy(v).cuda() for v in (a, w, bias))
+    da, dw = da.to(torch.bfloat16), dw.to(torch.bfloat16)
+    if epi == "residual":
+        res = rng.standard_normal((m, n)).astype(np.float32)
+        out = torch.from_numpy(res).cuda()
+        netcuda.op_gemm(da, dw, db, out, netcuda.PREC_BF16, netcuda.OUT_F32, epilogue=netcuda.EPI_RESIDUAL)
+        want = res + lin
+        tol = 1e-4
+    else:
+        out = torch.empty((m, n), dtype=torch.bfloat16, device="cuda")
+        netcuda.op_gemm(da, dw, db, out, netcuda.PREC_BF16, netcuda.OUT_BF16,
+                        epilogue=netcuda.EPI_RELU if epi == "relu" else netcuda.EPI_GELU)
+        want = np.maximum(lin, 0) if epi == "relu" else oracle.gelu(lin)
+        tol = 6e-3
+    torch.cuda.synchronize()
+    assert _max_rel(out.float().cpu().numpy(), want) <= tol
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 32), (64, 128, 784), (300, 200, 100), (4096, 512, 512)])
+def test_gemm_tf32_vs_oracle(netcuda, oracle, torch_cuda, m, n, k):
+    torch = torch_cuda
+    rng = np.random.default_rng(m + n + k)
+    # operands pre-truncated to tf32 (10 mantissa bits): products are exact in fp32 on both sides
+    a = _tf32_trunc(rng.uniform(-1, 1, (m, k)).astype(np.float32))
+    w = _tf32_trunc(rng.uniform(-1, 1, (n, k)).astype(np.float32))
+    bias = rng.uniform(-1, 1, n).astype(np.float32)
+    da, dw, db = (torch.from_numpy(v).cuda() for v in (a, w, bias))
+    out = torch.empty((m, n), dtype=torch.float32, device="cuda")
+    netcuda.op_gemm(da, dw, db, out, netcuda.PREC_TF32, netcuda.OUT_F32, epilogue=netcuda.EPI_RELU)
+    torch.cuda.synchronize()
+    want = np.maximum(oracle.linear(a, w, bias), 0)
+    assert _max_rel(out.cpu().numpy(), want) <= 1e-4
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (1, 4096, 4096), (77, 300, 200), (513, 4096, 4096), (16384, 256, 4096)])
+def test_gemm_int8_bit_exact(netcuda, torch_cuda, m, n, k):
+    torch = torch_cuda
+    rng = np.random.default_rng(m * 3 + n + k)
+    a = rng.integers(-128, 128, (m, k), dtype=np.int8)
+    w = rng.integers(-128, 128, (n, k), dtype=np.int8)
+    bias = rng.integers(-(1 << 14), 1 << 14, n, dtype=np.int32)
+    ldk = (k + 15) // 16 * 16
+    da = torch.zeros((m, ldk), dtype=torch.int8, device="cuda")
+    dw = torch.zeros((n, ldk), dtype=torch.int8, device="cuda")
+    da[:, :k] = torch.from_numpy(a).cuda()
+    dw[:, :k] = torch.from_numpy(w).cuda()
+    db = torch.from_numpy(bias).cuda()
+    # exact integer reference on the GPU in int64-free form: fp64 matmul is exact for |acc| < 2^53
+    acc = (da[:, :k].double() @ dw[:, :k].double().T).cpu().numpy().astype(np.int64) + bias.astype(np.int64)
+    out32 = torch.empty((m, n), dtype=torch.int32, device="cuda")
+    netcuda.op_gemm(da, dw, db, out32, netcuda.PREC_INT8, netcuda.OUT_S32, m=m, n=n, k=k, lda=ldk, ldw=ldk)
+    out8 = torch.empty((m, n), dtype=torch.int8, device="cuda")
+    netcuda.op_gemm(da, dw, db, out8, netcuda.PREC_INT8, netcuda.OUT_S8, epilogue=netcuda.EPI_RELU, m=m, n=n, k=k, lda=ldk, ldw=ldk)
+    out8s = torch.empty((m, n), dtype=torch.int8, device="cuda")
+    netcuda.op_gemm(da, dw, db, out8s, netcuda.PREC_INT8, netcuda.OUT_S8, m=m, n=n, k=k, lda=ldk, ldw=ldk)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out32.cpu().numpy().astype(np.int64), acc)
+    np.testing.assert_array_equal(out8.cpu().numpy().astype(np.int64), np.minimum(127, np.maximum(acc, 0) >> 7))
+    np.testing.assert_array_equal(out8s.cpu().numpy().astype(np.int64), np.clip(acc >> 7, -128, 127))
+
+
+def test_gemm_tensor_core_matches_cuda_core_variant_at_full_size(netcuda, torch_cuda):
+    """ViT-B fc1 at a full pass (M = 64 images * 197 tokens): tcgen05 kernel vs the CUDA-core kernel with
+    the same operand rounding -- a size the CPU oracle would need minutes for."""
+    torch = torch_cuda
+    m, n, k = 64 * 197, 3072, 768
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn((m, k), generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn((n, k), generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    b = torch.randn(n, generator=g, device="cuda")
+    o0 = torch.empty((m, n), dtype=torch.float32, device="cuda")
+    o1 = torch.empty_like(o0)
+    netcuda.op_gemm(a, w, b, o0, netcuda.PREC_BF16, netcuda.OUT_F32, variant=0)
+    netcuda.op_gemm(a, w, b, o1, netcuda.PREC_BF16, netcuda.OUT_F32, variant=1)
+    torch.cuda.synchronize()
+    err = ((o0 - o1).abs().max() / o1.abs().max()).item()
+    assert err <= 1e-4, err
+
+
+@pytest.mark.parametrize("rows,dim", [(1, 192), (197, 192), (1000, 768), (333, 1024), (64, 4096)])
+def test_layernorm_vs_oracle(netcuda, oracle, torch_cuda, rows, dim):
+    torch = torch_cuda
+    rng = np.random.default_rng(rows + dim)
+    x = (rng.standard_normal((rows, dim)) * 2 + 0.5).astype(np.float32)
+    g = rng.standard_normal(dim).astype(np.float32)
+    b = rng.standard_normal(dim).astype(np.float32)
+    dx, dg, db = (torch.from_numpy(v).cuda() for v in (x, g, b))
+    y = torch.empty((rows, dim), dtype=torch.bfloat16, device="cuda")
+    netcuda.op_layernorm(dx, dg, db, y)
+    torch.cuda.synchronize()
+    want = oracle.layernorm(x, g, b)
+    # bf16 output rounding (2^-9 relative) dominates
+    assert _max_rel(y.float().cpu().numpy(), want) <= 5e-3
+
+
+def test_layernorm_strided_rows(netcuda, oracle, torch_cuda):
+    """Final LayerNorm reads only the class-token rows: row pitch = tokens * dim."""
+    torch = torch_cuda
+    rng = np.random.default_rng(9)
+    B, T, D = 5, 7, 256
+    x = rng.standard_normal((B * T, D)).astype(np.float32)
+    g, b = rng.standard_normal(D).astype(np.float32), rng.standard_normal(D).astype(np.float32)
+    dx, dg, db = (torch.from_numpy(v).cuda() for v in (x, g, b))
+    y = torch.empty((B, D), dtype=torch.bfloat16, device="cuda")
+    netcuda.op_layernorm(dx, dg, db, y, rows=B, dim=D, ldx=T * D, ldy=D)
+    torch.cuda.synchronize()
+    want = oracle.layernorm(x[::T].copy(), g, b)
+    assert _max_rel(y.float().cpu().numpy(), want) <= 5e-3
+
+
+@pytest.mark.parametrize("batch,tokens,heads", [(2, 197, 3), (1, 5, 1), (3, 37, 2), (1, 577, 2), (2, 64, 12), (4, 16, 1), (1, 113, 1)])
+def test_attention_vs_oracle(netcuda, oracle, torch_cuda, batch, tokens, heads):
+    torch = torch_cuda
+    rng = np.random.default_rng(tokens * 5 + heads)
+    qkv = _bf16_round(torch, rng.standard_normal((batch * tokens, 3 * heads * 64)).astype(np.float32))
+    dq = torch.from_numpy(qkv).cuda().to(torch.bfloat16)
+    out = torch.full((batch * tokens, heads * 64), 55.0, dtype=torch.bfloat16, device="cuda")
+    netcuda.op_attention(dq, out, batch, tokens, heads)
+    torch.cuda.synchronize()
+    want = oracle.attention(qkv, batch, tokens, heads)
+    got = out.float().cpu().numpy()
+    # P is rounded to bf16 before P.V and the output is bf16: 1e-2 of max|ref| (north_star tolerance)
+    assert _max_rel(got, want) <= 1e-2
+
+
+def test_patchify_exact(netcuda, torch_cuda):
+    torch = torch_cuda
+    rng = np.random.default_rng(4)
+    B, S, P = 3, 64, 16
+    img = rng.uniform(-1, 1, (B, 3, S, S)).astype(np.float32)
+    g = S // P
+    dimg = torch.from_numpy(img).cuda()
+    out = torch.empty((B * g * g, 3 * P * P), dtype=torch.bfloat16, device="cuda")
+    netcuda.op_patchify(dimg, out, B, S, P)
+    torch.cuda.synchronize()
+    # column = c*P*P + py*P + px: the flattening order of a conv weight [D][3][P][P] (torchvision conv_proj)
+    want = img.reshape(B, 3, g, P, g, P).transpose(0, 2, 4, 1, 3, 5).reshape(B * g * g, 3 * P * P)
+    want = torch.from_numpy(want).to(torch.bfloat16)
+    assert torch.equal(out.cpu(), want)

@@ -1,0 +1,280 @@
+"""GPU parity tests of whole nets: the CUDA path driven through the C ABI (netcuda.Net) and through the
+C++ class behind net::net_abstract* (netcuda.HostNet), checked against the CPU oracle and the committed
+golden fixtures.
+
+Bars:
+  * NETCUDA_PREC_FP32: bit-equal to the oracle (same fmaf sequence);
+  * TF32 / BF16: max rel err <= 1e-2 on the outputs (relative to max |out| per sample) and identical arg-max;
+  * INT8: bit-exact at every batch size.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, c1_net, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- config C1: 784-128-64-10, batch 64 -----------------------------------------------------------
+
+def test_c1_golden_fp32_bit_equal(netcuda, oracle, torch_cuda):
+    """The golden fixture holds outputs of the reference's own host runtime (oracle/_ref)."""
+    g = np.load(os.path.join(GOLDEN, "mlp_c1.npz"))
+    npl, n_ins, w, b = c1_net(oracle)
+    net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_FP32)
+    net.upload_mlp(w, b)
+    got = net.forward(g["x"])
+    np.testing.assert_array_equal(got, g["y"])
+    assert net.last_forward_us > 0
+    net.close()
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_c1_tensor_core_precisions(netcuda, oracle, torch_cuda, prec):
+    g = np.load(os.path.join(GOLDEN, "mlp_c1.npz"))
+    npl, n_ins, w, b = c1_net(oracle)
+    net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PRECISIONS[prec])
+    net.upload_mlp(w, b)
+    got = net.forward(g["x"])
+    net.close()
+    assert rel_err(got, g["y"]) <= 1e-2  # north_star tolerance
+    np.testing.assert_array_equal(got.argmax(1), g["y"].argmax(1))
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_mlp_activation_modes_and_ragged_shapes(netcuda, oracle, torch_cuda, act):
+    rng = np.random.default_rng(21 + act)
+    npl, n_ins = [33, 17, 9, 4], 61  # nothing is a multiple of a tile or of 16 bytes
+    n_params = sum(a * b for a, b in zip([n_ins] + npl[:-1], npl))
+    w = rng.uniform(-1, 1, n_params).astype(np.float32)
+    b = rng.uniform(-1, 1, sum(npl)).astype(np.float32)
+    x = rng.uniform(-1, 1, (37, n_ins)).astype(np.float32)
+    want = oracle.mlp_forward(x, w, b, npl, n_ins, act)
+    for prec, tol in (("fp32", 0.0), ("tf32", 1e-2), ("bf16", 2e-2)):
+        net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PRECISIONS[prec], activation=act)
+        net.upload_mlp(w, b)
+        got = net.forward(x)
+        net.close()
+        if tol == 0.0:
+            np.testing.assert_array_equal(got, want)
+        else:
+            assert rel_err(got, want) <= tol, prec
+
+
+def test_mlp_edge_batches(netcuda, oracle, torch_cuda):
+    """Empty batch, batch 1 (the reference's contract), and a batch that needs several internal passes."""
+    npl, n_ins, w, b = c1_net(oracle)
+    net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_FP32, max_batch=50)
+    net.upload_mlp(w, b)
+    assert net.forward(np.zeros((0, n_ins), np.float32)).shape == (0, 10)
+    rng = np.random.default_rng(8)
+    for batch in (1, 49, 50, 51, 173):
+        x = rng.uniform(-1, 1, (batch, n_ins)).astype(np.float32)
+        np.testing.assert_array_equal(net.forward(x), oracle.mlp_forward(x, w, b, npl, n_ins))
+    net.close()
+    with pytest.raises(netcuda.NetcudaError):
+        fresh = netcuda.Net.mlp(npl, n_ins)
+        fresh.forward(np.zeros((1, n_ins), np.float32))  # forward before upload must fail loudly
+
+
+def test_forward_device_and_pinned_paths(netcuda, oracle, torch_cuda):
+    torch = torch_cuda
+    npl, n_ins, w, b = c1_net(oracle)
+    net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_FP32)
+    net.upload_mlp(w, b)
+    x = np.random.default_rng(3).uniform(-1, 1, (64, n_ins)).astype(np.float32)
+    want = oracle.mlp_forward(x, w, b, npl, n_ins)
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.empty((64, 10), dtype=torch.float32, device="cuda")
+    net.forward_device(dx, dy, 64, torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(dy.cpu().numpy(), want)
+    px = torch.from_numpy(x).pin_memory()
+    py = torch.empty((64, 10), dtype=torch.float32).pin_memory()
+    net.forward_into(px, py)  # page-locked buffers are DMA'd in place
+    np.testing.assert_array_equal(py.numpy(), want)
+    net.close()
+
+
+# ---- the C++ class through net::net_abstract* -------------------------------------------------------
+
+def test_cpp_class_drop_in(netcuda, oracle, torch_cuda):
+    npl, n_ins, w, b = c1_net(oracle)
+    g = np.load(os.path.join(GOLDEN, "mlp_c1.npz"))
+    net = netcuda.HostNet.mlp(npl, n_ins, w, b, precision=netcuda.PREC_FP32)
+    # one sample per call: exactly the reference's contract (src/netFPGA.cpp:266-289)
+    for i in (0, 17, 63):
+        np.testing.assert_array_equal(net.launch_forward(g["x"][i])[0], g["y"][i])
+    # batched extension: B * n_ins in, B * n_out out
+    np.testing.assert_array_equal(net.launch_forward(g["x"]), g["y"])
+    assert net.forward_us() > 0
+    with pytest.raises(ValueError):
+        net.launch_forward(np.zeros(n_ins + 1, np.float32))  # the reference would read out of bounds here
+    # get_net_data is the exact inverse of the constructor's flatten (the reference's is broken, App. A)
+    w2, b2, n_ins2, n_layers2 = net.get_net_data(w.size, b.size)
+    np.testing.assert_array_equal(w2, w)
+    np.testing.assert_array_equal(b2, b)
+    assert (n_ins2, n_layers2) == (n_ins, 3)
+    assert net.check_stubs() == 0
+    net.close()
+
+
+def test_cpp_class_random_init_matches_reference_rule(netcuda, oracle, torch_cuda):
+    """random=true draws float(rand()%200-100)/100, params first then biases (src/netFPGA.cpp:82-88)."""
+    npl, n_ins = [128, 64, 10], 784
+    net = netcuda.HostNet.mlp(npl, n_ins, random=True, seed=1, precision=netcuda.PREC_FP32)
+    w, b = oracle.rand_init(1, 109184, 202)
+    w2, b2, _, _ = net.get_net_data(w.size, b.size)
+    np.testing.assert_array_equal(w2, w)
+    np.testing.assert_array_equal(b2, b)
+    net.close()
+
+
+def test_cpp_class_move_and_copy(netcuda, oracle, torch_cuda):
+    npl, n_ins, w, b = c1_net(oracle)
+    net = netcuda.HostNet.mlp(npl, n_ins, w, b, precision=-1)  # the reference-shaped 3-argument constructor
+    x = np.random.default_rng(1).uniform(-1, 1, n_ins).astype(np.float32)
+    y = net.launch_forward(x)[0]
+    assert rel_err(y[None], oracle.mlp_forward(x[None], w, b, npl, n_ins)) <= 1e-2  # default precision is BF16
+    assert net.check_move_copy(x, y) == 0
+    net.close()
+
+
+# ---- config C5: INT8 wide MLP, bit-exact batch sweep ----------------------------------------------------
+
+def _int8_net(rng, npl, n_ins):
+    n_params = sum(a * b for a, b in zip([n_ins] + npl[:-1], npl))
+    # weights scaled so that hidden activations neither saturate nor die (about N(0, 20/128) per layer)
+    wq = np.clip(np.rint(rng.standard_normal(n_params) * 128.0 / np.sqrt(n_ins) * 1.4), -128, 127).astype(np.int8)
+    bq = rng.integers(-2000, 2000, sum(npl), dtype=np.int32)
+    return wq, bq
+
+
+def test_int8_small_bit_exact_all_activations(netcuda, oracle, torch_cuda):
+    rng = np.random.default_rng(31)
+    npl, n_ins = [64, 50, 32], 48
+    wq, bq = _int8_net(rng, npl, n_ins)
+    xq = rng.integers(-128, 128, (19, n_ins), dtype=np.int8)
+    for act in (0, 1, 2):
+        net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8, activation=act)
+        net.upload_mlp_i8(wq, bq)
+        np.testing.assert_array_equal(net.forward_i8(xq), oracle.mlp_forward_i8(xq, wq, bq, npl, n_ins, act))
+        net.close()
+
+
+def test_int8_float_api_quantises_like_oracle(netcuda, oracle, torch_cuda):
+    rng = np.random.default_rng(32)
+    npl, n_ins = [96, 40], 72
+    n_params = n_ins * 96 + 96 * 40
+    w = rng.uniform(-1, 1, n_params).astype(np.float32) * 0.3
+    b = rng.uniform(-1, 1, sum(npl)).astype(np.float32) * 0.1
+    x = rng.uniform(-1, 1, (11, n_ins)).astype(np.float32)
+    net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8)
+    net.upload_mlp(w, b)
+    got = net.forward(x)
+    net.close()
+    acc = oracle.mlp_forward_i8(oracle.quantize_q17(x), oracle.quantize_q17(w), oracle.quantize_bias(b), npl, n_ins)
+    np.testing.assert_array_equal(got, acc.astype(np.float32) * np.float32(1.0 / 16384.0))
+
+
+@pytest.mark.parametrize("batch", [1, 2, 16, 128, 1024, 16384])
+def test_c5_int8_wide_mlp_bit_exact(netcuda, oracle, torch_cuda, batch):
+    """8 x 4096 INT8.  The oracle checks up to 128 samples per batch (a few seconds of CPU); the rest of a
+    large batch is covered by a size-independent property: rows are independent, so forwarding the batch
+    must equal forwarding its permutation un-permuted, and duplicated inputs must give duplicated outputs."""
+    rng = np.random.default_rng(50)
+    npl, n_ins = [4096] * 8, 4096
+    wq, bq = _int8_net(rng, npl, n_ins)
+    net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8, max_batch=16384)
+    net.upload_mlp_i8(wq, bq)
+    xq = rng.integers(-128, 128, (batch, n_ins), dtype=np.int8)
+    got = net.forward_i8(xq)
+    probe = np.unique(np.concatenate([np.arange(min(batch, 64)), rng.integers(0, batch, 64)]))
+    want = oracle.mlp_forward_i8(xq[probe], wq, bq, npl, n_ins)
+    np.testing.assert_array_equal(got[probe], want)
+    assert np.abs(want).max() > 1000  # the net is alive (not all-zero activations)
+    if batch > 128:
+        perm = rng.permutation(batch)
+        np.testing.assert_array_equal(net.forward_i8(xq[perm])[np.argsort(perm)], got)
+    net.close()
+
+
+# ---- ViT ----------------------------------------------------------------------------------------------
+
+def _golden_vit():
+    g = np.load(os.path.join(GOLDEN, "vit_small.npz"))
+    cfg = dict(zip(("image_size", "patch_size", "dim", "depth", "heads", "mlp_dim", "n_classes"), [int(v) for v in g["cfg"]]))
+    return g, cfg
+
+
+def test_vit_golden_torchvision_fixture(netcuda, torch_cuda):
+    """Logits of torchvision's VisionTransformer (tests/golden/make_golden.py) on the same weights/inputs."""
+    g, cfg = _golden_vit()
+    net = netcuda.Net.vit(cfg)
+    net.upload_vit(g["flat"])
+    got = net.forward(g["images"].reshape(len(g["images"]), -1))
+    net.close()
+    assert rel_err(got, g["logits"]) <= 1e-2
+    np.testing.assert_array_equal(got.argmax(1), g["logits"].argmax(1))
+
+
+def test_vit_cpp_class(netcuda, torch_cuda):
+    g, cfg = _golden_vit()
+    net = netcuda.HostNet.vit(cfg, g["flat"])
+    got = net.launch_forward(g["images"])
+    net.close()
+    assert rel_err(got, g["logits"]) <= 1e-2
+
+
+@pytest.mark.parametrize("name,batch,depth", [("vit_tiny_16_224", 5, 12), ("vit_base_16_224", 3, 2)])
+def test_vit_real_shapes_vs_oracle(netcuda, oracle, torch_cuda, name, batch, depth):
+    """197-token configurations (ViT-Tiny in full; ViT-B at reduced depth so the CPU oracle stays in seconds)."""
+    cfg = dict(netcuda.VIT_PRESETS[name], depth=depth)
+    flat = netcuda.vit_random_params(cfg, seed=2)
+    x = np.random.default_rng(6).uniform(-1, 1, (batch, 3 * cfg["image_size"] ** 2)).astype(np.float32)
+    want = oracle.vit_forward(cfg, flat, x)
+    net = netcuda.Net.vit(cfg, max_batch=2)  # several internal passes, last one partial
+    net.upload_vit(flat)
+    got = net.forward(x)
+    assert rel_err(got, want) <= 1e-2
+    np.testing.assert_array_equal(got.argmax(1), want.argmax(1))
+    # tensor-core path == CUDA-core path with the same operand rounding (tight: accumulation order only + bf16 re-rounding)
+    net.set_gemm_variant(1)
+    got_ref = net.forward(x)
+    net.close()
+    assert rel_err(got, got_ref) <= 5e-3
+
+
+def test_vit_large_sequence_577(netcuda, oracle, torch_cuda):
+    """ViT-L/16-384 geometry (577 tokens, 16 heads) at depth 1."""
+    cfg = dict(netcuda.VIT_PRESETS["vit_large_16_384"], depth=1)
+    flat = netcuda.vit_random_params(cfg, seed=4)
+    x = np.random.default_rng(7).uniform(-1, 1, (2, 3 * 384 * 384)).astype(np.float32)
+    want = oracle.vit_forward(cfg, flat, x)
+    net = netcuda.Net.vit(cfg, max_batch=2)
+    net.upload_vit(flat)
+    got = net.forward(x)
+    net.close()
+    assert rel_err(got, want) <= 1e-2
+    np.testing.assert_array_equal(got.argmax(1), want.argmax(1))
+
+
+def test_vit_batch_independence_at_full_batch(netcuda, torch_cuda):
+    """Size-independent property at a bench-sized batch: logits of image i do not depend on its neighbours."""
+    torch = torch_cuda
+    cfg = netcuda.VIT_PRESETS["vit_tiny_16_224"]
+    flat = netcuda.vit_random_params(cfg, seed=1)
+    net = netcuda.Net.vit(cfg, max_batch=256)
+    net.upload_vit(flat)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand((256, net.n_in), generator=g, device="cuda") * 2 - 1
+    y = torch.empty((256, 1000), device="cuda")
+    net.forward_device(x, y, 256, torch.cuda.current_stream())
+    perm = torch.randperm(256, device="cuda")
+    y2 = torch.empty_like(y)
+    net.forward_device(x[perm].contiguous(), y2, 256, torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    net.close()
+    assert torch.equal(y2, y[perm])

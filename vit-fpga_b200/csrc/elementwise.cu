@@ -1,0 +1,219 @@
+// elementwise.cu -- the HBM-bound kernels of the forward path: LayerNorm, patch extraction, class
+// token rows, and the fp32 <-> operand-type conversions at the API boundary
+// (replacing the host scalar copy loops of src/netFPGA.cpp:266-267,285-289 for batched input).
+// All of them are one pass over their data with 128-bit accesses where alignment allows.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace nc
+{
+
+// ---- LayerNorm: one warp per row, row cached in registers, two-pass (mean, then variance) --------
+
+template <int MAXV> // MAXV float4 per lane -> dim <= 128 * MAXV
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float *__restrict__ x, long long ldx, const float *__restrict__ gamma, const float *__restrict__ beta,
+                 __nv_bfloat16 *__restrict__ y, long long ldy, int rows, int dim, float eps)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int nv = dim >> 2; // float4 per row
+    const float4 *xr = reinterpret_cast<const float4 *>(x + (long long)warp * ldx);
+    float4 v[MAXV];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; i++)
+    {
+        const int idx = i * 32 + lane;
+        if (idx < nv)
+        {
+            v[i] = xr[idx];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)dim;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; i++)
+    {
+        const int idx = i * 32 + lane;
+        if (idx < nv)
+        {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)dim + eps);
+    const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
+    const float4 *b4 = reinterpret_cast<const float4 *>(beta);
+    uint2 *yr = reinterpret_cast<uint2 *>(y + (long long)warp * ldy);
+#pragma unroll
+    for (int i = 0; i < MAXV; i++)
+    {
+        const int idx = i * 32 + lane;
+        if (idx < nv)
+        {
+            const float4 g = g4[idx], b = b4[idx];
+            uint2 o;
+            o.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+            o.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+            yr[idx] = o;
+        }
+    }
+}
+
+cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, const float *beta, void *y, long long ldy,
+                             int rows, int dim, float eps, cudaStream_t stream)
+{
+    if (rows <= 0) return cudaSuccess;
+    if (dim <= 0 || (dim & 3) || (ldx & 3) || (ldy & 3) || dim > 4096) return cudaErrorInvalidValue;
+    const int threads = 256, rows_per_block = threads / 32;
+    const int grid = (rows + rows_per_block - 1) / rows_per_block;
+    __nv_bfloat16 *yb = reinterpret_cast<__nv_bfloat16 *>(y);
+    if (dim <= 256)
+        layernorm_kernel<2><<<grid, threads, 0, stream>>>(x, ldx, gamma, beta, yb, ldy, rows, dim, eps);
+    else if (dim <= 1024)
+        layernorm_kernel<8><<<grid, threads, 0, stream>>>(x, ldx, gamma, beta, yb, ldy, rows, dim, eps);
+    else
+        layernorm_kernel<32><<<grid, threads, 0, stream>>>(x, ldx, gamma, beta, yb, ldy, rows, dim, eps);
+    return cudaGetLastError();
+}
+
+// ---- patch extraction: fp32 NCHW image -> bf16 patch rows (the im2col of a stride==kernel conv) ----
+// One thread converts 8 horizontally adjacent pixels (two float4 loads -> one 16-byte store).
+// Threads walk the image in its own memory order, so loads are fully coalesced; the two threads that
+// cover one 16-pixel patch row write adjacent 16-byte halves of the same 32-byte sector.
+
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float *__restrict__ img, __nv_bfloat16 *__restrict__ patches, long long total8, int S, int P, int g)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total8) return;
+    const int s8 = S >> 3;
+    const int x8 = (int)(t % s8);
+    long long r = t / s8;
+    const int yy = (int)(r % S);
+    r /= S;
+    const int ch = (int)(r % 3);
+    const long long b = r / 3;
+    const int x = x8 << 3;
+    const int gy = yy / P, py = yy - gy * P, gx = x / P, px = x - gx * P;
+    const float4 *src = reinterpret_cast<const float4 *>(img + (((b * 3 + ch) * S + yy) * (long long)S + x));
+    const float4 a = src[0], c = src[1];
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y);
+    o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(c.x, c.y);
+    o.w = pack_bf16x2(c.z, c.w);
+    const long long prow = (b * g + gy) * g + gx;
+    const int pcol = (ch * P + py) * P + px;
+    *reinterpret_cast<uint4 *>(patches + prow * (long long)(3 * P * P) + pcol) = o;
+}
+
+cudaError_t launch_patchify(const float *img, void *patches, int batch, int image_size, int patch_size, cudaStream_t stream)
+{
+    if (batch <= 0) return cudaSuccess;
+    if ((patch_size & 7) || (image_size % patch_size)) return cudaErrorInvalidValue;
+    const long long total8 = (long long)batch * 3 * image_size * (image_size >> 3);
+    const int threads = 256;
+    const long long grid = (total8 + threads - 1) / threads;
+    patchify_kernel<<<(unsigned)grid, threads, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16 *>(patches), total8, image_size,
+                                                          patch_size, image_size / patch_size);
+    return cudaGetLastError();
+}
+
+// ---- class-token rows of the residual stream ---------------------------------------------------------
+
+__global__ void cls_rows_kernel(float *__restrict__ x, const float *__restrict__ cls, const float *__restrict__ pos, int batch,
+                                int tokens, int dim)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)batch * dim) return;
+    const int b = (int)(i / dim), c = (int)(i % dim);
+    x[(long long)b * tokens * dim + c] = cls[c] + pos[c];
+}
+
+cudaError_t launch_cls_rows(float *x, const float *cls, const float *pos, int batch, int tokens, int dim, cudaStream_t stream)
+{
+    if (batch <= 0) return cudaSuccess;
+    const long long n = (long long)batch * dim;
+    cls_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, cls, pos, batch, tokens, dim);
+    return cudaGetLastError();
+}
+
+// ---- API-boundary conversions -------------------------------------------------------------------------
+
+template <typename OutT, int MODE> // MODE 0: bf16, 1: fp32 copy, 2: Q1.7 quantise, 3: int8 copy
+__global__ void __launch_bounds__(256)
+convert_rows_kernel(const void *__restrict__ in_, OutT *__restrict__ out, long long rows, int n, int ld)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * ld) return;
+    const long long r = i / ld;
+    const int c = (int)(i - r * ld);
+    if constexpr (MODE == 3)
+    {
+        out[i] = c < n ? reinterpret_cast<const int8_t *>(in_)[r * n + c] : (int8_t)0;
+    }
+    else
+    {
+        const float v = c < n ? reinterpret_cast<const float *>(in_)[r * n + c] : 0.0f;
+        if constexpr (MODE == 0)
+            out[i] = __float2bfloat16_rn(v);
+        else if constexpr (MODE == 1)
+            out[i] = v;
+        else
+        {
+            // clamp(rintf(x * 128), -128, 127): same expression as oracle_quantize_q17
+            float qv = rintf(v * 128.0f);
+            qv = fminf(127.0f, fmaxf(-128.0f, qv));
+            out[i] = (int8_t)qv;
+        }
+    }
+}
+
+template <typename OutT, int MODE>
+static cudaError_t launch_convert(const void *in, OutT *out, long long rows, int n, int ld, cudaStream_t stream)
+{
+    if (rows <= 0) return cudaSuccess;
+    const long long total = rows * ld;
+    convert_rows_kernel<OutT, MODE><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out, rows, n, ld);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_convert_rows_bf16(const float *in, void *out, long long rows, int n, int ld, cudaStream_t stream)
+{
+    return launch_convert<__nv_bfloat16, 0>(in, reinterpret_cast<__nv_bfloat16 *>(out), rows, n, ld, stream);
+}
+cudaError_t launch_convert_rows_f32(const float *in, float *out, long long rows, int n, int ld, cudaStream_t stream)
+{
+    return launch_convert<float, 1>(in, out, rows, n, ld, stream);
+}
+cudaError_t launch_quantize_rows_q17(const float *in, int8_t *out, long long rows, int n, int ld, cudaStream_t stream)
+{
+    return launch_convert<int8_t, 2>(in, out, rows, n, ld, stream);
+}
+cudaError_t launch_pad_rows_i8(const int8_t *in, int8_t *out, long long rows, int n, int ld, cudaStream_t stream)
+{
+    return launch_convert<int8_t, 3>(in, out, rows, n, ld, stream);
+}
+
+__global__ void dequant_q214_kernel(const int32_t *__restrict__ in, float *__restrict__ out, long long count)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (float)in[i] * (1.0f / 16384.0f);
+}
+
+cudaError_t launch_dequant_q214(const int32_t *in, float *out, long long count, cudaStream_t stream)
+{
+    if (count <= 0) return cudaSuccess;
+    dequant_q214_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(in, out, count);
+    return cudaGetLastError();
+}
+
+} // namespace nc

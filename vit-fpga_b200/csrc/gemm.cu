@@ -1,0 +1,290 @@
+// gemm.cu -- host launcher + tensor-map construction for the tcgen05 dense kernel, plus the two
+// CUDA-core dense kernels:
+//   * gemm_fp32_ordered_kernel: NETCUDA_PREC_FP32.  acc = bias, then fmaf in ascending k -- the exact
+//     operation sequence of oracle_mlp_forward_one (oracle/oracle_mlp.c), hence bit-equal results.
+//   * gemm_ref_kernel: same operand types and epilogues as the tcgen05 kernel, one thread per output.
+//     Selected with variant = 1; exists so the tensor-core path can be cross-checked on the GPU at
+//     full problem sizes.  It is a CUDA kernel, not a CPU fallback.
+#include "gemm_tcgen05.cuh"
+#include "kernels.h"
+
+#include <mutex>
+
+namespace nc
+{
+
+// ---- driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda) --------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+
+template <int KIND, int BN, int OUT, int STAGES>
+static cudaError_t opt_in_smem()
+{
+    return cudaFuncSetAttribute(gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmSmem<BN, STAGES>::TOTAL);
+}
+
+constexpr int STAGES_256 = 4;
+constexpr int STAGES_128 = 6;
+
+// cudaFuncSetAttribute is per device, so the opt-in runs once for every device that is used.
+cudaError_t gemm_global_init()
+{
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!g_encode_tiled)
+    {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return e;
+        if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    if (dev < 64 && done[dev]) return cudaSuccess;
+#define NC_OPT(K, O)                                                        \
+    if ((e = opt_in_smem<K, 256, O, STAGES_256>()) != cudaSuccess) return e; \
+    if ((e = opt_in_smem<K, 128, O, STAGES_128>()) != cudaSuccess) return e;
+    NC_OPT(KIND_BF16, OUT_BF16)
+    NC_OPT(KIND_BF16, OUT_F32)
+    NC_OPT(KIND_TF32, OUT_F32)
+    NC_OPT(KIND_I8, OUT_S8)
+    NC_OPT(KIND_I8, OUT_S32)
+#undef NC_OPT
+    if (dev < 64) done[dev] = true;
+    return cudaSuccess;
+}
+
+static int elem_size(int kind) { return kind == GK_BF16 ? 2 : kind == GK_I8 ? 1 : 4; }
+
+// 2-D K-major operand: dims {K, rows}, row pitch `pitch_bytes`, box {128 B of K, box_rows}, 128B swizzle.
+static cudaError_t make_operand_map(CUtensorMap *map, int kind, const void *ptr, long long k, long long rows,
+                                    long long pitch_bytes, int box_rows)
+{
+    if (!g_encode_tiled) return cudaErrorNotReady;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (pitch_bytes & 15) != 0 || k <= 0 || rows <= 0)
+        return cudaErrorInvalidValue;
+    const CUtensorMapDataType dt = kind == GK_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                   : kind == GK_I8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                                   : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)pitch_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)(GEMM_STAGE_ROW_BYTES / elem_size(kind)), (cuuint32_t)box_rows};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, dt, 2, const_cast<void *>(ptr), gdim, gstride, box, estride,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int KIND, int BN, int OUT, int STAGES>
+static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
+{
+    CUtensorMap map_a, map_w;
+    cudaError_t e = make_operand_map(&map_a, c.kind, c.a, c.k, c.a_rows > c.m ? c.a_rows : c.m, c.lda * elem_size(c.kind), GEMM_BM);
+    if (e != cudaSuccess) return e;
+    e = make_operand_map(&map_w, c.kind, c.w, c.k, c.n, c.ldw * elem_size(c.kind), BN);
+    if (e != cudaSuccess) return e;
+    GemmParams p;
+    p.M = c.m, p.N = c.n, p.K = c.k;
+    p.bias = c.bias, p.out = c.out, p.ldc = c.ldc, p.epi = c.epi;
+    p.remap_in = c.remap_in, p.remap_out = c.remap_out, p.pos = c.pos;
+    p.error_flag = c.error_flag;
+    const int tiles = ((c.m + GEMM_BM - 1) / GEMM_BM) * ((c.n + BN - 1) / BN);
+    const int sms = c.num_sms > 0 ? c.num_sms : 148;
+    const int grid = tiles < sms ? tiles : sms;
+    gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES><<<grid, GEMM_THREADS, GemmSmem<BN, STAGES>::TOTAL, stream>>>(map_a, map_w, p);
+    return cudaGetLastError();
+}
+
+template <int KIND, int OUT>
+static cudaError_t launch_tc_bn(const GemmCall &c, cudaStream_t stream)
+{
+    if (c.n <= 128) return launch_tc<KIND, 128, OUT, STAGES_128>(c, stream);
+    return launch_tc<KIND, 256, OUT, STAGES_256>(c, stream);
+}
+
+// ---- CUDA-core reference with identical operand types / epilogues ----------------------------------
+
+template <int KIND>
+__global__ void gemm_ref_kernel(const void *__restrict__ a_, long long lda, const void *__restrict__ w_, long long ldw,
+                                const void *__restrict__ bias_, void *out_, long long ldc, int out_type, int epi, int M, int N,
+                                int K, int remap_in, int remap_out, const float *__restrict__ pos)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y * blockDim.y + threadIdx.y;
+    if (row >= M || col >= N) return;
+    long long orow = row;
+    int prow = 0;
+    if (epi == EPI_PATCH)
+    {
+        const int b = row / remap_in, t = row - b * remap_in;
+        orow = (long long)b * remap_out + 1 + t;
+        prow = 1 + t;
+    }
+    if constexpr (KIND == KIND_I8)
+    {
+        const int8_t *a = reinterpret_cast<const int8_t *>(a_) + (long long)row * lda;
+        const int8_t *w = reinterpret_cast<const int8_t *>(w_) + (long long)col * ldw;
+        int acc = bias_ ? reinterpret_cast<const int *>(bias_)[col] : 0;
+        for (int k = 0; k < K; k++) acc += (int)a[k] * (int)w[k];
+        if (out_type == OUT_S32)
+        {
+            if (epi == EPI_RELU) acc = max(acc, 0);
+            reinterpret_cast<int *>(out_)[orow * ldc + col] = acc;
+        }
+        else
+        {
+            if (epi == EPI_REQUANT_RELU) acc = max(acc, 0);
+            reinterpret_cast<int8_t *>(out_)[orow * ldc + col] = (int8_t)min(127, max(-128, acc >> 7));
+        }
+    }
+    else
+    {
+        float acc = 0.0f;
+        if constexpr (KIND == KIND_BF16)
+        {
+            const __nv_bfloat16 *a = reinterpret_cast<const __nv_bfloat16 *>(a_) + (long long)row * lda;
+            const __nv_bfloat16 *w = reinterpret_cast<const __nv_bfloat16 *>(w_) + (long long)col * ldw;
+            for (int k = 0; k < K; k++) acc = fmaf(__bfloat162float(a[k]), __bfloat162float(w[k]), acc);
+        }
+        else
+        {
+            const float *a = reinterpret_cast<const float *>(a_) + (long long)row * lda;
+            const float *w = reinterpret_cast<const float *>(w_) + (long long)col * ldw;
+            for (int k = 0; k < K; k++) // tf32 operands: the tensor core ignores the low 13 mantissa bits
+                acc = fmaf(__uint_as_float(__float_as_uint(a[k]) & 0xFFFFE000u), __uint_as_float(__float_as_uint(w[k]) & 0xFFFFE000u), acc);
+        }
+        float v = acc + (bias_ ? reinterpret_cast<const float *>(bias_)[col] : 0.0f);
+        v = epi_act_f32(v, epi);
+        if (out_type == OUT_BF16)
+            reinterpret_cast<__nv_bfloat16 *>(out_)[orow * ldc + col] = __float2bfloat16_rn(v);
+        else
+        {
+            float *dst = reinterpret_cast<float *>(out_) + orow * ldc + col;
+            if (epi == EPI_RESIDUAL)
+                v += *dst;
+            else if (epi == EPI_PATCH)
+                v += pos[(long long)prow * N + col];
+            *dst = v;
+        }
+    }
+}
+
+template <int KIND>
+static cudaError_t launch_ref(const GemmCall &c, cudaStream_t stream)
+{
+    dim3 block(32, 8), grid((c.n + 31) / 32, (c.m + 7) / 8);
+    gemm_ref_kernel<KIND><<<grid, block, 0, stream>>>(c.a, c.lda, c.w, c.ldw, c.bias, c.out, c.ldc, c.out_type, c.epi, c.m, c.n,
+                                                      c.k, c.remap_in, c.remap_out, c.pos);
+    return cudaGetLastError();
+}
+
+// ---- NETCUDA_PREC_FP32: ordered fp32 on CUDA cores ------------------------------------------------
+
+__global__ void __launch_bounds__(256)
+gemm_fp32_ordered_kernel(const float *__restrict__ a, long long lda, const float *__restrict__ w, long long ldw,
+                         const float *__restrict__ bias, float *__restrict__ out, long long ldc, int relu, int M, int N, int K)
+{
+    __shared__ float As[16][65];
+    __shared__ float Ws[16][65];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            const int c = col0 + tx * 4 + j;
+            acc[i][j] = (bias != nullptr && c < N) ? bias[c] : 0.0f;
+        }
+    for (int k0 = 0; k0 < K; k0 += 16)
+    {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            const int e = threadIdx.x + i * 256;
+            const int r = e >> 4, kk = e & 15;
+            const bool kin = (k0 + kk) < K;
+            As[kk][r] = (kin && row0 + r < M) ? a[(long long)(row0 + r) * lda + k0 + kk] : 0.0f;
+            Ws[kk][r] = (kin && col0 + r < N) ? w[(long long)(col0 + r) * ldw + k0 + kk] : 0.0f;
+        }
+        __syncthreads();
+        const int kmax = (K - k0) < 16 ? (K - k0) : 16;
+        for (int kk = 0; kk < kmax; kk++) // strictly ascending k: same rounding sequence as the oracle
+        {
+            float av[4], wv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) wv[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(wv[j], av[i], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const int r = row0 + ty * 4 + i;
+        if (r >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            const int c = col0 + tx * 4 + j;
+            if (c >= N) continue;
+            float v = acc[i][j];
+            if (relu && v < 0.0f) v = 0.0f;
+            out[(long long)r * ldc + c] = v;
+        }
+    }
+}
+
+// ---- dispatcher -------------------------------------------------------------------------------------
+
+cudaError_t launch_gemm(const GemmCall &c, cudaStream_t stream)
+{
+    if (c.m <= 0 || c.n <= 0 || c.k <= 0) return cudaErrorInvalidValue;
+    if (c.kind == GK_FP32_SIMT)
+    {
+        if (c.out_type != OUT_F32 || (c.epi != EPI_NONE && c.epi != EPI_RELU)) return cudaErrorInvalidValue;
+        dim3 grid((c.n + 63) / 64, (c.m + 63) / 64);
+        gemm_fp32_ordered_kernel<<<grid, 256, 0, stream>>>((const float *)c.a, c.lda, (const float *)c.w, c.ldw,
+                                                         (const float *)c.bias, (float *)c.out, c.ldc, c.epi == EPI_RELU, c.m,
+                                                         c.n, c.k);
+        return cudaGetLastError();
+    }
+    if (c.variant == 1)
+    {
+        if (c.kind == GK_BF16) return launch_ref<KIND_BF16>(c, stream);
+        if (c.kind == GK_TF32) return launch_ref<KIND_TF32>(c, stream);
+        return launch_ref<KIND_I8>(c, stream);
+    }
+    if (c.kind == GK_BF16)
+    {
+        if (c.out_type == OUT_BF16) return launch_tc_bn<KIND_BF16, OUT_BF16>(c, stream);
+        if (c.out_type == OUT_F32) return launch_tc_bn<KIND_BF16, OUT_F32>(c, stream);
+    }
+    else if (c.kind == GK_TF32)
+    {
+        if (c.out_type == OUT_F32) return launch_tc_bn<KIND_TF32, OUT_F32>(c, stream);
+    }
+    else if (c.kind == GK_I8)
+    {
+        if (c.out_type == OUT_S8) return launch_tc_bn<KIND_I8, OUT_S8>(c, stream);
+        if (c.out_type == OUT_S32) return launch_tc_bn<KIND_I8, OUT_S32>(c, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+} // namespace nc

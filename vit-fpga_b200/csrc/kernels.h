@@ -1,0 +1,67 @@
+// kernels.h -- host-side launchers of every device kernel in the library (internal header).
+// Each launcher enqueues exactly one kernel on `stream` and returns the CUDA status of the launch.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nc
+{
+
+// Operand kinds of the dense kernel (match ptx.cuh KIND_*), plus the CUDA-core fp32 path.
+enum : int
+{
+    GK_BF16 = 0,
+    GK_TF32 = 1,
+    GK_I8 = 2,
+    GK_FP32_SIMT = 3
+};
+
+struct GemmCall
+{
+    int kind;                // GK_*
+    int variant;             // 0 = tcgen05, 1 = CUDA-core reference with identical operand types
+    const void *a;           // [M][lda] operand type
+    long long lda;
+    int a_rows;              // rows addressable behind `a` (>= M); TMA bounds
+    const void *w;           // [N][ldw]
+    long long ldw;
+    const void *bias;        // float[N] or int32[N] (int8 kind) or null
+    void *out;
+    long long ldc;
+    int out_type;            // OUT_* (gemm_tcgen05.cuh)
+    int epi;                 // EPI_*
+    int m, n, k;
+    int remap_in, remap_out; // EPI_PATCH
+    const float *pos;
+    int *error_flag;
+    int num_sms;
+};
+
+// out = epilogue(A . W^T + bias) -- tcgen05 path or reference path depending on call.variant / kind.
+cudaError_t launch_gemm(const GemmCall &call, cudaStream_t stream);
+// One-time per-process setup of the tcgen05 kernels (dynamic smem opt-in, driver entry point).
+cudaError_t gemm_global_init();
+
+// y = LayerNorm(x) * gamma + beta; x fp32 rows (pitch ldx), y bf16 rows (pitch ldy).
+cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, const float *beta, void *y, long long ldy,
+                             int rows, int dim, float eps, cudaStream_t stream);
+
+// softmax(q k^T / sqrt(64)) v per (image, head) on packed bf16 qkv rows; head_dim fixed at 64.
+cudaError_t launch_attention(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream);
+
+// fp32 NCHW -> bf16 patch rows [batch * np][3 * p * p].
+cudaError_t launch_patchify(const float *img, void *patches, int batch, int image_size, int patch_size, cudaStream_t stream);
+
+// x[b * tokens][:] = cls + pos[0]  (fp32 residual stream rows of the class token)
+cudaError_t launch_cls_rows(float *x, const float *cls, const float *pos, int batch, int tokens, int dim, cudaStream_t stream);
+
+// Row-wise conversions of the fp32 API inputs into the operand type, zero-padding [n, ld).
+cudaError_t launch_convert_rows_bf16(const float *in, void *out, long long rows, int n, int ld, cudaStream_t stream);
+cudaError_t launch_convert_rows_f32(const float *in, float *out, long long rows, int n, int ld, cudaStream_t stream);
+cudaError_t launch_quantize_rows_q17(const float *in, int8_t *out, long long rows, int n, int ld, cudaStream_t stream);
+cudaError_t launch_pad_rows_i8(const int8_t *in, int8_t *out, long long rows, int n, int ld, cudaStream_t stream);
+// out_f32 = (float)acc * 2^-14   (INT8 nets through the float API)
+cudaError_t launch_dequant_q214(const int32_t *in, float *out, long long count, cudaStream_t stream);
+
+} // namespace nc

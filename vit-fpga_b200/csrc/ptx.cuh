@@ -1,0 +1,216 @@
+// ptx.cuh -- thin inline-PTX wrappers for the sm_100a features the kernels use:
+// mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (MMA / TMEM alloc / TMEM load / commit / fences).
+// Every wrapper is one instruction (or one short sequence); no policy lives here.
+#pragma once
+
+#include <cuda.h> // CUtensorMap (type only; libcuda is resolved at run time, see tensormap.cuh)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nc
+{
+
+// Codes written to the per-handle error flag when a pipeline wait exceeds its budget.
+enum : int
+{
+    KERR_NONE = 0,
+    KERR_PRODUCER_EMPTY = 1,
+    KERR_MMA_FULL = 2,
+    KERR_MMA_TMEM_EMPTY = 3,
+    KERR_EPI_TMEM_FULL = 4,
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ------------------------------------------------------------------------------
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+// Make barrier initialisation visible to the async proxy (TMA, tcgen05.commit).
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// Order generic-proxy shared-memory writes before async-proxy reads (e.g. st.shared -> TMA store / UMMA).
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t"
+                 "}"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return done != 0;
+}
+
+// Bounded wait.  A correct pipeline never gets near the budget (~4 s); a broken one records
+// `code` in *err and traps, so a bug turns into a reported error instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *err, int code)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity))
+    {
+        if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 8000000000LL)
+        {
+            if (err) atomicExch(err, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+
+// ---- TMA -----------------------------------------------------------------------------------
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// 2-D tiled load global -> shared; completion (bytes) is signalled on `bar`.
+// c0 = coordinate along the contiguous (K) dimension, c1 = row coordinate, both in elements.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst_smem), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// ---- tcgen05: tensor memory ------------------------------------------------------------------
+
+// Whole-warp (.sync.aligned).  Writes the TMEM base address of `ncols` columns to *dst_smem.
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish()
+{
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// mbarrier arrive once every tcgen05.mma issued so far by this thread has completed.
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp receives row (lane) t.
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t *r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- tcgen05: descriptors and MMA ------------------------------------------------------------
+
+// Shared-memory matrix descriptor for a K-major operand tile whose rows are 128 bytes and which
+// was written by TMA with CU_TENSOR_MAP_SWIZZLE_128B (tile base 1024-byte aligned):
+//   [0,14)  start address >> 4        [16,30) leading byte offset >> 4 (ignored for swizzled K-major; 1)
+//   [32,46) stride byte offset >> 4 = 8 rows * 128 B = 1024 -> 64
+//   [46,48) descriptor version = 1 (sm_100)            [61,64) layout type 2 = SWIZZLE_128B
+// Advancing along K inside the 128-byte swizzle atom = adding (bytes >> 4) to the start address.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor (upper 32 bits of the "idesc" operand), dense, no negate, both operands K-major:
+//   [4,6) D format (1 = F32, 2 = S32)   [7,10) A format   [10,13) B format
+//   [17,23) N >> 3                      [24,29) M >> 4
+// kind::f16: format 0 = F16, 1 = BF16;  kind::tf32: 2 = TF32;  kind::i8: 0 = U8, 1 = S8.
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t d_fmt, uint32_t ab_fmt, uint32_t m, uint32_t n)
+{
+    return (d_fmt << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+enum : int
+{
+    KIND_BF16 = 0,
+    KIND_TF32 = 1,
+    KIND_I8 = 2
+};
+
+// D[tmem] (+)= A[smem] * B[smem]^T.  Single-thread instruction; `accumulate` = 0 overwrites D.
+template <int KIND>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    if constexpr (KIND == KIND_BF16)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    else if constexpr (KIND == KIND_TF32)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+}
+
+// ---- misc ------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi); // .x = lo (low 16 bits), .y = hi
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+// Exact-erf GELU, x * Phi(x).  erfc via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), arranged so
+// that the negative tail has no 1 - erf cancellation.
+__device__ __forceinline__ float gelu_erf(float x)
+{
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float q = poly * t * __expf(-z * z); // erfc(|z|)
+    const float cdf = x >= 0.0f ? fmaf(-0.5f, q, 1.0f) : 0.5f * q;
+    return x * cdf;
+}
+
+} // namespace nc

@@ -1,0 +1,846 @@
+// runtime.cu -- host runtime behind the C ABI of include/netcuda.h.
+//
+// Replaces the OpenCL plumbing of the reference's src/netFPGA.cpp: device discovery and context
+// (_init_program :367-400), buffer creation (_init_kernel :402-441), weight upload (_load_params
+// :484-515), the per-sample write/task/read triple (launch_forward :266-277) and teardown
+// (cleanup :639-651).  Differences by design: state is per handle (the reference uses namespace
+// globals, :21-56), inputs are batched, errors are returned instead of exit()ing, and the device
+// side is a sequence of sm_100a kernels (csrc/*.cu) instead of one FPGA task.
+//
+// HBM layout per handle
+//   weights  one arena; every tensor 256-byte aligned.  MLP: per layer W[out][ld(in)] in the operand
+//            type (fp32 / bf16 / int8; ld = fan-in rounded up to 16 bytes) + bias (fp32 or int32).
+//            ViT: bf16 W[out][in] for the six GEMMs per block + patch/head, fp32 for bias/LN/cls/pos.
+//   work     activations of one pass of `max_batch` samples (MLP: two ping-pong matrices;
+//            ViT: patches, fp32 residual stream x, bf16 LN-out / qkv / attention-out / MLP-hidden).
+//   staging  (host API only, lazily) 2 pinned host + 2 device input slots and a device/pinned output.
+#include "../../include/netcuda.h"
+#include "gemm_tcgen05.cuh"
+#include "kernels.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace nc;
+
+// ---- error reporting -----------------------------------------------------------------------------
+
+static thread_local char g_last_error[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(expr)                                                                                              \
+    do                                                                                                        \
+    {                                                                                                         \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            return fail(NETCUDA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+// ---- handle --------------------------------------------------------------------------------------
+
+struct MlpLayer
+{
+    int fan_in, fan_out;
+    long long ldw;   // elements
+    void *w;         // operand type
+    void *bias;      // float or int32
+};
+
+struct VitBlock
+{
+    float *ln1_g, *ln1_b, *qkv_b, *proj_b, *ln2_g, *ln2_b, *fc1_b, *fc2_b;
+    void *qkv_w, *proj_w, *fc1_w, *fc2_w; // bf16
+};
+
+struct netcuda_net
+{
+    netcuda_desc desc;
+    std::vector<int> npl;
+    int device = 0, num_sms = 148;
+    int max_batch = 0;
+    int gemm_variant = 0;
+    bool weights_loaded = false;
+    size_t n_in = 0, n_out = 0;
+    double flops_per_sample = 0;
+    uint64_t launches = 0;
+    int64_t last_us = 0;
+
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, compute_done[2] = {nullptr, nullptr};
+
+    int *h_err = nullptr; // mapped pinned: readable even after a device-side trap
+    int *d_err = nullptr;
+
+    // weights
+    char *arena = nullptr;
+    size_t arena_bytes = 0, arena_used = 0;
+    std::vector<MlpLayer> layers;
+    int elem = 4;        // operand element size (MLP)
+    long long max_ld = 0; // widest padded activation row (MLP)
+    // ViT
+    int T = 0, NP = 0, PK = 0;
+    void *patch_w = nullptr, *head_w = nullptr;
+    float *patch_b = nullptr, *cls = nullptr, *pos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr, *head_b = nullptr;
+    std::vector<VitBlock> blocks;
+
+    // work buffers
+    void *act[2] = {nullptr, nullptr};     // MLP ping-pong
+    int32_t *acc_out = nullptr;            // INT8 float API: last layer accumulators
+    void *patches = nullptr, *ybuf = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *cls_ln = nullptr;
+    float *x = nullptr;
+
+    // host-API staging (lazy)
+    void *pin_in[2] = {nullptr, nullptr}, *dev_in[2] = {nullptr, nullptr};
+    size_t stage_in_bytes = 0;
+    void *dev_out = nullptr, *pin_out = nullptr;
+    size_t out_bytes = 0;
+};
+
+static int check_handle(const netcuda_net *h)
+{
+    if (!h) return fail(NETCUDA_ERR_INVALID, "null handle");
+    return NETCUDA_OK;
+}
+
+static void *arena_take(netcuda_net *h, size_t bytes)
+{
+    const size_t off = (size_t)round_up((long long)h->arena_used, 256);
+    if (off + bytes > h->arena_bytes) return nullptr;
+    h->arena_used = off + bytes;
+    return h->arena + off;
+}
+
+static int operand_kind(int precision)
+{
+    switch (precision)
+    {
+    case NETCUDA_PREC_FP32: return GK_FP32_SIMT;
+    case NETCUDA_PREC_TF32: return GK_TF32;
+    case NETCUDA_PREC_BF16: return GK_BF16;
+    default: return GK_I8;
+    }
+}
+
+static size_t vit_param_count(const netcuda_desc *d)
+{
+    const size_t D = d->dim, F = d->mlp_dim, C = d->n_classes;
+    const size_t g = d->image_size / d->patch_size, N = g * g + 1, pk = 3u * d->patch_size * d->patch_size;
+    size_t n = D * pk + D + D + N * D;
+    n += (size_t)d->depth * (2 * D + 3 * D * D + 3 * D + D * D + D + 2 * D + F * D + F + D * F + D);
+    n += 2 * D + C * D + C;
+    return n;
+}
+
+static int validate_desc(const netcuda_desc *d)
+{
+    if (!d) return fail(NETCUDA_ERR_INVALID, "null descriptor");
+    if (d->precision < NETCUDA_PREC_FP32 || d->precision > NETCUDA_PREC_INT8)
+        return fail(NETCUDA_ERR_INVALID, "unknown precision %d", d->precision);
+    if (d->kind == NETCUDA_KIND_MLP)
+    {
+        if (d->n_ins <= 0 || d->n_layers <= 0 || !d->n_p_l) return fail(NETCUDA_ERR_INVALID, "MLP needs n_ins, n_layers, n_p_l");
+        for (int i = 0; i < d->n_layers; i++)
+            if (d->n_p_l[i] <= 0) return fail(NETCUDA_ERR_INVALID, "n_p_l[%d] must be positive", i);
+        if (d->activation < NETCUDA_ACT_RELU_HIDDEN || d->activation > NETCUDA_ACT_NONE)
+            return fail(NETCUDA_ERR_INVALID, "unknown activation %d", d->activation);
+        return NETCUDA_OK;
+    }
+    if (d->kind == NETCUDA_KIND_VIT)
+    {
+        if (d->precision != NETCUDA_PREC_BF16)
+            return fail(NETCUDA_ERR_UNSUPPORTED, "ViT nets run in NETCUDA_PREC_BF16 (got precision %d)", d->precision);
+        if (d->image_size <= 0 || d->patch_size <= 0 || d->image_size % d->patch_size || d->patch_size % 8)
+            return fail(NETCUDA_ERR_INVALID, "image_size must be a multiple of patch_size, patch_size a multiple of 8");
+        if (d->dim <= 0 || d->heads <= 0 || d->dim != d->heads * 64)
+            return fail(NETCUDA_ERR_UNSUPPORTED, "dim must equal heads * 64 (head_dim 64 only)");
+        if (d->depth <= 0 || d->mlp_dim <= 0 || d->n_classes <= 0 || d->dim % 8 || d->mlp_dim % 8)
+            return fail(NETCUDA_ERR_INVALID, "bad ViT dimensions");
+        return NETCUDA_OK;
+    }
+    return fail(NETCUDA_ERR_INVALID, "unknown net kind %d", d->kind);
+}
+
+// ---- C ABI: life cycle -----------------------------------------------------------------------------
+
+extern "C" int netcuda_abi_version(void) { return NETCUDA_ABI_VERSION; }
+extern "C" const char *netcuda_last_error(void) { return g_last_error; }
+
+extern "C" int netcuda_device_count(int *count)
+{
+    if (!count) return fail(NETCUDA_ERR_INVALID, "null count");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess)
+    {
+        *count = 0;
+        (void)cudaGetLastError();
+        return fail(NETCUDA_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_destroy(netcuda_net *h)
+{
+    if (!h) return NETCUDA_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    void *dev_ptrs[] = {h->arena, h->act[0], h->act[1], h->acc_out, h->patches, h->ybuf, h->qkv, h->att, h->hid, h->cls_ln, h->x,
+                        h->dev_in[0], h->dev_in[1], h->dev_out};
+    for (void *p : dev_ptrs)
+        if (p) cudaFree(p);
+    void *host_ptrs[] = {h->pin_in[0], h->pin_in[1], h->pin_out, h->h_err};
+    for (void *p : host_ptrs)
+        if (p) cudaFreeHost(p);
+    for (int i = 0; i < 2; i++)
+    {
+        if (h->h2d_done[i]) cudaEventDestroy(h->h2d_done[i]);
+        if (h->compute_done[i]) cudaEventDestroy(h->compute_done[i]);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    (void)cudaGetLastError();
+    delete h;
+    return NETCUDA_OK;
+}
+
+static int create_impl(const netcuda_desc *desc, netcuda_net *h)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        (void)cudaGetLastError();
+        return fail(NETCUDA_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+    }
+    if (desc->device < 0 || desc->device >= ndev) return fail(NETCUDA_ERR_INVALID, "device %d out of range [0,%d)", desc->device, ndev);
+    h->device = desc->device;
+    CK(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major != 10)
+        return fail(NETCUDA_ERR_NO_DEVICE, "device %d is sm_%d%d; this library contains sm_100a code only", h->device, prop.major, prop.minor);
+    h->num_sms = prop.multiProcessorCount;
+    CK(gemm_global_init());
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++)
+    {
+        CK(cudaEventCreateWithFlags(&h->h2d_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->compute_done[i], cudaEventDisableTiming));
+    }
+    CK(cudaHostAlloc((void **)&h->h_err, sizeof(int), cudaHostAllocMapped));
+    *h->h_err = 0;
+    CK(cudaHostGetDevicePointer((void **)&h->d_err, h->h_err, 0));
+
+    h->desc = *desc;
+    h->desc.n_p_l = nullptr;
+
+    if (desc->kind == NETCUDA_KIND_MLP)
+    {
+        h->npl.assign(desc->n_p_l, desc->n_p_l + desc->n_layers);
+        h->n_in = (size_t)desc->n_ins;
+        h->n_out = (size_t)h->npl.back();
+        h->max_batch = desc->max_batch > 0 ? desc->max_batch : 16384;
+        const int kind = operand_kind(desc->precision);
+        h->elem = kind == GK_BF16 ? 2 : kind == GK_I8 ? 1 : 4;
+        const int pad = kind == GK_FP32_SIMT ? 1 : 16 / h->elem; // TMA: row pitch multiple of 16 bytes
+        size_t bytes = 0;
+        long long fan_in = desc->n_ins;
+        h->max_ld = round_up(fan_in, pad);
+        double macs = 0;
+        for (int l = 0; l < desc->n_layers; l++)
+        {
+            MlpLayer L;
+            L.fan_in = (int)fan_in, L.fan_out = h->npl[l];
+            L.ldw = round_up(fan_in, pad);
+            L.w = L.bias = nullptr;
+            bytes += (size_t)round_up((long long)L.fan_out * L.ldw * h->elem, 256) + (size_t)round_up((long long)L.fan_out * 4, 256) + 512;
+            macs += (double)fan_in * L.fan_out;
+            h->layers.push_back(L);
+            fan_in = L.fan_out;
+            if (round_up(fan_in, pad) > h->max_ld) h->max_ld = round_up(fan_in, pad);
+        }
+        h->flops_per_sample = 2.0 * macs;
+        h->arena_bytes = bytes;
+        CK(cudaMalloc((void **)&h->arena, h->arena_bytes));
+        CK(cudaMemset(h->arena, 0, h->arena_bytes));
+        for (auto &L : h->layers)
+        {
+            L.w = arena_take(h, (size_t)L.fan_out * L.ldw * h->elem);
+            L.bias = arena_take(h, (size_t)L.fan_out * 4);
+            if (!L.w || !L.bias) return fail(NETCUDA_ERR_CUDA, "weight arena overflow");
+        }
+        const size_t act_bytes = (size_t)h->max_batch * h->max_ld * h->elem;
+        CK(cudaMalloc(&h->act[0], act_bytes));
+        CK(cudaMalloc(&h->act[1], act_bytes));
+        CK(cudaMemset(h->act[0], 0, act_bytes));
+        CK(cudaMemset(h->act[1], 0, act_bytes));
+        if (desc->precision == NETCUDA_PREC_INT8) CK(cudaMalloc((void **)&h->acc_out, (size_t)h->max_batch * h->n_out * 4));
+    }
+    else
+    {
+        const int D = desc->dim, F = desc->mlp_dim, C = desc->n_classes, P = desc->patch_size;
+        const int g = desc->image_size / P;
+        h->NP = g * g, h->T = h->NP + 1, h->PK = 3 * P * P;
+        h->n_in = (size_t)3 * desc->image_size * desc->image_size;
+        h->n_out = (size_t)C;
+        h->max_batch = desc->max_batch > 0 ? desc->max_batch : 256;
+        const double N = h->T;
+        // dense MACs per block: qkv 3D^2 + proj D^2 + fc1 D*F + fc2 F*D per token, attention 2*N*D per token
+        h->flops_per_sample = 2.0 * ((double)h->NP * h->PK * D +
+                                     desc->depth * (N * (4.0 * D * D + 2.0 * D * F) + 2.0 * N * N * D) + (double)D * C);
+        const size_t nparams = vit_param_count(desc);
+        h->arena_bytes = nparams * 4 + (size_t)(desc->depth * 12 + 16) * 256; // generous: every tensor as fp32 + alignment
+        CK(cudaMalloc((void **)&h->arena, h->arena_bytes));
+        auto take = [&](size_t bytes) { return arena_take(h, bytes); };
+        h->patch_w = take((size_t)D * h->PK * 2);
+        h->patch_b = (float *)take((size_t)D * 4);
+        h->cls = (float *)take((size_t)D * 4);
+        h->pos = (float *)take((size_t)h->T * D * 4);
+        h->blocks.resize(desc->depth);
+        for (auto &b : h->blocks)
+        {
+            b.ln1_g = (float *)take((size_t)D * 4), b.ln1_b = (float *)take((size_t)D * 4);
+            b.qkv_w = take((size_t)3 * D * D * 2), b.qkv_b = (float *)take((size_t)3 * D * 4);
+            b.proj_w = take((size_t)D * D * 2), b.proj_b = (float *)take((size_t)D * 4);
+            b.ln2_g = (float *)take((size_t)D * 4), b.ln2_b = (float *)take((size_t)D * 4);
+            b.fc1_w = take((size_t)F * D * 2), b.fc1_b = (float *)take((size_t)F * 4);
+            b.fc2_w = take((size_t)D * F * 2), b.fc2_b = (float *)take((size_t)D * 4);
+        }
+        h->lnf_g = (float *)take((size_t)D * 4), h->lnf_b = (float *)take((size_t)D * 4);
+        h->head_w = take((size_t)C * D * 2), h->head_b = (float *)take((size_t)C * 4);
+        if (!h->head_b) return fail(NETCUDA_ERR_CUDA, "weight arena overflow");
+
+        const size_t mb = (size_t)h->max_batch, rows = mb * h->T;
+        CK(cudaMalloc(&h->patches, mb * h->NP * h->PK * 2));
+        CK(cudaMalloc((void **)&h->x, rows * D * 4));
+        CK(cudaMalloc(&h->ybuf, rows * D * 2));
+        CK(cudaMalloc(&h->qkv, rows * 3 * D * 2));
+        CK(cudaMalloc(&h->att, rows * D * 2));
+        CK(cudaMalloc(&h->hid, rows * F * 2));
+        CK(cudaMalloc(&h->cls_ln, mb * D * 2));
+    }
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_create(const netcuda_desc *desc, netcuda_net **out)
+{
+    if (!out) return fail(NETCUDA_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int rc = validate_desc(desc);
+    if (rc != NETCUDA_OK) return rc;
+    netcuda_net *h = new netcuda_net();
+    rc = create_impl(desc, h);
+    if (rc != NETCUDA_OK)
+    {
+        char keep[sizeof(g_last_error)];
+        memcpy(keep, g_last_error, sizeof(keep));
+        netcuda_destroy(h);
+        memcpy(g_last_error, keep, sizeof(keep));
+        return rc;
+    }
+    *out = h;
+    return NETCUDA_OK;
+}
+
+// ---- weights ----------------------------------------------------------------------------------------
+
+// fp32 host tensor [rows][cols] -> device tensor [rows][ld] in the operand type, via a device scratch copy.
+static int upload_matrix(netcuda_net *h, const float *src, long long rows, int cols, long long ld, int kind, void *dst, float *scratch)
+{
+    CK(cudaMemcpyAsync(scratch, src, (size_t)rows * cols * 4, cudaMemcpyHostToDevice, h->stream));
+    cudaError_t e;
+    if (kind == GK_BF16)
+        e = launch_convert_rows_bf16(scratch, dst, rows, cols, (int)ld, h->stream);
+    else if (kind == GK_I8)
+        e = launch_quantize_rows_q17(scratch, (int8_t *)dst, rows, cols, (int)ld, h->stream);
+    else
+        e = launch_convert_rows_f32(scratch, (float *)dst, rows, cols, (int)ld, h->stream);
+    CK(e);
+    h->launches++;
+    CK(cudaStreamSynchronize(h->stream)); // scratch and the pageable source are reused by the caller
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_upload_mlp(netcuda_net *h, const float *w_flat, const float *b_flat)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (h->desc.kind != NETCUDA_KIND_MLP) return fail(NETCUDA_ERR_INVALID, "not an MLP handle");
+    if (!w_flat || !b_flat) return fail(NETCUDA_ERR_INVALID, "null weights");
+    CK(cudaSetDevice(h->device));
+    const int kind = operand_kind(h->desc.precision);
+    size_t biggest = 0;
+    for (auto &L : h->layers) biggest = std::max(biggest, (size_t)L.fan_in * L.fan_out);
+    float *scratch = nullptr;
+    CK(cudaMalloc((void **)&scratch, biggest * 4));
+    int rc = NETCUDA_OK;
+    for (auto &L : h->layers)
+    {
+        rc = upload_matrix(h, w_flat, L.fan_out, L.fan_in, L.ldw, kind, L.w, scratch);
+        if (rc != NETCUDA_OK) break;
+        if (kind == GK_I8)
+        {
+            // bias: Q2.14 int32, (int32) rintf(b * 16384) -- same expression as oracle_quantize_bias_q214
+            std::vector<int32_t> q(L.fan_out);
+            for (int j = 0; j < L.fan_out; j++) q[j] = (int32_t)rintf(b_flat[j] * 16384.0f);
+            cudaError_t e = cudaMemcpy(L.bias, q.data(), (size_t)L.fan_out * 4, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { rc = fail(NETCUDA_ERR_CUDA, "bias upload: %s", cudaGetErrorString(e)); break; }
+        }
+        else
+        {
+            cudaError_t e = cudaMemcpy(L.bias, b_flat, (size_t)L.fan_out * 4, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { rc = fail(NETCUDA_ERR_CUDA, "bias upload: %s", cudaGetErrorString(e)); break; }
+        }
+        w_flat += (size_t)L.fan_in * L.fan_out;
+        b_flat += L.fan_out;
+    }
+    cudaFree(scratch);
+    if (rc == NETCUDA_OK) h->weights_loaded = true;
+    return rc;
+}
+
+extern "C" int netcuda_upload_mlp_i8(netcuda_net *h, const int8_t *w_flat, const int32_t *b_flat)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (h->desc.kind != NETCUDA_KIND_MLP || h->desc.precision != NETCUDA_PREC_INT8)
+        return fail(NETCUDA_ERR_INVALID, "netcuda_upload_mlp_i8 needs an INT8 MLP handle");
+    if (!w_flat || !b_flat) return fail(NETCUDA_ERR_INVALID, "null weights");
+    CK(cudaSetDevice(h->device));
+    for (auto &L : h->layers)
+    {
+        CK(cudaMemcpy2D(L.w, (size_t)L.ldw, w_flat, (size_t)L.fan_in, (size_t)L.fan_in, (size_t)L.fan_out, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(L.bias, b_flat, (size_t)L.fan_out * 4, cudaMemcpyHostToDevice));
+        w_flat += (size_t)L.fan_in * L.fan_out;
+        b_flat += L.fan_out;
+    }
+    h->weights_loaded = true;
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_vit_param_count(const netcuda_desc *desc, size_t *count)
+{
+    if (!desc || !count) return fail(NETCUDA_ERR_INVALID, "null argument");
+    if (desc->kind != NETCUDA_KIND_VIT || desc->patch_size <= 0) return fail(NETCUDA_ERR_INVALID, "not a ViT descriptor");
+    *count = vit_param_count(desc);
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_upload_vit(netcuda_net *h, const float *flat, size_t count)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (h->desc.kind != NETCUDA_KIND_VIT) return fail(NETCUDA_ERR_INVALID, "not a ViT handle");
+    if (!flat || count != vit_param_count(&h->desc))
+        return fail(NETCUDA_ERR_INVALID, "ViT parameter count mismatch: got %zu, expected %zu", count, vit_param_count(&h->desc));
+    CK(cudaSetDevice(h->device));
+    const int D = h->desc.dim, F = h->desc.mlp_dim, C = h->desc.n_classes;
+    size_t biggest = std::max((size_t)D * h->PK, std::max((size_t)3 * D * D, std::max((size_t)F * D, (size_t)C * D)));
+    float *scratch = nullptr;
+    CK(cudaMalloc((void **)&scratch, biggest * 4));
+    const float *p = flat;
+    int rc = NETCUDA_OK;
+    auto mat = [&](void *dst, long long rows, int cols) {
+        if (rc == NETCUDA_OK) rc = upload_matrix(h, p, rows, cols, cols, GK_BF16, dst, scratch);
+        p += (size_t)rows * cols;
+    };
+    auto vec = [&](float *dst, size_t n) {
+        if (rc == NETCUDA_OK && cudaMemcpy(dst, p, n * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = fail(NETCUDA_ERR_CUDA, "ViT vector upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        p += n;
+    };
+    mat(h->patch_w, D, h->PK);
+    vec(h->patch_b, D);
+    vec(h->cls, D);
+    vec(h->pos, (size_t)h->T * D);
+    for (auto &b : h->blocks)
+    {
+        vec(b.ln1_g, D), vec(b.ln1_b, D);
+        mat(b.qkv_w, 3LL * D, D), vec(b.qkv_b, 3 * (size_t)D);
+        mat(b.proj_w, D, D), vec(b.proj_b, D);
+        vec(b.ln2_g, D), vec(b.ln2_b, D);
+        mat(b.fc1_w, F, D), vec(b.fc1_b, F);
+        mat(b.fc2_w, D, F), vec(b.fc2_b, D);
+    }
+    vec(h->lnf_g, D), vec(h->lnf_b, D);
+    mat(h->head_w, C, D), vec(h->head_b, C);
+    cudaFree(scratch);
+    if (rc == NETCUDA_OK) h->weights_loaded = true;
+    return rc;
+}
+
+// ---- forward: one pass over <= max_batch samples, everything on `s` -----------------------------------
+
+static cudaError_t run_gemm(netcuda_net *h, int kind, const void *a, long long lda, int a_rows, const void *w, long long ldw,
+                            const void *bias, void *out, long long ldc, int out_type, int epi, int m, int n, int k,
+                            cudaStream_t s, int remap_in = 0, int remap_out = 0, const float *pos = nullptr)
+{
+    GemmCall c;
+    c.kind = kind, c.variant = h->gemm_variant;
+    c.a = a, c.lda = lda, c.a_rows = a_rows, c.w = w, c.ldw = ldw, c.bias = bias;
+    c.out = out, c.ldc = ldc, c.out_type = out_type, c.epi = epi;
+    c.m = m, c.n = n, c.k = k;
+    c.remap_in = remap_in, c.remap_out = remap_out, c.pos = pos;
+    c.error_flag = h->d_err, c.num_sms = h->num_sms;
+    h->launches++;
+    return launch_gemm(c, s);
+}
+
+// MLP pass.  `in_f32` (fp32 [n][n_in]) or `in_i8` (int8 [n][n_in]); writes fp32 `out_f32` or int32 `out_i32`.
+static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, int n, float *out_f32, int32_t *out_i32, cudaStream_t s)
+{
+    const int prec = h->desc.precision, kind = operand_kind(prec);
+    const int L = (int)h->layers.size();
+    const long long ld0 = h->layers[0].ldw;
+    const void *cur;
+    long long cur_ld;
+    if (prec == NETCUDA_PREC_FP32)
+    {
+        cur = in_f32, cur_ld = (long long)h->n_in; // CUDA-core path reads the caller's matrix in place
+    }
+    else
+    {
+        cudaError_t e;
+        if (prec == NETCUDA_PREC_BF16)
+            e = launch_convert_rows_bf16(in_f32, h->act[0], n, (int)h->n_in, (int)ld0, s);
+        else if (prec == NETCUDA_PREC_TF32)
+            e = launch_convert_rows_f32(in_f32, (float *)h->act[0], n, (int)h->n_in, (int)ld0, s);
+        else if (in_i8)
+            e = launch_pad_rows_i8(in_i8, (int8_t *)h->act[0], n, (int)h->n_in, (int)ld0, s);
+        else
+            e = launch_quantize_rows_q17(in_f32, (int8_t *)h->act[0], n, (int)h->n_in, (int)ld0, s);
+        CK(e);
+        h->launches++;
+        cur = h->act[0], cur_ld = ld0;
+    }
+    int slot = 1;
+    for (int l = 0; l < L; l++)
+    {
+        const MlpLayer &ly = h->layers[l];
+        const bool last = (l == L - 1);
+        const bool relu = h->desc.activation == NETCUDA_ACT_RELU_ALL || (h->desc.activation == NETCUDA_ACT_RELU_HIDDEN && !last);
+        void *dst;
+        long long ldc;
+        int out_type, epi;
+        if (prec == NETCUDA_PREC_INT8)
+        {
+            if (last)
+                dst = out_i32 ? (void *)out_i32 : (void *)h->acc_out, ldc = ly.fan_out, out_type = OUT_S32, epi = relu ? EPI_RELU : EPI_NONE;
+            else
+                dst = h->act[slot], ldc = h->layers[l + 1].ldw, out_type = OUT_S8, epi = relu ? EPI_REQUANT_RELU : EPI_REQUANT;
+        }
+        else
+        {
+            epi = relu ? EPI_RELU : EPI_NONE;
+            if (last)
+                dst = out_f32, ldc = ly.fan_out, out_type = OUT_F32;
+            else
+            {
+                dst = h->act[slot], ldc = h->layers[l + 1].ldw;
+                out_type = prec == NETCUDA_PREC_BF16 ? OUT_BF16 : OUT_F32;
+            }
+        }
+        // the tensor maps are built with inner extent K = fan_in, so pad columns [fan_in, ld) are never read
+        const int a_rows = (cur == (const void *)in_f32) ? n : h->max_batch;
+        CK(run_gemm(h, kind, cur, cur_ld, a_rows, ly.w, ly.ldw, ly.bias, dst, ldc, out_type, epi, n, ly.fan_out, ly.fan_in, s));
+        cur = dst, cur_ld = ldc;
+        slot ^= 1;
+    }
+    if (prec == NETCUDA_PREC_INT8 && !out_i32)
+    {
+        CK(launch_dequant_q214(h->acc_out, out_f32, (long long)n * (long long)h->n_out, s));
+        h->launches++;
+    }
+    return NETCUDA_OK;
+}
+
+static int vit_pass(netcuda_net *h, const float *img, int n, float *logits, cudaStream_t s)
+{
+    const int D = h->desc.dim, F = h->desc.mlp_dim, C = h->desc.n_classes, T = h->T, NP = h->NP, PK = h->PK;
+    const int rows = n * T, cap = h->max_batch * T;
+    CK(launch_patchify(img, h->patches, n, h->desc.image_size, h->desc.patch_size, s));
+    h->launches++;
+    // patch embedding: x[b*T + 1 + t] = patches . patch_w^T + patch_b + pos[1 + t]
+    CK(run_gemm(h, GK_BF16, h->patches, PK, h->max_batch * NP, h->patch_w, PK, h->patch_b, h->x, D, OUT_F32, EPI_PATCH, n * NP, D, PK, s,
+                NP, T, h->pos));
+    CK(launch_cls_rows(h->x, h->cls, h->pos, n, T, D, s));
+    h->launches++;
+    for (auto &b : h->blocks)
+    {
+        CK(launch_layernorm(h->x, D, b.ln1_g, b.ln1_b, h->ybuf, D, rows, D, 1e-6f, s));
+        CK(run_gemm(h, GK_BF16, h->ybuf, D, cap, b.qkv_w, D, b.qkv_b, h->qkv, 3LL * D, OUT_BF16, EPI_NONE, rows, 3 * D, D, s));
+        CK(launch_attention(h->qkv, h->att, n, T, h->desc.heads, s));
+        CK(run_gemm(h, GK_BF16, h->att, D, cap, b.proj_w, D, b.proj_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, D, s));
+        CK(launch_layernorm(h->x, D, b.ln2_g, b.ln2_b, h->ybuf, D, rows, D, 1e-6f, s));
+        CK(run_gemm(h, GK_BF16, h->ybuf, D, cap, b.fc1_w, D, b.fc1_b, h->hid, F, OUT_BF16, EPI_GELU, rows, F, D, s));
+        CK(run_gemm(h, GK_BF16, h->hid, F, cap, b.fc2_w, F, b.fc2_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, F, s));
+        h->launches += 3;
+    }
+    // final LayerNorm on the class-token rows only (row pitch T*D), then the head
+    CK(launch_layernorm(h->x, (long long)T * D, h->lnf_g, h->lnf_b, h->cls_ln, D, n, D, 1e-6f, s));
+    h->launches++;
+    CK(run_gemm(h, GK_BF16, h->cls_ln, D, h->max_batch, h->head_w, D, h->head_b, logits, C, OUT_F32, EPI_NONE, n, C, D, s));
+    return NETCUDA_OK;
+}
+
+static int forward_device_impl(netcuda_net *h, const void *d_in, bool in_is_i8, size_t batch, void *d_out, bool out_is_i32, cudaStream_t s)
+{
+    if (!h->weights_loaded) return fail(NETCUDA_ERR_INVALID, "forward before weights were uploaded");
+    if (batch == 0) return NETCUDA_OK;
+    if (!d_in || !d_out) return fail(NETCUDA_ERR_INVALID, "null device buffer");
+    for (size_t done = 0; done < batch; done += (size_t)h->max_batch)
+    {
+        const int n = (int)std::min((size_t)h->max_batch, batch - done);
+        int rc;
+        if (h->desc.kind == NETCUDA_KIND_MLP)
+        {
+            const float *f = in_is_i8 ? nullptr : (const float *)d_in + done * h->n_in;
+            const int8_t *q = in_is_i8 ? (const int8_t *)d_in + done * h->n_in : nullptr;
+            rc = mlp_pass(h, f, q, n, out_is_i32 ? nullptr : (float *)d_out + done * h->n_out,
+                          out_is_i32 ? (int32_t *)d_out + done * h->n_out : nullptr, s);
+        }
+        else
+            rc = vit_pass(h, (const float *)d_in + done * h->n_in, n, (float *)d_out + done * h->n_out, s);
+        if (rc != NETCUDA_OK) return rc;
+    }
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_forward_device(netcuda_net *h, const void *d_in, size_t batch, void *d_out, void *stream)
+{
+    if (int rc = check_handle(h)) return rc;
+    CK(cudaSetDevice(h->device));
+    return forward_device_impl(h, d_in, false, batch, d_out, false, stream ? (cudaStream_t)stream : h->stream);
+}
+
+extern "C" int netcuda_forward_device_i8(netcuda_net *h, const int8_t *d_in, size_t batch, int32_t *d_out, void *stream)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (h->desc.kind != NETCUDA_KIND_MLP || h->desc.precision != NETCUDA_PREC_INT8)
+        return fail(NETCUDA_ERR_INVALID, "netcuda_forward_device_i8 needs an INT8 MLP handle");
+    CK(cudaSetDevice(h->device));
+    return forward_device_impl(h, d_in, true, batch, d_out, true, stream ? (cudaStream_t)stream : h->stream);
+}
+
+// ---- forward: host buffers, pipelined staging ------------------------------------------------------------
+
+static int kernel_error(netcuda_net *h)
+{
+    const int code = h->h_err ? *h->h_err : 0;
+    if (code != 0) return fail(NETCUDA_ERR_KERNEL, "tcgen05 pipeline time-out in the dense kernel (wait site %d)", code);
+    return NETCUDA_OK;
+}
+
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int ensure_staging(netcuda_net *h, size_t in_elem, size_t batch, size_t out_elem, bool need_pin_in, bool need_pin_out)
+{
+    const size_t slot_bytes = (size_t)h->max_batch * h->n_in * in_elem;
+    if (h->stage_in_bytes < slot_bytes)
+    {
+        for (int i = 0; i < 2; i++)
+        {
+            if (h->dev_in[i]) cudaFree(h->dev_in[i]);
+            if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
+            h->dev_in[i] = h->pin_in[i] = nullptr;
+        }
+        h->stage_in_bytes = 0;
+        for (int i = 0; i < 2; i++) CK(cudaMalloc(&h->dev_in[i], slot_bytes));
+        h->stage_in_bytes = slot_bytes;
+    }
+    if (need_pin_in && !h->pin_in[0])
+        for (int i = 0; i < 2; i++) CK(cudaHostAlloc(&h->pin_in[i], h->stage_in_bytes, cudaHostAllocDefault));
+    const size_t ob = batch * h->n_out * out_elem;
+    if (h->out_bytes < ob)
+    {
+        if (h->dev_out) cudaFree(h->dev_out);
+        if (h->pin_out) cudaFreeHost(h->pin_out);
+        h->dev_out = h->pin_out = nullptr;
+        h->out_bytes = 0;
+        CK(cudaMalloc(&h->dev_out, ob));
+        h->out_bytes = ob;
+    }
+    if (need_pin_out && !h->pin_out) CK(cudaHostAlloc(&h->pin_out, h->out_bytes, cudaHostAllocDefault));
+    return NETCUDA_OK;
+}
+
+static int forward_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_t batch, void *out, bool out_is_i32)
+{
+    if (!h->weights_loaded) return fail(NETCUDA_ERR_INVALID, "forward before weights were uploaded");
+    if (batch == 0) return NETCUDA_OK;
+    if (!in || !out) return fail(NETCUDA_ERR_INVALID, "null host buffer");
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t in_elem = in_is_i8 ? 1 : 4, out_elem = 4;
+    const bool pinned_in = is_pinned(in), pinned_out = is_pinned(out);
+    if (int rc = ensure_staging(h, in_elem, batch, out_elem, !pinned_in, !pinned_out)) return rc;
+
+    size_t chunk = 0;
+    for (size_t done = 0; done < batch; done += (size_t)h->max_batch, chunk++)
+    {
+        const int slot = (int)(chunk & 1);
+        const size_t n = std::min((size_t)h->max_batch, batch - done);
+        const size_t bytes = n * h->n_in * in_elem;
+        const char *src = (const char *)in + done * h->n_in * in_elem;
+        if (chunk >= 2) CK(cudaStreamWaitEvent(h->copy_stream, h->compute_done[slot], 0)); // device slot free again
+        if (!pinned_in)
+        {
+            if (chunk >= 2) CK(cudaEventSynchronize(h->h2d_done[slot])); // pinned slot drained
+            memcpy(h->pin_in[slot], src, bytes);
+            src = (const char *)h->pin_in[slot];
+        }
+        CK(cudaMemcpyAsync(h->dev_in[slot], src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaEventRecord(h->h2d_done[slot], h->copy_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->h2d_done[slot], 0));
+        char *dout = (char *)h->dev_out + done * h->n_out * out_elem;
+        if (int rc = forward_device_impl(h, h->dev_in[slot], in_is_i8, n, dout, out_is_i32, h->stream)) return rc;
+        CK(cudaEventRecord(h->compute_done[slot], h->stream));
+    }
+    const size_t ob = batch * h->n_out * out_elem;
+    void *host_dst = pinned_out ? out : h->pin_out;
+    CK(cudaMemcpyAsync(host_dst, h->dev_out, ob, cudaMemcpyDeviceToHost, h->stream));
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (int rc = kernel_error(h)) return rc;
+    if (e != cudaSuccess) return fail(NETCUDA_ERR_CUDA, "forward failed: %s", cudaGetErrorString(e));
+    if (!pinned_out) memcpy(out, h->pin_out, ob);
+    h->last_us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_forward(netcuda_net *h, const float *in, size_t batch, float *out)
+{
+    if (int rc = check_handle(h)) return rc;
+    CK(cudaSetDevice(h->device));
+    return forward_host_impl(h, in, false, batch, out, false);
+}
+
+extern "C" int netcuda_forward_i8(netcuda_net *h, const int8_t *in, size_t batch, int32_t *out)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (h->desc.kind != NETCUDA_KIND_MLP || h->desc.precision != NETCUDA_PREC_INT8)
+        return fail(NETCUDA_ERR_INVALID, "netcuda_forward_i8 needs an INT8 MLP handle");
+    CK(cudaSetDevice(h->device));
+    return forward_host_impl(h, in, true, batch, out, true);
+}
+
+// ---- introspection -----------------------------------------------------------------------------------------
+
+extern "C" int netcuda_n_in(const netcuda_net *h, size_t *n)
+{
+    if (!h || !n) return fail(NETCUDA_ERR_INVALID, "null argument");
+    *n = h->n_in;
+    return NETCUDA_OK;
+}
+extern "C" int netcuda_n_out(const netcuda_net *h, size_t *n)
+{
+    if (!h || !n) return fail(NETCUDA_ERR_INVALID, "null argument");
+    *n = h->n_out;
+    return NETCUDA_OK;
+}
+extern "C" int netcuda_last_forward_us(const netcuda_net *h, int64_t *us)
+{
+    if (!h || !us) return fail(NETCUDA_ERR_INVALID, "null argument");
+    *us = h->last_us;
+    return NETCUDA_OK;
+}
+extern "C" int netcuda_launch_count(const netcuda_net *h, uint64_t *count)
+{
+    if (!h || !count) return fail(NETCUDA_ERR_INVALID, "null argument");
+    *count = h->launches;
+    return NETCUDA_OK;
+}
+extern "C" int netcuda_flops_per_sample(const netcuda_net *h, double *flops)
+{
+    if (!h || !flops) return fail(NETCUDA_ERR_INVALID, "null argument");
+    *flops = h->flops_per_sample;
+    return NETCUDA_OK;
+}
+extern "C" int netcuda_set_gemm_variant(netcuda_net *h, int variant)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (variant != 0 && variant != 1) return fail(NETCUDA_ERR_INVALID, "variant must be 0 or 1");
+    h->gemm_variant = variant;
+    return NETCUDA_OK;
+}
+
+// ---- single-kernel entry points ---------------------------------------------------------------------------
+
+static int op_prologue(int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    {
+        (void)cudaGetLastError();
+        return fail(NETCUDA_ERR_NO_DEVICE, "device %d not available", device);
+    }
+    CK(cudaSetDevice(device));
+    CK(gemm_global_init());
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_op_gemm(int device, int precision, int variant, const void *d_a, int lda, const void *d_w, int ldw,
+                               const void *d_bias, void *d_out, int ldc, int out_type, int epilogue, int m, int n, int k, void *stream)
+{
+    if (int rc = op_prologue(device)) return rc;
+    static const int epi_map[] = {EPI_NONE, EPI_RELU, EPI_GELU, EPI_RESIDUAL, EPI_REQUANT};
+    if (epilogue < 0 || epilogue > NETCUDA_EPI_REQUANT) return fail(NETCUDA_ERR_INVALID, "unknown epilogue %d", epilogue);
+    GemmCall c;
+    c.kind = operand_kind(precision), c.variant = variant;
+    c.a = d_a, c.lda = lda, c.a_rows = m, c.w = d_w, c.ldw = ldw, c.bias = d_bias;
+    c.out = d_out, c.ldc = ldc, c.out_type = out_type, c.epi = epi_map[epilogue];
+    // int8 output always requantises; NETCUDA_EPI_RELU selects the clamp-at-zero form
+    if (out_type == NETCUDA_OUT_S8) c.epi = epilogue == NETCUDA_EPI_RELU ? EPI_REQUANT_RELU : EPI_REQUANT;
+    c.m = m, c.n = n, c.k = k;
+    c.remap_in = c.remap_out = 0, c.pos = nullptr;
+    c.error_flag = nullptr;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c.num_sms = prop.multiProcessorCount;
+    cudaError_t e = launch_gemm(c, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? NETCUDA_ERR_INVALID : NETCUDA_ERR_CUDA, "netcuda_op_gemm: %s", cudaGetErrorString(e));
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_op_layernorm(int device, const float *d_x, int ldx, const float *d_gamma, const float *d_beta, void *d_y, int ldy,
+                                    int rows, int dim, float eps, void *stream)
+{
+    if (int rc = op_prologue(device)) return rc;
+    CK(launch_layernorm(d_x, ldx, d_gamma, d_beta, d_y, ldy, rows, dim, eps, (cudaStream_t)stream));
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_op_attention(int device, const void *d_qkv, void *d_out, int batch, int tokens, int heads, void *stream)
+{
+    if (int rc = op_prologue(device)) return rc;
+    CK(launch_attention(d_qkv, d_out, batch, tokens, heads, (cudaStream_t)stream));
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_op_patchify(int device, const float *d_img, void *d_patches, int batch, int image_size, int patch_size, void *stream)
+{
+    if (int rc = op_prologue(device)) return rc;
+    CK(launch_patchify(d_img, d_patches, batch, image_size, patch_size, (cudaStream_t)stream));
+    return NETCUDA_OK;
+}

@@ -1,0 +1,324 @@
+// net_cuda.cpp -- cuda::net_cuda: the net::net_abstract implementation on top of the C ABI.
+//
+// Mirrors fpga::net_fpga member by member (reference src/netFPGA.cpp):
+//   constructor / flatten      :58-109   -> net_cuda(data, derivate, random)
+//   move / copy semantics      :111-204  -> rule-of-five below (without the reference's defects)
+//   get_net_data               :206-237  -> get_net_data (correct inverse of the flatten)
+//   launch_forward             :239-290  -> launch_forward (batched, validated)
+//   gradient stubs             :518-601  -> same observable behaviour (no-op / zeros)
+//   get_forward_performance    :603-611  -> microseconds of the last forward, transfers included
+//   destructor / cleanup       :613-651  -> ~net_cuda (per-instance, no globals)
+// This file contains no CUDA: it only calls the extern "C" functions of include/netcuda.h.
+#include <netCUDA.h>
+#include <netcuda.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+namespace cuda
+{
+    struct net_cuda::impl
+    {
+        netcuda_t *h = nullptr;
+        bool is_vit = false;
+        net_cuda_options opt;
+        // MLP host copy in the reference's flat layout (src/netFPGA.cpp:78-107)
+        std::size_t n_ins = 0;
+        std::vector<int32_t> n_p_l;
+        std::vector<float> params, bias;
+        // ViT host copy
+        vit_data vit;
+        signed long gradient_performance = 0;
+
+        ~impl()
+        {
+            if (h) netcuda_destroy(h);
+        }
+        void instantiate(); // build the device net from the host copies above
+    };
+
+    namespace
+    {
+        [[noreturn]] void throw_last(const char *what, int rc)
+        {
+            std::string msg = std::string(what) + ": " + netcuda_last_error();
+            if (rc == NETCUDA_ERR_INVALID) throw std::invalid_argument(msg);
+            throw std::runtime_error(msg);
+        }
+
+        net_cuda_options resolve(net_cuda_options o)
+        {
+            if (o.precision < 0)
+            {
+                o.precision = PREC_BF16;
+                if (const char *e = std::getenv("NETCUDA_PRECISION"))
+                {
+                    const std::string s(e);
+                    if (s == "fp32") o.precision = PREC_FP32;
+                    else if (s == "tf32") o.precision = PREC_TF32;
+                    else if (s == "bf16") o.precision = PREC_BF16;
+                    else if (s == "int8") o.precision = PREC_INT8;
+                    else throw std::invalid_argument("NETCUDA_PRECISION must be fp32, tf32, bf16 or int8");
+                }
+            }
+            if (o.device < 0)
+            {
+                o.device = 0;
+                if (const char *e = std::getenv("NETCUDA_DEVICE")) o.device = std::atoi(e);
+            }
+            return o;
+        }
+    }
+
+    net_cuda::net_cuda(const net::net_data &data, bool derivate, bool random) : net_cuda(data, net_cuda_options(), random)
+    {
+        (void)derivate; // ignored by the reference as well (src/netFPGA.cpp:58)
+    }
+
+    net_cuda::net_cuda(const net::net_data &data, const net_cuda_options &options, bool random) : p_(new impl)
+    {
+        try
+        {
+            p_->opt = resolve(options);
+            // depth comes from n_p_l.size(); data.n_layers is informational (src/netFPGA.cpp:59)
+            if (data.n_p_l.empty() || data.n_ins == 0) throw std::invalid_argument("net_cuda: empty net description");
+            p_->n_ins = data.n_ins;
+            std::size_t n_params = 0, n_neurons = 0, fan_in = data.n_ins;
+            for (std::size_t l = 0; l < data.n_p_l.size(); l++)
+            {
+                if (data.n_p_l[l] == 0) throw std::invalid_argument("net_cuda: layer with zero neurons");
+                p_->n_p_l.push_back((int32_t)data.n_p_l[l]);
+                n_params += data.n_p_l[l] * fan_in;
+                n_neurons += data.n_p_l[l];
+                fan_in = data.n_p_l[l];
+            }
+            p_->params.resize(n_params);
+            p_->bias.resize(n_neurons);
+            if (random)
+            {
+                // the reference's rule and order: all params, then all biases (src/netFPGA.cpp:82-88)
+                for (std::size_t i = 0; i < n_params; i++) p_->params[i] = float(rand() % 200 - 100) / 100;
+                for (std::size_t i = 0; i < n_neurons; i++) p_->bias[i] = float(rand() % 200 - 100) / 100;
+            }
+            else
+            {
+                if (data.params.size() < data.n_p_l.size() || data.bias.size() < data.n_p_l.size())
+                    throw std::invalid_argument("net_cuda: params/bias have fewer layers than n_p_l");
+                std::size_t pc = 0, nc = 0;
+                fan_in = data.n_ins;
+                for (std::size_t l = 0; l < data.n_p_l.size(); l++)
+                {
+                    if (data.params[l].size() != data.n_p_l[l] || data.bias[l].size() != data.n_p_l[l])
+                        throw std::invalid_argument("net_cuda: layer size does not match n_p_l");
+                    for (std::size_t j = 0; j < data.n_p_l[l]; j++)
+                    {
+                        if (data.params[l][j].size() != fan_in) throw std::invalid_argument("net_cuda: neuron fan-in mismatch");
+                        std::memcpy(&p_->params[pc], data.params[l][j].data(), fan_in * sizeof(float));
+                        pc += fan_in;
+                        p_->bias[nc++] = data.bias[l][j];
+                    }
+                    fan_in = data.n_p_l[l];
+                }
+            }
+            p_->instantiate();
+        }
+        catch (...)
+        {
+            delete p_;
+            throw;
+        }
+    }
+
+    net_cuda::net_cuda(const vit_data &vit, const net_cuda_options &options) : p_(new impl)
+    {
+        try
+        {
+            p_->opt = resolve(options);
+            p_->is_vit = true;
+            p_->vit = vit;
+            p_->instantiate();
+        }
+        catch (...)
+        {
+            delete p_;
+            throw;
+        }
+    }
+
+    void net_cuda::impl::instantiate()
+    {
+        impl *p = this;
+        netcuda_desc d;
+        std::memset(&d, 0, sizeof(d));
+        d.precision = p->opt.precision;
+        d.device = p->opt.device;
+        d.activation = p->opt.activation;
+        d.max_batch = p->opt.max_batch;
+        int rc;
+        if (p->is_vit)
+        {
+            d.kind = NETCUDA_KIND_VIT;
+            d.image_size = (int32_t)p->vit.image_size, d.patch_size = (int32_t)p->vit.patch_size;
+            d.dim = (int32_t)p->vit.dim, d.depth = (int32_t)p->vit.depth, d.heads = (int32_t)p->vit.heads;
+            d.mlp_dim = (int32_t)p->vit.mlp_dim, d.n_classes = (int32_t)p->vit.n_classes;
+            if ((rc = netcuda_create(&d, &p->h)) != NETCUDA_OK) throw_last("netcuda_create", rc);
+            if ((rc = netcuda_upload_vit(p->h, p->vit.params.data(), p->vit.params.size())) != NETCUDA_OK)
+                throw_last("netcuda_upload_vit", rc);
+        }
+        else
+        {
+            d.kind = NETCUDA_KIND_MLP;
+            d.n_ins = (int32_t)p->n_ins;
+            d.n_layers = (int32_t)p->n_p_l.size();
+            d.n_p_l = p->n_p_l.data();
+            if ((rc = netcuda_create(&d, &p->h)) != NETCUDA_OK) throw_last("netcuda_create", rc);
+            if ((rc = netcuda_upload_mlp(p->h, p->params.data(), p->bias.data())) != NETCUDA_OK) throw_last("netcuda_upload_mlp", rc);
+        }
+    }
+
+    net_cuda::~net_cuda() { delete p_; }
+
+    net_cuda::net_cuda(net_cuda &&rh) noexcept : p_(rh.p_) { rh.p_ = nullptr; }
+
+    net_cuda &net_cuda::operator=(net_cuda &&rh) noexcept
+    {
+        if (this != &rh)
+        {
+            delete p_;
+            p_ = rh.p_;
+            rh.p_ = nullptr;
+        }
+        return *this;
+    }
+
+    net_cuda &net_cuda::operator=(const net_cuda &rh)
+    {
+        if (this == &rh) return *this;
+        if (!rh.p_) throw std::invalid_argument("net_cuda: copy from a moved-from net");
+        impl *np = new impl;
+        try
+        {
+            np->is_vit = rh.p_->is_vit;
+            np->opt = rh.p_->opt;
+            np->n_ins = rh.p_->n_ins;
+            np->n_p_l = rh.p_->n_p_l;
+            np->params = rh.p_->params;
+            np->bias = rh.p_->bias;
+            np->vit = rh.p_->vit;
+            np->instantiate();
+        }
+        catch (...)
+        {
+            delete np;
+            throw;
+        }
+        delete p_;
+        p_ = np;
+        return *this;
+    }
+
+    net::net_data net_cuda::get_net_data()
+    {
+        if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        if (p_->is_vit) throw std::runtime_error("net_cuda::get_net_data: a ViT cannot be expressed as net::net_data");
+        net::net_data data;
+        data.n_ins = p_->n_ins;
+        data.n_layers = p_->n_p_l.size();
+        std::size_t pc = 0, nc = 0, fan_in = p_->n_ins;
+        for (std::size_t l = 0; l < p_->n_p_l.size(); l++)
+        {
+            const std::size_t fan_out = (std::size_t)p_->n_p_l[l];
+            data.n_p_l.push_back(fan_out);
+            data.params.emplace_back();
+            data.bias.emplace_back();
+            data.params[l].reserve(fan_out);
+            for (std::size_t j = 0; j < fan_out; j++)
+            {
+                data.params[l].emplace_back(p_->params.begin() + pc, p_->params.begin() + pc + fan_in);
+                pc += fan_in;
+                data.bias[l].push_back(p_->bias[nc++]);
+            }
+            fan_in = fan_out;
+        }
+        return data;
+    }
+
+    std::size_t net_cuda::n_in() const
+    {
+        std::size_t n = 0;
+        if (p_ && p_->h) netcuda_n_in(p_->h, &n);
+        return n;
+    }
+    std::size_t net_cuda::n_out() const
+    {
+        std::size_t n = 0;
+        if (p_ && p_->h) netcuda_n_out(p_->h, &n);
+        return n;
+    }
+    void *net_cuda::c_handle() const { return p_ ? p_->h : nullptr; }
+
+    void net_cuda::forward(const DATA_TYPE *inputs, std::size_t batch, DATA_TYPE *outputs)
+    {
+        if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        const int rc = netcuda_forward(p_->h, inputs, batch, outputs);
+        if (rc != NETCUDA_OK) throw_last("netcuda_forward", rc);
+    }
+
+    void net_cuda::forward_device(const void *d_inputs, std::size_t batch, void *d_outputs, void *stream)
+    {
+        if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        const int rc = netcuda_forward_device(p_->h, d_inputs, batch, d_outputs, stream);
+        if (rc != NETCUDA_OK) throw_last("netcuda_forward_device", rc);
+    }
+
+    std::vector<DATA_TYPE> net_cuda::launch_forward(const std::vector<DATA_TYPE> &inputs)
+    {
+        if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        const std::size_t ni = n_in(), no = n_out();
+        if (inputs.empty() || inputs.size() % ni != 0)
+            throw std::invalid_argument("net_cuda::launch_forward: inputs.size() must be a non-zero multiple of n_ins");
+        const std::size_t batch = inputs.size() / ni;
+        std::vector<DATA_TYPE> out(batch * no);
+        forward(inputs.data(), batch, out.data());
+        return out;
+    }
+
+    // Training is not implemented by the reference either: init_gradient's body is commented out
+    // (src/netFPGA.cpp:518-542) and launch_gradient returns `iterations` zeros (:578).
+    void net_cuda::init_gradient(const net::net_sets &sets) { (void)sets; }
+
+    std::vector<DATA_TYPE> net_cuda::launch_gradient(size_t iterations, DATA_TYPE error_threshold, DATA_TYPE multiplier)
+    {
+        (void)error_threshold;
+        (void)multiplier;
+        return std::vector<DATA_TYPE>(iterations, 0);
+    }
+
+    void net_cuda::print_inner_vals() {}
+
+    signed long net_cuda::get_gradient_performance() { return p_ ? p_->gradient_performance : 0; }
+
+    signed long net_cuda::get_forward_performance()
+    {
+        int64_t us = 0;
+        if (p_ && p_->h) netcuda_last_forward_us(p_->h, &us);
+        return (signed long)us;
+    }
+
+    // Image-filter side channel: a separate workload with an unknown device kernel (`image_process`,
+    // src/netFPGA.cpp:303) -- out of scope.  filter_image accepts and drops the frame;
+    // get_filtered_image answers like the reference does for an empty ring (:336-365): a 1080p header, no pixels.
+    void net_cuda::filter_image(const net::image_set &set) { (void)set; }
+
+    net::image_set net_cuda::get_filtered_image()
+    {
+        net::image_set out;
+        out.original_x_pos = 0;
+        out.original_y_pos = 0;
+        out.original_h = 1080;
+        out.original_w = 1920;
+        return out;
+    }
+}

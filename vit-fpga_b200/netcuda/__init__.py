@@ -1,0 +1,348 @@
+"""ctypes binding of the netCUDA C ABI (include/netcuda.h) and of the C++ class driver.
+
+This module is plumbing for tests/ and bench.py: the product is the native library.  It never
+imports the CPU oracle and has no fallback -- if libnetcuda.so is missing, importing fails; if no
+sm_100 GPU is visible, `Net(...)` raises `NetcudaError` carrying the library's own message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+ROOT = os.path.dirname(PKG)
+LIB_DIR = os.path.join(PKG, "lib")
+HEADER = os.path.join(ROOT, "include", "netcuda.h")
+
+KIND_MLP, KIND_VIT = 0, 1
+PREC_FP32, PREC_TF32, PREC_BF16, PREC_INT8 = 0, 1, 2, 3
+ACT_RELU_HIDDEN, ACT_RELU_ALL, ACT_NONE = 0, 1, 2
+OUT_F32, OUT_BF16, OUT_S8, OUT_S32 = 0, 1, 2, 3
+EPI_NONE, EPI_RELU, EPI_GELU, EPI_RESIDUAL, EPI_REQUANT = 0, 1, 2, 3, 4
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_KERNEL = 0, 1, 2, 3, 4, 5
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "int8": PREC_INT8}
+
+
+class NetcudaError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"netcuda error {code}: {message}")
+        self.code = code
+
+
+class Desc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("precision", C.c_int32), ("device", C.c_int32), ("activation", C.c_int32),
+                ("max_batch", C.c_int32), ("n_ins", C.c_int32), ("n_layers", C.c_int32), ("n_p_l", C.POINTER(C.c_int32)),
+                ("image_size", C.c_int32), ("patch_size", C.c_int32), ("dim", C.c_int32), ("depth", C.c_int32),
+                ("heads", C.c_int32), ("mlp_dim", C.c_int32), ("n_classes", C.c_int32)]
+
+
+def declared_symbols() -> list[str]:
+    """Every function include/netcuda.h declares (used by the CPU test that checks the exports)."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(netcuda_[a-z0-9_]+)\s*\(", text)))
+
+
+def _load(name: str) -> C.CDLL:
+    path = os.path.join(LIB_DIR, name)
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: run `python vit-fpga_b200/build.py` (there is no fallback path)")
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
+lib = _load("libnetcuda.so")
+lib.netcuda_last_error.restype = C.c_char_p
+hostlib = _load("libnetcuda_host.so")
+hostlib.nch_last_error.restype = C.c_char_p
+hostlib.nch_mlp_create.restype = C.c_void_p
+hostlib.nch_vit_create.restype = C.c_void_p
+hostlib.nch_launch_forward.restype = C.c_longlong
+hostlib.nch_forward_us.restype = C.c_long
+hostlib.nch_gradient_us.restype = C.c_long
+
+
+def _check(rc: int) -> None:
+    if rc != OK:
+        raise NetcudaError(rc, lib.netcuda_last_error().decode())
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = lib.netcuda_device_count(C.byref(n))
+    return n.value if rc == OK else 0
+
+
+def _ptr(t) -> C.c_void_p:
+    """Device/host pointer of a torch tensor or numpy array."""
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, np.ndarray):
+        return C.c_void_p(t.ctypes.data)
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(stream) -> C.c_void_p:
+    if stream is None:
+        return C.c_void_p(0)
+    return C.c_void_p(int(getattr(stream, "cuda_stream", stream)))
+
+
+VIT_PRESETS = {
+    "vit_tiny_16_224": dict(image_size=224, patch_size=16, dim=192, depth=12, heads=3, mlp_dim=768, n_classes=1000),
+    "vit_base_16_224": dict(image_size=224, patch_size=16, dim=768, depth=12, heads=12, mlp_dim=3072, n_classes=1000),
+    "vit_large_16_384": dict(image_size=384, patch_size=16, dim=1024, depth=24, heads=16, mlp_dim=4096, n_classes=1000),
+}
+
+
+def vit_param_count(cfg: dict) -> int:
+    d = Desc(kind=KIND_VIT, precision=PREC_BF16, **cfg)
+    n = C.c_size_t(0)
+    _check(lib.netcuda_vit_param_count(C.byref(d), C.byref(n)))
+    return n.value
+
+
+def vit_random_params(cfg: dict, seed: int = 0) -> np.ndarray:
+    """Random-init weights of the named architecture in the flat layout (synthetic benchmark weights).
+    Matrices ~ N(0, 0.02) like torchvision's trunc-normal init, LN gamma 1 +- 0.05, small biases."""
+    rng = np.random.default_rng(seed)
+    D, F, Cn = cfg["dim"], cfg["mlp_dim"], cfg["n_classes"]
+    g = cfg["image_size"] // cfg["patch_size"]
+    N, pk = g * g + 1, 3 * cfg["patch_size"] ** 2
+    parts = []
+
+    def mat(r, c, std=0.02):
+        parts.append((rng.standard_normal((r, c), dtype=np.float32) * std).ravel())
+
+    def vec(n, mean=0.0, std=0.02):
+        parts.append(mean + rng.standard_normal(n, dtype=np.float32) * std)
+
+    mat(D, pk, std=(1.0 / pk) ** 0.5)
+    vec(D), vec(D), mat(N, D)
+    for _ in range(cfg["depth"]):
+        vec(D, 1.0, 0.05), vec(D)
+        mat(3 * D, D, std=D ** -0.5), vec(3 * D)
+        mat(D, D, std=D ** -0.5), vec(D)
+        vec(D, 1.0, 0.05), vec(D)
+        mat(F, D, std=D ** -0.5), vec(F)
+        mat(D, F, std=F ** -0.5), vec(D)
+    vec(D, 1.0, 0.05), vec(D)
+    mat(Cn, D, std=0.05), vec(Cn)
+    flat = np.concatenate(parts).astype(np.float32)
+    assert flat.size == vit_param_count(cfg)
+    return flat
+
+
+class Net:
+    """One net on one GPU through the C ABI."""
+
+    def __init__(self, desc: Desc, keepalive=None):
+        self._h = C.c_void_p(0)
+        self._keep = keepalive
+        _check(lib.netcuda_create(C.byref(desc), C.byref(self._h)))
+        n = C.c_size_t(0)
+        _check(lib.netcuda_n_in(self._h, C.byref(n)))
+        self.n_in = n.value
+        _check(lib.netcuda_n_out(self._h, C.byref(n)))
+        self.n_out = n.value
+        self.precision = desc.precision
+        self.kind = desc.kind
+
+    @classmethod
+    def mlp(cls, npl, n_ins, precision=PREC_BF16, device=0, activation=ACT_RELU_HIDDEN, max_batch=0) -> "Net":
+        arr = (C.c_int32 * len(npl))(*[int(v) for v in npl])
+        d = Desc(kind=KIND_MLP, precision=precision, device=device, activation=activation, max_batch=max_batch, n_ins=int(n_ins),
+                 n_layers=len(npl), n_p_l=C.cast(arr, C.POINTER(C.c_int32)))
+        return cls(d, keepalive=arr)
+
+    @classmethod
+    def vit(cls, cfg: dict, device=0, max_batch=0) -> "Net":
+        d = Desc(kind=KIND_VIT, precision=PREC_BF16, device=device, max_batch=max_batch, **cfg)
+        return cls(d)
+
+    def close(self) -> None:
+        if self._h:
+            lib.netcuda_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights
+    def upload_mlp(self, w_flat, b_flat) -> None:
+        w = np.ascontiguousarray(w_flat, dtype=np.float32)
+        b = np.ascontiguousarray(b_flat, dtype=np.float32)
+        _check(lib.netcuda_upload_mlp(self._h, _ptr(w), _ptr(b)))
+
+    def upload_mlp_i8(self, wq, bq) -> None:
+        w = np.ascontiguousarray(wq, dtype=np.int8)
+        b = np.ascontiguousarray(bq, dtype=np.int32)
+        _check(lib.netcuda_upload_mlp_i8(self._h, _ptr(w), _ptr(b)))
+
+    def upload_vit(self, flat) -> None:
+        f = np.ascontiguousarray(flat, dtype=np.float32)
+        _check(lib.netcuda_upload_vit(self._h, _ptr(f), C.c_size_t(f.size)))
+
+    # ---- forward
+    def forward(self, x) -> np.ndarray:
+        """Host fp32 in -> host fp32 out.  Accepts numpy arrays or (pinned) CPU torch tensors."""
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            batch = x.size // self.n_in
+            assert batch * self.n_in == x.size
+            out = np.empty((batch, self.n_out), dtype=np.float32)
+            _check(lib.netcuda_forward(self._h, _ptr(x), C.c_size_t(batch), _ptr(out)))
+            return out
+        raise TypeError("forward expects a numpy array; use forward_into for torch tensors")
+
+    def forward_into(self, x, out) -> None:
+        """Host torch tensors (ideally pinned): x fp32 [batch, n_in] -> out fp32 [batch, n_out]."""
+        batch = x.numel() // self.n_in
+        _check(lib.netcuda_forward(self._h, _ptr(x), C.c_size_t(batch), _ptr(out)))
+
+    def forward_i8(self, xq) -> np.ndarray:
+        xq = np.ascontiguousarray(xq, dtype=np.int8)
+        batch = xq.size // self.n_in
+        out = np.empty((batch, self.n_out), dtype=np.int32)
+        _check(lib.netcuda_forward_i8(self._h, _ptr(xq), C.c_size_t(batch), _ptr(out)))
+        return out
+
+    def forward_device(self, d_in, d_out, batch: int, stream=None) -> None:
+        """Device tensors; asynchronous on `stream` (torch stream or raw handle)."""
+        _check(lib.netcuda_forward_device(self._h, _ptr(d_in), C.c_size_t(batch), _ptr(d_out), _stream(stream)))
+
+    def forward_device_i8(self, d_in, d_out, batch: int, stream=None) -> None:
+        _check(lib.netcuda_forward_device_i8(self._h, _ptr(d_in), C.c_size_t(batch), _ptr(d_out), _stream(stream)))
+
+    # ---- introspection
+    @property
+    def launches(self) -> int:
+        n = C.c_uint64(0)
+        _check(lib.netcuda_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    @property
+    def flops_per_sample(self) -> float:
+        f = C.c_double(0)
+        _check(lib.netcuda_flops_per_sample(self._h, C.byref(f)))
+        return f.value
+
+    @property
+    def last_forward_us(self) -> int:
+        n = C.c_int64(0)
+        _check(lib.netcuda_last_forward_us(self._h, C.byref(n)))
+        return n.value
+
+    def set_gemm_variant(self, variant: int) -> None:
+        _check(lib.netcuda_set_gemm_variant(self._h, C.c_int(variant)))
+
+
+# ---- single-kernel entry points (torch CUDA tensors) -------------------------------------------------
+
+def op_gemm(a, w, bias, out, precision, out_type, epilogue=EPI_NONE, variant=0, m=None, n=None, k=None, lda=None, ldw=None,
+            ldc=None, device=0, stream=None) -> None:
+    m = a.shape[0] if m is None else m
+    n = w.shape[0] if n is None else n
+    k = a.shape[1] if k is None else k
+    lda = a.stride(0) if lda is None else lda
+    ldw = w.stride(0) if ldw is None else ldw
+    ldc = out.stride(0) if ldc is None else ldc
+    _check(lib.netcuda_op_gemm(C.c_int(device), C.c_int(precision), C.c_int(variant), _ptr(a), C.c_int(lda), _ptr(w), C.c_int(ldw),
+                               _ptr(bias), _ptr(out), C.c_int(ldc), C.c_int(out_type), C.c_int(epilogue), C.c_int(m), C.c_int(n),
+                               C.c_int(k), _stream(stream)))
+
+
+def op_layernorm(x, gamma, beta, y, eps=1e-6, rows=None, dim=None, ldx=None, ldy=None, device=0, stream=None) -> None:
+    rows = x.shape[0] if rows is None else rows
+    dim = x.shape[1] if dim is None else dim
+    ldx = x.stride(0) if ldx is None else ldx
+    ldy = y.stride(0) if ldy is None else ldy
+    _check(lib.netcuda_op_layernorm(C.c_int(device), _ptr(x), C.c_int(ldx), _ptr(gamma), _ptr(beta), _ptr(y), C.c_int(ldy),
+                                    C.c_int(rows), C.c_int(dim), C.c_float(eps), _stream(stream)))
+
+
+def op_attention(qkv, out, batch, tokens, heads, device=0, stream=None) -> None:
+    _check(lib.netcuda_op_attention(C.c_int(device), _ptr(qkv), _ptr(out), C.c_int(batch), C.c_int(tokens), C.c_int(heads),
+                                    _stream(stream)))
+
+
+def op_patchify(img, patches, batch, image_size, patch_size, device=0, stream=None) -> None:
+    _check(lib.netcuda_op_patchify(C.c_int(device), _ptr(img), _ptr(patches), C.c_int(batch), C.c_int(image_size),
+                                   C.c_int(patch_size), _stream(stream)))
+
+
+# ---- the C++ class, driven through net::net_abstract* --------------------------------------------------
+
+class HostNet:
+    """cuda::net_cuda behind a net::net_abstract pointer (vit-fpga_b200/host/host_capi.cpp)."""
+
+    def __init__(self, handle, n_in, n_out):
+        if not handle:
+            raise RuntimeError("net_cuda construction failed: " + hostlib.nch_last_error().decode())
+        self._h = C.c_void_p(handle)
+        self.n_in, self.n_out = n_in, n_out
+
+    @classmethod
+    def mlp(cls, npl, n_ins, w=None, b=None, random=False, seed=1, precision=-1, device=0, activation=ACT_RELU_HIDDEN,
+            max_batch=0) -> "HostNet":
+        arr = np.ascontiguousarray(npl, dtype=np.int32)
+        wp = _ptr(np.ascontiguousarray(w, dtype=np.float32)) if w is not None else C.c_void_p(0)
+        bp = _ptr(np.ascontiguousarray(b, dtype=np.float32)) if b is not None else C.c_void_p(0)
+        h = hostlib.nch_mlp_create(_ptr(arr), C.c_int(len(arr)), C.c_int(n_ins), wp, bp, C.c_int(int(random)), C.c_uint(seed),
+                                   C.c_int(precision), C.c_int(device), C.c_int(activation), C.c_int(max_batch))
+        return cls(h, int(n_ins), int(arr[-1]))
+
+    @classmethod
+    def vit(cls, cfg: dict, flat, device=0, max_batch=0) -> "HostNet":
+        f = np.ascontiguousarray(flat, dtype=np.float32)
+        h = hostlib.nch_vit_create(C.c_int(cfg["image_size"]), C.c_int(cfg["patch_size"]), C.c_int(cfg["dim"]), C.c_int(cfg["depth"]),
+                                   C.c_int(cfg["heads"]), C.c_int(cfg["mlp_dim"]), C.c_int(cfg["n_classes"]), _ptr(f),
+                                   C.c_size_t(f.size), C.c_int(device), C.c_int(max_batch))
+        return cls(h, 3 * cfg["image_size"] ** 2, cfg["n_classes"])
+
+    def launch_forward(self, x) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32).ravel()
+        cap = (x.size // max(self.n_in, 1) + 1) * self.n_out
+        out = np.empty(cap, dtype=np.float32)
+        n = hostlib.nch_launch_forward(self._h, _ptr(x), C.c_size_t(x.size), _ptr(out), C.c_size_t(cap))
+        if n < 0:
+            raise ValueError(hostlib.nch_last_error().decode())
+        return out[:n].reshape(-1, self.n_out)
+
+    def get_net_data(self, n_params, n_neurons):
+        w = np.empty(n_params, dtype=np.float32)
+        b = np.empty(n_neurons, dtype=np.float32)
+        n_ins, n_layers = C.c_size_t(0), C.c_size_t(0)
+        rc = hostlib.nch_get_net_data(self._h, _ptr(w), C.c_size_t(n_params), _ptr(b), C.c_size_t(n_neurons), C.byref(n_ins),
+                                      C.byref(n_layers))
+        if rc != 0:
+            raise RuntimeError(f"get_net_data rc={rc}: " + hostlib.nch_last_error().decode())
+        return w, b, n_ins.value, n_layers.value
+
+    def forward_us(self) -> int:
+        return int(hostlib.nch_forward_us(self._h))
+
+    def check_stubs(self) -> int:
+        return int(hostlib.nch_check_stubs(self._h))
+
+    def check_move_copy(self, x, expect) -> int:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        e = np.ascontiguousarray(expect, dtype=np.float32)
+        return int(hostlib.nch_check_move_copy(self._h, _ptr(x), C.c_size_t(x.size), _ptr(e), C.c_size_t(e.size)))
+
+    def close(self) -> None:
+        if self._h:
+            hostlib.nch_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
