@@ -30,8 +30,8 @@ namespace cuda
     enum precision_t
     {
         PREC_FP32 = 0, // CUDA-core fp32, bit-equal to the CPU oracle
-        PREC_TF32 = 1,
-        PREC_BF16 = 2, // default for float nets
+        PREC_TF32 = 1, // default for nets built from net::net_data (the reference's DATA_TYPE is float)
+        PREC_BF16 = 2, // default (and only) precision of vision transformers
         PREC_INT8 = 3  // Q1.7 fixed point, bit-exact
     };
     enum activation_t
@@ -43,7 +43,7 @@ namespace cuda
 
     struct net_cuda_options
     {
-        int precision;  // precision_t; -1 = take NETCUDA_PRECISION from the environment, else BF16
+        int precision;  // precision_t; -1 = take NETCUDA_PRECISION from the environment, else TF32 (MLP) / BF16 (ViT)
         int device;     // CUDA ordinal; -1 = NETCUDA_DEVICE from the environment, else 0
         int activation; // activation_t
         int max_batch;  // samples per internal pass, 0 = library default

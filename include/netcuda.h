@@ -142,6 +142,22 @@ int netcuda_launch_count(const netcuda_t *h, uint64_t *count);
 /* Algorithmic multiply-accumulate FLOPs (2*MACs of the dense contractions) per sample. */
 int netcuda_flops_per_sample(const netcuda_t *h, double *flops);
 
+/* Per-kernel timing (replaces the reference's single PERFORMANCE stopwatch, src/netFPGA.cpp:262-284,
+ * with one CUDA-event pair around every kernel this handle launches, recorded on the launching stream).
+ * Off by default; while on, each launch costs two extra event records.  netcuda_profile_read waits for
+ * the recorded work, adds the durations up per launch-site label ("qkv", "fc1", "layernorm", ...), writes
+ * up to `cap` entries, returns the number of labels in *count and clears the records. */
+typedef struct netcuda_kernel_stat
+{
+    char label[32];
+    uint64_t launches;
+    double ms;    /* summed device time of those launches (CUDA events)                     */
+    double flops; /* summed algorithmic FLOPs / integer ops (2*MACs); 0 for HBM-bound kernels */
+    double bytes; /* summed algorithmic bytes (minimum HBM traffic: operands read once + output written once) */
+} netcuda_kernel_stat;
+int netcuda_profile_enable(netcuda_t *h, int on);
+int netcuda_profile_read(netcuda_t *h, netcuda_kernel_stat *stats, int cap, int *count);
+
 /* Select a debugging/measurement variant of the dense kernel for this handle:
  * 0 = default (tcgen05), 1 = CUDA-core reference GEMM with the same operand rounding. */
 int netcuda_set_gemm_variant(netcuda_t *h, int variant);

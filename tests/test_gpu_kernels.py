@@ -42,7 +42,10 @@ GEMM_SHAPES = [
 
 @pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
 @pytest.mark.parametrize("out_bf16", [False, True])
-def test_gemm_bf16_vs_oracle(netcuda, oracle, torch_cuda, m, n, k, out_bf16):
+@pytest.mark.parametrize("pitch", ["odd", "aligned"])
+def test_gemm_bf16_vs_oracle(netcuda, oracle, torch_cuda, m, n, k, out_bf16, pitch):
+    """pitch "aligned": rows of the output are multiples of 16 bytes -> smem slab + TMA-store epilogue;
+    pitch "odd": direct-store epilogue (what e.g. a 10-wide fp32 output layer gets)."""
     torch = torch_cuda
     rng = np.random.default_rng(m * 7 + n * 3 + k)
     a = _bf16_round(torch, rng.uniform(-1, 1, (m, k)).astype(np.float32))
@@ -54,9 +57,10 @@ def test_gemm_bf16_vs_oracle(netcuda, oracle, torch_cuda, m, n, k, out_bf16):
     da[:, :k] = torch.from_numpy(a).cuda().to(torch.bfloat16)
     dw[:, :k] = torch.from_numpy(w).cuda().to(torch.bfloat16)
     db = torch.from_numpy(bias).cuda()
-    ldc = n + 3  # odd pitch: the epilogue must not assume alignment of rows
-    if out_bf16:
-        ldc = n + 2
+    if pitch == "odd":
+        ldc = n + 2 if out_bf16 else n + 3  # the epilogue must not assume alignment of rows
+    else:
+        ldc = (n + 8 + 7) // 8 * 8  # 16-byte multiple for both types, still wider than N
     out = torch.full((m, ldc), -77.0, dtype=torch.bfloat16 if out_bf16 else torch.float32, device="cuda")
     netcuda.op_gemm(da, dw, db, out, netcuda.PREC_BF16, netcuda.OUT_BF16 if out_bf16 else netcuda.OUT_F32,
                     m=m, n=n, k=k, lda=ldk, ldw=ldk, ldc=ldc)

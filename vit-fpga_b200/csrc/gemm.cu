@@ -84,10 +84,32 @@ static cudaError_t make_operand_map(CUtensorMap *map, int kind, const void *ptr,
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// Output matrix as a 2-D tensor {N, M} for the epilogue's TMA stores: box = one epilogue slab
+// (slab_cols columns x 32 rows), 128B-swizzled when a slab row is 128 bytes.
+template <int BN, int OUT>
+static cudaError_t make_out_map(CUtensorMap *map, void *ptr, long long n, long long m, long long pitch_bytes)
+{
+    if (!g_encode_tiled) return cudaErrorNotReady;
+    constexpr int cols = slab_cols<BN, OUT>();
+    constexpr int row_bytes = cols * OutTraits<OUT>::ELEM;
+    const CUtensorMapDataType dt = OUT == OUT_BF16  ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                   : OUT == OUT_S8  ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                   : OUT == OUT_S32 ? CU_TENSOR_MAP_DATA_TYPE_INT32
+                                                    : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)m};
+    cuuint64_t gstride[1] = {(cuuint64_t)pitch_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)cols, 32};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, dt, 2, ptr, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <int KIND, int BN, int OUT, int STAGES>
 static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
 {
-    CUtensorMap map_a, map_w;
+    CUtensorMap map_a, map_w, map_out;
     cudaError_t e = make_operand_map(&map_a, c.kind, c.a, c.k, c.a_rows > c.m ? c.a_rows : c.m, c.lda * elem_size(c.kind), GEMM_BM);
     if (e != cudaSuccess) return e;
     e = make_operand_map(&map_w, c.kind, c.w, c.k, c.n, c.ldw * elem_size(c.kind), BN);
@@ -97,10 +119,24 @@ static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
     p.bias = c.bias, p.out = c.out, p.ldc = c.ldc, p.epi = c.epi;
     p.remap_in = c.remap_in, p.remap_out = c.remap_out, p.pos = c.pos;
     p.error_flag = c.error_flag;
+    // TMA-store epilogue whenever the output is addressable by a tensor map; otherwise direct stores
+    const long long pitch_bytes = c.ldc * OutTraits<OUT>::ELEM;
+    // (TMA bounds the innermost dimension in 16-byte units, so N must be a whole number of them as well)
+    p.tma_store = (c.epi != EPI_PATCH && (reinterpret_cast<uintptr_t>(c.out) & 15u) == 0 && (pitch_bytes & 15) == 0 &&
+                   ((c.n * (long long)OutTraits<OUT>::ELEM) & 15) == 0)
+                      ? 1
+                      : 0;
+    if (p.tma_store)
+    {
+        e = make_out_map<BN, OUT>(&map_out, c.out, c.n, c.m, pitch_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    else
+        map_out = map_a; // never dereferenced
     const int tiles = ((c.m + GEMM_BM - 1) / GEMM_BM) * ((c.n + BN - 1) / BN);
     const int sms = c.num_sms > 0 ? c.num_sms : 148;
     const int grid = tiles < sms ? tiles : sms;
-    gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES><<<grid, GEMM_THREADS, GemmSmem<BN, STAGES>::TOTAL, stream>>>(map_a, map_w, p);
+    gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES><<<grid, GEMM_THREADS, GemmSmem<BN, STAGES>::TOTAL, stream>>>(map_a, map_w, map_out, p);
     return cudaGetLastError();
 }
 

@@ -6,15 +6,20 @@
 // K-major, exactly the reference's row-major W[out][in] and sample-major activations, so no
 // transposes are needed anywhere.
 //
-// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
-//   warp 0    TMA producer: 128B-swizzled [128 x 128B] A tile + [BN x 128B] W tile per stage
-//   warp 1    MMA issuer:   one thread issues tcgen05.mma (UMMA 128 x BN x 32B) into TMEM
-//   warp 2    TMEM allocator (2 accumulator stages x BN fp32/int32 columns)
-//   warps 4-7 epilogue: tcgen05.ld -> +bias -> activation -> warp-private smem transpose ->
-//             row-contiguous (coalesced) global stores; overlaps the next tile's MMAs
+// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
+//   warp 0     TMA producer: 128B-swizzled [128 x 128B] A tile + [BN x 128B] W tile per stage
+//   warp 1     MMA issuer:   one thread issues tcgen05.mma (UMMA 128 x BN x 32B) into TMEM
+//   warp 2     TMEM allocator (2 accumulator stages x BN fp32/int32 columns)
+//   warps 4-11 epilogue: warp w reads TMEM lanes [32(w%4), +32) x columns [(w-4)/4 * BN/2, +BN/2):
+//              tcgen05.ld -> +bias -> activation -> convert -> 128B-swizzled smem slab -> one TMA
+//              store (or TMA reduce-add for the residual epilogue) per 32-row x 128-byte slab.
+//              Runs concurrently with the next tile's MMAs (double-buffered accumulator).
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
 // All byte geometry is independent of the operand type: a stage row is always 128 bytes
 // (64 bf16 / 32 tf32 / 128 int8), one UMMA consumes 32 bytes of K.
+//
+// Outputs that a TMA store cannot address (row pitch not a multiple of 16 bytes, or the row-remapping
+// patch-embedding epilogue) take the "direct" epilogue: each lane writes its own accumulator row.
 #pragma once
 
 #include "ptx.cuh"
@@ -47,6 +52,7 @@ struct GemmParams
     void *out;         // OUT_* typed, row pitch ldc elements
     long long ldc;
     int epi;
+    int tma_store; // 1: epilogue through smem slabs + TMA store (tma_out valid); 0: direct stores
     // EPI_PATCH: input row r = b * remap_in + t  ->  output row b * remap_out + 1 + t, and
     // pos[(1 + t) * N + col] is added (cls token occupies output row b * remap_out).
     int remap_in, remap_out;
@@ -55,8 +61,41 @@ struct GemmParams
 };
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_STAGE_ROW_BYTES = 128;
+constexpr int GEMM_SLAB_BYTES = 32 * 128; // 32 rows x 128 bytes per epilogue warp
+
+template <int OUT>
+struct OutTraits;
+template <>
+struct OutTraits<OUT_F32>
+{
+    static constexpr int ELEM = 4;
+};
+template <>
+struct OutTraits<OUT_S32>
+{
+    static constexpr int ELEM = 4;
+};
+template <>
+struct OutTraits<OUT_BF16>
+{
+    static constexpr int ELEM = 2;
+};
+template <>
+struct OutTraits<OUT_S8>
+{
+    static constexpr int ELEM = 1;
+};
+
+// Columns of the output covered by one TMA-store slab of an epilogue warp (host and device agree on this):
+// a 128-byte row, except int8 where the warp's whole column range (BN/2 <= 128 bytes) is one slab.
+template <int BN, int OUT>
+__host__ __device__ constexpr int slab_cols()
+{
+    return (128 / OutTraits<OUT>::ELEM) < (BN / 2) ? (128 / OutTraits<OUT>::ELEM) : (BN / 2);
+}
 
 template <int BN, int STAGES>
 struct GemmSmem
@@ -64,13 +103,13 @@ struct GemmSmem
     static constexpr int A_BYTES = GEMM_BM * GEMM_STAGE_ROW_BYTES;
     static constexpr int B_BYTES = BN * GEMM_STAGE_ROW_BYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGING_WORDS_PER_WARP = 32 * 33;
-    static constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
-    static constexpr int OFF_BIAS = OFF_STAGING + 4 * STAGING_WORDS_PER_WARP * 4;
-    static constexpr int OFF_BARS = OFF_BIAS + 4 * BN * 4;
+    static constexpr int OFF_SLABS = STAGES * STAGE_BYTES; // 1024-byte aligned (stage sizes are multiples of 1024)
+    static constexpr int OFF_BIAS = OFF_SLABS + GEMM_EPI_WARPS * GEMM_SLAB_BYTES;
+    static constexpr int OFF_BARS = OFF_BIAS + 2 * BN * 4; // bias slice, double-buffered by tile parity
     static constexpr int NUM_BARS = 2 * STAGES + 4;
     static constexpr int OFF_TMEM_PTR = OFF_BARS + NUM_BARS * 8;
-    static constexpr int TOTAL = OFF_TMEM_PTR + 16 + 1024; // +1024: manual alignment slack
+    static constexpr int TOTAL = OFF_TMEM_PTR + 16; // the dynamic smem window itself is 1024-byte aligned (checked in the kernel)
+    static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 };
 
 template <int KIND>
@@ -103,22 +142,101 @@ __device__ __forceinline__ float epi_act_f32(float v, int epi)
     return v;
 }
 
+// 32 accumulator columns of one row (+ bias, activation / requantisation) -> 32 output elements packed
+// into `w` (32 words for 4-byte outputs, 16 for bf16, 8 for int8).  `bias` points at 32 words in smem.
+template <int OUT>
+__device__ __forceinline__ void epi_convert32(const uint32_t *v, const uint32_t *bias, int epi, uint32_t *w)
+{
+    if constexpr (OUT == OUT_F32)
+    {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++)
+        {
+            const uint4 b = *reinterpret_cast<const uint4 *>(bias + 4 * j4);
+            w[4 * j4 + 0] = __float_as_uint(epi_act_f32(__uint_as_float(v[4 * j4 + 0]) + __uint_as_float(b.x), epi));
+            w[4 * j4 + 1] = __float_as_uint(epi_act_f32(__uint_as_float(v[4 * j4 + 1]) + __uint_as_float(b.y), epi));
+            w[4 * j4 + 2] = __float_as_uint(epi_act_f32(__uint_as_float(v[4 * j4 + 2]) + __uint_as_float(b.z), epi));
+            w[4 * j4 + 3] = __float_as_uint(epi_act_f32(__uint_as_float(v[4 * j4 + 3]) + __uint_as_float(b.w), epi));
+        }
+    }
+    else if constexpr (OUT == OUT_S32)
+    {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++)
+        {
+            const uint4 b = *reinterpret_cast<const uint4 *>(bias + 4 * j4);
+            const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+            {
+                int a = (int)v[4 * j4 + e] + (int)bb[e];
+                if (epi == EPI_RELU) a = max(a, 0);
+                w[4 * j4 + e] = (uint32_t)a;
+            }
+        }
+    }
+    else if constexpr (OUT == OUT_BF16)
+    {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++)
+        {
+            const uint4 b = *reinterpret_cast<const uint4 *>(bias + 4 * j4);
+            const float f0 = epi_act_f32(__uint_as_float(v[4 * j4 + 0]) + __uint_as_float(b.x), epi);
+            const float f1 = epi_act_f32(__uint_as_float(v[4 * j4 + 1]) + __uint_as_float(b.y), epi);
+            const float f2 = epi_act_f32(__uint_as_float(v[4 * j4 + 2]) + __uint_as_float(b.z), epi);
+            const float f3 = epi_act_f32(__uint_as_float(v[4 * j4 + 3]) + __uint_as_float(b.w), epi);
+            w[2 * j4 + 0] = pack_bf16x2(f0, f1);
+            w[2 * j4 + 1] = pack_bf16x2(f2, f3);
+        }
+    }
+    else
+    {
+        // int8 requantisation: q = clamp((relu?)(acc + bias) >> 7, -128, 127)
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++)
+        {
+            const uint4 b = *reinterpret_cast<const uint4 *>(bias + 4 * j4);
+            const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
+            uint32_t word = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+            {
+                int a = (int)v[4 * j4 + e] + (int)bb[e];
+                if (epi == EPI_REQUANT_RELU) a = max(a, 0);
+                a = min(127, max(-128, a >> 7));
+                word |= ((uint32_t)a & 0xFFu) << (8 * e);
+            }
+            w[j4] = word;
+        }
+    }
+}
+
 template <int KIND, int BN, int OUT, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
-                       const GemmParams p)
+                       const __grid_constant__ CUtensorMap tma_out, const GemmParams p)
 {
     using L = GemmSmem<BN, STAGES>;
     constexpr int ELEM = KindTraits<KIND>::ELEM;
     constexpr int BK = GEMM_STAGE_ROW_BYTES / ELEM; // elements of K per stage
     constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (power of two >= 32)
     constexpr uint32_t IDESC = KindTraits<KIND>::idesc(BN);
+    constexpr int OELEM = OutTraits<OUT>::ELEM;
+    constexpr int WARP_COLS = BN / 2;               // columns per epilogue warp
+    constexpr int SLAB_COLS = slab_cols<BN, OUT>(); // columns per TMA-store slab
+    constexpr int SLAB_ROW_BYTES = SLAB_COLS * OELEM;
+    constexpr bool SLAB_SWIZZLED = SLAB_ROW_BYTES == 128; // int8 slabs (<= 128 B rows handled unswizzled when 64 B)
     static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
+    static_assert(SLAB_ROW_BYTES == 128 || SLAB_ROW_BYTES == 64, "slab rows are 128 bytes (64 for int8 at BN = 128)");
 
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw_addr = smem_u32(smem_raw);
-    const uint32_t base = (raw_addr + 1023u) & ~1023u; // SWIZZLE_128B tiles need 1024-byte alignment
-    uint8_t *smem = smem_raw + (base - raw_addr);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = smem_u32(smem_raw); // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t *smem = smem_raw;
+    if ((base & 1023u) != 0)
+    {
+        if (threadIdx.x == 0 && p.error_flag) atomicExch(p.error_flag, KERR_SMEM_ALIGN);
+        return; // uniform: every thread of every CTA sees the same window offset
+    }
 
     const uint32_t bars = base + L::OFF_BARS;
     auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -139,6 +257,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_w);
+        if (p.tma_store) tma_prefetch_desc(&tma_out);
     }
     if (warp == 1 && lane == 0)
     {
@@ -150,7 +269,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         for (int a = 0; a < 2; a++)
         {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4); // one arrive per epilogue warp
+            mbar_init(tempty_bar(a), GEMM_EPI_WARPS); // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -172,6 +291,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
             {
+                // n-fastest tile order: the CTAs of one wave share a few A row-blocks and all of W in L2
                 const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
                 for (int kb = 0; kb < num_kb; kb++)
                 {
@@ -229,165 +349,158 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     else if (warp >= 4)
     {
         // ===================== epilogue =====================
-        const int q = warp & 3; // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
-        uint32_t *stg = reinterpret_cast<uint32_t *>(smem + L::OFF_STAGING) + q * L::STAGING_WORDS_PER_WARP;
-        uint32_t *bias_s = reinterpret_cast<uint32_t *>(smem + L::OFF_BIAS) + q * BN;
-        uint32_t acc = 0, acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        const int ew = warp - 4;          // 0..7
+        const int q = warp & 3;           // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
+        const int wcol = (ew >> 2) * WARP_COLS; // first tile column of this warp
+        const int et = threadIdx.x - 128; // 0..255 among the epilogue threads
+        uint32_t *bias_all = reinterpret_cast<uint32_t *>(smem + L::OFF_BIAS);
+        uint8_t *slab = smem + L::OFF_SLABS + ew * GEMM_SLAB_BYTES;
+        const uint32_t slab_addr = base + L::OFF_SLABS + ew * GEMM_SLAB_BYTES;
+        uint32_t acc = 0, acc_phase = 0, parity = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, parity ^= 1u)
         {
             const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
             const int col0 = n_blk * BN;
             const int row0 = m_blk * GEMM_BM + q * 32;
 
-            // warp-private copy of this tile's bias slice (bit pattern: float or int32)
-            for (int i = lane; i < BN; i += 32)
+            // this tile's bias slice (bit pattern: float or int32), shared by the 8 epilogue warps
+            uint32_t *bias_s = bias_all + parity * BN;
+            for (int i = et; i < BN; i += 32 * GEMM_EPI_WARPS)
             {
                 const int c = col0 + i;
                 bias_s[i] = (p.bias != nullptr && c < p.N) ? reinterpret_cast<const uint32_t *>(p.bias)[c] : 0u;
             }
-            // per-lane output row (identity, or patch-embedding remap) and position-embedding row
-            long long my_orow = row0 + lane;
-            int my_prow = 0;
-            if (p.epi == EPI_PATCH)
-            {
-                const int r = row0 + lane;
-                const int b = r / p.remap_in, t = r - b * p.remap_in;
-                my_orow = (long long)b * p.remap_out + 1 + t;
-                my_prow = 1 + t;
-            }
-            __syncwarp();
+            named_bar_sync(1, 32 * GEMM_EPI_WARPS);
 
             mbar_wait(tfull_bar(acc), acc_phase, p.error_flag, KERR_EPI_TMEM_FULL);
             tcgen05_fence_after();
-            const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + wcol;
 
-            if constexpr (OUT == OUT_BF16)
+            if (p.tma_store)
             {
-                // 64 columns per pass: 32 packed bf16x2 words per row -> one 128-byte row segment per store
-                __nv_bfloat16 *out = reinterpret_cast<__nv_bfloat16 *>(p.out);
-                for (int c = 0; c < BN / 64; c++)
+                // ---- smem slab + TMA store: 32 rows x SLAB_COLS columns per store ----
+                constexpr int GROUPS_PER_SLAB = SLAB_COLS / 32; // tcgen05.ld groups (32 columns) per slab
+                constexpr int WORDS_PER_GROUP = 32 * OELEM / 4; // packed words one group contributes to a row
+                for (int sb = 0; sb < WARP_COLS / SLAB_COLS; sb++)
                 {
-                    if (col0 + c * 64 >= p.N) break;
-                    uint32_t v[64];
-                    tmem_ld_32x32(t_base + c * 64, v);
-                    tmem_ld_32x32(t_base + c * 64 + 32, v + 32);
-                    tmem_ld_wait();
+                    const int scol = wcol + sb * SLAB_COLS; // tile column of this slab
+                    if (col0 + scol >= p.N) break;          // warp-uniform
+                    uint32_t w[GROUPS_PER_SLAB * WORDS_PER_GROUP];
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
+                    for (int g = 0; g < GROUPS_PER_SLAB; g++)
                     {
-                        const float lo = epi_act_f32(__uint_as_float(v[2 * j]) + __uint_as_float(bias_s[c * 64 + 2 * j]), p.epi);
-                        const float hi = epi_act_f32(__uint_as_float(v[2 * j + 1]) + __uint_as_float(bias_s[c * 64 + 2 * j + 1]), p.epi);
-                        stg[lane * 33 + j] = pack_bf16x2(lo, hi);
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_base + sb * SLAB_COLS + g * 32, v);
+                        tmem_ld_wait();
+                        epi_convert32<OUT>(v, bias_s + scol + g * 32, p.epi, w + g * WORDS_PER_GROUP);
                     }
+                    // the previous store of this warp must have finished reading the slab
+                    if (lane == 0) tma_store_wait_read();
                     __syncwarp();
-                    const int gcol = col0 + c * 64 + 2 * lane;
-#pragma unroll 8
-                    for (int r = 0; r < 32; r++)
-                    {
-                        const uint32_t w = stg[r * 33 + lane];
-                        const long long grow = row0 + r;
-                        if (grow < p.M)
-                        {
-                            __nv_bfloat16 *dst = out + grow * p.ldc + gcol;
-                            if (gcol + 1 < p.N)
-                                *reinterpret_cast<uint32_t *>(dst) = w;
-                            else if (gcol < p.N)
-                                *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(w & 0xFFFFu);
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-            else if constexpr (OUT == OUT_F32 || OUT == OUT_S32)
-            {
-                uint32_t *out = reinterpret_cast<uint32_t *>(p.out);
-                for (int c = 0; c < BN / 32; c++)
-                {
-                    if (col0 + c * 32 >= p.N) break;
-                    uint32_t v[32];
-                    tmem_ld_32x32(t_base + c * 32, v);
-                    tmem_ld_wait();
+                    // lane = row; 16-byte chunk j of the row goes to chunk (j ^ (row & 7)) (128B swizzle)
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
+                    for (int j = 0; j < SLAB_ROW_BYTES / 16; j++)
                     {
-                        uint32_t w;
-                        if constexpr (OUT == OUT_F32)
-                            w = __float_as_uint(epi_act_f32(__uint_as_float(v[j]) + __uint_as_float(bias_s[c * 32 + j]), p.epi));
+                        const int cj = SLAB_SWIZZLED ? (j ^ (lane & 7)) : j;
+                        *reinterpret_cast<uint4 *>(slab + lane * SLAB_ROW_BYTES + cj * 16) =
+                            make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0)
+                    {
+                        if (p.epi == EPI_RESIDUAL)
+                            tma_reduce_add_2d(&tma_out, slab_addr, col0 + scol, row0);
                         else
-                        {
-                            int a = (int)v[j] + (int)bias_s[c * 32 + j];
-                            if (p.epi == EPI_RELU) a = max(a, 0);
-                            w = (uint32_t)a;
-                        }
-                        stg[lane * 33 + j] = w;
+                            tma_store_2d(&tma_out, slab_addr, col0 + scol, row0);
+                        tma_store_commit();
                     }
-                    __syncwarp();
-                    const int gcol = col0 + c * 32 + lane;
-#pragma unroll 8
-                    for (int r = 0; r < 32; r++)
-                    {
-                        uint32_t w = stg[r * 33 + lane];
-                        const long long orow = __shfl_sync(0xffffffffu, my_orow, r);
-                        const int prow = __shfl_sync(0xffffffffu, my_prow, r);
-                        if (row0 + r < p.M && gcol < p.N)
-                        {
-                            uint32_t *dst = out + orow * p.ldc + gcol;
-                            if constexpr (OUT == OUT_F32)
-                            {
-                                if (p.epi == EPI_RESIDUAL)
-                                    w = __float_as_uint(__uint_as_float(*dst) + __uint_as_float(w));
-                                else if (p.epi == EPI_PATCH)
-                                    w = __float_as_uint(__uint_as_float(w) + p.pos[(long long)prow * p.N + gcol]);
-                            }
-                            *dst = w;
-                        }
-                    }
-                    __syncwarp();
                 }
             }
             else
             {
-                // OUT_S8 requantisation: q = clamp((relu?)(acc + bias) >> 7, -128, 127); 8 packed words per row
-                int8_t *out = reinterpret_cast<int8_t *>(p.out);
-                for (int c = 0; c < BN / 32; c++)
+                // ---- direct epilogue: every lane writes its own accumulator row ----
+                const int r = row0 + lane;
+                long long orow = r;
+                int prow = 0;
+                if (p.epi == EPI_PATCH)
                 {
-                    if (col0 + c * 32 >= p.N) break;
+                    const int b = r / p.remap_in, t = r - b * p.remap_in;
+                    orow = (long long)b * p.remap_out + 1 + t;
+                    prow = 1 + t;
+                }
+                const bool row_ok = r < p.M;
+                for (int g = 0; g < WARP_COLS / 32; g++)
+                {
+                    const int gcol = col0 + wcol + g * 32; // first global column of the group
+                    if (gcol >= p.N) break;                // warp-uniform
                     uint32_t v[32];
-                    tmem_ld_32x32(t_base + c * 32, v);
+                    tmem_ld_32x32(t_base + g * 32, v);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
+                    uint32_t w[32 * OELEM / 4];
+                    const int act = (p.epi == EPI_RESIDUAL || p.epi == EPI_PATCH) ? EPI_NONE : p.epi;
+                    epi_convert32<OUT>(v, bias_s + wcol + g * 32, act, w);
+                    if (!row_ok) continue;
+                    if constexpr (OUT == OUT_F32)
                     {
-                        uint32_t w = 0;
-#pragma unroll
-                        for (int e = 0; e < 4; e++)
+                        float *dst = reinterpret_cast<float *>(p.out) + orow * p.ldc + gcol;
+                        const bool vec = gcol + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+                        if (vec)
                         {
-                            int a = (int)v[4 * j + e] + (int)bias_s[c * 32 + 4 * j + e];
-                            if (p.epi == EPI_REQUANT_RELU) a = max(a, 0);
-                            a = min(127, max(-128, a >> 7));
-                            w |= ((uint32_t)a & 0xFFu) << (8 * e);
-                        }
-                        stg[lane * 9 + j] = w;
-                    }
-                    __syncwarp();
+                            float4 add[8];
+                            if (p.epi == EPI_RESIDUAL || p.epi == EPI_PATCH)
+                            {
+                                const float4 *src = p.epi == EPI_RESIDUAL
+                                                        ? reinterpret_cast<const float4 *>(dst)
+                                                        : reinterpret_cast<const float4 *>(p.pos + (long long)prow * p.N + gcol);
 #pragma unroll
-                    for (int it = 0; it < 8; it++)
-                    {
-                        const int r = it * 4 + (lane >> 3), j = lane & 7;
-                        const uint32_t w = stg[r * 9 + j];
-                        const long long grow = row0 + r;
-                        const int gcol = col0 + c * 32 + 4 * j;
-                        if (grow < p.M)
-                        {
-                            int8_t *dst = out + grow * p.ldc + gcol;
-                            if (gcol + 3 < p.N)
-                                *reinterpret_cast<uint32_t *>(dst) = w;
+                                for (int j = 0; j < 8; j++) add[j] = src[j]; // 8 independent loads in flight
+                            }
                             else
-                                for (int e = 0; e < 4; e++)
-                                    if (gcol + e < p.N) dst[e] = (int8_t)((w >> (8 * e)) & 0xFFu);
+                            {
+#pragma unroll
+                                for (int j = 0; j < 8; j++) add[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; j++)
+                                reinterpret_cast<float4 *>(dst)[j] =
+                                    make_float4(__uint_as_float(w[4 * j]) + add[j].x, __uint_as_float(w[4 * j + 1]) + add[j].y,
+                                                __uint_as_float(w[4 * j + 2]) + add[j].z, __uint_as_float(w[4 * j + 3]) + add[j].w);
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                if (gcol + j < p.N)
+                                {
+                                    float val = __uint_as_float(w[j]);
+                                    if (p.epi == EPI_RESIDUAL) val += dst[j];
+                                    if (p.epi == EPI_PATCH) val += p.pos[(long long)prow * p.N + gcol + j];
+                                    dst[j] = val;
+                                }
                         }
                     }
-                    __syncwarp();
+                    else if constexpr (OUT == OUT_S32)
+                    {
+                        uint32_t *dst = reinterpret_cast<uint32_t *>(p.out) + orow * p.ldc + gcol;
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (gcol + j < p.N) dst[j] = w[j];
+                    }
+                    else if constexpr (OUT == OUT_BF16)
+                    {
+                        uint16_t *dst = reinterpret_cast<uint16_t *>(p.out) + orow * p.ldc + gcol;
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (gcol + j < p.N) dst[j] = (uint16_t)(w[j >> 1] >> (16 * (j & 1)));
+                    }
+                    else
+                    {
+                        uint8_t *dst = reinterpret_cast<uint8_t *>(p.out) + orow * p.ldc + gcol;
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (gcol + j < p.N) dst[j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+                    }
                 }
             }
 
@@ -401,6 +514,8 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                 acc_phase ^= 1u;
             }
         }
+        // shared memory must stay valid until the last bulk store has read it
+        if (lane == 0) tma_store_wait_read();
     }
 
     tcgen05_fence_before();

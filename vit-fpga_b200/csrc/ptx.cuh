@@ -19,6 +19,7 @@ enum : int
     KERR_MMA_FULL = 2,
     KERR_MMA_TMEM_EMPTY = 3,
     KERR_EPI_TMEM_FULL = 4,
+    KERR_SMEM_ALIGN = 5,
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,6 +93,32 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst_smem), "l"(map), "r"(bar), "r"(c0), "r"(c1)
                  : "memory");
+}
+
+// 2-D tiled store shared -> global (bulk async-group completion).  Out-of-bounds rows / columns of the
+// box are clipped by the hardware, so ragged tile edges need no predicates.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src_smem, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// Same, but global += shared (element-wise add performed at L2, type taken from the tensor map).
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, uint32_t src_smem, int c0, int c1)
+{
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// All committed bulk stores of this thread have finished READING shared memory (the source may be reused).
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Named barrier among `nthreads` threads of the CTA (id 0 is __syncthreads).
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ---- tcgen05: tensor memory ------------------------------------------------------------------
@@ -198,18 +225,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
-// Exact-erf GELU, x * Phi(x).  erfc via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), arranged so
-// that the negative tail has no 1 - erf cancellation.
+// Exact-erf GELU, x * Phi(x).  erfc via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7) with the two
+// transcendental steps on the MUFU (rcp.approx, ex2.approx: ~1e-7 relative each), arranged so that the
+// negative tail has no 1 - erf cancellation.  ~17 issue slots per element.
 __device__ __forceinline__ float gelu_erf(float x)
 {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float ax = fabsf(x);
+    const float z = ax * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
     poly = fmaf(poly, t, 0.254829592f);
-    const float q = poly * t * __expf(-z * z); // erfc(|z|)
-    const float cdf = x >= 0.0f ? fmaf(-0.5f, q, 1.0f) : 0.5f * q;
+    const float zs = ax * 0.84932180028801904272f; // sqrt(log2(e) / 2): zs^2 = z^2 * log2(e)
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-zs * zs));
+    const float hq = 0.5f * (poly * t) * e;                 // erfc(|z|) / 2
+    const float cdf = x >= 0.0f ? 1.0f - hq : hq;
     return x * cdf;
 }
 

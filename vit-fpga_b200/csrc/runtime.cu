@@ -104,6 +104,18 @@ struct netcuda_net
     void *patches = nullptr, *ybuf = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *cls_ln = nullptr;
     float *x = nullptr;
 
+    // per-kernel profiling (netcuda_profile_enable)
+    bool profiling = false;
+    std::vector<std::string> prof_labels;
+    struct ProfRec
+    {
+        int label;
+        cudaEvent_t start, stop;
+        double flops, bytes;
+    };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_free;
+
     // host-API staging (lazy)
     void *pin_in[2] = {nullptr, nullptr}, *dev_in[2] = {nullptr, nullptr};
     size_t stage_in_bytes = 0;
@@ -116,6 +128,51 @@ static int check_handle(const netcuda_net *h)
     if (!h) return fail(NETCUDA_ERR_INVALID, "null handle");
     return NETCUDA_OK;
 }
+
+// Every kernel launch of a forward pass goes through one KernelScope: it counts the launch and, when
+// profiling is on, brackets it with a CUDA-event pair on the launching stream.
+struct KernelScope
+{
+    cudaStream_t s;
+    cudaEvent_t stop = nullptr;
+    KernelScope(netcuda_net *h, cudaStream_t stream, const char *label, double flops, double bytes) : s(stream)
+    {
+        h->launches++;
+        if (!h->profiling) return;
+        int li = -1;
+        for (size_t i = 0; i < h->prof_labels.size(); i++)
+            if (h->prof_labels[i] == label) li = (int)i;
+        if (li < 0)
+        {
+            h->prof_labels.push_back(label);
+            li = (int)h->prof_labels.size() - 1;
+        }
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        for (int i = 0; i < 2; i++)
+        {
+            if (!h->prof_free.empty())
+            {
+                ev[i] = h->prof_free.back();
+                h->prof_free.pop_back();
+            }
+            else if (cudaEventCreate(&ev[i]) != cudaSuccess)
+            {
+                (void)cudaGetLastError();
+                if (ev[0]) h->prof_free.push_back(ev[0]);
+                return;
+            }
+        }
+        cudaEventRecord(ev[0], s);
+        stop = ev[1];
+        h->prof_recs.push_back({li, ev[0], ev[1], flops, bytes});
+    }
+    ~KernelScope()
+    {
+        if (stop) cudaEventRecord(stop, s);
+    }
+    KernelScope(const KernelScope &) = delete;
+    KernelScope &operator=(const KernelScope &) = delete;
+};
 
 static void *arena_take(netcuda_net *h, size_t bytes)
 {
@@ -213,6 +270,12 @@ extern "C" int netcuda_destroy(netcuda_net *h)
         if (h->h2d_done[i]) cudaEventDestroy(h->h2d_done[i]);
         if (h->compute_done[i]) cudaEventDestroy(h->compute_done[i]);
     }
+    for (auto &r : h->prof_recs)
+    {
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    for (cudaEvent_t e : h->prof_free) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     (void)cudaGetLastError();
@@ -373,7 +436,6 @@ static int upload_matrix(netcuda_net *h, const float *src, long long rows, int c
     else
         e = launch_convert_rows_f32(scratch, (float *)dst, rows, cols, (int)ld, h->stream);
     CK(e);
-    h->launches++;
     CK(cudaStreamSynchronize(h->stream)); // scratch and the pageable source are reused by the caller
     return NETCUDA_OK;
 }
@@ -485,8 +547,10 @@ extern "C" int netcuda_upload_vit(netcuda_net *h, const float *flat, size_t coun
 
 // ---- forward: one pass over <= max_batch samples, everything on `s` -----------------------------------
 
-static cudaError_t run_gemm(netcuda_net *h, int kind, const void *a, long long lda, int a_rows, const void *w, long long ldw,
-                            const void *bias, void *out, long long ldc, int out_type, int epi, int m, int n, int k,
+static int out_elem_size(int out_type) { return out_type == OUT_BF16 ? 2 : out_type == OUT_S8 ? 1 : 4; }
+
+static cudaError_t run_gemm(netcuda_net *h, const char *label, int kind, const void *a, long long lda, int a_rows, const void *w,
+                            long long ldw, const void *bias, void *out, long long ldc, int out_type, int epi, int m, int n, int k,
                             cudaStream_t s, int remap_in = 0, int remap_out = 0, const float *pos = nullptr)
 {
     GemmCall c;
@@ -496,7 +560,11 @@ static cudaError_t run_gemm(netcuda_net *h, int kind, const void *a, long long l
     c.m = m, c.n = n, c.k = k;
     c.remap_in = remap_in, c.remap_out = remap_out, c.pos = pos;
     c.error_flag = h->d_err, c.num_sms = h->num_sms;
-    h->launches++;
+    const double es = kind == GK_BF16 ? 2 : kind == GK_I8 ? 1 : 4;
+    double bytes = ((double)m * k + (double)n * k) * es + (double)m * n * out_elem_size(out_type) + (double)n * 4;
+    if (epi == EPI_RESIDUAL) bytes += (double)m * n * 4;
+    if (epi == EPI_PATCH) bytes += (double)remap_in * n * 4;
+    KernelScope scope(h, s, label, 2.0 * m * n * k, bytes);
     return launch_gemm(c, s);
 }
 
@@ -514,6 +582,7 @@ static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, in
     }
     else
     {
+        KernelScope scope(h, s, "convert_in", 0.0, (double)n * ((double)h->n_in * (in_i8 ? 1 : 4) + (double)ld0 * h->elem));
         cudaError_t e;
         if (prec == NETCUDA_PREC_BF16)
             e = launch_convert_rows_bf16(in_f32, h->act[0], n, (int)h->n_in, (int)ld0, s);
@@ -524,7 +593,6 @@ static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, in
         else
             e = launch_quantize_rows_q17(in_f32, (int8_t *)h->act[0], n, (int)h->n_in, (int)ld0, s);
         CK(e);
-        h->launches++;
         cur = h->act[0], cur_ld = ld0;
     }
     int slot = 1;
@@ -556,15 +624,23 @@ static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, in
         }
         // the tensor maps are built with inner extent K = fan_in, so pad columns [fan_in, ld) are never read
         const int a_rows = (cur == (const void *)in_f32) ? n : h->max_batch;
-        CK(run_gemm(h, kind, cur, cur_ld, a_rows, ly.w, ly.ldw, ly.bias, dst, ldc, out_type, epi, n, ly.fan_out, ly.fan_in, s));
+        CK(run_gemm(h, "mlp_layer", kind, cur, cur_ld, a_rows, ly.w, ly.ldw, ly.bias, dst, ldc, out_type, epi, n, ly.fan_out, ly.fan_in, s));
         cur = dst, cur_ld = ldc;
         slot ^= 1;
     }
     if (prec == NETCUDA_PREC_INT8 && !out_i32)
     {
+        KernelScope scope(h, s, "dequant_out", 0.0, (double)n * (double)h->n_out * 8.0);
         CK(launch_dequant_q214(h->acc_out, out_f32, (long long)n * (long long)h->n_out, s));
-        h->launches++;
     }
+    return NETCUDA_OK;
+}
+
+static int run_layernorm(netcuda_net *h, const char *label, const float *x, long long ldx, const float *g, const float *b, void *y,
+                         long long ldy, int rows, int dim, cudaStream_t s)
+{
+    KernelScope scope(h, s, label, 0.0, (double)rows * dim * 6.0 + (double)dim * 8.0);
+    CK(launch_layernorm(x, ldx, g, b, y, ldy, rows, dim, 1e-6f, s));
     return NETCUDA_OK;
 }
 
@@ -572,28 +648,33 @@ static int vit_pass(netcuda_net *h, const float *img, int n, float *logits, cuda
 {
     const int D = h->desc.dim, F = h->desc.mlp_dim, C = h->desc.n_classes, T = h->T, NP = h->NP, PK = h->PK;
     const int rows = n * T, cap = h->max_batch * T;
-    CK(launch_patchify(img, h->patches, n, h->desc.image_size, h->desc.patch_size, s));
-    h->launches++;
+    {
+        KernelScope scope(h, s, "patchify", 0.0, (double)n * (double)h->n_in * 6.0);
+        CK(launch_patchify(img, h->patches, n, h->desc.image_size, h->desc.patch_size, s));
+    }
     // patch embedding: x[b*T + 1 + t] = patches . patch_w^T + patch_b + pos[1 + t]
-    CK(run_gemm(h, GK_BF16, h->patches, PK, h->max_batch * NP, h->patch_w, PK, h->patch_b, h->x, D, OUT_F32, EPI_PATCH, n * NP, D, PK, s,
-                NP, T, h->pos));
-    CK(launch_cls_rows(h->x, h->cls, h->pos, n, T, D, s));
-    h->launches++;
+    CK(run_gemm(h, "patch_embed", GK_BF16, h->patches, PK, h->max_batch * NP, h->patch_w, PK, h->patch_b, h->x, D, OUT_F32, EPI_PATCH,
+                n * NP, D, PK, s, NP, T, h->pos));
+    {
+        KernelScope scope(h, s, "cls_rows", 0.0, (double)n * D * 4.0 + (double)D * 8.0);
+        CK(launch_cls_rows(h->x, h->cls, h->pos, n, T, D, s));
+    }
     for (auto &b : h->blocks)
     {
-        CK(launch_layernorm(h->x, D, b.ln1_g, b.ln1_b, h->ybuf, D, rows, D, 1e-6f, s));
-        CK(run_gemm(h, GK_BF16, h->ybuf, D, cap, b.qkv_w, D, b.qkv_b, h->qkv, 3LL * D, OUT_BF16, EPI_NONE, rows, 3 * D, D, s));
-        CK(launch_attention(h->qkv, h->att, n, T, h->desc.heads, s));
-        CK(run_gemm(h, GK_BF16, h->att, D, cap, b.proj_w, D, b.proj_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, D, s));
-        CK(launch_layernorm(h->x, D, b.ln2_g, b.ln2_b, h->ybuf, D, rows, D, 1e-6f, s));
-        CK(run_gemm(h, GK_BF16, h->ybuf, D, cap, b.fc1_w, D, b.fc1_b, h->hid, F, OUT_BF16, EPI_GELU, rows, F, D, s));
-        CK(run_gemm(h, GK_BF16, h->hid, F, cap, b.fc2_w, F, b.fc2_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, F, s));
-        h->launches += 3;
+        if (int rc = run_layernorm(h, "layernorm", h->x, D, b.ln1_g, b.ln1_b, h->ybuf, D, rows, D, s)) return rc;
+        CK(run_gemm(h, "qkv", GK_BF16, h->ybuf, D, cap, b.qkv_w, D, b.qkv_b, h->qkv, 3LL * D, OUT_BF16, EPI_NONE, rows, 3 * D, D, s));
+        {
+            KernelScope scope(h, s, "attention", 4.0 * n * (double)T * T * D, (double)rows * D * 8.0);
+            CK(launch_attention(h->qkv, h->att, n, T, h->desc.heads, s));
+        }
+        CK(run_gemm(h, "proj", GK_BF16, h->att, D, cap, b.proj_w, D, b.proj_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, D, s));
+        if (int rc = run_layernorm(h, "layernorm", h->x, D, b.ln2_g, b.ln2_b, h->ybuf, D, rows, D, s)) return rc;
+        CK(run_gemm(h, "fc1", GK_BF16, h->ybuf, D, cap, b.fc1_w, D, b.fc1_b, h->hid, F, OUT_BF16, EPI_GELU, rows, F, D, s));
+        CK(run_gemm(h, "fc2", GK_BF16, h->hid, F, cap, b.fc2_w, F, b.fc2_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, F, s));
     }
     // final LayerNorm on the class-token rows only (row pitch T*D), then the head
-    CK(launch_layernorm(h->x, (long long)T * D, h->lnf_g, h->lnf_b, h->cls_ln, D, n, D, 1e-6f, s));
-    h->launches++;
-    CK(run_gemm(h, GK_BF16, h->cls_ln, D, h->max_batch, h->head_w, D, h->head_b, logits, C, OUT_F32, EPI_NONE, n, C, D, s));
+    if (int rc = run_layernorm(h, "layernorm_cls", h->x, (long long)T * D, h->lnf_g, h->lnf_b, h->cls_ln, D, n, D, s)) return rc;
+    CK(run_gemm(h, "head", GK_BF16, h->cls_ln, D, h->max_batch, h->head_w, D, h->head_b, logits, C, OUT_F32, EPI_NONE, n, C, D, s));
     return NETCUDA_OK;
 }
 
@@ -777,6 +858,45 @@ extern "C" int netcuda_flops_per_sample(const netcuda_net *h, double *flops)
     *flops = h->flops_per_sample;
     return NETCUDA_OK;
 }
+extern "C" int netcuda_profile_enable(netcuda_net *h, int on)
+{
+    if (int rc = check_handle(h)) return rc;
+    h->profiling = on != 0;
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_profile_read(netcuda_net *h, netcuda_kernel_stat *stats, int cap, int *count)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (!count || (cap > 0 && !stats)) return fail(NETCUDA_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(h->device));
+    std::vector<netcuda_kernel_stat> acc(h->prof_labels.size());
+    for (size_t i = 0; i < acc.size(); i++)
+    {
+        memset(&acc[i], 0, sizeof(acc[i]));
+        snprintf(acc[i].label, sizeof(acc[i].label), "%s", h->prof_labels[i].c_str());
+    }
+    int rc = NETCUDA_OK;
+    for (auto &r : h->prof_recs)
+    {
+        float ms = 0.0f;
+        cudaError_t e = cudaEventSynchronize(r.stop);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.start, r.stop);
+        if (e != cudaSuccess && rc == NETCUDA_OK) rc = fail(NETCUDA_ERR_CUDA, "profile read: %s", cudaGetErrorString(e));
+        acc[r.label].launches++;
+        acc[r.label].ms += ms;
+        acc[r.label].flops += r.flops;
+        acc[r.label].bytes += r.bytes;
+        h->prof_free.push_back(r.start);
+        h->prof_free.push_back(r.stop);
+    }
+    h->prof_recs.clear();
+    *count = (int)acc.size();
+    for (int i = 0; i < cap && i < (int)acc.size(); i++) stats[i] = acc[i];
+    h->prof_labels.clear();
+    return rc;
+}
+
 extern "C" int netcuda_set_gemm_variant(netcuda_net *h, int variant)
 {
     if (int rc = check_handle(h)) return rc;

@@ -48,11 +48,11 @@ namespace cuda
             throw std::runtime_error(msg);
         }
 
-        net_cuda_options resolve(net_cuda_options o)
+        net_cuda_options resolve(net_cuda_options o, int default_precision)
         {
             if (o.precision < 0)
             {
-                o.precision = PREC_BF16;
+                o.precision = default_precision;
                 if (const char *e = std::getenv("NETCUDA_PRECISION"))
                 {
                     const std::string s(e);
@@ -81,7 +81,7 @@ namespace cuda
     {
         try
         {
-            p_->opt = resolve(options);
+            p_->opt = resolve(options, PREC_TF32);
             // depth comes from n_p_l.size(); data.n_layers is informational (src/netFPGA.cpp:59)
             if (data.n_p_l.empty() || data.n_ins == 0) throw std::invalid_argument("net_cuda: empty net description");
             p_->n_ins = data.n_ins;
@@ -135,7 +135,7 @@ namespace cuda
     {
         try
         {
-            p_->opt = resolve(options);
+            p_->opt = resolve(options, PREC_BF16);
             p_->is_vit = true;
             p_->vit = vit;
             p_->instantiate();

@@ -40,6 +40,10 @@ class Desc(C.Structure):
                 ("heads", C.c_int32), ("mlp_dim", C.c_int32), ("n_classes", C.c_int32)]
 
 
+class KernelStat(C.Structure):
+    _fields_ = [("label", C.c_char * 32), ("launches", C.c_uint64), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
+
+
 def declared_symbols() -> list[str]:
     """Every function include/netcuda.h declares (used by the CPU test that checks the exports)."""
     text = open(HEADER).read()
@@ -238,6 +242,17 @@ class Net:
         n = C.c_int64(0)
         _check(lib.netcuda_last_forward_us(self._h, C.byref(n)))
         return n.value
+
+    def profile_enable(self, on: bool) -> None:
+        _check(lib.netcuda_profile_enable(self._h, C.c_int(int(on))))
+
+    def profile_read(self) -> dict:
+        """{label: {"launches", "ms", "flops", "bytes"}} for everything launched since the last read."""
+        buf = (KernelStat * 64)()
+        n = C.c_int(0)
+        _check(lib.netcuda_profile_read(self._h, buf, C.c_int(64), C.byref(n)))
+        return {buf[i].label.decode(): dict(launches=int(buf[i].launches), ms=buf[i].ms, flops=buf[i].flops, bytes=buf[i].bytes)
+                for i in range(min(n.value, 64))}
 
     def set_gemm_variant(self, variant: int) -> None:
         _check(lib.netcuda_set_gemm_variant(self._h, C.c_int(variant)))
