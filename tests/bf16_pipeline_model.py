@@ -7,23 +7,26 @@ and the GELU output.  This model applies the same roundings to an otherwise fp32
 
     |cuda - model|   measures kernel arithmetic (accumulation order, exp2/erf approximations), and
     |model - fp32|   is the budget that bf16 operands cost -- not something a kernel can win back.
+
+Everything between two rounding points is evaluated in float64, so the model does not depend on which
+matmul kernels (and which reduced-precision fast paths) the host CPU's BLAS picks.
 """
 import numpy as np
 import torch
 
 
 def _bf(x):
-    return x.to(torch.bfloat16).float()
+    return x.float().to(torch.bfloat16).double()
 
 
 def vit_forward_bf16_model(cfg: dict, flat: np.ndarray, images: np.ndarray, rounding: bool = True) -> np.ndarray:
     r = _bf if rounding else (lambda t: t)
-    flat = torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float32))
+    flat = torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float64))
     D, F, C, P, S, H = cfg["dim"], cfg["mlp_dim"], cfg["n_classes"], cfg["patch_size"], cfg["image_size"], cfg["heads"]
     g = S // P
     NP, PK = g * g, 3 * P * P
     T = NP + 1
-    imgs = torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32)).reshape(-1, 3, S, S)
+    imgs = torch.from_numpy(np.ascontiguousarray(images, dtype=np.float64)).reshape(-1, 3, S, S)
     B = imgs.shape[0]
     pos_ = [0]
 
@@ -35,7 +38,7 @@ def vit_forward_bf16_model(cfg: dict, flat: np.ndarray, images: np.ndarray, roun
 
     pw, pb, cls, pos = take(D, PK), take(D), take(D), take(T, D)
     patches = imgs.reshape(B, 3, g, P, g, P).permute(0, 2, 4, 1, 3, 5).reshape(B, NP, PK)
-    x = torch.empty(B, T, D)
+    x = torch.empty(B, T, D, dtype=torch.float64)
     x[:, 1:] = r(patches) @ r(pw).T + pb + pos[1:]
     x[:, 0] = cls + pos[0]
     ln = torch.nn.functional.layer_norm
@@ -55,4 +58,4 @@ def vit_forward_bf16_model(cfg: dict, flat: np.ndarray, images: np.ndarray, roun
     gf, bfin, hw, hb = take(D), take(D), take(C, D), take(C)
     assert pos_[0] == flat.numel()
     c = r(ln(x[:, 0], (D,), gf, bfin, 1e-6))
-    return (c @ r(hw).T + hb).numpy()
+    return (c @ r(hw).T + hb).float().numpy()

@@ -190,7 +190,11 @@ def test_layernorm_strided_rows(netcuda, oracle, torch_cuda):
     assert _max_rel(y.float().cpu().numpy(), want) <= 5e-3
 
 
-@pytest.mark.parametrize("batch,tokens,heads", [(2, 197, 3), (1, 5, 1), (3, 37, 2), (1, 577, 2), (2, 64, 12), (4, 16, 1), (1, 113, 1)])
+ATTENTION_SHAPES = [(2, 197, 3), (1, 5, 1), (3, 37, 2), (1, 577, 2), (2, 64, 12), (4, 16, 1), (1, 113, 1),
+                    (1, 128, 1), (2, 129, 2), (2, 256, 1), (3, 200, 2), (1, 257, 1), (40, 197, 12)]
+
+
+@pytest.mark.parametrize("batch,tokens,heads", ATTENTION_SHAPES)
 def test_attention_vs_oracle(netcuda, oracle, torch_cuda, batch, tokens, heads):
     torch = torch_cuda
     rng = np.random.default_rng(tokens * 5 + heads)
@@ -203,6 +207,22 @@ def test_attention_vs_oracle(netcuda, oracle, torch_cuda, batch, tokens, heads):
     got = out.float().cpu().numpy()
     # P is rounded to bf16 before P.V and the output is bf16: 1e-2 of max|ref| (north_star tolerance)
     assert _max_rel(got, want) <= 1e-2
+
+
+def test_attention_tcgen05_matches_mma_sync_kernel(netcuda, torch_cuda, monkeypatch):
+    """Both attention kernels on a full ViT-B pass worth of heads (256 images x 12 heads x 197 tokens)."""
+    torch = torch_cuda
+    batch, tokens, heads = 256, 197, 12
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = torch.randn((batch * tokens, 3 * heads * 64), generator=g, device="cuda").to(torch.bfloat16)
+    o0 = torch.empty((batch * tokens, heads * 64), dtype=torch.bfloat16, device="cuda")
+    o1 = torch.empty_like(o0)
+    netcuda.op_attention(qkv, o0, batch, tokens, heads)
+    monkeypatch.setenv("NETCUDA_ATTENTION_VARIANT", "1")
+    netcuda.op_attention(qkv, o1, batch, tokens, heads)
+    torch.cuda.synchronize()
+    err = ((o0.float() - o1.float()).abs().max() / o1.float().abs().max()).item()
+    assert err <= 1e-2, err
 
 
 def test_patchify_exact(netcuda, torch_cuda):

@@ -5,7 +5,18 @@
 // rows [q | k | v] of 3*heads*64 columns per token, so no re-layout kernel runs between the GEMM and
 // attention, and the output [token][heads*64] is directly the A operand of the output projection.
 //
-// Round-1 kernel: flash-style single pass with mma.sync m16n8k16 (bf16 in, fp32 accumulate).
+// Two kernels:
+//  (1) attention_tc_kernel (tokens <= 256, i.e. every 224-pixel ViT): tcgen05.  One persistent CTA per SM
+//      walks over (image, head) items.  Per item: TMA loads Q (two 128-row tiles), K and V of the head
+//      (128B-swizzled, double-buffered across items); S = Q.K^T with UMMA 128 x n_pad x 16 into tensor
+//      memory; two softmax warpgroups (one per query tile, thread = query row) read S from TMEM, take the
+//      exact row max, write the un-normalised bf16 P back into the same TMEM columns; O = P.V is a UMMA
+//      with the A operand in TMEM and V consumed MN-major straight from its row-major [key][64] tile;
+//      the warpgroup scales O by 1/rowsum and writes 128-byte rows.  S and P never touch smem or HBM.
+//  (2) attention_kernel (longer sequences, e.g. 577 tokens at 384 pixels): flash-style single pass with
+//      mma.sync m16n8k16 (bf16 in, fp32 accumulate), described below.
+//
+// mma.sync kernel:
 //   - one CTA per (query block, head, image); K and V of the head live in shared memory once
 //     (197 keys: 2 x 26 KB; 577 keys: 2 x 74 KB), XOR-swizzled in 16-byte chunks so ldmatrix is
 //     bank-conflict free; rows >= tokens are zero-filled and masked to -inf before the softmax;
@@ -223,10 +234,275 @@ static cudaError_t launch_attention_nw(const __nv_bfloat16 *q, __nv_bfloat16 *o,
     return cudaGetLastError();
 }
 
-cudaError_t launch_attention(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream)
+// =====================================================================================================
+// tcgen05 kernel
+// =====================================================================================================
+
+constexpr int ATC_THREADS = 384;
+constexpr int ATC_Q_BYTES = 128 * 128;  // one query tile: 128 rows x 64 bf16
+constexpr int ATC_KV_BYTES = 256 * 128; // up to 256 keys x 64 bf16
+constexpr int ATC_BUF_BYTES = 2 * ATC_Q_BYTES + 2 * ATC_KV_BYTES;
+constexpr int ATC_OFF_BARS = 2 * ATC_BUF_BYTES;
+constexpr int ATC_NUM_BARS = 4 + 8;
+constexpr int ATC_OFF_TMEM_PTR = ATC_OFF_BARS + ATC_NUM_BARS * 8;
+constexpr int ATC_SMEM = ATC_OFF_TMEM_PTR + 16;
+constexpr int ATC_REGION_COLS = 256; // TMEM columns per query tile: S at [0, n_pad), P over [0, n_pad/2), O at [128, 192)
+constexpr int ATC_O_COL = 128;
+
+enum : int
+{
+    KERR_ATT_PRODUCER = 11,
+    KERR_ATT_MMA_FULL = 12,
+    KERR_ATT_MMA_SFREE = 13,
+    KERR_ATT_MMA_PFULL = 14,
+    KERR_ATT_WG_SFULL = 15,
+    KERR_ATT_WG_OFULL = 16,
+};
+
+struct AttnTcParams
+{
+    __nv_bfloat16 *out; // [batch * tokens][heads * 64]
+    int batch, tokens, heads;
+    int n_pad;    // keys padded to a multiple of 16 (UMMA N of the S tile, UMMA K extent of P.V)
+    int n_mtiles; // 1 or 2 query tiles of 128 rows
+    int *error_flag;
+};
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const AttnTcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t atc_smem[];
+    const uint32_t base = smem_u32(atc_smem);
+    if ((base & 1023u) != 0)
+    {
+        if (threadIdx.x == 0 && p.error_flag) atomicExch(p.error_flag, KERR_SMEM_ALIGN);
+        return;
+    }
+    const uint32_t bars = base + ATC_OFF_BARS;
+    auto full_bar = [&](int b) { return bars + 8u * b; };
+    auto empty_bar = [&](int b) { return bars + 8u * (2 + b); };
+    auto sfull_bar = [&](int t) { return bars + 8u * (4 + t); };
+    auto pfull_bar = [&](int t) { return bars + 8u * (6 + t); };
+    auto ofull_bar = [&](int t) { return bars + 8u * (8 + t); };
+    auto sfree_bar = [&](int t) { return bars + 8u * (10 + t); };
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(atc_smem + ATC_OFF_TMEM_PTR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items = p.batch * p.heads;
+    const int D = p.heads * ATT_HD;
+
+    if (warp == 0 && lane == 0)
+    {
+        tma_prefetch_desc(&tma_q);
+        tma_prefetch_desc(&tma_kv);
+    }
+    if (warp == 1 && lane == 0)
+    {
+        for (int b = 0; b < 2; b++)
+        {
+            mbar_init(full_bar(b), 1);
+            mbar_init(empty_bar(b), 1);
+            mbar_init(sfull_bar(b), 1);
+            mbar_init(pfull_bar(b), 4); // one arrive per softmax warp
+            mbar_init(ofull_bar(b), 1);
+            mbar_init(sfree_bar(b), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2)
+    {
+        tmem_alloc(base + ATC_OFF_TMEM_PTR, 512);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0)
+    {
+        // ===================== TMA producer =====================
+        if (lane == 0)
+        {
+            const uint32_t tx = (uint32_t)(p.n_mtiles * ATC_Q_BYTES + 2 * p.n_pad * 128);
+            int it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, it++)
+            {
+                const int buf = it & 1;
+                const int b = item / p.heads, h = item - b * p.heads;
+                mbar_wait(empty_bar(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u, p.error_flag, KERR_ATT_PRODUCER);
+                mbar_arrive_expect_tx(full_bar(buf), tx);
+                const uint32_t dst = base + buf * ATC_BUF_BYTES;
+                const int row = b * p.tokens;
+                for (int t = 0; t < p.n_mtiles; t++) tma_load_2d(dst + t * ATC_Q_BYTES, &tma_q, full_bar(buf), h * ATT_HD, row + t * 128);
+                tma_load_2d(dst + 2 * ATC_Q_BYTES, &tma_kv, full_bar(buf), D + h * ATT_HD, row);
+                tma_load_2d(dst + 2 * ATC_Q_BYTES + ATC_KV_BYTES, &tma_kv, full_bar(buf), 2 * D + h * ATT_HD, row);
+            }
+        }
+    }
+    else if (warp == 1)
+    {
+        // ===================== MMA issuer =====================
+        if (lane == 0)
+        {
+            const uint32_t idesc_s = umma_idesc(1, 1, 128, (uint32_t)p.n_pad);
+            const uint32_t idesc_o = umma_idesc(1, 1, 128, ATT_HD) | UMMA_IDESC_B_MN_MAJOR;
+            const int ksteps = p.n_pad / 16;
+            int it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, it++)
+            {
+                const int buf = it & 1;
+                const uint32_t ph = (uint32_t)it & 1u;
+                const uint32_t sm = base + buf * ATC_BUF_BYTES;
+                mbar_wait(full_bar(buf), (uint32_t)(it >> 1) & 1u, p.error_flag, KERR_ATT_MMA_FULL);
+                tcgen05_fence_after();
+                const uint64_t k_desc = umma_smem_desc_sw128(sm + 2 * ATC_Q_BYTES);
+                for (int t = 0; t < p.n_mtiles; t++)
+                {
+                    // S_t = Q_t . K^T: region t must have been drained by the previous item's epilogue
+                    mbar_wait(sfree_bar(t), ph ^ 1u, p.error_flag, KERR_ATT_MMA_SFREE);
+                    tcgen05_fence_after();
+                    const uint64_t q_desc = umma_smem_desc_sw128(sm + t * ATC_Q_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        umma_ss<KIND_BF16>(tmem_base + t * ATC_REGION_COLS, q_desc + 2u * k, k_desc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+                    tcgen05_commit(sfull_bar(t));
+                }
+                // V tile [key][64] read MN-major: one UMMA K step = 16 keys = 2048 bytes of the tile
+                const uint64_t v_desc = umma_smem_desc_sw128(sm + 2 * ATC_Q_BYTES + ATC_KV_BYTES);
+                for (int t = 0; t < p.n_mtiles; t++)
+                {
+                    mbar_wait(pfull_bar(t), ph, p.error_flag, KERR_ATT_MMA_PFULL);
+                    tcgen05_fence_after();
+                    const uint32_t region = tmem_base + t * ATC_REGION_COLS;
+                    for (int k = 0; k < ksteps; k++)
+                        umma_ts_bf16(region + ATC_O_COL, region + 8u * k, v_desc + (uint64_t)(128u * k), idesc_o, k != 0 ? 1u : 0u);
+                    tcgen05_commit(ofull_bar(t));
+                }
+                tcgen05_commit(empty_bar(buf)); // every MMA that reads this smem buffer has been issued
+            }
+        }
+    }
+    else if (warp >= 4 && (warp - 4) / 4 < p.n_mtiles)
+    {
+        // ===================== softmax + output warpgroups (one per query tile) =====================
+        const int t = (warp - 4) >> 2; // query tile
+        const int q = warp & 3;        // TMEM lane quarter
+        const int qrow = t * 128 + q * 32 + lane; // query row within the image
+        const uint32_t region = tmem_base + ((uint32_t)(q * 32) << 16) + t * ATC_REGION_COLS;
+        const float sl = 0.125f * 1.4426950408889634f; // 1/sqrt(64) * log2(e)
+        const int nchunks = (p.tokens + 31) >> 5;
+        int it = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, it++)
+        {
+            const uint32_t ph = (uint32_t)it & 1u;
+            const int b = item / p.heads, h = item - b * p.heads;
+            mbar_wait(sfull_bar(t), ph, p.error_flag, KERR_ATT_WG_SFULL);
+            tcgen05_fence_after();
+            // pass 1: exact row maximum over the valid keys
+            float mx = -INFINITY;
+            for (int c = 0; c < nchunks; c++)
+            {
+                uint32_t v[32];
+                tmem_ld_32x32(region + c * 32, v);
+                tmem_ld_wait();
+                const int valid = p.tokens - c * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if (j < valid) mx = fmaxf(mx, __uint_as_float(v[j]));
+            }
+            // pass 2: p = 2^((s - max) * scale); P (bf16) overwrites the first half of the S columns it came from
+            const float msc = mx * sl;
+            float sum = 0.0f;
+            for (int c = 0; c < nchunks; c++)
+            {
+                uint32_t v[32], w[16];
+                tmem_ld_32x32(region + c * 32, v);
+                tmem_ld_wait();
+                const int valid = p.tokens - c * 32;
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                {
+                    const float p0 = (2 * j < valid) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl, -msc)) : 0.0f;
+                    const float p1 = (2 * j + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl, -msc)) : 0.0f;
+                    sum += p0 + p1;
+                    w[j] = pack_bf16x2(p0, p1);
+                }
+                tmem_st_32x16(region + c * 16, w);
+            }
+            tmem_st_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pfull_bar(t));
+
+            // O = P.V / rowsum
+            mbar_wait(ofull_bar(t), ph, p.error_flag, KERR_ATT_WG_OFULL);
+            tcgen05_fence_after();
+            uint32_t o[64];
+            tmem_ld_32x32(region + ATC_O_COL, o);
+            tmem_ld_32x32(region + ATC_O_COL + 32, o + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sfree_bar(t)); // region t may be overwritten by the next item's S
+            if (qrow < p.tokens)
+            {
+                const float inv = 1.0f / sum;
+                uint4 *dst = reinterpret_cast<uint4 *>(p.out + ((long long)b * p.tokens + qrow) * D + h * ATT_HD);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                {
+                    uint4 pk;
+                    pk.x = pack_bf16x2(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
+                    pk.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
+                    pk.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
+                    pk.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
+                    dst[j] = pk;
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2)
+    {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag,
+                                       int num_sms)
+{
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+    if (e != cudaSuccess) return e;
+    AttnTcParams p;
+    p.out = reinterpret_cast<__nv_bfloat16 *>(out);
+    p.batch = batch, p.tokens = tokens, p.heads = heads;
+    p.n_pad = (tokens + 15) & ~15;
+    p.n_mtiles = tokens > 128 ? 2 : 1;
+    p.error_flag = error_flag;
+    const long long D = (long long)heads * ATT_HD, rows = (long long)batch * tokens;
+    // rows past the last token of the last image are zero-filled by TMA; a tile that runs into the next image reads
+    // that image's (finite) rows: extra keys are masked in the softmax, extra query rows are never stored
+    CUtensorMap map_q, map_kv;
+    e = encode_tma_2d(&map_q, 2, qkv, 3 * D, rows, 3 * D * 2, ATT_HD, 128, true);
+    if (e != cudaSuccess) return e;
+    e = encode_tma_2d(&map_kv, 2, qkv, 3 * D, rows, 3 * D * 2, ATT_HD, p.n_pad, true);
+    if (e != cudaSuccess) return e;
+    const int items = batch * heads;
+    const int sms = num_sms > 0 ? num_sms : 148;
+    attention_tc_kernel<<<items < sms ? items : sms, ATC_THREADS, ATC_SMEM, stream>>>(map_q, map_kv, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_attention(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag, int num_sms,
+                             int variant)
 {
     if (batch <= 0) return cudaSuccess;
     if (tokens <= 0 || heads <= 0 || heads > 65535 || batch > 65535) return cudaErrorInvalidValue;
+    if (tokens <= 256 && variant == 0) return launch_attention_tc(qkv, out, batch, tokens, heads, stream, error_flag, num_sms);
     const int tpad = (tokens + 15) & ~15;
     const size_t smem = (size_t)tpad * 128 * 2;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;

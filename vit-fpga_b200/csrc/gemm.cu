@@ -20,6 +20,24 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode_tiled = nullptr;
 
+cudaError_t encode_tma_2d(void *map_out, int dtype_bytes, const void *ptr, long long dim0, long long dim1, long long pitch_bytes,
+                          int box0, int box1, bool swizzle128)
+{
+    if (!g_encode_tiled) return cudaErrorNotReady;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (pitch_bytes & 15) != 0 || dim0 <= 0 || dim1 <= 0) return cudaErrorInvalidValue;
+    const CUtensorMapDataType dt = dtype_bytes == 2   ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                   : dtype_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                                      : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    cuuint64_t gdim[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+    cuuint64_t gstride[1] = {(cuuint64_t)pitch_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = g_encode_tiled(reinterpret_cast<CUtensorMap *>(map_out), dt, 2, const_cast<void *>(ptr), gdim, gstride, box, estride,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <int KIND, int BN, int OUT, int STAGES>
 static cudaError_t opt_in_smem()
 {

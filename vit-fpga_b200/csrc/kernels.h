@@ -43,12 +43,19 @@ cudaError_t launch_gemm(const GemmCall &call, cudaStream_t stream);
 // One-time per-process setup of the tcgen05 kernels (dynamic smem opt-in, driver entry point).
 cudaError_t gemm_global_init();
 
+// 2-D row-major tensor map {dim0 (contiguous), dim1} with a {box0, box1} box; 128B swizzle when box0 spans
+// 128 bytes and `swizzle128` is set.  dtype_bytes selects the element type (1: u8, 2: bf16, 4: f32).
+cudaError_t encode_tma_2d(void *map_out, int dtype_bytes, const void *ptr, long long dim0, long long dim1, long long pitch_bytes,
+                          int box0, int box1, bool swizzle128);
+
 // y = LayerNorm(x) * gamma + beta; x fp32 rows (pitch ldx), y bf16 rows (pitch ldy).
 cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, const float *beta, void *y, long long ldy,
                              int rows, int dim, float eps, cudaStream_t stream);
 
 // softmax(q k^T / sqrt(64)) v per (image, head) on packed bf16 qkv rows; head_dim fixed at 64.
-cudaError_t launch_attention(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream);
+// tokens <= 256: tcgen05 kernel (S and P in tensor memory); longer sequences: mma.sync flash kernel.
+cudaError_t launch_attention(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag = nullptr,
+                             int num_sms = 0, int variant = 0);
 
 // fp32 NCHW -> bf16 patch rows [batch * np][3 * p * p].
 cudaError_t launch_patchify(const float *img, void *patches, int batch, int image_size, int patch_size, cudaStream_t stream);

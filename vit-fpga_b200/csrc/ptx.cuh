@@ -161,6 +161,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t *r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 32 lanes x 16 consecutive 32-bit columns: thread t of the warp writes row (lane) t.
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+                   "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- tcgen05: descriptors and MMA ------------------------------------------------------------
 
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are 128 bytes and which
@@ -189,6 +200,8 @@ __host__ __device__ constexpr uint32_t umma_idesc(uint32_t d_fmt, uint32_t ab_fm
     return (d_fmt << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+constexpr uint32_t UMMA_IDESC_B_MN_MAJOR = 1u << 16; // B operand is N-contiguous ("MN-major") instead of K-contiguous
+
 enum : int
 {
     KIND_BF16 = 0,
@@ -215,6 +228,16 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
                      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
                      : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 rows x 16 bf16 per instruction) is read from tensor
+// memory, lane = row, two bf16 per 32-bit column.  Used for P.V in attention, where P never leaves TMEM.
+__device__ __forceinline__ void umma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                 : "memory");
 }
 
 // ---- misc ------------------------------------------------------------------------------------

@@ -22,6 +22,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -665,7 +666,7 @@ static int vit_pass(netcuda_net *h, const float *img, int n, float *logits, cuda
         CK(run_gemm(h, "qkv", GK_BF16, h->ybuf, D, cap, b.qkv_w, D, b.qkv_b, h->qkv, 3LL * D, OUT_BF16, EPI_NONE, rows, 3 * D, D, s));
         {
             KernelScope scope(h, s, "attention", 4.0 * n * (double)T * T * D, (double)rows * D * 8.0);
-            CK(launch_attention(h->qkv, h->att, n, T, h->desc.heads, s));
+            CK(launch_attention(h->qkv, h->att, n, T, h->desc.heads, s, h->d_err, h->num_sms, h->gemm_variant));
         }
         CK(run_gemm(h, "proj", GK_BF16, h->att, D, cap, b.proj_w, D, b.proj_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, D, s));
         if (int rc = run_layernorm(h, "layernorm", h->x, D, b.ln2_g, b.ln2_b, h->ybuf, D, rows, D, s)) return rc;
@@ -954,7 +955,9 @@ extern "C" int netcuda_op_layernorm(int device, const float *d_x, int ldx, const
 extern "C" int netcuda_op_attention(int device, const void *d_qkv, void *d_out, int batch, int tokens, int heads, void *stream)
 {
     if (int rc = op_prologue(device)) return rc;
-    CK(launch_attention(d_qkv, d_out, batch, tokens, heads, (cudaStream_t)stream));
+    // NETCUDA_ATTENTION_VARIANT=1 selects the mma.sync kernel for any sequence length (cross-check / profiling)
+    const char *env = getenv("NETCUDA_ATTENTION_VARIANT");
+    CK(launch_attention(d_qkv, d_out, batch, tokens, heads, (cudaStream_t)stream, nullptr, 0, env ? atoi(env) : 0));
     return NETCUDA_OK;
 }
 
