@@ -157,6 +157,11 @@ def test_gemm_tensor_core_matches_cuda_core_variant_at_full_size(netcuda, torch_
     torch.cuda.synchronize()
     err = ((o0 - o1).abs().max() / o1.abs().max()).item()
     assert err <= 1e-4, err
+    # CTA-pair kernel (default for M > 128) vs one CTA per tile: same K order, same epilogue -> identical bits
+    o2 = torch.empty_like(o0)
+    netcuda.op_gemm(a, w, b, o2, netcuda.PREC_BF16, netcuda.OUT_F32, variant=2)
+    torch.cuda.synchronize()
+    assert torch.equal(o0, o2)
 
 
 @pytest.mark.parametrize("rows,dim", [(1, 192), (197, 192), (1000, 768), (333, 1024), (64, 4096)])

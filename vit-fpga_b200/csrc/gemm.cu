@@ -38,15 +38,16 @@ cudaError_t encode_tma_2d(void *map_out, int dtype_bytes, const void *ptr, long 
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <int KIND, int BN, int OUT, int STAGES>
+template <int KIND, int BN, int OUT, int STAGES, int CG>
 static cudaError_t opt_in_smem()
 {
-    return cudaFuncSetAttribute(gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                GemmSmem<BN, STAGES>::TOTAL);
+    return cudaFuncSetAttribute(gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmSmem<BN, STAGES, CG>::TOTAL);
 }
 
-constexpr int STAGES_256 = 4;
-constexpr int STAGES_128 = 6;
+constexpr int STAGES_256 = 4;      // 1 CTA per tile, BN = 256: 48 KB per stage
+constexpr int STAGES_128 = 6;      // 1 CTA per tile, BN = 128: 32 KB per stage
+constexpr int STAGES_256_PAIR = 6; // CTA pair, BN = 256: 16 KB of A + 16 KB of W per CTA and stage
 
 // cudaFuncSetAttribute is per device, so the opt-in runs once for every device that is used.
 cudaError_t gemm_global_init()
@@ -67,9 +68,10 @@ cudaError_t gemm_global_init()
         g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
     }
     if (dev < 64 && done[dev]) return cudaSuccess;
-#define NC_OPT(K, O)                                                        \
-    if ((e = opt_in_smem<K, 256, O, STAGES_256>()) != cudaSuccess) return e; \
-    if ((e = opt_in_smem<K, 128, O, STAGES_128>()) != cudaSuccess) return e;
+#define NC_OPT(K, O)                                                                 \
+    if ((e = opt_in_smem<K, 256, O, STAGES_256_PAIR, 2>()) != cudaSuccess) return e; \
+    if ((e = opt_in_smem<K, 256, O, STAGES_256, 1>()) != cudaSuccess) return e;      \
+    if ((e = opt_in_smem<K, 128, O, STAGES_128, 1>()) != cudaSuccess) return e;
     NC_OPT(KIND_BF16, OUT_BF16)
     NC_OPT(KIND_BF16, OUT_F32)
     NC_OPT(KIND_TF32, OUT_F32)
@@ -124,13 +126,13 @@ static cudaError_t make_out_map(CUtensorMap *map, void *ptr, long long n, long l
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <int KIND, int BN, int OUT, int STAGES>
+template <int KIND, int BN, int OUT, int STAGES, int CG>
 static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
 {
     CUtensorMap map_a, map_w, map_out;
     cudaError_t e = make_operand_map(&map_a, c.kind, c.a, c.k, c.a_rows > c.m ? c.a_rows : c.m, c.lda * elem_size(c.kind), GEMM_BM);
     if (e != cudaSuccess) return e;
-    e = make_operand_map(&map_w, c.kind, c.w, c.k, c.n, c.ldw * elem_size(c.kind), BN);
+    e = make_operand_map(&map_w, c.kind, c.w, c.k, c.n, c.ldw * elem_size(c.kind), BN / CG);
     if (e != cudaSuccess) return e;
     GemmParams p;
     p.M = c.m, p.N = c.n, p.K = c.k;
@@ -151,18 +153,28 @@ static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
     }
     else
         map_out = map_a; // never dereferenced
-    const int tiles = ((c.m + GEMM_BM - 1) / GEMM_BM) * ((c.n + BN - 1) / BN);
+    const int tiles = ((c.m + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * ((c.n + BN - 1) / BN);
     const int sms = c.num_sms > 0 ? c.num_sms : 148;
-    const int grid = tiles < sms ? tiles : sms;
-    gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES><<<grid, GEMM_THREADS, GemmSmem<BN, STAGES>::TOTAL, stream>>>(map_a, map_w, map_out, p);
-    return cudaGetLastError();
+    const int slots = sms / CG; // tiles in flight: one per CTA, or one per CTA pair
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(CG * (tiles < slots ? tiles : slots)));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GemmSmem<BN, STAGES, CG>::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES, CG>, map_a, map_w, map_out, p);
 }
 
 template <int KIND, int OUT>
 static cudaError_t launch_tc_bn(const GemmCall &c, cudaStream_t stream)
 {
-    if (c.n <= 128) return launch_tc<KIND, 128, OUT, STAGES_128>(c, stream);
-    return launch_tc<KIND, 256, OUT, STAGES_256>(c, stream);
+    if (c.n <= 128) return launch_tc<KIND, 128, OUT, STAGES_128, 1>(c, stream);
+    // more than one 128-row block: pair the SMs (256-row tiles, half the W traffic per SM); variant 2 forces single CTAs
+    if (c.m > GEMM_BM && c.variant != 2) return launch_tc<KIND, 256, OUT, STAGES_256_PAIR, 2>(c, stream);
+    return launch_tc<KIND, 256, OUT, STAGES_256, 1>(c, stream);
 }
 
 // ---- CUDA-core reference with identical operand types / epilogues ----------------------------------

@@ -6,6 +6,12 @@
 // K-major, exactly the reference's row-major W[out][in] and sample-major activations, so no
 // transposes are needed anywhere.
 //
+// CG = 2 (the large-problem configuration): two CTAs on neighbouring SMs form a cluster and share one
+// 256 x BN accumulator tile (tcgen05 cta_group::2).  Each CTA loads its own 128 rows of A and HALF of the
+// W tile, so per SM a k-block costs 32 KB of L2->smem traffic instead of 48 KB and the ring holds 6 stages;
+// the leader CTA's thread issues the 256-row UMMAs for the pair, both CTAs run their own epilogue.
+// CG = 1: one CTA per tile (small M).
+//
 // Structure (one persistent CTA per SM, 384 threads, warp-specialised):
 //   warp 0     TMA producer: 128B-swizzled [128 x 128B] A tile + [BN x 128B] W tile per stage
 //   warp 1     MMA issuer:   one thread issues tcgen05.mma (UMMA 128 x BN x 32B) into TMEM
@@ -97,11 +103,11 @@ __host__ __device__ constexpr int slab_cols()
     return (128 / OutTraits<OUT>::ELEM) < (BN / 2) ? (128 / OutTraits<OUT>::ELEM) : (BN / 2);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG = 1>
 struct GemmSmem
 {
     static constexpr int A_BYTES = GEMM_BM * GEMM_STAGE_ROW_BYTES;
-    static constexpr int B_BYTES = BN * GEMM_STAGE_ROW_BYTES;
+    static constexpr int B_BYTES = (BN / CG) * GEMM_STAGE_ROW_BYTES; // a CTA of a pair stages half of the W tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OFF_SLABS = STAGES * STAGE_BYTES; // 1024-byte aligned (stage sizes are multiples of 1024)
     static constexpr int OFF_BIAS = OFF_SLABS + GEMM_EPI_WARPS * GEMM_SLAB_BYTES;
@@ -118,19 +124,19 @@ template <>
 struct KindTraits<KIND_BF16>
 {
     static constexpr int ELEM = 2;
-    __host__ __device__ static constexpr uint32_t idesc(int bn) { return umma_idesc(1, 1, GEMM_BM, bn); }
+    __host__ __device__ static constexpr uint32_t idesc(int m, int bn) { return umma_idesc(1, 1, m, bn); }
 };
 template <>
 struct KindTraits<KIND_TF32>
 {
     static constexpr int ELEM = 4;
-    __host__ __device__ static constexpr uint32_t idesc(int bn) { return umma_idesc(1, 2, GEMM_BM, bn); }
+    __host__ __device__ static constexpr uint32_t idesc(int m, int bn) { return umma_idesc(1, 2, m, bn); }
 };
 template <>
 struct KindTraits<KIND_I8>
 {
     static constexpr int ELEM = 1;
-    __host__ __device__ static constexpr uint32_t idesc(int bn) { return umma_idesc(2, 1, GEMM_BM, bn); }
+    __host__ __device__ static constexpr uint32_t idesc(int m, int bn) { return umma_idesc(2, 1, m, bn); }
 };
 
 // ---- epilogue helpers --------------------------------------------------------------------------
@@ -211,16 +217,18 @@ __device__ __forceinline__ void epi_convert32(const uint32_t *v, const uint32_t 
     }
 }
 
-template <int KIND, int BN, int OUT, int STAGES>
+template <int KIND, int BN, int OUT, int STAGES, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                        const __grid_constant__ CUtensorMap tma_out, const GemmParams p)
 {
-    using L = GemmSmem<BN, STAGES>;
+    using L = GemmSmem<BN, STAGES, CG>;
     constexpr int ELEM = KindTraits<KIND>::ELEM;
     constexpr int BK = GEMM_STAGE_ROW_BYTES / ELEM; // elements of K per stage
     constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (power of two >= 32)
-    constexpr uint32_t IDESC = KindTraits<KIND>::idesc(BN);
+    constexpr uint32_t IDESC = KindTraits<KIND>::idesc(GEMM_BM * CG, BN);
+    constexpr int TILE_M = GEMM_BM * CG;            // rows of one accumulator tile (per CTA pair when CG = 2)
+    static_assert(CG == 1 || CG == 2, "a tile belongs to one CTA or to a CTA pair");
     constexpr int OELEM = OutTraits<OUT>::ELEM;
     constexpr int WARP_COLS = BN / 2;               // columns per epilogue warp
     constexpr int SLAB_COLS = slab_cols<BN, OUT>(); // columns per TMA-store slab
@@ -248,10 +256,12 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+    const int tiles_m = (p.M + TILE_M - 1) / TILE_M;
     const int tiles_n = (p.N + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (p.K + BK - 1) / BK;
+    const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0; // 0 = leader of the pair
+    const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG; // both CTAs of a pair walk the same tiles
 
     if (warp == 0 && lane == 0)
     {
@@ -269,17 +279,28 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         for (int a = 0; a < 2; a++)
         {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), GEMM_EPI_WARPS); // one arrive per epilogue warp
+            mbar_init(tempty_bar(a), GEMM_EPI_WARPS * CG); // one arrive per epilogue warp (of both CTAs of a pair)
         }
         fence_barrier_init();
     }
     if (warp == 2)
     {
-        tmem_alloc(base + L::OFF_TMEM_PTR, TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (CG == 2)
+        {
+            tmem_alloc_pair(base + L::OFF_TMEM_PTR, TMEM_COLS);
+            tmem_relinquish_pair();
+        }
+        else
+        {
+            tmem_alloc(base + L::OFF_TMEM_PTR, TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2)
+        cluster_sync_all(); // the peer's barriers must be initialised before anything signals them
+    else
+        __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -289,17 +310,27 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         if (lane == 0)
         {
             uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+            for (int tile = tile0; tile < num_tiles; tile += tile_step)
             {
                 // n-fastest tile order: the CTAs of one wave share a few A row-blocks and all of W in L2
                 const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
                 for (int kb = 0; kb < num_kb; kb++)
                 {
                     mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag, KERR_PRODUCER_EMPTY);
-                    mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
                     const uint32_t a_dst = base + stage * L::STAGE_BYTES;
-                    tma_load_2d(a_dst, &tma_a, full_bar(stage), kb * BK, m_blk * GEMM_BM);
-                    tma_load_2d(a_dst + L::A_BYTES, &tma_w, full_bar(stage), kb * BK, n_blk * BN);
+                    if constexpr (CG == 2)
+                    {
+                        // the leader's barrier collects the bytes of both CTAs' loads of this stage
+                        if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
+                        tma_load_2d_pair(a_dst, &tma_a, full_bar(stage), kb * BK, m_blk * TILE_M + cta_rank * GEMM_BM);
+                        tma_load_2d_pair(a_dst + L::A_BYTES, &tma_w, full_bar(stage), kb * BK, n_blk * BN + cta_rank * (BN / 2));
+                    }
+                    else
+                    {
+                        mbar_arrive_expect_tx(full_bar(stage), L::STAGE_BYTES);
+                        tma_load_2d(a_dst, &tma_a, full_bar(stage), kb * BK, m_blk * GEMM_BM);
+                        tma_load_2d(a_dst + L::A_BYTES, &tma_w, full_bar(stage), kb * BK, n_blk * BN);
+                    }
                     if (++stage == STAGES)
                     {
                         stage = 0;
@@ -312,10 +343,10 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     else if (warp == 1)
     {
         // ===================== MMA issuer =====================
-        if (lane == 0)
+        if (lane == 0 && cta_rank == 0)
         {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+            for (int tile = tile0; tile < num_tiles; tile += tile_step)
             {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.error_flag, KERR_MMA_TMEM_EMPTY);
                 tcgen05_fence_after();
@@ -329,15 +360,28 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                     const uint64_t b_desc = umma_smem_desc_sw128(a_addr + L::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < 4; k++) // 4 x 32 bytes of K per stage; +2 = 32 B >> 4
-                        umma_ss<KIND>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, IDESC, (kb | k) != 0 ? 1u : 0u);
-                    tcgen05_commit(empty_bar(stage)); // frees the smem slot once these MMAs retire
+                    {
+                        if constexpr (CG == 2)
+                            umma_ss_pair<KIND>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        else
+                            umma_ss<KIND>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+                    if constexpr (CG == 2)
+                        tcgen05_commit_pair(empty_bar(stage));
+                    else
+                        tcgen05_commit(empty_bar(stage));
                     if (++stage == STAGES)
                     {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                tcgen05_commit(tfull_bar(acc)); // accumulator complete -> epilogue
+                // accumulator complete -> epilogue warps (of both CTAs of a pair)
+                if constexpr (CG == 2)
+                    tcgen05_commit_pair(tfull_bar(acc));
+                else
+                    tcgen05_commit(tfull_bar(acc));
                 if (++acc == 2)
                 {
                     acc = 0;
@@ -357,11 +401,11 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         uint8_t *slab = smem + L::OFF_SLABS + ew * GEMM_SLAB_BYTES;
         const uint32_t slab_addr = base + L::OFF_SLABS + ew * GEMM_SLAB_BYTES;
         uint32_t acc = 0, acc_phase = 0, parity = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, parity ^= 1u)
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, parity ^= 1u)
         {
             const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
             const int col0 = n_blk * BN;
-            const int row0 = m_blk * GEMM_BM + q * 32;
+            const int row0 = m_blk * TILE_M + cta_rank * GEMM_BM + q * 32;
 
             // this tile's bias slice (bit pattern: float or int32), shared by the 8 epilogue warps
             uint32_t *bias_s = bias_all + parity * BN;
@@ -507,7 +551,13 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             // all of this warp's TMEM reads of the tile are complete -> hand the accumulator back
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0)
+            {
+                if constexpr (CG == 2)
+                    mbar_arrive_leader(tempty_bar(acc)); // the MMA issuer lives in the leader CTA
+                else
+                    mbar_arrive(tempty_bar(acc));
+            }
             if (++acc == 2)
             {
                 acc = 0;
@@ -519,11 +569,17 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2)
+        cluster_sync_all(); // neither CTA may exit (or free TMEM) while the other can still touch its smem / barriers
+    else
+        __syncthreads();
     if (warp == 2)
     {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if constexpr (CG == 2)
+            tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else
+            tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 

@@ -172,6 +172,54 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t *r)
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pairs (cta_group::2): two SMs of one cluster share a 256-row UMMA ---------------------------
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// A shared::cta address is also the shared::cluster address of the same location in the executing CTA; clearing
+// bit 24 turns it into the address of that location in the even (leader) CTA of the pair.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+
+// TMA load issued by either CTA of a pair; the bytes are accounted on the LEADER CTA's mbarrier.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst_smem), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// Arrive on the leader CTA's copy of a barrier from either CTA of the pair.
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair()
+{
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// Arrive (once the pair's MMAs issued so far have completed) on the barrier at this smem offset in BOTH CTAs.
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+
 // ---- tcgen05: descriptors and MMA ------------------------------------------------------------
 
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are 128 bytes and which
@@ -226,6 +274,28 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
     else
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+}
+
+// CTA-pair form: issued by one thread of the leader CTA; M = 256 rows (128 per CTA), each CTA's smem holds
+// its 128 rows of A and its half of the N rows of B at the same offsets.
+template <int KIND>
+__device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    if constexpr (KIND == KIND_BF16)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    else if constexpr (KIND == KIND_TF32)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
                      : "memory");
 }

@@ -901,7 +901,7 @@ extern "C" int netcuda_profile_read(netcuda_net *h, netcuda_kernel_stat *stats, 
 extern "C" int netcuda_set_gemm_variant(netcuda_net *h, int variant)
 {
     if (int rc = check_handle(h)) return rc;
-    if (variant != 0 && variant != 1) return fail(NETCUDA_ERR_INVALID, "variant must be 0 or 1");
+    if (variant < 0 || variant > 2) return fail(NETCUDA_ERR_INVALID, "variant must be 0, 1 or 2");
     h->gemm_variant = variant;
     return NETCUDA_OK;
 }
