@@ -253,11 +253,12 @@ def test_vit_real_shapes_vs_oracle(netcuda, oracle, torch_cuda, name, batch, dep
     got = net.forward(x)
     assert rel_err(got, want) <= 1e-2
     np.testing.assert_array_equal(got.argmax(1), want.argmax(1))
-    # tensor-core path == CUDA-core path with the same operand rounding (tight: accumulation order only + bf16 re-rounding)
+    # tcgen05 kernels == CUDA-core GEMM + mma.sync attention with the same operand types (differences: accumulation
+    # order, and the flash kernel rounds P relative to a running max) -- both inside the bf16 budget
     net.set_gemm_variant(1)
     got_ref = net.forward(x)
     net.close()
-    assert rel_err(got, got_ref) <= 5e-3
+    assert rel_err(got, got_ref) <= 1e-2
 
 
 def test_vit_large_sequence_577(netcuda, oracle, torch_cuda):

@@ -26,6 +26,8 @@
 #include "kernels.h"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace nc
 {
 
@@ -266,6 +268,7 @@ struct AttnTcParams
     int n_pad;    // keys padded to a multiple of 16 (UMMA N of the S tile, UMMA K extent of P.V)
     int n_mtiles; // 1 or 2 query tiles of 128 rows
     int *error_flag;
+    long long *debug; // optional [32 items][12 warps][8] clock64 stamps of CTA 0 (profiling aid; null in production)
 };
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
@@ -331,6 +334,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                 const int buf = it & 1;
                 const int b = item / p.heads, h = item - b * p.heads;
                 mbar_wait(empty_bar(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u, p.error_flag, KERR_ATT_PRODUCER);
+                if (p.debug && blockIdx.x == 0 && it < 32) p.debug[(it * 12 + 0) * 8] = clock64();
                 mbar_arrive_expect_tx(full_bar(buf), tx);
                 const uint32_t dst = base + buf * ATC_BUF_BYTES;
                 const int row = b * p.tokens;
@@ -343,43 +347,74 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     else if (warp == 1)
     {
         // ===================== MMA issuer =====================
+        // One thread serves both query tiles.  The two softmax warpgroups run independently of each other, so the
+        // issuer does not follow a fixed order: it polls, per tile, "S of the next item may start" (K/Q landed,
+        // previous O of this tile drained) and "P of the current item is ready" and issues whichever is.
         if (lane == 0)
         {
             const uint32_t idesc_s = umma_idesc(1, 1, 128, (uint32_t)p.n_pad);
             const uint32_t idesc_o = umma_idesc(1, 1, 128, ATT_HD) | UMMA_IDESC_B_MN_MAJOR;
             const int ksteps = p.n_pad / 16;
-            int it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, it++)
+            const int n_it = blockIdx.x < items ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            int it_s[2] = {0, 0}, it_pv[2] = {0, 0};
+            if (p.n_mtiles == 1) it_s[1] = it_pv[1] = n_it;
+            long long t0 = clock64();
+            while (it_pv[0] < n_it || it_pv[1] < n_it)
             {
-                const int buf = it & 1;
-                const uint32_t ph = (uint32_t)it & 1u;
-                const uint32_t sm = base + buf * ATC_BUF_BYTES;
-                mbar_wait(full_bar(buf), (uint32_t)(it >> 1) & 1u, p.error_flag, KERR_ATT_MMA_FULL);
-                tcgen05_fence_after();
-                const uint64_t k_desc = umma_smem_desc_sw128(sm + 2 * ATC_Q_BYTES);
-                for (int t = 0; t < p.n_mtiles; t++)
-                {
-                    // S_t = Q_t . K^T: region t must have been drained by the previous item's epilogue
-                    mbar_wait(sfree_bar(t), ph ^ 1u, p.error_flag, KERR_ATT_MMA_SFREE);
-                    tcgen05_fence_after();
-                    const uint64_t q_desc = umma_smem_desc_sw128(sm + t * ATC_Q_BYTES);
+                bool progress = false;
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        umma_ss<KIND_BF16>(tmem_base + t * ATC_REGION_COLS, q_desc + 2u * k, k_desc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-                    tcgen05_commit(sfull_bar(t));
-                }
-                // V tile [key][64] read MN-major: one UMMA K step = 16 keys = 2048 bytes of the tile
-                const uint64_t v_desc = umma_smem_desc_sw128(sm + 2 * ATC_Q_BYTES + ATC_KV_BYTES);
-                for (int t = 0; t < p.n_mtiles; t++)
+                for (int t = 0; t < 2; t++)
                 {
-                    mbar_wait(pfull_bar(t), ph, p.error_flag, KERR_ATT_MMA_PFULL);
-                    tcgen05_fence_after();
-                    const uint32_t region = tmem_base + t * ATC_REGION_COLS;
-                    for (int k = 0; k < ksteps; k++)
-                        umma_ts_bf16(region + ATC_O_COL, region + 8u * k, v_desc + (uint64_t)(128u * k), idesc_o, k != 0 ? 1u : 0u);
-                    tcgen05_commit(ofull_bar(t));
+                    // S_t = Q_t . K^T of item it_s[t]: the P of the previous item (same columns) must have been consumed.
+                    // The very first S_1 is held back until tile 0 has finished its first softmax: the two warpgroups then
+                    // stay half a period apart, so that one is in its exp2 (MUFU-bound) pass while the other one waits for
+                    // its MMAs, reduces the row max or stores O, instead of both fighting for the MUFU at the same time.
+                    if (it_s[t] < n_it && it_pv[t] == it_s[t] && !(t == 1 && it_s[1] == 0 && it_pv[0] == 0))
+                    {
+                        const int i = it_s[t], buf = i & 1;
+                        if (mbar_test_wait(full_bar(buf), (uint32_t)(i >> 1) & 1u) && mbar_test_wait(sfree_bar(t), ((uint32_t)i & 1u) ^ 1u))
+                        {
+                            tcgen05_fence_after();
+                            const uint32_t sm = base + buf * ATC_BUF_BYTES;
+                            const uint64_t q_desc = umma_smem_desc_sw128(sm + t * ATC_Q_BYTES);
+                            const uint64_t k_desc = umma_smem_desc_sw128(sm + 2 * ATC_Q_BYTES);
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                umma_ss<KIND_BF16>(tmem_base + t * ATC_REGION_COLS, q_desc + 2u * k, k_desc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+                            tcgen05_commit(sfull_bar(t));
+                            if (p.debug && blockIdx.x == 0 && i < 32) p.debug[(i * 12 + 1) * 8 + t] = clock64();
+                            it_s[t]++;
+                            progress = true;
+                        }
+                    }
+                    // O_t = P_t . V of item it_pv[t].  V tile [key][64] read MN-major: one UMMA K step = 16 keys = 2048 bytes
+                    if (it_pv[t] < it_s[t])
+                    {
+                        const int i = it_pv[t], buf = i & 1;
+                        if (mbar_test_wait(pfull_bar(t), (uint32_t)i & 1u))
+                        {
+                            tcgen05_fence_after();
+                            const uint64_t v_desc = umma_smem_desc_sw128(base + buf * ATC_BUF_BYTES + 2 * ATC_Q_BYTES + ATC_KV_BYTES);
+                            const uint32_t region = tmem_base + t * ATC_REGION_COLS;
+                            for (int k = 0; k < ksteps; k++)
+                                umma_ts_bf16(region + ATC_O_COL, region + 8u * k, v_desc + (uint64_t)(128u * k), idesc_o, k != 0 ? 1u : 0u);
+                            tcgen05_commit(ofull_bar(t));
+                            if (p.debug && blockIdx.x == 0 && i < 32) p.debug[(i * 12 + 1) * 8 + 2 + t] = clock64();
+                            it_pv[t]++;
+                            // both tiles are past item i: every MMA that reads its smem buffer has been issued
+                            if (it_pv[t ^ 1] > i) tcgen05_commit(empty_bar(buf));
+                            progress = true;
+                        }
+                    }
                 }
-                tcgen05_commit(empty_bar(buf)); // every MMA that reads this smem buffer has been issued
+                if (progress)
+                    t0 = clock64();
+                else if (clock64() - t0 > 8000000000LL)
+                {
+                    if (p.error_flag) atomicExch(p.error_flag, KERR_ATT_MMA_FULL);
+                    __threadfence_system();
+                    __trap();
+                }
             }
         }
     }
@@ -391,53 +426,116 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         const int qrow = t * 128 + q * 32 + lane; // query row within the image
         const uint32_t region = tmem_base + ((uint32_t)(q * 32) << 16) + t * ATC_REGION_COLS;
         const float sl = 0.125f * 1.4426950408889634f; // 1/sqrt(64) * log2(e)
-        const int nchunks = (p.tokens + 31) >> 5;
+        const int nfull = p.tokens >> 5, tail = p.tokens & 31; // full 32-key chunks, keys in the ragged last chunk
+        const int nchunks = nfull + (tail ? 1 : 0);
         int it = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, it++)
         {
             const uint32_t ph = (uint32_t)it & 1u;
             const int b = item / p.heads, h = item - b * p.heads;
+            auto stamp = [&](int slot) {
+                if (p.debug && blockIdx.x == 0 && lane == 0 && it < 32) p.debug[(it * 12 + warp) * 8 + slot] = clock64();
+            };
+            stamp(0);
             mbar_wait(sfull_bar(t), ph, p.error_flag, KERR_ATT_WG_SFULL);
             tcgen05_fence_after();
-            // pass 1: exact row maximum over the valid keys
+            stamp(1);
+
+            // ---- pass 1: exact row maximum over the valid keys (chunk c + 1 is in flight while c is reduced) ----
             float mx = -INFINITY;
-            for (int c = 0; c < nchunks; c++)
             {
-                uint32_t v[32];
-                tmem_ld_32x32(region + c * 32, v);
-                tmem_ld_wait();
-                const int valid = p.tokens - c * 32;
+                uint32_t va[32], vb[32];
+                auto reduce = [&](const uint32_t *v, int c) {
+                    if (c < nfull)
+                    {
+                        float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
 #pragma unroll
-                for (int j = 0; j < 32; j++)
-                    if (j < valid) mx = fmaxf(mx, __uint_as_float(v[j]));
-            }
-            // pass 2: p = 2^((s - max) * scale); P (bf16) overwrites the first half of the S columns it came from
-            const float msc = mx * sl;
-            float sum = 0.0f;
-            for (int c = 0; c < nchunks; c++)
-            {
-                uint32_t v[32], w[16];
-                tmem_ld_32x32(region + c * 32, v);
-                tmem_ld_wait();
-                const int valid = p.tokens - c * 32;
+                        for (int j = 4; j < 32; j += 4)
+                        {
+                            m0 = fmaxf(m0, __uint_as_float(v[j])), m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+                            m2 = fmaxf(m2, __uint_as_float(v[j + 2])), m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+                        }
+                        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+                    }
+                    else
+                    {
 #pragma unroll
-                for (int j = 0; j < 16; j++)
+                        for (int j = 0; j < 32; j++)
+                            if (j < tail) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    }
+                };
+                tmem_ld_32x32(region, va);
+                for (int c = 0; c < nchunks; c += 2)
                 {
-                    const float p0 = (2 * j < valid) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl, -msc)) : 0.0f;
-                    const float p1 = (2 * j + 1 < valid) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl, -msc)) : 0.0f;
-                    sum += p0 + p1;
-                    w[j] = pack_bf16x2(p0, p1);
+                    tmem_ld_wait();
+                    if (c + 1 < nchunks) tmem_ld_32x32(region + (c + 1) * 32, vb);
+                    reduce(va, c);
+                    if (c + 1 < nchunks)
+                    {
+                        tmem_ld_wait();
+                        if (c + 2 < nchunks) tmem_ld_32x32(region + (c + 2) * 32, va);
+                        reduce(vb, c + 1);
+                    }
                 }
-                tmem_st_32x16(region + c * 16, w);
             }
+
+            stamp(2);
+            // ---- pass 2: p = 2^((s - max) * scale); P (bf16) overwrites the first half of the S columns it came from ----
+            const float msc = mx * sl;
+            float sum0 = 0.0f, sum1 = 0.0f;
+            {
+                uint32_t va[32], vb[32];
+                auto expo = [&](const uint32_t *v, int c) {
+                    uint32_t w[16];
+                    if (c < nfull)
+                    {
+#pragma unroll
+                        for (int j = 0; j < 16; j++)
+                        {
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl, -msc));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl, -msc));
+                            sum0 += p0, sum1 += p1;
+                            w[j] = pack_bf16x2(p0, p1);
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j = 0; j < 16; j++)
+                        {
+                            const float p0 = (2 * j < tail) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl, -msc)) : 0.0f;
+                            const float p1 = (2 * j + 1 < tail) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl, -msc)) : 0.0f;
+                            sum0 += p0, sum1 += p1;
+                            w[j] = pack_bf16x2(p0, p1);
+                        }
+                    }
+                    tmem_st_32x16(region + c * 16, w);
+                };
+                tmem_ld_32x32(region, va);
+                for (int c = 0; c < nchunks; c += 2)
+                {
+                    tmem_ld_wait();
+                    if (c + 1 < nchunks) tmem_ld_32x32(region + (c + 1) * 32, vb);
+                    expo(va, c);
+                    if (c + 1 < nchunks)
+                    {
+                        tmem_ld_wait();
+                        if (c + 2 < nchunks) tmem_ld_32x32(region + (c + 2) * 32, va);
+                        expo(vb, c + 1);
+                    }
+                }
+            }
+            const float sum = sum0 + sum1;
             tmem_st_wait();
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(pfull_bar(t));
+            stamp(3);
 
-            // O = P.V / rowsum
+            // ---- O = P.V / rowsum ----
             mbar_wait(ofull_bar(t), ph, p.error_flag, KERR_ATT_WG_OFULL);
             tcgen05_fence_after();
+            stamp(4);
             uint32_t o[64];
             tmem_ld_32x32(region + ATC_O_COL, o);
             tmem_ld_32x32(region + ATC_O_COL + 32, o + 32);
@@ -460,6 +558,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                     dst[j] = pk;
                 }
             }
+            stamp(5);
         }
     }
 
@@ -483,6 +582,8 @@ static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, in
     p.n_pad = (tokens + 15) & ~15;
     p.n_mtiles = tokens > 128 ? 2 : 1;
     p.error_flag = error_flag;
+    p.debug = nullptr;
+    if (const char *dbg = getenv("NETCUDA_ATTENTION_DEBUG_PTR")) p.debug = reinterpret_cast<long long *>(strtoull(dbg, nullptr, 0));
     const long long D = (long long)heads * ATT_HD, rows = (long long)batch * tokens;
     // rows past the last token of the last image are zero-filled by TMA; a tile that runs into the next image reads
     // that image's (finite) rows: extra keys are masked in the softmax, extra query rows are never stored
