@@ -56,6 +56,22 @@ def load_peaks():
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic_per_launch(prof, prof_steps):
+    """dram__bytes_read + dram__bytes_write per GEMM launch from the committed ncu --set full capture (profiles/ncu_traffic.json),
+    averaged over the GEMM launches of a step with the same weighting as roofline.achieved; None when no capture is committed or the
+    capture was taken at another pass size."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    per = json.load(open(path)).get("per_launch_bytes", {})
+    num = den = 0.0
+    for k in ("qkv", "proj", "fc1", "fc2"):
+        if k in per and k in prof:
+            num += per[k] * prof[k]["launches"]
+            den += prof[k]["launches"]
+    return num / den if den else None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -207,13 +223,16 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.rand((per_gpu, n_in), generator=gen, device=dev) * 2 - 1  # uniform [-1, 1): MIN/MAX_RANGE of def/defines.h:11-12
     y = torch.empty((per_gpu, n_out), device=dev)
-    gathered = torch.empty((world * per_gpu, n_out), device=dev) if world > 1 else None
+    from netcuda.sharding import gather_outputs, shard_bounds
+
+    lo, hi = shard_bounds(world * per_gpu, world, rank)  # this rank's slice of the global batch
+    assert hi - lo == per_gpu
     stream = torch.cuda.current_stream()
+    gathered = [None]
 
     def step():
         net.forward_device(x, y, per_gpu, stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, y)
+        gathered[0] = gather_outputs(y, world * per_gpu, world)  # NCCL all-gather of the logits (no-op on one GPU)
 
     def fence():
         if world > 1:
@@ -301,8 +320,9 @@ def main():
         "peak_source": peaks["source"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
         "frac_of_burst_peak": round(achieved / peaks["burst"], 4),
         "flops_per_launch": gemm_flops / max(gemm_launches, 1), "ms_per_launch": gemm_ms / max(gemm_launches, 1),
+        "algorithmic_bytes_per_launch": sum(v["bytes"] for k, v in prof.items() if k in GEMM_LABELS) / max(gemm_launches, 1),
         "share_of_step": round(gemm_ms / all_ms, 4) if all_ms > 0 else None,
-        "traffic": None,  # filled from the ncu --set full capture under profiles/ 
+        "traffic": ncu_traffic_per_launch(prof, prof_steps),
         "whole_step_tflops": round(value / world * flops_per_image / 1e12, 2),
         "whole_step_frac_of_burst_peak": round(value / world * flops_per_image / 1e12 / peaks["burst"], 4),
         "per_kernel": per_kernel,
