@@ -227,7 +227,10 @@ def main():
 
     lo, hi = shard_bounds(world * per_gpu, world, rank)  # this rank's slice of the global batch
     assert hi - lo == per_gpu
-    stream = torch.cuda.current_stream()
+    # everything (kernels, the logits all-gather, the timing events) runs on one explicit side stream
+    torch.cuda.synchronize()  # inputs were generated on the default stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     gathered = [None]
 
     def step():
@@ -255,7 +258,11 @@ def main():
     fence()
     t_b = time.perf_counter()
     launches = net.launches - l0
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    wall_ms = (t_b - t_a) * 1e3
+    ev_ms = e0.elapsed_time(e1)
+    if abs(ev_ms - wall_ms) > 0.05 * wall_ms + 2.0:  # the host waits on the device here, so the two clocks must agree
+        raise SystemExit(f"timing inconsistency: CUDA events {ev_ms:.2f} ms vs host clock {wall_ms:.2f} ms around the same region")
+    ms = torch.tensor([ev_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())

@@ -89,10 +89,16 @@ def _ptr(t) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
+CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: names the default stream explicitly (a NULL stream argument means "the handle's own stream")
+
+
 def _stream(stream) -> C.c_void_p:
+    """None -> NULL (the handle's own stream); a torch stream / raw handle -> that stream.  torch's default stream has the raw
+    handle 0, which the C ABI would read as NULL, so it is passed as cudaStreamLegacy."""
     if stream is None:
         return C.c_void_p(0)
-    return C.c_void_p(int(getattr(stream, "cuda_stream", stream)))
+    raw = int(getattr(stream, "cuda_stream", stream))
+    return C.c_void_p(raw if raw != 0 else CUDA_STREAM_LEGACY)
 
 
 VIT_PRESETS = {
