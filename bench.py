@@ -38,7 +38,7 @@ sys.path.insert(0, os.path.join(ROOT, "vit-fpga_b200"))
 
 WORKLOADS = {
     # name: (preset, images per GPU per step, internal pass size)
-    "vit_base_16_224_b1024": ("vit_base_16_224", 1024, 256),
+    "vit_base_16_224_b1024": ("vit_base_16_224", 1024, 512),
     "vit_tiny_16_224_b256": ("vit_tiny_16_224", 256, 256),
     "vit_large_16_384_b64": ("vit_large_16_384", 64, 32),
 }

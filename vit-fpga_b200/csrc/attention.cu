@@ -325,6 +325,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    griddep_launch_dependents();
+    griddep_wait(); // the qkv matrix is the previous kernel's output
 
     // the producer / MMA / allocator warps need few registers; the softmax warps hold a score row each
     if (warp < 4)
@@ -589,7 +591,8 @@ static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, in
     case NCV:                                                                                                                  \
         e = cudaFuncSetAttribute(attention_tc_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);               \
         if (e != cudaSuccess) return e;                                                                                        \
-        attention_tc_kernel<NCV><<<grid, ATC_THREADS, ATC_SMEM, stream>>>(map_q, map_kv, p);                                     \
+        e = launch_pdl(attention_tc_kernel<NCV>, dim3(grid), dim3(ATC_THREADS), (size_t)ATC_SMEM, stream, 1, map_q, map_kv, p);   \
+        if (e != cudaSuccess) return e;                                                                                        \
         break;
     switch ((tokens + 31) / 32)
     {

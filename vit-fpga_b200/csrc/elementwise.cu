@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float *__restrict__ x, long long ldx, const float *__restrict__ gamma, const float *__restrict__ beta,
                  __nv_bfloat16 *__restrict__ y, long long ldy, int rows, int dim, float eps)
 {
+    griddep_launch_dependents();
+    griddep_wait(); // x is the previous kernel's output, y the previous-but-one's input
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -76,11 +78,11 @@ cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, 
     const int grid = (rows + rows_per_block - 1) / rows_per_block;
     __nv_bfloat16 *yb = reinterpret_cast<__nv_bfloat16 *>(y);
     if (dim <= 256)
-        layernorm_kernel<2><<<grid, threads, 0, stream>>>(x, ldx, gamma, beta, yb, ldy, rows, dim, eps);
+        return launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(threads), 0, stream, 1, x, ldx, gamma, beta, yb, ldy, rows, dim, eps);
     else if (dim <= 1024)
-        layernorm_kernel<8><<<grid, threads, 0, stream>>>(x, ldx, gamma, beta, yb, ldy, rows, dim, eps);
+        return launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(threads), 0, stream, 1, x, ldx, gamma, beta, yb, ldy, rows, dim, eps);
     else
-        layernorm_kernel<32><<<grid, threads, 0, stream>>>(x, ldx, gamma, beta, yb, ldy, rows, dim, eps);
+        return launch_pdl(layernorm_kernel<32>, dim3(grid), dim3(threads), 0, stream, 1, x, ldx, gamma, beta, yb, ldy, rows, dim, eps);
     return cudaGetLastError();
 }
 
@@ -92,6 +94,8 @@ cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, 
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float *__restrict__ img, __nv_bfloat16 *__restrict__ patches, long long total8, int S, int P, int g)
 {
+    griddep_launch_dependents();
+    griddep_wait();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total8) return;
     const int s8 = S >> 3;
@@ -122,9 +126,8 @@ cudaError_t launch_patchify(const float *img, void *patches, int batch, int imag
     const long long total8 = (long long)batch * 3 * image_size * (image_size >> 3);
     const int threads = 256;
     const long long grid = (total8 + threads - 1) / threads;
-    patchify_kernel<<<(unsigned)grid, threads, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16 *>(patches), total8, image_size,
-                                                          patch_size, image_size / patch_size);
-    return cudaGetLastError();
+    return launch_pdl(patchify_kernel, dim3((unsigned)grid), dim3(threads), 0, stream, 1, img, reinterpret_cast<__nv_bfloat16 *>(patches), total8,
+                      image_size, patch_size, image_size / patch_size);
 }
 
 // ---- class-token rows of the residual stream ---------------------------------------------------------
@@ -132,6 +135,8 @@ cudaError_t launch_patchify(const float *img, void *patches, int batch, int imag
 __global__ void cls_rows_kernel(float *__restrict__ x, const float *__restrict__ cls, const float *__restrict__ pos, int batch,
                                 int tokens, int dim)
 {
+    griddep_launch_dependents();
+    griddep_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)batch * dim) return;
     const int b = (int)(i / dim), c = (int)(i % dim);
@@ -142,8 +147,7 @@ cudaError_t launch_cls_rows(float *x, const float *cls, const float *pos, int ba
 {
     if (batch <= 0) return cudaSuccess;
     const long long n = (long long)batch * dim;
-    cls_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, cls, pos, batch, tokens, dim);
-    return cudaGetLastError();
+    return launch_pdl(cls_rows_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, 1, x, cls, pos, batch, tokens, dim);
 }
 
 // ---- API-boundary conversions -------------------------------------------------------------------------

@@ -156,16 +156,8 @@ static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
     const int tiles = ((c.m + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * ((c.n + BN - 1) / BN);
     const int sms = c.num_sms > 0 ? c.num_sms : 148;
     const int slots = sms / CG; // tiles in flight: one per CTA, or one per CTA pair
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(CG * (tiles < slots ? tiles : slots)));
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = GemmSmem<BN, STAGES, CG>::TOTAL;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES, CG>, map_a, map_w, map_out, p);
+    return launch_pdl(gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES, CG>, dim3((unsigned)(CG * (tiles < slots ? tiles : slots))),
+                      dim3(GEMM_THREADS), (size_t)GemmSmem<BN, STAGES, CG>::TOTAL, stream, CG, map_a, map_w, map_out, p);
 }
 
 template <int KIND, int OUT>

@@ -303,6 +303,9 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // everything above overlapped the previous kernel's tail; from here on its outputs are read (and its inputs overwritten)
+    griddep_launch_dependents();
+    griddep_wait();
 
     if (warp == 0)
     {
@@ -564,8 +567,9 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                 acc_phase ^= 1u;
             }
         }
-        // shared memory must stay valid until the last bulk store has read it
-        if (lane == 0) tma_store_wait_read();
+        // The bulk stores must have COMPLETED (not only read their smem source) before this CTA exits: a dependent kernel
+        // released by griddepcontrol.wait is only ordered after what the exited CTAs of this grid have made visible.
+        if (lane == 0) tma_store_wait_all();
     }
 
     tcgen05_fence_before();

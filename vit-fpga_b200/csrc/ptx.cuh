@@ -24,6 +24,13 @@ enum : int
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// Kernels of a forward pass are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel may start
+// (set up barriers, allocate TMEM, prefetch descriptors) while its predecessor in the stream drains; griddep_wait()
+// returns once the predecessor has completed and its writes are visible, and must precede every global access.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- mbarrier ------------------------------------------------------------------------------
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
