@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the workload's)")
     ap.add_argument("--max-batch", type=int, default=0, help="images per internal pass")
+    ap.add_argument("--gemm-variant", type=int, default=0, help="netcuda_set_gemm_variant (A/B measurements; 0 = product path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -219,6 +220,8 @@ def main():
 
     net = nc.Net.vit(cfg, device=local, max_batch=max_batch)
     net.upload_vit(nc.vit_random_params(cfg, seed=0))
+    if args.gemm_variant:
+        net.set_gemm_variant(args.gemm_variant)
     n_in, n_out = net.n_in, net.n_out
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.rand((per_gpu, n_in), generator=gen, device=dev) * 2 - 1  # uniform [-1, 1): MIN/MAX_RANGE of def/defines.h:11-12

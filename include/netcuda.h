@@ -160,7 +160,8 @@ int netcuda_profile_read(netcuda_t *h, netcuda_kernel_stat *stats, int cap, int 
 
 /* Select a debugging/measurement variant of the dense kernel for this handle:
  * 0 = default (tcgen05, CTA pairs on large problems), 1 = CUDA-core reference GEMM with the same operand
- * rounding (also selects the mma.sync attention kernel), 2 = tcgen05 with one CTA per tile everywhere. */
+ * rounding (also selects the mma.sync attention kernel), 2 = tcgen05 with one CTA per tile everywhere,
+ * 3 = default but with 16 instead of 8 epilogue warps in the GELU GEMM (A/B measurement). */
 int netcuda_set_gemm_variant(netcuda_t *h, int variant);
 
 const char *netcuda_last_error(void);

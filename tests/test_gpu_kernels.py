@@ -162,6 +162,16 @@ def test_gemm_tensor_core_matches_cuda_core_variant_at_full_size(netcuda, torch_
     netcuda.op_gemm(a, w, b, o2, netcuda.PREC_BF16, netcuda.OUT_F32, variant=2)
     torch.cuda.synchronize()
     assert torch.equal(o0, o2)
+    # GELU epilogue: 8 epilogue warps (default) vs 16 (variant 3) vs one CTA per tile (variant 2): identical bits
+    g16 = torch.empty((m, n), dtype=torch.bfloat16, device="cuda")
+    g8, g1 = torch.empty_like(g16), torch.empty_like(g16)
+    netcuda.op_gemm(a, w, b, g16, netcuda.PREC_BF16, netcuda.OUT_BF16, epilogue=netcuda.EPI_GELU, variant=0)
+    netcuda.op_gemm(a, w, b, g8, netcuda.PREC_BF16, netcuda.OUT_BF16, epilogue=netcuda.EPI_GELU, variant=3)
+    netcuda.op_gemm(a, w, b, g1, netcuda.PREC_BF16, netcuda.OUT_BF16, epilogue=netcuda.EPI_GELU, variant=2)
+    torch.cuda.synchronize()
+    assert torch.equal(g16, g8) and torch.equal(g16, g1)
+    want = torch.nn.functional.gelu(o1)  # exact-erf GELU of the CUDA-core result
+    assert ((g16.float() - want).abs().max() / want.abs().max()).item() <= 6e-3
 
 
 @pytest.mark.parametrize("rows,dim", [(1, 192), (197, 192), (1000, 768), (333, 1024), (64, 4096)])

@@ -38,16 +38,18 @@ cudaError_t encode_tma_2d(void *map_out, int dtype_bytes, const void *ptr, long 
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <int KIND, int BN, int OUT, int STAGES, int CG>
+template <int KIND, int BN, int OUT, int STAGES, int CG, int EW>
 static cudaError_t opt_in_smem()
 {
-    return cudaFuncSetAttribute(gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                GemmSmem<BN, STAGES, CG>::TOTAL);
+    return cudaFuncSetAttribute(gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES, CG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmSmem<BN, STAGES, CG, EW>::TOTAL);
 }
 
+// smem ring depth: what fits next to the epilogue slabs (EW x 4 KB) in 227 KB
 constexpr int STAGES_256 = 4;      // 1 CTA per tile, BN = 256: 48 KB per stage
 constexpr int STAGES_128 = 6;      // 1 CTA per tile, BN = 128: 32 KB per stage
 constexpr int STAGES_256_PAIR = 6; // CTA pair, BN = 256: 16 KB of A + 16 KB of W per CTA and stage
+constexpr int STAGES_256_PAIR_EW16 = 5; // the same with 16 epilogue warps (64 KB of slabs)
 
 // cudaFuncSetAttribute is per device, so the opt-in runs once for every device that is used.
 cudaError_t gemm_global_init()
@@ -68,16 +70,17 @@ cudaError_t gemm_global_init()
         g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
     }
     if (dev < 64 && done[dev]) return cudaSuccess;
-#define NC_OPT(K, O)                                                                 \
-    if ((e = opt_in_smem<K, 256, O, STAGES_256_PAIR, 2>()) != cudaSuccess) return e; \
-    if ((e = opt_in_smem<K, 256, O, STAGES_256, 1>()) != cudaSuccess) return e;      \
-    if ((e = opt_in_smem<K, 128, O, STAGES_128, 1>()) != cudaSuccess) return e;
+#define NC_OPT(K, O)                                                                    \
+    if ((e = opt_in_smem<K, 256, O, STAGES_256_PAIR, 2, 8>()) != cudaSuccess) return e; \
+    if ((e = opt_in_smem<K, 256, O, STAGES_256, 1, 8>()) != cudaSuccess) return e;      \
+    if ((e = opt_in_smem<K, 128, O, STAGES_128, 1, 8>()) != cudaSuccess) return e;
     NC_OPT(KIND_BF16, OUT_BF16)
     NC_OPT(KIND_BF16, OUT_F32)
     NC_OPT(KIND_TF32, OUT_F32)
     NC_OPT(KIND_I8, OUT_S8)
     NC_OPT(KIND_I8, OUT_S32)
 #undef NC_OPT
+    if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_EW16, 2, 16>()) != cudaSuccess) return e;
     if (dev < 64) done[dev] = true;
     return cudaSuccess;
 }
@@ -106,11 +109,11 @@ static cudaError_t make_operand_map(CUtensorMap *map, int kind, const void *ptr,
 
 // Output matrix as a 2-D tensor {N, M} for the epilogue's TMA stores: box = one epilogue slab
 // (slab_cols columns x 32 rows), 128B-swizzled when a slab row is 128 bytes.
-template <int BN, int OUT>
+template <int BN, int OUT, int EW>
 static cudaError_t make_out_map(CUtensorMap *map, void *ptr, long long n, long long m, long long pitch_bytes)
 {
     if (!g_encode_tiled) return cudaErrorNotReady;
-    constexpr int cols = slab_cols<BN, OUT>();
+    constexpr int cols = slab_cols<BN, OUT, EW>();
     constexpr int row_bytes = cols * OutTraits<OUT>::ELEM;
     const CUtensorMapDataType dt = OUT == OUT_BF16  ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                    : OUT == OUT_S8  ? CU_TENSOR_MAP_DATA_TYPE_UINT8
@@ -126,7 +129,7 @@ static cudaError_t make_out_map(CUtensorMap *map, void *ptr, long long n, long l
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <int KIND, int BN, int OUT, int STAGES, int CG>
+template <int KIND, int BN, int OUT, int STAGES, int CG, int EW = 8>
 static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
 {
     CUtensorMap map_a, map_w, map_out;
@@ -148,7 +151,7 @@ static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
                       : 0;
     if (p.tma_store)
     {
-        e = make_out_map<BN, OUT>(&map_out, c.out, c.n, c.m, pitch_bytes);
+        e = make_out_map<BN, OUT, EW>(&map_out, c.out, c.n, c.m, pitch_bytes);
         if (e != cudaSuccess) return e;
     }
     else
@@ -156,8 +159,8 @@ static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
     const int tiles = ((c.m + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * ((c.n + BN - 1) / BN);
     const int sms = c.num_sms > 0 ? c.num_sms : 148;
     const int slots = sms / CG; // tiles in flight: one per CTA, or one per CTA pair
-    return launch_pdl(gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES, CG>, dim3((unsigned)(CG * (tiles < slots ? tiles : slots))),
-                      dim3(GEMM_THREADS), (size_t)GemmSmem<BN, STAGES, CG>::TOTAL, stream, CG, map_a, map_w, map_out, p);
+    return launch_pdl(gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES, CG, EW>, dim3((unsigned)(CG * (tiles < slots ? tiles : slots))),
+                      dim3(gemm_threads(EW)), (size_t)GemmSmem<BN, STAGES, CG, EW>::TOTAL, stream, CG, map_a, map_w, map_out, p);
 }
 
 template <int KIND, int OUT>
@@ -165,7 +168,14 @@ static cudaError_t launch_tc_bn(const GemmCall &c, cudaStream_t stream)
 {
     if (c.n <= 128) return launch_tc<KIND, 128, OUT, STAGES_128, 1>(c, stream);
     // more than one 128-row block: pair the SMs (256-row tiles, half the W traffic per SM); variant 2 forces single CTAs
-    if (c.m > GEMM_BM && c.variant != 2) return launch_tc<KIND, 256, OUT, STAGES_256_PAIR, 2>(c, stream);
+    if (c.m > GEMM_BM && c.variant != 2)
+    {
+        // variant 3: 16 epilogue warps for the GELU epilogue.  Measured on ViT-B fc1 (ncu, round 1): 212.5 us vs 203.5 us with
+        // 8 warps -- the epilogue is bound by MUFU/FMA work per element, not by the number of warps -- so it is not the default.
+        if constexpr (KIND == KIND_BF16 && OUT == OUT_BF16)
+            if (c.epi == EPI_GELU && c.variant == 3) return launch_tc<KIND, 256, OUT, STAGES_256_PAIR_EW16, 2, 16>(c, stream);
+        return launch_tc<KIND, 256, OUT, STAGES_256_PAIR, 2>(c, stream);
+    }
     return launch_tc<KIND, 256, OUT, STAGES_256, 1>(c, stream);
 }
 

@@ -67,9 +67,11 @@ struct GemmParams
 };
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_EPI_WARPS = 8;
-constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_STAGE_ROW_BYTES = 128;
+// EW = number of epilogue warps (8 or 16): warp w serves TMEM lanes [32 (w % 4), +32) and columns
+// [(w - 4) / 4 * BN / (EW / 4), + BN / (EW / 4)).  16 warps (4 per scheduler) are for epilogues whose per-element work is
+// heavy (exact-erf GELU: 14 issue slots) so that the epilogue keeps pace with the MMAs; they cost 32 KB more smem (one stage).
+__host__ __device__ constexpr int gemm_threads(int ew) { return 128 + 32 * ew; }
 constexpr int GEMM_SLAB_BYTES = 32 * 128; // 32 rows x 128 bytes per epilogue warp
 
 template <int OUT>
@@ -96,21 +98,21 @@ struct OutTraits<OUT_S8>
 };
 
 // Columns of the output covered by one TMA-store slab of an epilogue warp (host and device agree on this):
-// a 128-byte row, except int8 where the warp's whole column range (BN/2 <= 128 bytes) is one slab.
-template <int BN, int OUT>
+// a 128-byte row, or the warp's whole column range when that is narrower than 128 bytes.
+template <int BN, int OUT, int EW>
 __host__ __device__ constexpr int slab_cols()
 {
-    return (128 / OutTraits<OUT>::ELEM) < (BN / 2) ? (128 / OutTraits<OUT>::ELEM) : (BN / 2);
+    return (128 / OutTraits<OUT>::ELEM) < (BN / (EW / 4)) ? (128 / OutTraits<OUT>::ELEM) : (BN / (EW / 4));
 }
 
-template <int BN, int STAGES, int CG = 1>
+template <int BN, int STAGES, int CG, int EW>
 struct GemmSmem
 {
     static constexpr int A_BYTES = GEMM_BM * GEMM_STAGE_ROW_BYTES;
     static constexpr int B_BYTES = (BN / CG) * GEMM_STAGE_ROW_BYTES; // a CTA of a pair stages half of the W tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OFF_SLABS = STAGES * STAGE_BYTES; // 1024-byte aligned (stage sizes are multiples of 1024)
-    static constexpr int OFF_BIAS = OFF_SLABS + GEMM_EPI_WARPS * GEMM_SLAB_BYTES;
+    static constexpr int OFF_BIAS = OFF_SLABS + EW * GEMM_SLAB_BYTES;
     static constexpr int OFF_BARS = OFF_BIAS + 2 * BN * 4; // bias slice, double-buffered by tile parity
     static constexpr int NUM_BARS = 2 * STAGES + 4;
     static constexpr int OFF_TMEM_PTR = OFF_BARS + NUM_BARS * 8;
@@ -217,12 +219,12 @@ __device__ __forceinline__ void epi_convert32(const uint32_t *v, const uint32_t 
     }
 }
 
-template <int KIND, int BN, int OUT, int STAGES, int CG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int KIND, int BN, int OUT, int STAGES, int CG, int EW>
+__global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                        const __grid_constant__ CUtensorMap tma_out, const GemmParams p)
 {
-    using L = GemmSmem<BN, STAGES, CG>;
+    using L = GemmSmem<BN, STAGES, CG, EW>;
     constexpr int ELEM = KindTraits<KIND>::ELEM;
     constexpr int BK = GEMM_STAGE_ROW_BYTES / ELEM; // elements of K per stage
     constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (power of two >= 32)
@@ -230,12 +232,14 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     constexpr int TILE_M = GEMM_BM * CG;            // rows of one accumulator tile (per CTA pair when CG = 2)
     static_assert(CG == 1 || CG == 2, "a tile belongs to one CTA or to a CTA pair");
     constexpr int OELEM = OutTraits<OUT>::ELEM;
-    constexpr int WARP_COLS = BN / 2;               // columns per epilogue warp
-    constexpr int SLAB_COLS = slab_cols<BN, OUT>(); // columns per TMA-store slab
+    constexpr int WARP_COLS = BN / (EW / 4);        // columns per epilogue warp
+    constexpr int SLAB_COLS = slab_cols<BN, OUT, EW>(); // columns per TMA-store slab
     constexpr int SLAB_ROW_BYTES = SLAB_COLS * OELEM;
-    constexpr bool SLAB_SWIZZLED = SLAB_ROW_BYTES == 128; // int8 slabs (<= 128 B rows handled unswizzled when 64 B)
+    constexpr bool SLAB_SWIZZLED = SLAB_ROW_BYTES == 128; // narrower slab rows (32 / 64 bytes) are stored unswizzled
     static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
-    static_assert(SLAB_ROW_BYTES == 128 || SLAB_ROW_BYTES == 64, "slab rows are 128 bytes (64 for int8 at BN = 128)");
+    static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
+    static_assert(SLAB_ROW_BYTES == 128 || SLAB_ROW_BYTES == 64 || SLAB_ROW_BYTES == 32, "slab rows are 128, 64 or 32 bytes");
+    static_assert(WARP_COLS % 32 == 0, "an epilogue warp handles whole 32-column TMEM groups");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = smem_u32(smem_raw); // SWIZZLE_128B tiles need 1024-byte alignment
@@ -279,7 +283,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         for (int a = 0; a < 2; a++)
         {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), GEMM_EPI_WARPS * CG); // one arrive per epilogue warp (of both CTAs of a pair)
+            mbar_init(tempty_bar(a), EW * CG); // one arrive per epilogue warp (of both CTAs of a pair)
         }
         fence_barrier_init();
     }
@@ -307,6 +311,11 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     griddep_launch_dependents();
     griddep_wait();
 
+    if (warp < 4)
+    {
+    // 16 epilogue warps: 640 threads x 96 registers at launch; the four non-epilogue warps hand back 56 each, which lets
+    // every epilogue thread grow to 104 (128 x 40 + 512 x 104 <= 640 x 96: a larger request would block forever)
+    if constexpr (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0)
     {
         // ===================== TMA producer =====================
@@ -393,13 +402,15 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             }
         }
     }
-    else if (warp >= 4)
+    }
+    else
     {
         // ===================== epilogue =====================
-        const int ew = warp - 4;          // 0..7
+        if constexpr (EW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const int ew = warp - 4;          // 0..EW-1
         const int q = warp & 3;           // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
         const int wcol = (ew >> 2) * WARP_COLS; // first tile column of this warp
-        const int et = threadIdx.x - 128; // 0..255 among the epilogue threads
+        const int et = threadIdx.x - 128; // index among the epilogue threads
         uint32_t *bias_all = reinterpret_cast<uint32_t *>(smem + L::OFF_BIAS);
         uint8_t *slab = smem + L::OFF_SLABS + ew * GEMM_SLAB_BYTES;
         const uint32_t slab_addr = base + L::OFF_SLABS + ew * GEMM_SLAB_BYTES;
@@ -410,14 +421,14 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             const int col0 = n_blk * BN;
             const int row0 = m_blk * TILE_M + cta_rank * GEMM_BM + q * 32;
 
-            // this tile's bias slice (bit pattern: float or int32), shared by the 8 epilogue warps
+            // this tile's bias slice (bit pattern: float or int32), shared by the epilogue warps
             uint32_t *bias_s = bias_all + parity * BN;
-            for (int i = et; i < BN; i += 32 * GEMM_EPI_WARPS)
+            for (int i = et; i < BN; i += 32 * EW)
             {
                 const int c = col0 + i;
                 bias_s[i] = (p.bias != nullptr && c < p.N) ? reinterpret_cast<const uint32_t *>(p.bias)[c] : 0u;
             }
-            named_bar_sync(1, 32 * GEMM_EPI_WARPS);
+            named_bar_sync(1, 32 * EW);
 
             mbar_wait(tfull_bar(acc), acc_phase, p.error_flag, KERR_EPI_TMEM_FULL);
             tcgen05_fence_after();

@@ -666,7 +666,7 @@ static int vit_pass(netcuda_net *h, const float *img, int n, float *logits, cuda
         CK(run_gemm(h, "qkv", GK_BF16, h->ybuf, D, cap, b.qkv_w, D, b.qkv_b, h->qkv, 3LL * D, OUT_BF16, EPI_NONE, rows, 3 * D, D, s));
         {
             KernelScope scope(h, s, "attention", 4.0 * n * (double)T * T * D, (double)rows * D * 8.0);
-            CK(launch_attention(h->qkv, h->att, n, T, h->desc.heads, s, h->d_err, h->num_sms, h->gemm_variant));
+            CK(launch_attention(h->qkv, h->att, n, T, h->desc.heads, s, h->d_err, h->num_sms, h->gemm_variant == 1 ? 1 : 0));
         }
         CK(run_gemm(h, "proj", GK_BF16, h->att, D, cap, b.proj_w, D, b.proj_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, D, s));
         if (int rc = run_layernorm(h, "layernorm", h->x, D, b.ln2_g, b.ln2_b, h->ybuf, D, rows, D, s)) return rc;
@@ -901,7 +901,7 @@ extern "C" int netcuda_profile_read(netcuda_net *h, netcuda_kernel_stat *stats, 
 extern "C" int netcuda_set_gemm_variant(netcuda_net *h, int variant)
 {
     if (int rc = check_handle(h)) return rc;
-    if (variant < 0 || variant > 2) return fail(NETCUDA_ERR_INVALID, "variant must be 0, 1 or 2");
+    if (variant < 0 || variant > 3) return fail(NETCUDA_ERR_INVALID, "variant must be 0..3");
     h->gemm_variant = variant;
     return NETCUDA_OK;
 }
