@@ -3,8 +3,7 @@
 The CUDA path keeps the residual stream, biases, LayerNorm statistics, softmax statistics and every
 accumulator in fp32 and rounds to bf16 exactly where a tensor-core operand is produced: weights, patch
 pixels, LayerNorm outputs, the packed qkv, the un-normalised softmax numerators P, the attention output
-and the GELU output; inside the attention kernel a score row is held as fp16 differences to its running
-maximum (see _softmax_numerators).  This model applies the same roundings to an otherwise fp32 forward, so that
+and the GELU output.  This model applies the same roundings to an otherwise fp32 forward, so that
 
     |cuda - model|   measures kernel arithmetic (accumulation order, exp2/erf approximations), and
     |model - fp32|   is the budget that bf16 operands cost -- not something a kernel can win back.
@@ -18,23 +17,6 @@ import torch
 
 def _bf(x):
     return x.float().to(torch.bfloat16).double()
-
-
-def _softmax_numerators(s, sqrt_hd, rounding):
-    """exp(s / sqrt(hd) - max) the way attention_tc_kernel forms it: the score row is read once, in chunks of 32 keys; every score
-    is kept as an fp16 difference to the running row maximum after its chunk, and re-centred on the final maximum afterwards."""
-    if not rounding:
-        return torch.exp((s - s.max(-1, keepdim=True).values) / sqrt_hd)
-    T = s.shape[-1]
-    run = torch.full(s.shape[:-1] + (1,), -float("inf"), dtype=s.dtype)
-    parts, centers = [], []
-    for c0 in range(0, T, 32):
-        chunk = s[..., c0:c0 + 32]
-        run = torch.maximum(run, chunk.max(-1, keepdim=True).values)
-        parts.append((chunk - run).float().half().double())  # fp32 subtraction on the GPU, then round-to-nearest fp16
-        centers.append(run)
-    m = run
-    return torch.cat([torch.exp((d + (c - m)) / sqrt_hd) for d, c in zip(parts, centers)], dim=-1)
 
 
 def vit_forward_bf16_model(cfg: dict, flat: np.ndarray, images: np.ndarray, rounding: bool = True) -> np.ndarray:
@@ -66,7 +48,8 @@ def vit_forward_bf16_model(cfg: dict, flat: np.ndarray, images: np.ndarray, roun
         y = r(ln(x, (D,), g1, b1, 1e-6))
         qkv = r(y @ r(qw).T + qb).reshape(B, T, 3, H, D // H)
         q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
-        pe = _softmax_numerators(q @ k.transpose(-1, -2), float(np.sqrt(D // H)), rounding)
+        s = (q @ k.transpose(-1, -2)) / float(np.sqrt(D // H))
+        pe = torch.exp(s - s.max(-1, keepdim=True).values)
         o = (r(pe) @ v) / pe.sum(-1, keepdim=True)  # the row sum is taken from the fp32 numerators
         x = x + r(o.permute(0, 2, 1, 3).reshape(B, T, D)) @ r(ow).T + ob
         y = r(ln(x, (D,), g2, b2, 1e-6))

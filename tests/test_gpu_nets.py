@@ -8,7 +8,7 @@ Bars, error = max |out - ref| relative to max |ref| per sample
     <= 1e-2 and identical arg-max -- the north_star tolerance;
   * BF16 on narrow nets (the 128-wide golden ViT, MLPs with the reference's unscaled +-1 weights): the
     operand rounding alone (2^-9 per weight and per activation) costs more than 1e-2 on the worst sample --
-    0.94e-2 on the golden ViT, reproduced to 7 digits by a CPU model of the rounding points
+    1.14e-2 on the golden ViT, reproduced to 7 digits by a CPU model of the rounding points
     (tests/bf16_pipeline_model.py).  There the bar is split: <= 2e-3 against that rounding model (what the
     kernels control) and <= 2e-2 against the fp32 reference (what bf16 operands cost);
   * INT8: bit-exact at every batch size.
@@ -228,7 +228,7 @@ def test_vit_golden_torchvision_fixture(netcuda, torch_cuda):
     net.close()
     model = vit_forward_bf16_model(cfg, g["flat"], g["images"])
     assert rel_err(got, model) <= 2e-3        # kernel arithmetic vs the same roundings on the CPU
-    assert rel_err(got, g["logits"]) <= 2e-2  # bf16 operand budget on a 128-wide net (0.94e-2 measured and modelled)
+    assert rel_err(got, g["logits"]) <= 2e-2  # bf16 operand budget on a 128-wide net (1.14e-2 measured and modelled)
     np.testing.assert_array_equal(got.argmax(1), g["logits"].argmax(1))
 
 

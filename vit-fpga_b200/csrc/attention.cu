@@ -13,6 +13,10 @@
 //      exact row max, write the un-normalised bf16 P back into the same TMEM columns; O = P.V is a UMMA
 //      with the A operand in TMEM and V consumed MN-major straight from its row-major [key][64] tile;
 //      the warpgroup scales O by 1/rowsum and writes 128-byte rows.  S and P never touch smem or HBM.
+//      Measured alternatives (round 1, 256 x 12 x 197, us per launch): this two-pass softmax 126; a single-read
+//      softmax that keeps the row as fp16 differences in registers (setmaxnreg 232) 134; P through shared
+//      memory with an SS-mode P.V (single-buffered V) 171.  The kernel is paced by the TMEM read port and by
+//      the serial S -> softmax -> P.V -> O chain of each warpgroup, see tools/attn_timeline.py.
 //  (2) attention_kernel (longer sequences, e.g. 577 tokens at 384 pixels): flash-style single pass with
 //      mma.sync m16n8k16 (bf16 in, fp32 accumulate), described below.
 //
@@ -27,7 +31,6 @@
 #include "ptx.cuh"
 
 #include <cstdlib>
-#include <cuda_fp16.h>
 
 namespace nc
 {
@@ -272,9 +275,6 @@ struct AttnTcParams
     long long *debug; // optional [32 items][12 warps][8] clock64 stamps of CTA 0 (profiling aid; null in production)
 };
 
-// NC = number of 32-key chunks of a score row (ceil(tokens / 32), 1..8): the softmax warps keep a whole row in
-// registers (as fp16 differences to a running maximum), so the chunk loops must unroll completely.
-template <int NC>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const AttnTcParams p)
 {
@@ -328,10 +328,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     griddep_launch_dependents();
     griddep_wait(); // the qkv matrix is the previous kernel's output
 
-    // the producer / MMA / allocator warps need few registers; the softmax warps hold a score row each
-    if (warp < 4)
-    {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0)
     {
         // ===================== TMA producer =====================
@@ -428,24 +424,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             }
         }
     }
-    }
-    else
-    {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    if ((warp - 4) / 4 < p.n_mtiles)
+    else if (warp >= 4 && (warp - 4) / 4 < p.n_mtiles)
     {
         // ===================== softmax + output warpgroups (one per query tile) =====================
-        // The kernel is bound by the TMEM read port (~64 B/clk/SM), so S is read exactly ONCE.  While chunk c streams
-        // in, the thread keeps d = s - m_c (m_c = running row maximum after chunk c) as packed fp16 in registers: d <= 0,
-        // and |d| is small exactly for the keys that carry weight, so the fp16 rounding (2^-11 |d|) is far below the bf16
-        // rounding of P.  Once the true maximum M is known, p = 2^((d + m_c - M) * scale) comes from registers.
         const int t = (warp - 4) >> 2; // query tile
         const int q = warp & 3;        // TMEM lane quarter
         const int qrow = t * 128 + q * 32 + lane; // query row within the image
         const uint32_t region = tmem_base + ((uint32_t)(q * 32) << 16) + t * ATC_REGION_COLS;
         const float sl = 0.125f * 1.4426950408889634f; // 1/sqrt(64) * log2(e)
-        const int tail = p.tokens - (NC - 1) * 32;     // valid keys in the last chunk (1..32)
-        if (p.n_mtiles == 2 && t == 1) named_bar_arrive(2, 256);  // tile 0 takes the first turn in the exp2 pass
+        const int nfull = p.tokens >> 5, tail = p.tokens & 31; // full 32-key chunks, keys in the ragged last chunk
+        const int nchunks = nfull + (tail ? 1 : 0);
         int it = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, it++)
         {
@@ -459,65 +447,91 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             tcgen05_fence_after();
             stamp(1);
 
-            // ---- pass A: the only read of S.  Chunk c + 1 is in flight while chunk c is reduced and packed. ----
-            uint32_t dh[NC][16]; // 32 keys per chunk as fp16x2 differences to center[c]
-            float center[NC];
-            float m_run = -INFINITY;
+            // ---- pass 1: exact row maximum over the valid keys (chunk c + 1 is in flight while c is reduced) ----
+            float mx = -INFINITY;
             {
-                uint32_t v[2][32];
-                tmem_ld_32x32(region, v[0]);
+                uint32_t va[32], vb[32];
+                auto reduce = [&](const uint32_t *v, int c) {
+                    if (c < nfull)
+                    {
+                        float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
 #pragma unroll
-                for (int c = 0; c < NC; c++)
+                        for (int j = 4; j < 32; j += 4)
+                        {
+                            m0 = fmaxf(m0, __uint_as_float(v[j])), m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+                            m2 = fmaxf(m2, __uint_as_float(v[j + 2])), m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+                        }
+                        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (j < tail) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    }
+                };
+                tmem_ld_32x32(region, va);
+                for (int c = 0; c < nchunks; c += 2)
                 {
                     tmem_ld_wait();
-                    if (c + 1 < NC) tmem_ld_32x32(region + (c + 1) * 32, v[(c + 1) & 1]);
-                    const uint32_t *vc = v[c & 1];
-                    float f[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j++) f[j] = (c < NC - 1 || j < tail) ? __uint_as_float(vc[j]) : -INFINITY;
-                    float m0 = fmaxf(f[0], f[1]), m1 = fmaxf(f[2], f[3]), m2 = fmaxf(f[4], f[5]), m3 = fmaxf(f[6], f[7]);
-#pragma unroll
-                    for (int j = 8; j < 32; j += 8)
+                    if (c + 1 < nchunks) tmem_ld_32x32(region + (c + 1) * 32, vb);
+                    reduce(va, c);
+                    if (c + 1 < nchunks)
                     {
-                        m0 = fmaxf(m0, fmaxf(f[j], f[j + 1])), m1 = fmaxf(m1, fmaxf(f[j + 2], f[j + 3]));
-                        m2 = fmaxf(m2, fmaxf(f[j + 4], f[j + 5])), m3 = fmaxf(m3, fmaxf(f[j + 6], f[j + 7]));
-                    }
-                    m_run = fmaxf(m_run, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3))); // finite: chunk 0 always holds a valid key
-                    center[c] = m_run;
-#pragma unroll
-                    for (int j = 0; j < 16; j++)
-                    {
-                        const __half2 hp = __floats2half2_rn(f[2 * j] - m_run, f[2 * j + 1] - m_run); // masked keys: -inf -> p = 0
-                        dh[c][j] = *reinterpret_cast<const uint32_t *>(&hp);
+                        tmem_ld_wait();
+                        if (c + 2 < nchunks) tmem_ld_32x32(region + (c + 2) * 32, va);
+                        reduce(vb, c + 1);
                     }
                 }
             }
-            stamp(2);
 
-            // ---- pass B (registers only): P (bf16) goes over the S columns, which are dead by now ----
-            // The exp2 pass saturates the MUFU, everything else of an iteration does not use it: the two warpgroups take
-            // turns (named barriers 2 + t, 128 waiting + 128 arriving threads), so that one is in pass B while the other
-            // reads TMEM, waits for its MMAs or stores O.
-            if (p.n_mtiles == 2) named_bar_sync(2 + t, 256);
+            stamp(2);
+            // ---- pass 2: p = 2^((s - max) * scale); P (bf16) overwrites the first half of the S columns it came from ----
+            const float msc = mx * sl;
             float sum0 = 0.0f, sum1 = 0.0f;
-#pragma unroll
-            for (int c = 0; c < NC; c++)
             {
-                const float off = (center[c] - m_run) * sl; // <= 0: re-centres chunk c on the true row maximum
-                uint32_t w[16];
+                uint32_t va[32], vb[32];
+                auto expo = [&](const uint32_t *v, int c) {
+                    uint32_t w[16];
+                    if (c < nfull)
+                    {
 #pragma unroll
-                for (int j = 0; j < 16; j++)
+                        for (int j = 0; j < 16; j++)
+                        {
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl, -msc));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl, -msc));
+                            sum0 += p0, sum1 += p1;
+                            w[j] = pack_bf16x2(p0, p1);
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j = 0; j < 16; j++)
+                        {
+                            const float p0 = (2 * j < tail) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl, -msc)) : 0.0f;
+                            const float p1 = (2 * j + 1 < tail) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl, -msc)) : 0.0f;
+                            sum0 += p0, sum1 += p1;
+                            w[j] = pack_bf16x2(p0, p1);
+                        }
+                    }
+                    tmem_st_32x16(region + c * 16, w);
+                };
+                tmem_ld_32x32(region, va);
+                for (int c = 0; c < nchunks; c += 2)
                 {
-                    const float2 d = __half22float2(*reinterpret_cast<const __half2 *>(&dh[c][j]));
-                    const float p0 = ex2_approx(fmaf(d.x, sl, off));
-                    const float p1 = ex2_approx(fmaf(d.y, sl, off));
-                    sum0 += p0, sum1 += p1;
-                    w[j] = pack_bf16x2(p0, p1);
+                    tmem_ld_wait();
+                    if (c + 1 < nchunks) tmem_ld_32x32(region + (c + 1) * 32, vb);
+                    expo(va, c);
+                    if (c + 1 < nchunks)
+                    {
+                        tmem_ld_wait();
+                        if (c + 2 < nchunks) tmem_ld_32x32(region + (c + 2) * 32, va);
+                        expo(vb, c + 1);
+                    }
                 }
-                tmem_st_32x16(region + c * 16, w);
             }
             const float sum = sum0 + sum1;
-            if (p.n_mtiles == 2) named_bar_arrive(2 + (t ^ 1), 256); // the other warpgroup's turn
             tmem_st_wait();
             tcgen05_fence_before();
             __syncwarp();
@@ -553,7 +567,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             stamp(5);
         }
     }
-    }
 
     tcgen05_fence_before();
     __syncthreads();
@@ -567,7 +580,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
 static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag,
                                        int num_sms)
 {
-    cudaError_t e;
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+    if (e != cudaSuccess) return e;
     AttnTcParams p;
     p.out = reinterpret_cast<__nv_bfloat16 *>(out);
     p.batch = batch, p.tokens = tokens, p.heads = heads;
@@ -586,29 +600,7 @@ static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, in
     if (e != cudaSuccess) return e;
     const int items = batch * heads;
     const int sms = num_sms > 0 ? num_sms : 148;
-    const int grid = items < sms ? items : sms;
-#define NC_ATT_CASE(NCV)                                                                                                       \
-    case NCV:                                                                                                                  \
-        e = cudaFuncSetAttribute(attention_tc_kernel<NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);               \
-        if (e != cudaSuccess) return e;                                                                                        \
-        e = launch_pdl(attention_tc_kernel<NCV>, dim3(grid), dim3(ATC_THREADS), (size_t)ATC_SMEM, stream, 1, map_q, map_kv, p);   \
-        if (e != cudaSuccess) return e;                                                                                        \
-        break;
-    switch ((tokens + 31) / 32)
-    {
-        NC_ATT_CASE(1)
-        NC_ATT_CASE(2)
-        NC_ATT_CASE(3)
-        NC_ATT_CASE(4)
-        NC_ATT_CASE(5)
-        NC_ATT_CASE(6)
-        NC_ATT_CASE(7)
-        NC_ATT_CASE(8)
-    default:
-        return cudaErrorInvalidValue;
-    }
-#undef NC_ATT_CASE
-    return cudaGetLastError();
+    return launch_pdl(attention_tc_kernel, dim3(items < sms ? items : sms), dim3(ATC_THREADS), (size_t)ATC_SMEM, stream, 1, map_q, map_kv, p);
 }
 
 cudaError_t launch_attention(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag, int num_sms,

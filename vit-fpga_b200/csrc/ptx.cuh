@@ -143,11 +143,6 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads)
-{
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 // ---- tcgen05: tensor memory ------------------------------------------------------------------
 
 // Whole-warp (.sync.aligned).  Writes the TMEM base address of `ncols` columns to *dst_smem.
