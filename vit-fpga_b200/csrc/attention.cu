@@ -245,6 +245,9 @@ static cudaError_t launch_attention_nw(const __nv_bfloat16 *q, __nv_bfloat16 *o,
 // =====================================================================================================
 
 constexpr int ATC_THREADS = 384;
+// Warp roles: softmax warpgroups = warps 0-3 (query tile 0) and 4-7 (tile 1); producer, MMA issuer and TMEM allocator take the
+// highest warp ids, which the warp scheduler favours: a ready MMA / TMA issue must not queue behind softmax arithmetic.
+constexpr int ATC_W_PRODUCER = 8, ATC_W_MMA = 9, ATC_W_ALLOC = 10;
 constexpr int ATC_Q_BYTES = 128 * 128;  // one query tile: 128 rows x 64 bf16
 constexpr int ATC_KV_BYTES = 256 * 128; // up to 256 keys x 64 bf16
 constexpr int ATC_BUF_BYTES = 2 * ATC_Q_BYTES + 2 * ATC_KV_BYTES;
@@ -298,12 +301,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     const int items = p.batch * p.heads;
     const int D = p.heads * ATT_HD;
 
-    if (warp == 0 && lane == 0)
+    if (warp == ATC_W_PRODUCER && lane == 0)
     {
         tma_prefetch_desc(&tma_q);
         tma_prefetch_desc(&tma_kv);
     }
-    if (warp == 1 && lane == 0)
+    if (warp == ATC_W_MMA && lane == 0)
     {
         for (int b = 0; b < 2; b++)
         {
@@ -316,7 +319,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         }
         fence_barrier_init();
     }
-    if (warp == 2)
+    if (warp == ATC_W_ALLOC)
     {
         tmem_alloc(base + ATC_OFF_TMEM_PTR, 512);
         tmem_relinquish();
@@ -328,7 +331,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     griddep_launch_dependents();
     griddep_wait(); // the qkv matrix is the previous kernel's output
 
-    if (warp == 0)
+    if (warp == ATC_W_PRODUCER)
     {
         // ===================== TMA producer =====================
         if (lane == 0)
@@ -340,7 +343,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                 const int buf = it & 1;
                 const int b = item / p.heads, h = item - b * p.heads;
                 mbar_wait(empty_bar(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u, p.error_flag, KERR_ATT_PRODUCER);
-                if (p.debug && blockIdx.x == 0 && it < 32) p.debug[(it * 12 + 0) * 8] = clock64();
+                if (p.debug && blockIdx.x == 0 && it < 32) p.debug[(it * 12 + ATC_W_PRODUCER) * 8] = clock64();
                 mbar_arrive_expect_tx(full_bar(buf), tx);
                 const uint32_t dst = base + buf * ATC_BUF_BYTES;
                 const int row = b * p.tokens;
@@ -350,7 +353,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             }
         }
     }
-    else if (warp == 1)
+    else if (warp == ATC_W_MMA)
     {
         // ===================== MMA issuer =====================
         // One thread serves both query tiles.  The two softmax warpgroups run independently of each other, so the
@@ -388,7 +391,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                             for (int k = 0; k < 4; k++)
                                 umma_ss<KIND_BF16>(tmem_base + t * ATC_REGION_COLS, q_desc + 2u * k, k_desc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
                             tcgen05_commit(sfull_bar(t));
-                            if (p.debug && blockIdx.x == 0 && i < 32) p.debug[(i * 12 + 1) * 8 + t] = clock64();
+                            if (p.debug && blockIdx.x == 0 && i < 32) p.debug[(i * 12 + ATC_W_MMA) * 8 + t] = clock64();
                             it_s[t]++;
                             progress = true;
                         }
@@ -405,7 +408,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                             for (int k = 0; k < ksteps; k++)
                                 umma_ts_bf16(region + ATC_O_COL, region + 8u * k, v_desc + (uint64_t)(128u * k), idesc_o, k != 0 ? 1u : 0u);
                             tcgen05_commit(ofull_bar(t));
-                            if (p.debug && blockIdx.x == 0 && i < 32) p.debug[(i * 12 + 1) * 8 + 2 + t] = clock64();
+                            if (p.debug && blockIdx.x == 0 && i < 32) p.debug[(i * 12 + ATC_W_MMA) * 8 + 2 + t] = clock64();
                             it_pv[t]++;
                             // both tiles are past item i: every MMA that reads its smem buffer has been issued
                             if (it_pv[t ^ 1] > i) tcgen05_commit(empty_bar(buf));
@@ -424,10 +427,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             }
         }
     }
-    else if (warp >= 4 && (warp - 4) / 4 < p.n_mtiles)
+    else if (warp < 8 && (warp >> 2) < p.n_mtiles)
     {
         // ===================== softmax + output warpgroups (one per query tile) =====================
-        const int t = (warp - 4) >> 2; // query tile
+        const int t = warp >> 2; // query tile
         const int q = warp & 3;        // TMEM lane quarter
         const int qrow = t * 128 + q * 32 + lane; // query row within the image
         const uint32_t region = tmem_base + ((uint32_t)(q * 32) << 16) + t * ATC_REGION_COLS;
@@ -570,7 +573,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
 
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 2)
+    if (warp == ATC_W_ALLOC)
     {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, 512);

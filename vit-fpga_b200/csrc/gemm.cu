@@ -8,6 +8,7 @@
 #include "gemm_tcgen05.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace nc
@@ -142,6 +143,8 @@ static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
     p.bias = c.bias, p.out = c.out, p.ldc = c.ldc, p.epi = c.epi;
     p.remap_in = c.remap_in, p.remap_out = c.remap_out, p.pos = c.pos;
     p.error_flag = c.error_flag;
+    p.debug = nullptr;
+    if (const char *dbg = getenv("NETCUDA_GEMM_DEBUG_PTR")) p.debug = reinterpret_cast<long long *>(strtoull(dbg, nullptr, 0));
     // TMA-store epilogue whenever the output is addressable by a tensor map; otherwise direct stores
     const long long pitch_bytes = c.ldc * OutTraits<OUT>::ELEM;
     // (TMA bounds the innermost dimension in 16-byte units, so N must be a whole number of them as well)

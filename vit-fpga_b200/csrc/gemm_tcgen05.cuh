@@ -13,10 +13,10 @@
 // CG = 1: one CTA per tile (small M).
 //
 // Structure (one persistent CTA per SM, 384 threads, warp-specialised):
-//   warp 0     TMA producer: 128B-swizzled [128 x 128B] A tile + [BN x 128B] W tile per stage
-//   warp 1     MMA issuer:   one thread issues tcgen05.mma (UMMA 128 x BN x 32B) into TMEM
-//   warp 2     TMEM allocator (2 accumulator stages x BN fp32/int32 columns)
-//   warps 4-11 epilogue: warp w reads TMEM lanes [32(w%4), +32) x columns [(w-4)/4 * BN/2, +BN/2):
+//   warp 8     TMA producer: 128B-swizzled [128 x 128B] A tile + [BN x 128B] W tile per stage
+//   warp 9     MMA issuer:   one thread issues tcgen05.mma (UMMA 128 x BN x 32B) into TMEM
+//   warp 10    TMEM allocator (2 accumulator stages x BN fp32/int32 columns)
+//   warps 0-7  epilogue: warp w reads TMEM lanes [32(w%4), +32) x columns [w/4 * BN/2, +BN/2):
 //              tcgen05.ld -> +bias -> activation -> convert -> 128B-swizzled smem slab -> one TMA
 //              store (or TMA reduce-add for the residual epilogue) per 32-row x 128-byte slab.
 //              Runs concurrently with the next tile's MMAs (double-buffered accumulator).
@@ -64,6 +64,7 @@ struct GemmParams
     int remap_in, remap_out;
     const float *pos;
     int *error_flag;
+    long long *debug; // optional clock64 stamps of cluster 0: [tile < 40][warp 0..11 of CTA 0, 12..23 of CTA 1][4] (profiling aid)
 };
 
 constexpr int GEMM_BM = 128;
@@ -219,6 +220,59 @@ __device__ __forceinline__ void epi_convert32(const uint32_t *v, const uint32_t 
     }
 }
 
+// The same for the 16 / sizeof(out) columns that make one 16-byte chunk of an output row (8 bf16, 4 fp32 / int32, 16 int8):
+// `v` holds that many accumulator columns, `w` receives the 4 packed words.
+template <int OUT>
+__device__ __forceinline__ uint4 epi_convert_chunk(const uint32_t *v, const uint32_t *bias, int epi)
+{
+    uint4 w;
+    if constexpr (OUT == OUT_F32)
+    {
+        const uint4 b = *reinterpret_cast<const uint4 *>(bias);
+        w.x = __float_as_uint(epi_act_f32(__uint_as_float(v[0]) + __uint_as_float(b.x), epi));
+        w.y = __float_as_uint(epi_act_f32(__uint_as_float(v[1]) + __uint_as_float(b.y), epi));
+        w.z = __float_as_uint(epi_act_f32(__uint_as_float(v[2]) + __uint_as_float(b.z), epi));
+        w.w = __float_as_uint(epi_act_f32(__uint_as_float(v[3]) + __uint_as_float(b.w), epi));
+    }
+    else if constexpr (OUT == OUT_S32)
+    {
+        const uint4 b = *reinterpret_cast<const uint4 *>(bias);
+        int a0 = (int)v[0] + (int)b.x, a1 = (int)v[1] + (int)b.y, a2 = (int)v[2] + (int)b.z, a3 = (int)v[3] + (int)b.w;
+        if (epi == EPI_RELU) a0 = max(a0, 0), a1 = max(a1, 0), a2 = max(a2, 0), a3 = max(a3, 0);
+        w = make_uint4((uint32_t)a0, (uint32_t)a1, (uint32_t)a2, (uint32_t)a3);
+    }
+    else if constexpr (OUT == OUT_BF16)
+    {
+        const uint4 b0 = *reinterpret_cast<const uint4 *>(bias), b1 = *reinterpret_cast<const uint4 *>(bias + 4);
+        const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) f[e] = epi_act_f32(__uint_as_float(v[e]) + __uint_as_float(bb[e]), epi);
+        w = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+    else
+    {
+        uint32_t word[4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; j4++)
+        {
+            const uint4 b = *reinterpret_cast<const uint4 *>(bias + 4 * j4);
+            const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
+            word[j4] = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+            {
+                int a = (int)v[4 * j4 + e] + (int)bb[e];
+                if (epi == EPI_REQUANT_RELU) a = max(a, 0);
+                a = min(127, max(-128, a >> 7));
+                word[j4] |= ((uint32_t)a & 0xFFu) << (8 * e);
+            }
+        }
+        w = make_uint4(word[0], word[1], word[2], word[3]);
+    }
+    return w;
+}
+
 template <int KIND, int BN, int OUT, int STAGES, int CG, int EW>
 __global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
@@ -231,6 +285,11 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     constexpr uint32_t IDESC = KindTraits<KIND>::idesc(GEMM_BM * CG, BN);
     constexpr int TILE_M = GEMM_BM * CG;            // rows of one accumulator tile (per CTA pair when CG = 2)
     static_assert(CG == 1 || CG == 2, "a tile belongs to one CTA or to a CTA pair");
+    const int epi = p.epi; // (a compile-time epilogue was measured: same speed, so one instantiation serves all epilogues of a type)
+    // Warp roles.  The epilogue warps take the LOW warp ids: the scheduler favours the highest warp id among ready warps,
+    // and the single MMA-issuing thread must never queue behind epilogue arithmetic (measured on the GELU GEMM: the issue
+    // loop of a tile took 8.5 k cycles instead of 6.1 k when the issuer was warp 1 and the epilogue warps 4..11).
+    constexpr int W_PRODUCER = EW, W_MMA = EW + 1, W_ALLOC = EW + 2;
     constexpr int OELEM = OutTraits<OUT>::ELEM;
     constexpr int WARP_COLS = BN / (EW / 4);        // columns per epilogue warp
     constexpr int SLAB_COLS = slab_cols<BN, OUT, EW>(); // columns per TMA-store slab
@@ -267,13 +326,13 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0; // 0 = leader of the pair
     const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG; // both CTAs of a pair walk the same tiles
 
-    if (warp == 0 && lane == 0)
+    if (warp == W_PRODUCER && lane == 0)
     {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_w);
         if (p.tma_store) tma_prefetch_desc(&tma_out);
     }
-    if (warp == 1 && lane == 0)
+    if (warp == W_MMA && lane == 0)
     {
         for (int s = 0; s < STAGES; s++)
         {
@@ -287,7 +346,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         }
         fence_barrier_init();
     }
-    if (warp == 2)
+    if (warp == W_ALLOC)
     {
         if constexpr (CG == 2)
         {
@@ -311,12 +370,12 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     griddep_launch_dependents();
     griddep_wait();
 
-    if (warp < 4)
+    if (warp >= EW)
     {
     // 16 epilogue warps: 640 threads x 96 registers at launch; the four non-epilogue warps hand back 56 each, which lets
     // every epilogue thread grow to 104 (128 x 40 + 512 x 104 <= 640 x 96: a larger request would block forever)
     if constexpr (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0)
+    if (warp == W_PRODUCER)
     {
         // ===================== TMA producer =====================
         if (lane == 0)
@@ -352,7 +411,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             }
         }
     }
-    else if (warp == 1)
+    else if (warp == W_MMA)
     {
         // ===================== MMA issuer =====================
         if (lane == 0 && cta_rank == 0)
@@ -360,8 +419,12 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step)
             {
+                int tl = (tile - tile0) / tile_step;
+                const bool dbg = p.debug != nullptr && tile0 == 0 && tl < 40;
+                if (dbg) p.debug[(tl * 24 + 11) * 4 + 0] = clock64();
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.error_flag, KERR_MMA_TMEM_EMPTY);
                 tcgen05_fence_after();
+                if (dbg) p.debug[(tl * 24 + 11) * 4 + 1] = clock64();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kb; kb++)
                 {
@@ -394,6 +457,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                     tcgen05_commit_pair(tfull_bar(acc));
                 else
                     tcgen05_commit(tfull_bar(acc));
+                if (dbg) p.debug[(tl * 24 + 11) * 4 + 2] = clock64();
                 if (++acc == 2)
                 {
                     acc = 0;
@@ -407,10 +471,10 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     {
         // ===================== epilogue =====================
         if constexpr (EW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-        const int ew = warp - 4;          // 0..EW-1
+        const int ew = warp;              // 0..EW-1
         const int q = warp & 3;           // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
         const int wcol = (ew >> 2) * WARP_COLS; // first tile column of this warp
-        const int et = threadIdx.x - 128; // index among the epilogue threads
+        const int et = threadIdx.x;       // index among the epilogue threads
         uint32_t *bias_all = reinterpret_cast<uint32_t *>(smem + L::OFF_BIAS);
         uint8_t *slab = smem + L::OFF_SLABS + ew * GEMM_SLAB_BYTES;
         const uint32_t slab_addr = base + L::OFF_SLABS + ew * GEMM_SLAB_BYTES;
@@ -430,44 +494,54 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             }
             named_bar_sync(1, 32 * EW);
 
+            const int tl = (tile - tile0) / tile_step;
+            const bool dbg = p.debug != nullptr && tile0 == 0 && tl < 40 && lane == 0 && warp < 11;
+            long long *dslot = p.debug + (tl * 24 + cta_rank * 12 + warp) * 4;
+            if (dbg) dslot[0] = clock64();
             mbar_wait(tfull_bar(acc), acc_phase, p.error_flag, KERR_EPI_TMEM_FULL);
             tcgen05_fence_after();
+            if (dbg) dslot[1] = clock64();
             const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + wcol;
 
             if (p.tma_store)
             {
                 // ---- smem slab + TMA store: 32 rows x SLAB_COLS columns per store ----
-                constexpr int GROUPS_PER_SLAB = SLAB_COLS / 32; // tcgen05.ld groups (32 columns) per slab
-                constexpr int WORDS_PER_GROUP = 32 * OELEM / 4; // packed words one group contributes to a row
+                // A slab row is produced 16 bytes at a time in a ROLLED loop (the next chunk's accumulator columns are in
+                // flight while the current chunk is converted).  Keeping this loop small matters more than unrolling it: with the
+                // 32-column groups fully unrolled the GELU epilogue was ~25 KB of code that streamed through the 6 KB L0
+                // instruction cache of every scheduler and evicted the MMA issuer's loop (fc1 lost 15 % to that).
+                constexpr int CHUNK_COLS = 16 / OELEM;              // accumulator columns per 16-byte output chunk
+                constexpr int CHUNKS_PER_ROW = SLAB_ROW_BYTES / 16; // 8 (4 / 2 for the narrow slabs); always even
                 for (int sb = 0; sb < WARP_COLS / SLAB_COLS; sb++)
                 {
                     const int scol = wcol + sb * SLAB_COLS; // tile column of this slab
                     if (col0 + scol >= p.N) break;          // warp-uniform
-                    uint32_t w[GROUPS_PER_SLAB * WORDS_PER_GROUP];
-#pragma unroll
-                    for (int g = 0; g < GROUPS_PER_SLAB; g++)
-                    {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_base + sb * SLAB_COLS + g * 32, v);
-                        tmem_ld_wait();
-                        epi_convert32<OUT>(v, bias_s + scol + g * 32, p.epi, w + g * WORDS_PER_GROUP);
-                    }
                     // the previous store of this warp must have finished reading the slab
                     if (lane == 0) tma_store_wait_read();
                     __syncwarp();
-                    // lane = row; 16-byte chunk j of the row goes to chunk (j ^ (row & 7)) (128B swizzle)
-#pragma unroll
-                    for (int j = 0; j < SLAB_ROW_BYTES / 16; j++)
+                    const uint32_t t_slab = t_base + sb * SLAB_COLS;
+                    const uint32_t *bias_slab = bias_s + scol;
+                    uint8_t *row = slab + lane * SLAB_ROW_BYTES;
+                    uint32_t v0[CHUNK_COLS], v1[CHUNK_COLS];
+                    tmem_ld_32xN<CHUNK_COLS>(t_slab, v0);
+#pragma unroll 1
+                    for (int j = 0; j < CHUNKS_PER_ROW; j += 2)
                     {
-                        const int cj = SLAB_SWIZZLED ? (j ^ (lane & 7)) : j;
-                        *reinterpret_cast<uint4 *>(slab + lane * SLAB_ROW_BYTES + cj * 16) =
-                            make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                        tmem_ld_wait();
+                        tmem_ld_32xN<CHUNK_COLS>(t_slab + (j + 1) * CHUNK_COLS, v1);
+                        // lane = row; 16-byte chunk j of the row goes to chunk (j ^ (row & 7)) (128B swizzle)
+                        *reinterpret_cast<uint4 *>(row + ((SLAB_SWIZZLED ? (j ^ (lane & 7)) : j) << 4)) =
+                            epi_convert_chunk<OUT>(v0, bias_slab + j * CHUNK_COLS, epi);
+                        tmem_ld_wait();
+                        if (j + 2 < CHUNKS_PER_ROW) tmem_ld_32xN<CHUNK_COLS>(t_slab + (j + 2) * CHUNK_COLS, v0);
+                        *reinterpret_cast<uint4 *>(row + ((SLAB_SWIZZLED ? ((j + 1) ^ (lane & 7)) : (j + 1)) << 4)) =
+                            epi_convert_chunk<OUT>(v1, bias_slab + (j + 1) * CHUNK_COLS, epi);
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0)
                     {
-                        if (p.epi == EPI_RESIDUAL)
+                        if (epi == EPI_RESIDUAL)
                             tma_reduce_add_2d(&tma_out, slab_addr, col0 + scol, row0);
                         else
                             tma_store_2d(&tma_out, slab_addr, col0 + scol, row0);
@@ -481,7 +555,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                 const int r = row0 + lane;
                 long long orow = r;
                 int prow = 0;
-                if (p.epi == EPI_PATCH)
+                if (epi == EPI_PATCH)
                 {
                     const int b = r / p.remap_in, t = r - b * p.remap_in;
                     orow = (long long)b * p.remap_out + 1 + t;
@@ -496,7 +570,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                     tmem_ld_32x32(t_base + g * 32, v);
                     tmem_ld_wait();
                     uint32_t w[32 * OELEM / 4];
-                    const int act = (p.epi == EPI_RESIDUAL || p.epi == EPI_PATCH) ? EPI_NONE : p.epi;
+                    const int act = (epi == EPI_RESIDUAL || epi == EPI_PATCH) ? EPI_NONE : epi;
                     epi_convert32<OUT>(v, bias_s + wcol + g * 32, act, w);
                     if (!row_ok) continue;
                     if constexpr (OUT == OUT_F32)
@@ -506,9 +580,9 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                         if (vec)
                         {
                             float4 add[8];
-                            if (p.epi == EPI_RESIDUAL || p.epi == EPI_PATCH)
+                            if (epi == EPI_RESIDUAL || epi == EPI_PATCH)
                             {
-                                const float4 *src = p.epi == EPI_RESIDUAL
+                                const float4 *src = epi == EPI_RESIDUAL
                                                         ? reinterpret_cast<const float4 *>(dst)
                                                         : reinterpret_cast<const float4 *>(p.pos + (long long)prow * p.N + gcol);
 #pragma unroll
@@ -532,8 +606,8 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                                 if (gcol + j < p.N)
                                 {
                                     float val = __uint_as_float(w[j]);
-                                    if (p.epi == EPI_RESIDUAL) val += dst[j];
-                                    if (p.epi == EPI_PATCH) val += p.pos[(long long)prow * p.N + gcol + j];
+                                    if (epi == EPI_RESIDUAL) val += dst[j];
+                                    if (epi == EPI_PATCH) val += p.pos[(long long)prow * p.N + gcol + j];
                                     dst[j] = val;
                                 }
                         }
@@ -563,6 +637,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             }
 
             // all of this warp's TMEM reads of the tile are complete -> hand the accumulator back
+            if (dbg) dslot[2] = clock64();
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0)
@@ -588,7 +663,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         cluster_sync_all(); // neither CTA may exit (or free TMEM) while the other can still touch its smem / barriers
     else
         __syncthreads();
-    if (warp == 2)
+    if (warp == W_ALLOC)
     {
         tcgen05_fence_after();
         if constexpr (CG == 2)

@@ -936,9 +936,9 @@ extern "C" int netcuda_op_gemm(int device, int precision, int variant, const voi
     c.m = m, c.n = n, c.k = k;
     c.remap_in = c.remap_out = 0, c.pos = nullptr;
     c.error_flag = nullptr;
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    c.num_sms = prop.multiProcessorCount;
+    int sms = 0; // (cudaGetDeviceProperties costs milliseconds per call; the attribute query does not)
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    c.num_sms = sms;
     cudaError_t e = launch_gemm(c, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? NETCUDA_ERR_INVALID : NETCUDA_ERR_CUDA, "netcuda_op_gemm: %s", cudaGetErrorString(e));
     return NETCUDA_OK;
