@@ -292,3 +292,58 @@ def test_vit_batch_independence_at_full_batch(netcuda, torch_cuda):
     torch.cuda.synchronize()
     net.close()
     assert torch.equal(y2, y[perm])
+
+
+# ---- runtime plumbing -------------------------------------------------------------------------------------
+
+def test_forward_device_runs_on_the_stream_it_is_given(netcuda, oracle, torch_cuda):
+    """Regression test: torch's default stream has the raw handle 0, which the C ABI reads as "the handle's own stream".
+    The binding must pass it as cudaStreamLegacy, otherwise work and the caller's events / reads live on different streams."""
+    torch = torch_cuda
+    npl, n_ins, w, b = c1_net(oracle)
+    net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_FP32, max_batch=4096)
+    net.upload_mlp(w, b)
+    x_src = torch.rand((4096, n_ins), device="cuda") * 2 - 1
+    want = oracle.mlp_forward(x_src.cpu().numpy(), w, b, npl, n_ins)
+    for stream in (torch.cuda.current_stream(), torch.cuda.Stream()):
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            x = torch.zeros_like(x_src)
+            y = torch.zeros((4096, 10), device="cuda")
+            spin = torch.empty(1 << 26, device="cuda")
+            for _ in range(20):
+                spin.normal_()    # keeps `stream` busy ...
+            x.copy_(x_src)        # ... so the input appears late: a forward on any other stream would read zeros
+            net.forward_device(x, y, 4096, stream)
+            got = y.cpu().numpy()  # stream-ordered read-back on the same stream
+        np.testing.assert_array_equal(got, want)
+    net.close()
+
+
+def test_per_kernel_profile_api(netcuda, torch_cuda):
+    torch = torch_cuda
+    cfg = dict(netcuda.VIT_PRESETS["vit_tiny_16_224"], depth=2)
+    net = netcuda.Net.vit(cfg, max_batch=8)
+    net.upload_vit(netcuda.vit_random_params(cfg, seed=3))
+    x = torch.rand((8, net.n_in), device="cuda")
+    y = torch.empty((8, 1000), device="cuda")
+    s = torch.cuda.Stream()
+    l0 = net.launches
+    net.forward_device(x, y, 8, s)
+    s.synchronize()
+    per_pass = net.launches - l0
+    assert per_pass == 3 + 2 * 7 + 2  # patchify, patch-embed, cls rows; 7 kernels per block; final LayerNorm, head
+    assert net.profile_read() == {}   # nothing is recorded while profiling is off
+    net.profile_enable(True)
+    net.forward_device(x, y, 8, s)
+    prof = net.profile_read()
+    net.profile_enable(False)
+    assert sum(v["launches"] for v in prof.values()) == per_pass
+    assert prof["layernorm"]["launches"] == 4 and prof["attention"]["launches"] == 2
+    assert all(v["ms"] > 0 for v in prof.values())
+    D, F, T = cfg["dim"], cfg["mlp_dim"], 197
+    assert prof["fc1"]["flops"] == 2 * (2.0 * 8 * T * D * F)
+    flops = sum(v["flops"] for v in prof.values())
+    assert abs(flops - 8 * net.flops_per_sample) / flops < 1e-9  # the labels add up to the advertised FLOPs per sample
+    assert net.profile_read() == {}
+    net.close()

@@ -13,12 +13,12 @@ for _ in range(3):
     nc.op_attention(qkv, out, batch, tokens, heads)
 torch.cuda.synchronize()
 d = dbg.cpu().numpy().reshape(32, 12, 8)
-t0 = d[0, 8, 0]
+t0 = d[0, 0, 0]
 np.set_printoptions(linewidth=220)
-print("producer issue (rel):", (d[:21, 8, 0] - t0))
+print("producer issue (rel):", (d[:21, 0, 0] - t0))
 print("mma S0,S1,PV0,PV1 per item:")
-print(d[:21, 9, :4] - t0)
-for w in (0, 4):
+print(d[:21, 1, :4] - t0)
+for w in (4, 8):
     print(f"warp {w}: wait_start, S ready, pass1 done, pass2 done(arrive), O ready, stores done")
     print(d[:21, w, :6] - t0)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
