@@ -314,9 +314,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             mbar_init(full_bar(b), 1);
             mbar_init(empty_bar(b), 1);
             mbar_init(sfull_bar(b), 1);
-            mbar_init(pfull_bar(b), 4); // one arrive per softmax warp
+            // one arrive per softmax warp that owns at least one real query row (197 tokens: 4 warps for tile 0, 3 for tile 1)
+            const int rows_b = min(max(p.tokens - b * 128, 1), 128);
+            mbar_init(pfull_bar(b), (rows_b + 31) / 32);
             mbar_init(ofull_bar(b), 1);
-            mbar_init(sfree_bar(b), 4);
+            mbar_init(sfree_bar(b), (rows_b + 31) / 32);
         }
         fence_barrier_init();
     }
@@ -428,7 +430,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             }
         }
     }
-    else if (warp >= 4 && ((warp - 4) >> 2) < p.n_mtiles)
+    else if (warp >= 4 && ((warp - 4) >> 2) < p.n_mtiles && ((warp - 4) >> 2) * 128 + (warp & 3) * 32 < p.tokens)
     {
         // ===================== softmax + output warpgroups (one per query tile) =====================
         const int t = (warp - 4) >> 2; // query tile
