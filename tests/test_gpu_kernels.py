@@ -206,7 +206,8 @@ def test_layernorm_strided_rows(netcuda, oracle, torch_cuda):
 
 
 ATTENTION_SHAPES = [(2, 197, 3), (1, 5, 1), (3, 37, 2), (1, 577, 2), (2, 64, 12), (4, 16, 1), (1, 113, 1),
-                    (1, 128, 1), (2, 129, 2), (2, 256, 1), (3, 200, 2), (1, 257, 1), (40, 197, 12)]
+                    (1, 128, 1), (2, 129, 2), (2, 256, 1), (3, 200, 2), (1, 257, 1), (40, 197, 12),
+                    (3, 577, 4), (2, 300, 1), (1, 1025, 2), (2, 640, 3), (5, 513, 1)]  # > 256 tokens: key-blocked kernel
 
 
 @pytest.mark.parametrize("batch,tokens,heads", ATTENTION_SHAPES)

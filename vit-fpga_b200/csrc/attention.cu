@@ -583,6 +583,341 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     }
 }
 
+// =====================================================================================================
+// tcgen05 kernel for long sequences (tokens > 256, e.g. 577 tokens at 384 pixels): key-blocked variant
+// =====================================================================================================
+// Same building blocks as attention_tc_kernel; a work item is (image, head, PAIR of 128-row query tiles) and walks over the
+// keys in n_kb blocks of kb <= 256 keys.  Per block: S = Q.K_blk^T into TMEM, the softmax warpgroup folds the block into a
+// running row maximum m and row sum l (online softmax), writes bf16 P over S, O_blk = P.V_blk comes back through TMEM and is
+// accumulated in REGISTERS: O = O * 2^((m_old - m_new) * scale) + O_blk.  Q tiles stay resident for the whole item
+// (double-buffered across items), K / V blocks stream through a two-slot ring.
+
+constexpr int ATL_OFF_KV = 4 * ATC_Q_BYTES;                  // after 2 item slots x 2 query tiles
+constexpr int ATL_OFF_BARS = ATL_OFF_KV + 4 * ATC_KV_BYTES;  // 2 step slots x (K + V)
+constexpr int ATL_NUM_BARS = 16;
+constexpr int ATL_OFF_TMEM_PTR = ATL_OFF_BARS + ATL_NUM_BARS * 8;
+constexpr int ATL_SMEM = ATL_OFF_TMEM_PTR + 16;
+static_assert(ATL_SMEM <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
+
+struct AttnLongParams
+{
+    __nv_bfloat16 *out; // [batch * tokens][heads * 64]
+    int batch, tokens, heads;
+    int kb;       // keys per block: multiple of 16, <= 256
+    int n_kb;     // key blocks per item
+    int n_qtiles; // 128-row query tiles per (image, head)
+    int n_qpairs; // work items per (image, head)
+    int *error_flag;
+};
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attention_tc_long_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const AttnLongParams p)
+{
+    extern __shared__ __align__(1024) uint8_t atl_smem[];
+    const uint32_t base = smem_u32(atl_smem);
+    if ((base & 1023u) != 0)
+    {
+        if (threadIdx.x == 0 && p.error_flag) atomicExch(p.error_flag, KERR_SMEM_ALIGN);
+        return;
+    }
+    const uint32_t bars = base + ATL_OFF_BARS;
+    auto qfull_bar = [&](int b) { return bars + 8u * b; };
+    auto qempty_bar = [&](int b) { return bars + 8u * (2 + b); };
+    auto kvfull_bar = [&](int b) { return bars + 8u * (4 + b); };
+    auto kvempty_bar = [&](int b) { return bars + 8u * (6 + b); };
+    auto sfull_bar = [&](int t) { return bars + 8u * (8 + t); };
+    auto pfull_bar = [&](int t) { return bars + 8u * (10 + t); };
+    auto ofull_bar = [&](int t) { return bars + 8u * (12 + t); };
+    auto sfree_bar = [&](int t) { return bars + 8u * (14 + t); };
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(atl_smem + ATL_OFF_TMEM_PTR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items = p.batch * p.heads * p.n_qpairs;
+    const int D = p.heads * ATT_HD;
+    const int n_it = blockIdx.x < items ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0; // items of this CTA
+    // query tiles of this CTA's ii-th item (2, or 1 for the last pair of an odd tile count)
+    auto tiles_of = [&](int ii) { return min(2, p.n_qtiles - 2 * ((blockIdx.x + ii * (int)gridDim.x) % p.n_qpairs)); };
+
+    if (warp == ATC_W_PRODUCER && lane == 0)
+    {
+        tma_prefetch_desc(&tma_q);
+        tma_prefetch_desc(&tma_kv);
+    }
+    if (warp == ATC_W_MMA && lane == 0)
+    {
+        for (int b = 0; b < 2; b++)
+        {
+            mbar_init(qfull_bar(b), 1);
+            mbar_init(qempty_bar(b), 1);
+            mbar_init(kvfull_bar(b), 1);
+            mbar_init(kvempty_bar(b), 1);
+            mbar_init(sfull_bar(b), 1);
+            mbar_init(pfull_bar(b), 4); // one arrive per softmax warp
+            mbar_init(ofull_bar(b), 1);
+            mbar_init(sfree_bar(b), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == ATC_W_ALLOC)
+    {
+        tmem_alloc(base + ATL_OFF_TMEM_PTR, 512);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    griddep_launch_dependents();
+    griddep_wait();
+
+    if (warp < 4)
+    {
+        // the softmax warps keep 64 output accumulators per thread on top of a score chunk: they take the registers
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == ATC_W_PRODUCER)
+        {
+            if (lane == 0)
+            {
+                const uint32_t tx_kv = (uint32_t)(2 * p.kb * 128);
+                int st = 0;
+                for (int ii = 0; ii < n_it; ii++)
+                {
+                    const int item = blockIdx.x + ii * gridDim.x;
+                    const int bh = item / p.n_qpairs, qp = item - bh * p.n_qpairs;
+                    const int b = bh / p.heads, h = bh - b * p.heads;
+                    const int row = b * p.tokens, nt = tiles_of(ii), qb = ii & 1;
+                    mbar_wait(qempty_bar(qb), ((uint32_t)(ii >> 1) & 1u) ^ 1u, p.error_flag, KERR_ATT_PRODUCER);
+                    mbar_arrive_expect_tx(qfull_bar(qb), (uint32_t)(nt * ATC_Q_BYTES));
+                    for (int t = 0; t < nt; t++)
+                        tma_load_2d(base + (qb * 2 + t) * ATC_Q_BYTES, &tma_q, qfull_bar(qb), h * ATT_HD, row + (2 * qp + t) * 128);
+                    for (int kbi = 0; kbi < p.n_kb; kbi++, st++)
+                    {
+                        const int sb = st & 1;
+                        mbar_wait(kvempty_bar(sb), ((uint32_t)(st >> 1) & 1u) ^ 1u, p.error_flag, KERR_ATT_PRODUCER);
+                        mbar_arrive_expect_tx(kvfull_bar(sb), tx_kv);
+                        const uint32_t dst = base + ATL_OFF_KV + sb * 2 * ATC_KV_BYTES;
+                        tma_load_2d(dst, &tma_kv, kvfull_bar(sb), D + h * ATT_HD, row + kbi * p.kb);
+                        tma_load_2d(dst + ATC_KV_BYTES, &tma_kv, kvfull_bar(sb), 2 * D + h * ATT_HD, row + kbi * p.kb);
+                    }
+                }
+            }
+        }
+        else if (warp == ATC_W_MMA)
+        {
+            // one thread serves both query tiles and polls, per tile, "S of the next key block may start" / "P is ready"
+            if (lane == 0)
+            {
+                const uint32_t idesc_s = umma_idesc(1, 1, 128, (uint32_t)p.kb);
+                const uint32_t idesc_o = umma_idesc(1, 1, 128, ATT_HD) | UMMA_IDESC_B_MN_MAJOR;
+                const int ksteps = p.kb / 16, n_steps = n_it * p.n_kb;
+                int s_step[2] = {0, 0}, pv_step[2] = {0, 0}; // next step (item-major, key block minor) per tile
+                uint32_t cnt_s[2] = {0, 0}, cnt_pv[2] = {0, 0}; // steps the tile really took part in (barrier phases)
+                long long t0 = clock64();
+                while (pv_step[0] < n_steps || pv_step[1] < n_steps)
+                {
+                    bool progress = false;
+#pragma unroll
+                    for (int t = 0; t < 2; t++)
+                    {
+                        if (s_step[t] < n_steps && pv_step[t] == s_step[t])
+                        {
+                            const int step = s_step[t], ii = step / p.n_kb, kbi = step - ii * p.n_kb, sb = step & 1, qb = ii & 1;
+                            if (t == 1 && tiles_of(ii) < 2)
+                            {
+                                // tile 1 does not exist in this item: pass, and release what only waited for it
+                                s_step[1]++, pv_step[1]++;
+                                if (kbi == p.n_kb - 1 && s_step[0] > step) tcgen05_commit(qempty_bar(qb));
+                                if (pv_step[0] > step) tcgen05_commit(kvempty_bar(sb));
+                                progress = true;
+                            }
+                            else if (mbar_test_wait(kvfull_bar(sb), (uint32_t)(step >> 1) & 1u) && mbar_test_wait(qfull_bar(qb), (uint32_t)(ii >> 1) & 1u) &&
+                                     mbar_test_wait(sfree_bar(t), (cnt_s[t] & 1u) ^ 1u))
+                            {
+                                tcgen05_fence_after();
+                                const uint64_t q_desc = umma_smem_desc_sw128(base + (qb * 2 + t) * ATC_Q_BYTES);
+                                const uint64_t k_desc = umma_smem_desc_sw128(base + ATL_OFF_KV + sb * 2 * ATC_KV_BYTES);
+#pragma unroll
+                                for (int k = 0; k < 4; k++)
+                                    umma_ss<KIND_BF16>(tmem_base + t * ATC_REGION_COLS, q_desc + 2u * k, k_desc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+                                tcgen05_commit(sfull_bar(t));
+                                s_step[t]++, cnt_s[t]++;
+                                if (kbi == p.n_kb - 1 && s_step[t ^ 1] > step) tcgen05_commit(qempty_bar(qb)); // last use of the Q tiles
+                                progress = true;
+                            }
+                        }
+                        if (pv_step[t] < s_step[t])
+                        {
+                            const int step = pv_step[t], sb = step & 1;
+                            if (mbar_test_wait(pfull_bar(t), cnt_pv[t] & 1u))
+                            {
+                                tcgen05_fence_after();
+                                const uint64_t v_desc = umma_smem_desc_sw128(base + ATL_OFF_KV + sb * 2 * ATC_KV_BYTES + ATC_KV_BYTES);
+                                const uint32_t region = tmem_base + t * ATC_REGION_COLS;
+                                for (int k = 0; k < ksteps; k++)
+                                    umma_ts_bf16(region + ATC_O_COL, region + 8u * k, v_desc + (uint64_t)(128u * k), idesc_o, k != 0 ? 1u : 0u);
+                                tcgen05_commit(ofull_bar(t));
+                                pv_step[t]++, cnt_pv[t]++;
+                                if (pv_step[t ^ 1] > step) tcgen05_commit(kvempty_bar(sb)); // both tiles are done with this K / V block
+                                progress = true;
+                            }
+                        }
+                    }
+                    if (progress)
+                        t0 = clock64();
+                    else if (clock64() - t0 > 8000000000LL)
+                    {
+                        if (p.error_flag) atomicExch(p.error_flag, KERR_ATT_MMA_FULL);
+                        __threadfence_system();
+                        __trap();
+                    }
+                }
+            }
+        }
+    }
+    else
+    {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        // ===================== softmax + output warpgroups (one per query tile of the pair) =====================
+        const int t = (warp - 4) >> 2;
+        const int q = warp & 3;
+        const uint32_t region = tmem_base + ((uint32_t)(q * 32) << 16) + t * ATC_REGION_COLS;
+        const float sl = 0.125f * 1.4426950408889634f; // 1/sqrt(64) * log2(e)
+        const int kchunks = (p.kb + 31) >> 5;          // 32-key chunks of a block (P is written for all of them)
+        uint32_t cnt = 0;                              // steps this tile took part in (barrier phase)
+        for (int ii = 0; ii < n_it; ii++)
+        {
+            if (t >= tiles_of(ii)) continue;
+            const int item = blockIdx.x + ii * gridDim.x;
+            const int bh = item / p.n_qpairs, qp = item - bh * p.n_qpairs;
+            const int b = bh / p.heads, h = bh - b * p.heads;
+            const int qrow = (2 * qp + t) * 128 + q * 32 + lane; // query row within the image
+            float o[64];
+#pragma unroll
+            for (int j = 0; j < 64; j++) o[j] = 0.0f;
+            float m_run = -INFINITY, l_run = 0.0f;
+            for (int kbi = 0; kbi < p.n_kb; kbi++, cnt++)
+            {
+                const uint32_t ph = cnt & 1u;
+                const int valid_keys = min(p.kb, p.tokens - kbi * p.kb); // >= 1 by construction of n_kb
+                const int nfull = valid_keys >> 5, tail = valid_keys & 31;
+                const int nchunks = nfull + (tail ? 1 : 0);
+                mbar_wait(sfull_bar(t), ph, p.error_flag, KERR_ATT_WG_SFULL);
+                tcgen05_fence_after();
+                // pass 1: block maximum over the valid keys
+                float bmax = -INFINITY;
+                for (int c = 0; c < nchunks; c++)
+                {
+                    uint32_t v[32];
+                    tmem_ld_32x32(region + c * 32, v);
+                    tmem_ld_wait();
+                    const int lim = c < nfull ? 32 : tail;
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (j < lim) bmax = fmaxf(bmax, __uint_as_float(v[j]));
+                }
+                const float m_new = fmaxf(m_run, bmax);
+                const float alpha = ex2_approx((m_run - m_new) * sl); // 0 for the first block (m_run = -inf)
+                const float msc = m_new * sl;
+                m_run = m_new;
+                // pass 2: p = 2^((s - m) * scale), bf16 P over the S columns; fully masked chunks are written as zeros
+                float sum0 = 0.0f, sum1 = 0.0f;
+                for (int c = 0; c < kchunks; c++)
+                {
+                    uint32_t w[16];
+                    if (c < nchunks)
+                    {
+                        uint32_t v[32];
+                        tmem_ld_32x32(region + c * 32, v);
+                        tmem_ld_wait();
+                        const int lim = c < nfull ? 32 : tail;
+#pragma unroll
+                        for (int j = 0; j < 16; j++)
+                        {
+                            const float p0 = (2 * j < lim) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl, -msc)) : 0.0f;
+                            const float p1 = (2 * j + 1 < lim) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl, -msc)) : 0.0f;
+                            sum0 += p0, sum1 += p1;
+                            w[j] = pack_bf16x2(p0, p1);
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) w[j] = 0u;
+                    }
+                    tmem_st_32x16(region + c * 16, w);
+                }
+                l_run = fmaf(l_run, alpha, sum0 + sum1);
+                tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pfull_bar(t));
+
+                // O = O * alpha + P.V_blk
+                mbar_wait(ofull_bar(t), ph, p.error_flag, KERR_ATT_WG_OFULL);
+                tcgen05_fence_after();
+                uint32_t ob[64];
+                tmem_ld_32x32(region + ATC_O_COL, ob);
+                tmem_ld_32x32(region + ATC_O_COL + 32, ob + 32);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sfree_bar(t)); // region t may be overwritten by the next block's S
+#pragma unroll
+                for (int j = 0; j < 64; j++) o[j] = fmaf(o[j], alpha, __uint_as_float(ob[j]));
+            }
+            if (qrow < p.tokens)
+            {
+                const float inv = 1.0f / l_run;
+                uint4 *dst = reinterpret_cast<uint4 *>(p.out + ((long long)b * p.tokens + qrow) * D + h * ATT_HD);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                {
+                    uint4 pk;
+                    pk.x = pack_bf16x2(o[8 * j + 0] * inv, o[8 * j + 1] * inv);
+                    pk.y = pack_bf16x2(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
+                    pk.z = pack_bf16x2(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
+                    pk.w = pack_bf16x2(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
+                    dst[j] = pk;
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == ATC_W_ALLOC)
+    {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static cudaError_t launch_attention_tc_long(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag,
+                                            int num_sms)
+{
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATL_SMEM);
+    if (e != cudaSuccess) return e;
+    AttnLongParams p;
+    p.out = reinterpret_cast<__nv_bfloat16 *>(out);
+    p.batch = batch, p.tokens = tokens, p.heads = heads;
+    p.n_kb = (tokens + 255) / 256;                            // fewest blocks of at most 256 keys ...
+    p.kb = (((tokens + p.n_kb - 1) / p.n_kb) + 15) & ~15;     // ... of equal size, rounded up to the UMMA granularity
+    p.n_kb = (tokens + p.kb - 1) / p.kb;                      // (every block then holds at least one valid key)
+    p.n_qtiles = (tokens + 127) / 128;
+    p.n_qpairs = (p.n_qtiles + 1) / 2;
+    p.error_flag = error_flag;
+    const long long D = (long long)heads * ATT_HD, rows = (long long)batch * tokens;
+    CUtensorMap map_q, map_kv;
+    e = encode_tma_2d(&map_q, 2, qkv, 3 * D, rows, 3 * D * 2, ATT_HD, 128, true);
+    if (e != cudaSuccess) return e;
+    e = encode_tma_2d(&map_kv, 2, qkv, 3 * D, rows, 3 * D * 2, ATT_HD, p.kb, true);
+    if (e != cudaSuccess) return e;
+    const long long items = (long long)batch * heads * p.n_qpairs;
+    const int sms = num_sms > 0 ? num_sms : 148;
+    return launch_pdl(attention_tc_long_kernel, dim3((unsigned)(items < sms ? items : sms)), dim3(ATC_THREADS), (size_t)ATL_SMEM, stream, 1, map_q,
+                      map_kv, p);
+}
+
 static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag,
                                        int num_sms)
 {
@@ -615,6 +950,7 @@ cudaError_t launch_attention(const void *qkv, void *out, int batch, int tokens, 
     if (batch <= 0) return cudaSuccess;
     if (tokens <= 0 || heads <= 0 || heads > 65535 || batch > 65535) return cudaErrorInvalidValue;
     if (tokens <= 256 && variant == 0) return launch_attention_tc(qkv, out, batch, tokens, heads, stream, error_flag, num_sms);
+    if (variant == 0) return launch_attention_tc_long(qkv, out, batch, tokens, heads, stream, error_flag, num_sms);
     const int tpad = (tokens + 15) & ~15;
     const size_t smem = (size_t)tpad * 128 * 2;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
