@@ -16,7 +16,9 @@
 //      Measured alternatives (round 1, 256 x 12 x 197, us per launch): this two-pass softmax 126; a single-read
 //      softmax that keeps the row as fp16 differences in registers (setmaxnreg 232) 134; P through shared
 //      memory with an SS-mode P.V (single-buffered V) 171.  The kernel is paced by the TMEM read port and by
-//      the serial S -> softmax -> P.V -> O chain of each warpgroup, see tools/attn_timeline.py.
+//      the serial S -> softmax -> P.V -> O chain of each warpgroup, see tools/attn_timeline.py.  Issuing P.V in
+//      64-key groups while the softmax is still running (O moved to columns [192, 256)) was slower as well
+//      (147 us): the A-from-TMEM MMAs and the softmax's tcgen05.ld then compete for the TMEM read port.
 //  (2) attention_kernel (longer sequences, e.g. 577 tokens at 384 pixels): flash-style single pass with
 //      mma.sync m16n8k16 (bf16 in, fp32 accumulate), described below.
 //
