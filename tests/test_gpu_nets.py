@@ -172,6 +172,27 @@ def test_int8_small_bit_exact_all_activations(netcuda, oracle, torch_cuda):
         net.close()
 
 
+@pytest.mark.parametrize("batch", [1, 77, 128, 129])
+def test_int8_split_k_small_batch_bit_exact(netcuda, oracle, torch_cuda, batch):
+    """Up to 128 samples a long-K int8 layer is split along K over the whole GPU (int32 partial sums through TMA reduce-adds,
+    then a finalize kernel); 129 samples take the single-pass kernels.  Same integers either way, for every activation mode."""
+    rng = np.random.default_rng(40 + batch)
+    npl, n_ins = [1000, 2176, 12], 2176  # 17 and 8 k-blocks of 128 bytes; fan-outs that are not tile multiples
+    n_params = sum(a * b for a, b in zip([n_ins] + npl[:-1], npl))
+    wq = np.clip(np.rint(rng.standard_normal(n_params) * 4), -128, 127).astype(np.int8)
+    bq = rng.integers(-3000, 3000, sum(npl), dtype=np.int32)
+    xq = rng.integers(-128, 128, (batch, n_ins), dtype=np.int8)
+    for act in (0, 1, 2):
+        net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8, activation=act)
+        net.upload_mlp_i8(wq, bq)
+        want = oracle.mlp_forward_i8(xq, wq, bq, npl, n_ins, act)
+        np.testing.assert_array_equal(net.forward_i8(xq), want)
+        np.testing.assert_array_equal(net.forward_i8(xq), want)  # the workspace is left zeroed for the next call
+        net.set_gemm_variant(2)  # single-pass kernels only
+        np.testing.assert_array_equal(net.forward_i8(xq), want)
+        net.close()
+
+
 def test_int8_float_api_quantises_like_oracle(netcuda, oracle, torch_cuda):
     rng = np.random.default_rng(32)
     npl, n_ins = [96, 40], 72

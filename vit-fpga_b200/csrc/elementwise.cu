@@ -207,6 +207,43 @@ cudaError_t launch_pad_rows_i8(const int8_t *in, int8_t *out, long long rows, in
     return launch_convert<int8_t, 3>(in, out, rows, n, ld, stream);
 }
 
+__global__ void __launch_bounds__(256)
+splitk_finalize_kernel(int32_t *__restrict__ ws, const int32_t *__restrict__ bias, void *__restrict__ out, long long ldo, int out_is_s8, int relu,
+                       int m, int n)
+{
+    // 4 consecutive columns per thread: int4 in, one packed word (int8) or one int4 (int32) out
+    const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n4 = n >> 2;
+    if (i4 >= (long long)m * n4) return;
+    const int row = (int)(i4 / n4), col = (int)(i4 - (long long)row * n4) * 4;
+    int4 *wp = reinterpret_cast<int4 *>(ws + (long long)row * n + col);
+    const int4 a = *wp, b = *reinterpret_cast<const int4 *>(bias + col);
+    *wp = make_int4(0, 0, 0, 0);
+    int v[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+        if (relu) v[e] = max(v[e], 0);
+    if (out_is_s8)
+    {
+        uint32_t word = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) word |= ((uint32_t)min(127, max(-128, v[e] >> 7)) & 0xFFu) << (8 * e);
+        *reinterpret_cast<uint32_t *>(reinterpret_cast<int8_t *>(out) + (long long)row * ldo + col) = word;
+    }
+    else
+        *reinterpret_cast<int4 *>(reinterpret_cast<int32_t *>(out) + (long long)row * ldo + col) = make_int4(v[0], v[1], v[2], v[3]);
+}
+
+cudaError_t launch_splitk_finalize(int32_t *ws, const int32_t *bias, void *out, long long ldo, bool out_is_s8, bool relu, int m, int n,
+                                   cudaStream_t stream)
+{
+    if (m <= 0 || n <= 0) return cudaSuccess;
+    if ((n & 3) || (ldo & 3)) return cudaErrorInvalidValue;
+    const long long total = (long long)m * (n >> 2);
+    splitk_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ws, bias, out, ldo, out_is_s8 ? 1 : 0, relu ? 1 : 0, m, n);
+    return cudaGetLastError();
+}
+
 __global__ void dequant_q214_kernel(const int32_t *__restrict__ in, float *__restrict__ out, long long count)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -143,6 +143,7 @@ static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
     p.bias = c.bias, p.out = c.out, p.ldc = c.ldc, p.epi = c.epi;
     p.remap_in = c.remap_in, p.remap_out = c.remap_out, p.pos = c.pos;
     p.error_flag = c.error_flag;
+    p.k_splits = c.k_splits > 1 ? c.k_splits : 1;
     p.debug = nullptr;
     if (const char *dbg = getenv("NETCUDA_GEMM_DEBUG_PTR")) p.debug = reinterpret_cast<long long *>(strtoull(dbg, nullptr, 0));
     // TMA-store epilogue whenever the output is addressable by a tensor map; otherwise direct stores
@@ -159,7 +160,8 @@ static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
     }
     else
         map_out = map_a; // never dereferenced
-    const int tiles = ((c.m + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * ((c.n + BN - 1) / BN);
+    if (p.k_splits > 1 && !(p.tma_store && OUT == OUT_S32 && c.epi == EPI_SPLITK)) return cudaErrorInvalidValue;
+    const int tiles = ((c.m + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * ((c.n + BN - 1) / BN) * p.k_splits;
     const int sms = c.num_sms > 0 ? c.num_sms : 148;
     const int slots = sms / CG; // tiles in flight: one per CTA, or one per CTA pair
     return launch_pdl(gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES, CG, EW>, dim3((unsigned)(CG * (tiles < slots ? tiles : slots))),

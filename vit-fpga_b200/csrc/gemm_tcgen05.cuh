@@ -48,7 +48,8 @@ enum : int
     EPI_RESIDUAL = 3, // out(fp32) += acc + bias
     EPI_REQUANT = 4,  // int8: q = clamp(relu?(acc + bias) >> 7)
     EPI_REQUANT_RELU = 5,
-    EPI_PATCH = 6 // fp32 out with row remap + position embedding (patch embedding)
+    EPI_PATCH = 6, // fp32 out with row remap + position embedding (patch embedding)
+    EPI_SPLITK = 7 // int32 out: this CTA's K slice is ADDED to the output (TMA reduce-add), no bias -- see GemmParams::k_splits
 };
 
 struct GemmParams
@@ -59,6 +60,10 @@ struct GemmParams
     long long ldc;
     int epi;
     int tma_store; // 1: epilogue through smem slabs + TMA store (tma_out valid); 0: direct stores
+    // Split-K (integer kinds, few tiles, long K: weight streaming at small batch): every tile is computed by k_splits CTAs,
+    // each over a contiguous range of k-blocks, and the partial sums meet in the int32 output through TMA reduce-adds
+    // (exact and order-independent for integers).  The caller zeroes the output first and applies bias / requantisation after.
+    int k_splits;
     // EPI_PATCH: input row r = b * remap_in + t  ->  output row b * remap_out + 1 + t, and
     // pos[(1 + t) * N + col] is added (cls token occupies output row b * remap_out).
     int remap_in, remap_out;
@@ -323,6 +328,8 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     const int tiles_n = (p.N + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (p.K + BK - 1) / BK;
+    const int S = p.k_splits > 1 ? p.k_splits : 1;
+    const int num_work = num_tiles * S; // work item = (tile, K slice); K slice fastest
     const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0; // 0 = leader of the pair
     const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG; // both CTAs of a pair walk the same tiles
 
@@ -381,11 +388,13 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         if (lane == 0)
         {
             uint32_t stage = 0, phase = 0;
-            for (int tile = tile0; tile < num_tiles; tile += tile_step)
+            for (int work = tile0; work < num_work; work += tile_step)
             {
                 // n-fastest tile order: the CTAs of one wave share a few A row-blocks and all of W in L2
+                const int tile = work / S, ks = work - tile * S;
                 const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
-                for (int kb = 0; kb < num_kb; kb++)
+                const int kb0 = ks * num_kb / S, kb1 = (ks + 1) * num_kb / S;
+                for (int kb = kb0; kb < kb1; kb++)
                 {
                     mbar_wait(empty_bar(stage), phase ^ 1u, p.error_flag, KERR_PRODUCER_EMPTY);
                     const uint32_t a_dst = base + stage * L::STAGE_BYTES;
@@ -417,16 +426,17 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         if (lane == 0 && cta_rank == 0)
         {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int tile = tile0; tile < num_tiles; tile += tile_step)
+            for (int work = tile0; work < num_work; work += tile_step)
             {
-                int tl = (tile - tile0) / tile_step;
+                const int ks = work % S, kb0 = ks * num_kb / S, kb1 = (ks + 1) * num_kb / S;
+                int tl = (work - tile0) / tile_step;
                 const bool dbg = p.debug != nullptr && tile0 == 0 && tl < 40;
                 if (dbg) p.debug[(tl * 24 + 11) * 4 + 0] = clock64();
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.error_flag, KERR_MMA_TMEM_EMPTY);
                 tcgen05_fence_after();
                 if (dbg) p.debug[(tl * 24 + 11) * 4 + 1] = clock64();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_kb; kb++)
+                for (int kb = kb0; kb < kb1; kb++)
                 {
                     mbar_wait(full_bar(stage), phase, p.error_flag, KERR_MMA_FULL);
                     tcgen05_fence_after();
@@ -437,9 +447,9 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                     for (int k = 0; k < 4; k++) // 4 x 32 bytes of K per stage; +2 = 32 B >> 4
                     {
                         if constexpr (CG == 2)
-                            umma_ss_pair<KIND>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                            umma_ss_pair<KIND>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, IDESC, (kb != kb0 || k != 0) ? 1u : 0u);
                         else
-                            umma_ss<KIND>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                            umma_ss<KIND>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, IDESC, (kb != kb0 || k != 0) ? 1u : 0u);
                     }
                     // frees the smem slot (in both CTAs of a pair) once these MMAs retire
                     if constexpr (CG == 2)
@@ -479,8 +489,9 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         uint8_t *slab = smem + L::OFF_SLABS + ew * GEMM_SLAB_BYTES;
         const uint32_t slab_addr = base + L::OFF_SLABS + ew * GEMM_SLAB_BYTES;
         uint32_t acc = 0, acc_phase = 0, parity = 0;
-        for (int tile = tile0; tile < num_tiles; tile += tile_step, parity ^= 1u)
+        for (int work = tile0; work < num_work; work += tile_step, parity ^= 1u)
         {
+            const int tile = work / S;
             const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
             const int col0 = n_blk * BN;
             const int row0 = m_blk * TILE_M + cta_rank * GEMM_BM + q * 32;
@@ -494,7 +505,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             }
             named_bar_sync(1, 32 * EW);
 
-            const int tl = (tile - tile0) / tile_step;
+            const int tl = (work - tile0) / tile_step;
             const bool dbg = p.debug != nullptr && tile0 == 0 && tl < 40 && lane == 0 && warp < 11;
             long long *dslot = p.debug + (tl * 24 + cta_rank * 12 + warp) * 4;
             if (dbg) dslot[0] = clock64();
@@ -541,7 +552,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                     __syncwarp();
                     if (lane == 0)
                     {
-                        if (epi == EPI_RESIDUAL)
+                        if (epi == EPI_RESIDUAL || epi == EPI_SPLITK)
                             tma_reduce_add_2d(&tma_out, slab_addr, col0 + scol, row0);
                         else
                             tma_store_2d(&tma_out, slab_addr, col0 + scol, row0);

@@ -57,6 +57,7 @@ struct GemmCall
     int out_type;            // OUT_* (gemm_tcgen05.cuh)
     int epi;                 // EPI_*
     int m, n, k;
+    int k_splits;            // > 1: split-K with reduce-add into an int32 output (epi must be EPI_SPLITK), see gemm_tcgen05.cuh
     int remap_in, remap_out; // EPI_PATCH
     const float *pos;
     int *error_flag;
@@ -93,6 +94,10 @@ cudaError_t launch_convert_rows_bf16(const float *in, void *out, long long rows,
 cudaError_t launch_convert_rows_f32(const float *in, float *out, long long rows, int n, int ld, cudaStream_t stream);
 cudaError_t launch_quantize_rows_q17(const float *in, int8_t *out, long long rows, int n, int ld, cudaStream_t stream);
 cudaError_t launch_pad_rows_i8(const int8_t *in, int8_t *out, long long rows, int n, int ld, cudaStream_t stream);
+// Second half of a split-K int8 layer: v = ws + bias (optionally max(v, 0)); out = int8 requantisation (clamp(v >> 7)) or the
+// int32 itself; ws is set back to zero for the next layer.
+cudaError_t launch_splitk_finalize(int32_t *ws, const int32_t *bias, void *out, long long ldo, bool out_is_s8, bool relu, int m, int n,
+                                   cudaStream_t stream);
 // out_f32 = (float)acc * 2^-14   (INT8 nets through the float API)
 cudaError_t launch_dequant_q214(const int32_t *in, float *out, long long count, cudaStream_t stream);
 
