@@ -368,3 +368,37 @@ def test_per_kernel_profile_api(netcuda, torch_cuda):
     assert abs(flops - 8 * net.flops_per_sample) / flops < 1e-9  # the labels add up to the advertised FLOPs per sample
     assert net.profile_read() == {}
     net.close()
+
+
+def test_small_mlp_pass_graph_replay(netcuda, oracle, torch_cuda):
+    """Small passes of deeper MLPs are replayed from a CUDA graph while the caller presents the same buffers; new buffers, a new
+    batch size or the default (uncapturable) stream must all still give the oracle's integers."""
+    torch = torch_cuda
+    rng = np.random.default_rng(77)
+    npl, n_ins = [256, 192, 128, 96, 64], 320
+    n_params = sum(a * b for a, b in zip([n_ins] + npl[:-1], npl))
+    wq = np.clip(np.rint(rng.standard_normal(n_params) * 6), -128, 127).astype(np.int8)
+    bq = rng.integers(-3000, 3000, sum(npl), dtype=np.int32)
+    net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8)
+    net.upload_mlp_i8(wq, bq)
+    side = torch.cuda.Stream()
+    bufs = [(torch.from_numpy(rng.integers(-128, 128, (b, n_ins), dtype=np.int8)).cuda(), torch.empty((b, 64), dtype=torch.int32, device="cuda"))
+            for b in (33, 33, 200)]
+    torch.cuda.synchronize()
+    for stream in (side, torch.cuda.current_stream()):
+        for rep in range(3):
+            for x, y in bufs:  # alternating buffers: capture, replace, capture again ...
+                with torch.cuda.stream(stream):
+                    y.zero_()
+                    net.forward_device_i8(x, y, x.shape[0], stream)
+                    net.forward_device_i8(x, y, x.shape[0], stream)  # ... and an immediate replay
+                    got = y.cpu().numpy()
+                np.testing.assert_array_equal(got, oracle.mlp_forward_i8(x.cpu().numpy(), wq, bq, npl, n_ins))
+    x, y = bufs[0]
+    x.copy_(torch.from_numpy(rng.integers(-128, 128, (33, n_ins), dtype=np.int8)).cuda())  # same buffer, new contents
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        net.forward_device_i8(x, y, 33, side)
+        got = y.cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.mlp_forward_i8(x.cpu().numpy(), wq, bq, npl, n_ins))
+    net.close()
