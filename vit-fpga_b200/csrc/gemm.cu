@@ -141,6 +141,8 @@ static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
     GemmParams p;
     p.M = c.m, p.N = c.n, p.K = c.k;
     p.bias = c.bias, p.out = c.out, p.ldc = c.ldc, p.epi = c.epi;
+    static const bool gelu_scalar = getenv("NETCUDA_GELU_SCALAR") != nullptr; // A/B switch: one element per FFMA chain
+    if (OUT == OUT_BF16 && c.epi == EPI_GELU && !gelu_scalar) p.epi = EPI_GELU_X2;
     p.remap_in = c.remap_in, p.remap_out = c.remap_out, p.pos = c.pos;
     p.error_flag = c.error_flag;
     p.k_splits = c.k_splits > 1 ? c.k_splits : 1;

@@ -49,7 +49,8 @@ enum : int
     EPI_REQUANT = 4,  // int8: q = clamp(relu?(acc + bias) >> 7)
     EPI_REQUANT_RELU = 5,
     EPI_PATCH = 6, // fp32 out with row remap + position embedding (patch embedding)
-    EPI_SPLITK = 7 // int32 out: this CTA's K slice is ADDED to the output (TMA reduce-add), no bias -- see GemmParams::k_splits
+    EPI_SPLITK = 7, // int32 out: this CTA's K slice is ADDED to the output (TMA reduce-add), no bias -- see GemmParams::k_splits
+    EPI_GELU_X2 = 8 // EPI_GELU evaluated two elements at a time on the packed fp32 pipe (same bits; chosen by the launcher)
 };
 
 struct GemmParams
@@ -152,7 +153,7 @@ struct KindTraits<KIND_I8>
 __device__ __forceinline__ float epi_act_f32(float v, int epi)
 {
     if (epi == EPI_RELU) return fmaxf(v, 0.0f);
-    if (epi == EPI_GELU) return gelu_erf(v);
+    if (epi == EPI_GELU || epi == EPI_GELU_X2) return gelu_erf(v); // (the packed form lives in epi_convert_chunk)
     return v;
 }
 
@@ -226,33 +227,50 @@ __device__ __forceinline__ void epi_convert32(const uint32_t *v, const uint32_t 
 }
 
 // The same for the 16 / sizeof(out) columns that make one 16-byte chunk of an output row (8 bf16, 4 fp32 / int32, 16 int8):
-// `v` holds that many accumulator columns, `w` receives the 4 packed words.
+// `v` holds that many accumulator columns, `b` the matching bias words (already in registers: the caller reads them from smem
+// before it waits for the accumulator columns, so their latency hides behind the TMEM load); returns the 4 packed words.
+template <int N>
+__device__ __forceinline__ void load_bias_chunk(const uint32_t *bias, uint32_t (&b)[N])
+{
+#pragma unroll
+    for (int i = 0; i < N / 4; i++)
+    {
+        const uint4 t = *reinterpret_cast<const uint4 *>(bias + 4 * i);
+        b[4 * i] = t.x, b[4 * i + 1] = t.y, b[4 * i + 2] = t.z, b[4 * i + 3] = t.w;
+    }
+}
+
 template <int OUT>
-__device__ __forceinline__ uint4 epi_convert_chunk(const uint32_t *v, const uint32_t *bias, int epi)
+__device__ __forceinline__ uint4 epi_convert_chunk(const uint32_t *v, const uint32_t *b, int epi)
 {
     uint4 w;
     if constexpr (OUT == OUT_F32)
     {
-        const uint4 b = *reinterpret_cast<const uint4 *>(bias);
-        w.x = __float_as_uint(epi_act_f32(__uint_as_float(v[0]) + __uint_as_float(b.x), epi));
-        w.y = __float_as_uint(epi_act_f32(__uint_as_float(v[1]) + __uint_as_float(b.y), epi));
-        w.z = __float_as_uint(epi_act_f32(__uint_as_float(v[2]) + __uint_as_float(b.z), epi));
-        w.w = __float_as_uint(epi_act_f32(__uint_as_float(v[3]) + __uint_as_float(b.w), epi));
+        w.x = __float_as_uint(epi_act_f32(__uint_as_float(v[0]) + __uint_as_float(b[0]), epi));
+        w.y = __float_as_uint(epi_act_f32(__uint_as_float(v[1]) + __uint_as_float(b[1]), epi));
+        w.z = __float_as_uint(epi_act_f32(__uint_as_float(v[2]) + __uint_as_float(b[2]), epi));
+        w.w = __float_as_uint(epi_act_f32(__uint_as_float(v[3]) + __uint_as_float(b[3]), epi));
     }
     else if constexpr (OUT == OUT_S32)
     {
-        const uint4 b = *reinterpret_cast<const uint4 *>(bias);
-        int a0 = (int)v[0] + (int)b.x, a1 = (int)v[1] + (int)b.y, a2 = (int)v[2] + (int)b.z, a3 = (int)v[3] + (int)b.w;
+        int a0 = (int)v[0] + (int)b[0], a1 = (int)v[1] + (int)b[1], a2 = (int)v[2] + (int)b[2], a3 = (int)v[3] + (int)b[3];
         if (epi == EPI_RELU) a0 = max(a0, 0), a1 = max(a1, 0), a2 = max(a2, 0), a3 = max(a3, 0);
         w = make_uint4((uint32_t)a0, (uint32_t)a1, (uint32_t)a2, (uint32_t)a3);
     }
     else if constexpr (OUT == OUT_BF16)
     {
-        const uint4 b0 = *reinterpret_cast<const uint4 *>(bias), b1 = *reinterpret_cast<const uint4 *>(bias + 4);
-        const uint32_t bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float f[8];
+        if (epi == EPI_GELU_X2)
+        {
 #pragma unroll
-        for (int e = 0; e < 8; e++) f[e] = epi_act_f32(__uint_as_float(v[e]) + __uint_as_float(bb[e]), epi);
+            for (int e = 0; e < 8; e += 2)
+                gelu_erf_x2(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(b[e]), __uint_as_float(b[e + 1]), f[e], f[e + 1]);
+        }
+        else
+        {
+#pragma unroll
+            for (int e = 0; e < 8; e++) f[e] = epi_act_f32(__uint_as_float(v[e]) + __uint_as_float(b[e]), epi);
+        }
         w = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
     }
     else
@@ -261,13 +279,11 @@ __device__ __forceinline__ uint4 epi_convert_chunk(const uint32_t *v, const uint
 #pragma unroll
         for (int j4 = 0; j4 < 4; j4++)
         {
-            const uint4 b = *reinterpret_cast<const uint4 *>(bias + 4 * j4);
-            const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
             word[j4] = 0;
 #pragma unroll
             for (int e = 0; e < 4; e++)
             {
-                int a = (int)v[4 * j4 + e] + (int)bb[e];
+                int a = (int)v[4 * j4 + e] + (int)b[4 * j4 + e];
                 if (epi == EPI_REQUANT_RELU) a = max(a, 0);
                 a = min(127, max(-128, a >> 7));
                 word[j4] |= ((uint32_t)a & 0xFFu) << (8 * e);
@@ -484,7 +500,6 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         const int ew = warp;              // 0..EW-1
         const int q = warp & 3;           // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
         const int wcol = (ew >> 2) * WARP_COLS; // first tile column of this warp
-        const int et = threadIdx.x;       // index among the epilogue threads
         uint32_t *bias_all = reinterpret_cast<uint32_t *>(smem + L::OFF_BIAS);
         uint8_t *slab = smem + L::OFF_SLABS + ew * GEMM_SLAB_BYTES;
         const uint32_t slab_addr = base + L::OFF_SLABS + ew * GEMM_SLAB_BYTES;
@@ -496,14 +511,18 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             const int col0 = n_blk * BN;
             const int row0 = m_blk * TILE_M + cta_rank * GEMM_BM + q * 32;
 
-            // this tile's bias slice (bit pattern: float or int32), shared by the epilogue warps
+            // This tile's bias slice (bit pattern: float or int32).  Every warp fetches the WARP_COLS values of its own column range
+            // into registers before it waits for the accumulator and parks them in smem afterwards (the four warps of a column
+            // range write identical words).  No barrier among the epilogue warps: once tfull(t) has completed, every warp has
+            // handed back the accumulator of tile t - 2, i.e. is done reading the slice of the same parity.
             uint32_t *bias_s = bias_all + parity * BN;
-            for (int i = et; i < BN; i += 32 * EW)
+            uint32_t bias_r[WARP_COLS / 32];
+#pragma unroll
+            for (int i = 0; i < WARP_COLS / 32; i++)
             {
-                const int c = col0 + i;
-                bias_s[i] = (p.bias != nullptr && c < p.N) ? reinterpret_cast<const uint32_t *>(p.bias)[c] : 0u;
+                const int c = col0 + wcol + i * 32 + lane;
+                bias_r[i] = (p.bias != nullptr && c < p.N) ? __ldg(reinterpret_cast<const uint32_t *>(p.bias) + c) : 0u;
             }
-            named_bar_sync(1, 32 * EW);
 
             const int tl = (work - tile0) / tile_step;
             const bool dbg = p.debug != nullptr && tile0 == 0 && tl < 40 && lane == 0 && warp < 11;
@@ -512,6 +531,9 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             mbar_wait(tfull_bar(acc), acc_phase, p.error_flag, KERR_EPI_TMEM_FULL);
             tcgen05_fence_after();
             if (dbg) dslot[1] = clock64();
+#pragma unroll
+            for (int i = 0; i < WARP_COLS / 32; i++) bias_s[wcol + i * 32 + lane] = bias_r[i];
+            __syncwarp();
             const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + wcol;
 
             if (p.tma_store)
@@ -533,20 +555,21 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                     const uint32_t t_slab = t_base + sb * SLAB_COLS;
                     const uint32_t *bias_slab = bias_s + scol;
                     uint8_t *row = slab + lane * SLAB_ROW_BYTES;
-                    uint32_t v0[CHUNK_COLS], v1[CHUNK_COLS];
+                    uint32_t v0[CHUNK_COLS], v1[CHUNK_COLS], b0[CHUNK_COLS], b1[CHUNK_COLS];
                     tmem_ld_32xN<CHUNK_COLS>(t_slab, v0);
 #pragma unroll 1
                     for (int j = 0; j < CHUNKS_PER_ROW; j += 2)
                     {
+                        load_bias_chunk<CHUNK_COLS>(bias_slab + j * CHUNK_COLS, b0);
+                        load_bias_chunk<CHUNK_COLS>(bias_slab + (j + 1) * CHUNK_COLS, b1);
                         tmem_ld_wait();
                         tmem_ld_32xN<CHUNK_COLS>(t_slab + (j + 1) * CHUNK_COLS, v1);
                         // lane = row; 16-byte chunk j of the row goes to chunk (j ^ (row & 7)) (128B swizzle)
-                        *reinterpret_cast<uint4 *>(row + ((SLAB_SWIZZLED ? (j ^ (lane & 7)) : j) << 4)) =
-                            epi_convert_chunk<OUT>(v0, bias_slab + j * CHUNK_COLS, epi);
+                        *reinterpret_cast<uint4 *>(row + ((SLAB_SWIZZLED ? (j ^ (lane & 7)) : j) << 4)) = epi_convert_chunk<OUT>(v0, b0, epi);
                         tmem_ld_wait();
                         if (j + 2 < CHUNKS_PER_ROW) tmem_ld_32xN<CHUNK_COLS>(t_slab + (j + 2) * CHUNK_COLS, v0);
                         *reinterpret_cast<uint4 *>(row + ((SLAB_SWIZZLED ? ((j + 1) ^ (lane & 7)) : (j + 1)) << 4)) =
-                            epi_convert_chunk<OUT>(v1, bias_slab + (j + 1) * CHUNK_COLS, epi);
+                            epi_convert_chunk<OUT>(v1, b1, epi);
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
