@@ -84,6 +84,13 @@ namespace cuda
         void filter_image(const net::image_set &set) override;
         net::image_set get_filtered_image() override;
 
+        // ---- weight files (netcuda.h, "weight files"): the flat layout of src/netFPGA.cpp:91-106 on disk ----
+        // Writes this net (the fp32 values it was constructed from) to `path`.
+        void save(const char *path) const;
+        // Builds the net a file describes.  options.precision < 0 = the file's natural precision
+        // (TF32 for an fp32 MLP file unless NETCUDA_PRECISION says otherwise, BF16 for a ViT).
+        static net_cuda load(const char *path, const net_cuda_options &options = net_cuda_options());
+
         // ---- extensions beyond the abstract interface ----
         // Batched forward on raw host buffers (pinned buffers are DMA'd in place).
         void forward(const DATA_TYPE *inputs, std::size_t batch, DATA_TYPE *outputs);

@@ -109,6 +109,47 @@ int netcuda_vit_param_count(const netcuda_desc *desc, size_t *count);
 /* Upload a ViT from that flat fp32 layout. */
 int netcuda_upload_vit(netcuda_t *h, const float *flat, size_t count);
 
+/* ---- weight files ------------------------------------------------------- *
+ * On-disk image of the flat in-memory layout the reference builds at src/netFPGA.cpp:91-106 (and that
+ * get_net_data, :206-237, is meant to invert), so that a net survives the process:
+ *
+ *   offset  0  char[8]  "NETCUDAW"
+ *           8  u32 version (1)      12  u32 kind (NETCUDA_KIND_*)   16  u32 dtype (NETCUDA_FILE_*)
+ *          20  u32 activation       24  u32 n_ins                   28  u32 n_layers
+ *          32  u32 image_size, patch_size, dim, depth, heads, mlp_dim, n_classes   (ViT; 0 for an MLP)
+ *          60  u32 reserved (0)     64  u64 n_weights               72  u64 n_biases
+ *          80  u32 crc32 (IEEE, of every byte after the 96-byte header)           84  12 bytes 0
+ *          96  i32 n_p_l[n_layers], zero-padded to a multiple of 16 bytes
+ *          ..  weights: n_weights elements (f32, or i8 for NETCUDA_FILE_Q17), zero-padded to 16 bytes;
+ *              MLP: all W[out][in] back to back; ViT: the flat vector of netcuda_vit_param_count
+ *          ..  biases: n_biases elements (f32, or i32 Q2.14 for NETCUDA_FILE_Q17); none for a ViT
+ * Little endian.  The file functions are pure host code (no GPU needed) except netcuda_create_from_file. */
+#define NETCUDA_FILE_F32 0 /* fp32 weights and biases                   */
+#define NETCUDA_FILE_Q17 1 /* int8 Q1.7 weights, int32 Q2.14 biases     */
+#define NETCUDA_FILE_MAX_LAYERS 64
+
+typedef struct netcuda_file_info
+{
+    netcuda_desc desc; /* kind, activation, n_ins, n_layers, ViT dims; precision = the file's natural one
+                          (INT8 for Q17, BF16 for a ViT, TF32 for an fp32 MLP); n_p_l points at n_p_l below */
+    int32_t n_p_l[NETCUDA_FILE_MAX_LAYERS];
+    int32_t dtype; /* NETCUDA_FILE_* */
+    uint64_t n_weights, n_biases;
+} netcuda_file_info;
+
+int netcuda_file_write_mlp(const char *path, const int32_t *n_p_l, int n_layers, int n_ins, int activation,
+                           const float *w_flat, const float *b_flat);
+int netcuda_file_write_mlp_i8(const char *path, const int32_t *n_p_l, int n_layers, int n_ins, int activation,
+                              const int8_t *w_flat, const int32_t *b_flat);
+int netcuda_file_write_vit(const char *path, const netcuda_desc *desc, const float *flat, size_t count);
+/* Header only (validates magic, version, sizes against the file length). */
+int netcuda_file_info_read(const char *path, netcuda_file_info *info);
+/* Payload into caller buffers of exactly n_weights / n_biases elements of the file's dtype; checks the CRC. */
+int netcuda_file_read(const char *path, void *weights, size_t weight_bytes, void *biases, size_t bias_bytes);
+/* netcuda_create + upload from a file.  precision < 0 = the file's natural precision (an fp32 MLP file can be
+ * opened as FP32 / TF32 / BF16 / INT8, a Q17 file only as INT8, a ViT only as BF16); max_batch 0 = default. */
+int netcuda_create_from_file(const char *path, int precision, int device, int max_batch, netcuda_t **out);
+
 /* ---- forward ---------------------------------------------------------------------------- */
 
 /* Host-to-host forward: `in` holds batch*n_in floats, `out` receives batch*n_out floats.

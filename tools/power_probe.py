@@ -45,6 +45,8 @@ ops = {
     "cublas_fc2_shape": (lambda: torch.matmul(hid, w_fc2.t(), out=att), 2.0 * M * F * D),
     "cublas_qkv_shape": (lambda: torch.matmul(y, w_qkv.t(), out=qkv), 2.0 * M * 3 * D * D),
 }
+if os.environ.get("PROBE_ONLY"):
+    ops = {k: ops[k] for k in os.environ["PROBE_ONLY"].split(",")}
 out = {}
 dur = float(os.environ.get("PROBE_SECONDS", "1.5"))
 for name, (fn, flops) in ops.items():
@@ -70,7 +72,7 @@ for name, (fn, flops) in ops.items():
     time.sleep(0.3)
 proc.terminate()
 step = {"qkv": 24, "fc1_gelu": 24, "fc2_residual": 24, "proj_residual": 24, "attention": 24, "layernorm": 48}
-if all(out[k]["mj_per_launch"] for k in step):
+if all(k in out and out[k]["mj_per_launch"] for k in step):
     tot = sum(out[k]["mj_per_launch"] * v for k, v in step.items()) / 1e3
     print("joules per 1024-image step (sum of kernel classes):", round(tot, 2), {k: round(out[k]["mj_per_launch"] * v / 1e3, 2) for k, v in step.items()})
     print("time per step if run back to back at these sustained rates (ms):", round(sum(out[k]["us"] * v for k, v in step.items()) / 1e3, 2))

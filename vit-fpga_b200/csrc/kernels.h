@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <cstdarg>
+
 namespace nc
 {
 
@@ -100,5 +102,8 @@ cudaError_t launch_splitk_finalize(int32_t *ws, const int32_t *bias, void *out, 
                                    cudaStream_t stream);
 // out_f32 = (float)acc * 2^-14   (INT8 nets through the float API)
 cudaError_t launch_dequant_q214(const int32_t *in, float *out, long long count, cudaStream_t stream);
+
+// Sets the calling thread's netcuda_last_error() text and returns `code` (runtime.cu; shared with weights_io.cu).
+int set_last_error_v(int code, const char *fmt, va_list ap);
 
 } // namespace nc

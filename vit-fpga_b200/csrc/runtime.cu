@@ -33,11 +33,17 @@ using namespace nc;
 
 static thread_local char g_last_error[512] = "";
 
+int nc::set_last_error_v(int code, const char *fmt, va_list ap)
+{
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    return code;
+}
+
 static int fail(int code, const char *fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
-    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    nc::set_last_error_v(code, fmt, ap);
     va_end(ap);
     return code;
 }

@@ -94,6 +94,38 @@ void *nch_vit_create(int image_size, int patch_size, int dim, int depth, int hea
     }
 }
 
+// net_cuda::save / net_cuda::load (weight files).  nch_load returns a net behind net::net_abstract*, or NULL.
+int nch_save(void *net, const char *path)
+{
+    try
+    {
+        cuda::net_cuda *n = dynamic_cast<cuda::net_cuda *>(static_cast<net::net_abstract *>(net));
+        if (!n) return 10;
+        n->save(path);
+        return 0;
+    }
+    catch (const std::exception &e)
+    {
+        set_err(e.what());
+        return 1;
+    }
+}
+
+void *nch_load(const char *path, int precision, int device, int max_batch, size_t *n_in, size_t *n_out)
+{
+    try
+    {
+        cuda::net_cuda *n = new cuda::net_cuda(cuda::net_cuda::load(path, make_opt(precision, device, 0, max_batch)));
+        *n_in = n->n_in(), *n_out = n->n_out();
+        return static_cast<net::net_abstract *>(n);
+    }
+    catch (const std::exception &e)
+    {
+        set_err(e.what());
+        return nullptr;
+    }
+}
+
 void nch_destroy(void *net) { delete static_cast<net::net_abstract *>(net); }
 
 // launch_forward through the vtable; returns the number of outputs, or -1 on error.

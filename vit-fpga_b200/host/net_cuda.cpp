@@ -178,6 +178,69 @@ namespace cuda
         }
     }
 
+    void net_cuda::save(const char *path) const
+    {
+        if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        int rc;
+        if (p_->is_vit)
+        {
+            netcuda_desc d;
+            std::memset(&d, 0, sizeof(d));
+            d.kind = NETCUDA_KIND_VIT, d.precision = NETCUDA_PREC_BF16;
+            d.image_size = (int32_t)p_->vit.image_size, d.patch_size = (int32_t)p_->vit.patch_size;
+            d.dim = (int32_t)p_->vit.dim, d.depth = (int32_t)p_->vit.depth, d.heads = (int32_t)p_->vit.heads;
+            d.mlp_dim = (int32_t)p_->vit.mlp_dim, d.n_classes = (int32_t)p_->vit.n_classes;
+            rc = netcuda_file_write_vit(path, &d, p_->vit.params.data(), p_->vit.params.size());
+        }
+        else
+            rc = netcuda_file_write_mlp(path, p_->n_p_l.data(), (int)p_->n_p_l.size(), (int)p_->n_ins, p_->opt.activation,
+                                        p_->params.data(), p_->bias.data());
+        if (rc != NETCUDA_OK) throw_last("net_cuda::save", rc);
+    }
+
+    net_cuda net_cuda::load(const char *path, const net_cuda_options &options)
+    {
+        netcuda_file_info info;
+        int rc = netcuda_file_info_read(path, &info);
+        if (rc != NETCUDA_OK) throw_last("net_cuda::load", rc);
+        if (info.dtype != NETCUDA_FILE_F32)
+            throw std::invalid_argument("net_cuda::load: the file holds Q1.7 integers; net_cuda keeps DATA_TYPE (float) nets -- use netcuda_create_from_file");
+        std::vector<float> w((std::size_t)info.n_weights), b((std::size_t)info.n_biases);
+        rc = netcuda_file_read(path, w.data(), w.size() * sizeof(float), b.data(), b.size() * sizeof(float));
+        if (rc != NETCUDA_OK) throw_last("net_cuda::load", rc);
+        if (info.desc.kind == NETCUDA_KIND_VIT)
+        {
+            vit_data v;
+            v.image_size = (std::size_t)info.desc.image_size, v.patch_size = (std::size_t)info.desc.patch_size;
+            v.dim = (std::size_t)info.desc.dim, v.depth = (std::size_t)info.desc.depth, v.heads = (std::size_t)info.desc.heads;
+            v.mlp_dim = (std::size_t)info.desc.mlp_dim, v.n_classes = (std::size_t)info.desc.n_classes;
+            v.params.swap(w);
+            return net_cuda(v, options);
+        }
+        // back to the nested form the reference's constructor takes (def/defines.h:14-23)
+        net::net_data data;
+        data.n_ins = (std::size_t)info.desc.n_ins;
+        data.n_layers = (std::size_t)info.desc.n_layers;
+        std::size_t pc = 0, nc = 0, fan_in = data.n_ins;
+        for (int l = 0; l < info.desc.n_layers; l++)
+        {
+            const std::size_t fan_out = (std::size_t)info.n_p_l[l];
+            data.n_p_l.push_back(fan_out);
+            data.params.emplace_back();
+            data.bias.emplace_back();
+            for (std::size_t j = 0; j < fan_out; j++)
+            {
+                data.params[l].emplace_back(w.begin() + pc, w.begin() + pc + fan_in);
+                pc += fan_in;
+                data.bias[l].push_back(b[nc++]);
+            }
+            fan_in = fan_out;
+        }
+        net_cuda_options o = options;
+        o.activation = info.desc.activation;
+        return net_cuda(data, o, false);
+    }
+
     net_cuda::~net_cuda() { delete p_; }
 
     net_cuda::net_cuda(net_cuda &&rh) noexcept : p_(rh.p_) { rh.p_ = nullptr; }

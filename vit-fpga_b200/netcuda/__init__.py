@@ -40,6 +40,14 @@ class Desc(C.Structure):
                 ("heads", C.c_int32), ("mlp_dim", C.c_int32), ("n_classes", C.c_int32)]
 
 
+FILE_F32, FILE_Q17, FILE_MAX_LAYERS = 0, 1, 64
+
+
+class FileInfo(C.Structure):
+    _fields_ = [("desc", Desc), ("n_p_l", C.c_int32 * FILE_MAX_LAYERS), ("dtype", C.c_int32), ("n_weights", C.c_uint64),
+                ("n_biases", C.c_uint64)]
+
+
 class KernelStat(C.Structure):
     _fields_ = [("label", C.c_char * 32), ("launches", C.c_uint64), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
 
@@ -64,6 +72,7 @@ hostlib = _load("libnetcuda_host.so")
 hostlib.nch_last_error.restype = C.c_char_p
 hostlib.nch_mlp_create.restype = C.c_void_p
 hostlib.nch_vit_create.restype = C.c_void_p
+hostlib.nch_load.restype = C.c_void_p
 hostlib.nch_launch_forward.restype = C.c_longlong
 hostlib.nch_forward_us.restype = C.c_long
 hostlib.nch_gradient_us.restype = C.c_long
@@ -146,13 +155,63 @@ def vit_random_params(cfg: dict, seed: int = 0) -> np.ndarray:
     return flat
 
 
+# ---- weight files (host only: no GPU needed) -----------------------------------------------------------
+
+def _npl_arr(npl):
+    return (C.c_int32 * len(npl))(*[int(v) for v in npl])
+
+
+def file_write_mlp(path, npl, n_ins, w_flat, b_flat, activation=ACT_RELU_HIDDEN) -> None:
+    w = np.ascontiguousarray(w_flat, dtype=np.float32)
+    b = np.ascontiguousarray(b_flat, dtype=np.float32)
+    _check(lib.netcuda_file_write_mlp(os.fsencode(path), _npl_arr(npl), C.c_int(len(npl)), C.c_int(int(n_ins)), C.c_int(activation),
+                                      _ptr(w), _ptr(b)))
+
+
+def file_write_mlp_i8(path, npl, n_ins, wq, bq, activation=ACT_RELU_HIDDEN) -> None:
+    w = np.ascontiguousarray(wq, dtype=np.int8)
+    b = np.ascontiguousarray(bq, dtype=np.int32)
+    _check(lib.netcuda_file_write_mlp_i8(os.fsencode(path), _npl_arr(npl), C.c_int(len(npl)), C.c_int(int(n_ins)), C.c_int(activation),
+                                         _ptr(w), _ptr(b)))
+
+
+def file_write_vit(path, cfg: dict, flat) -> None:
+    f = np.ascontiguousarray(flat, dtype=np.float32)
+    d = Desc(kind=KIND_VIT, precision=PREC_BF16, **cfg)
+    _check(lib.netcuda_file_write_vit(os.fsencode(path), C.byref(d), _ptr(f), C.c_size_t(f.size)))
+
+
+def file_info(path) -> dict:
+    info = FileInfo()
+    _check(lib.netcuda_file_info_read(os.fsencode(path), C.byref(info)))
+    d = info.desc
+    out = dict(kind=d.kind, dtype=info.dtype, precision=d.precision, activation=d.activation, n_ins=d.n_ins,
+               npl=[int(info.n_p_l[i]) for i in range(d.n_layers)], n_weights=int(info.n_weights), n_biases=int(info.n_biases))
+    if d.kind == KIND_VIT:
+        out["cfg"] = {k: int(getattr(d, k)) for k in ("image_size", "patch_size", "dim", "depth", "heads", "mlp_dim", "n_classes")}
+    return out
+
+
+def file_read(path):
+    """(weights, biases) as numpy arrays of the file's dtype (biases is empty for a ViT)."""
+    info = file_info(path)
+    q = info["dtype"] == FILE_Q17
+    w = np.empty(info["n_weights"], dtype=np.int8 if q else np.float32)
+    b = np.empty(info["n_biases"], dtype=np.int32 if q else np.float32)
+    _check(lib.netcuda_file_read(os.fsencode(path), _ptr(w), C.c_size_t(w.nbytes), _ptr(b), C.c_size_t(b.nbytes)))
+    return w, b
+
+
 class Net:
     """One net on one GPU through the C ABI."""
 
-    def __init__(self, desc: Desc, keepalive=None):
+    def __init__(self, desc: Desc, keepalive=None, handle=None):
         self._h = C.c_void_p(0)
         self._keep = keepalive
-        _check(lib.netcuda_create(C.byref(desc), C.byref(self._h)))
+        if handle is not None:
+            self._h = handle
+        else:
+            _check(lib.netcuda_create(C.byref(desc), C.byref(self._h)))
         n = C.c_size_t(0)
         _check(lib.netcuda_n_in(self._h, C.byref(n)))
         self.n_in = n.value
@@ -172,6 +231,15 @@ class Net:
     def vit(cls, cfg: dict, device=0, max_batch=0) -> "Net":
         d = Desc(kind=KIND_VIT, precision=PREC_BF16, device=device, max_batch=max_batch, **cfg)
         return cls(d)
+
+    @classmethod
+    def from_file(cls, path, precision=-1, device=0, max_batch=0) -> "Net":
+        """netcuda_create_from_file: build the net a weight file describes and upload its weights."""
+        h = C.c_void_p(0)
+        _check(lib.netcuda_create_from_file(os.fsencode(path), C.c_int(precision), C.c_int(device), C.c_int(max_batch), C.byref(h)))
+        info = file_info(path)
+        d = Desc(kind=info["kind"], precision=info["precision"] if precision < 0 else precision)
+        return cls(d, handle=h)
 
     def close(self) -> None:
         if self._h:
@@ -326,6 +394,17 @@ class HostNet:
                                    C.c_int(cfg["heads"]), C.c_int(cfg["mlp_dim"]), C.c_int(cfg["n_classes"]), _ptr(f),
                                    C.c_size_t(f.size), C.c_int(device), C.c_int(max_batch))
         return cls(h, 3 * cfg["image_size"] ** 2, cfg["n_classes"])
+
+    @classmethod
+    def load(cls, path, precision=-1, device=0, max_batch=0) -> "HostNet":
+        """cuda::net_cuda::load: a net from a weight file."""
+        ni, no = C.c_size_t(0), C.c_size_t(0)
+        h = hostlib.nch_load(os.fsencode(path), C.c_int(precision), C.c_int(device), C.c_int(max_batch), C.byref(ni), C.byref(no))
+        return cls(h, ni.value, no.value)
+
+    def save(self, path) -> None:
+        if hostlib.nch_save(self._h, os.fsencode(path)) != 0:
+            raise RuntimeError("net_cuda::save failed: " + hostlib.nch_last_error().decode())
 
     def launch_forward(self, x) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float32).ravel()
