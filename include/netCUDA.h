@@ -94,6 +94,10 @@ namespace cuda
         // ---- extensions beyond the abstract interface ----
         // Batched forward on raw host buffers (pinned buffers are DMA'd in place).
         void forward(const DATA_TYPE *inputs, std::size_t batch, DATA_TYPE *outputs);
+        // Non-blocking forward (netcuda_submit / netcuda_wait): returns a ticket; the buffers must stay valid (and should be
+        // page-locked) until wait(ticket) returns.  Up to 4 calls in flight; the copy of call i+1 overlaps the kernels of call i.
+        std::uint64_t submit(const DATA_TYPE *inputs, std::size_t batch, DATA_TYPE *outputs);
+        void wait(std::uint64_t ticket);
         // Device-resident forward on `stream` (cudaStream_t as void*; nullptr = the net's stream).
         void forward_device(const void *d_inputs, std::size_t batch, void *d_outputs, void *stream = nullptr);
         std::size_t n_in() const;

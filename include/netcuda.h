@@ -159,6 +159,18 @@ int netcuda_create_from_file(const char *path, int precision, int device, int ma
  * Replaces the H2D / task / D2H triple at src/netFPGA.cpp:266-277. */
 int netcuda_forward(netcuda_t *h, const float *in, size_t batch, float *out);
 
+/* Asynchronous form of netcuda_forward: the reference chains write -> task -> read with events
+ * but then blocks in the read (src/netFPGA.cpp:273-277), so its caller can never overlap two samples.
+ * netcuda_submit enqueues the same H2D / kernels / D2H sequence and returns a ticket at once; the H2D copy of call
+ * i+1 runs on the copy engine while the kernels of call i execute.  `in` and `out` must stay valid until
+ * netcuda_wait(ticket) returns; they should be page-locked (cudaHostAlloc / cudaHostRegister) -- pageable buffers
+ * work but are staged with host memcpys inside submit / wait.  Up to 4 calls may be in flight per handle; a fifth
+ * submit first retires the oldest.  Tickets start at 1.  netcuda_query sets *done without blocking.
+ * One thread per handle (distinct handles may be driven from distinct threads). */
+int netcuda_submit(netcuda_t *h, const float *in, size_t batch, float *out, uint64_t *ticket);
+int netcuda_wait(netcuda_t *h, uint64_t ticket);
+int netcuda_query(netcuda_t *h, uint64_t ticket, int *done);
+
 /* Device-resident forward on `stream` (asynchronous; no host copies): the roofline path.
  * d_in: fp32 [batch][n_in], d_out: fp32 [batch][n_out]. */
 int netcuda_forward_device(netcuda_t *h, const void *d_in, size_t batch, void *d_out, void *stream);

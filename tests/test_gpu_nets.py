@@ -402,3 +402,69 @@ def test_small_mlp_pass_graph_replay(netcuda, oracle, torch_cuda):
         got = y.cpu().numpy()
     np.testing.assert_array_equal(got, oracle.mlp_forward_i8(x.cpu().numpy(), wq, bq, npl, n_ins))
     net.close()
+
+
+def test_async_submit_wait(netcuda, oracle, torch_cuda):
+    """netcuda_submit / netcuda_wait: calls in flight give exactly what the blocking call gives -- waited out of order,
+    with more submits than ring slots, with pinned and pageable buffers, with batches of one pass and of several."""
+    torch = torch_cuda
+    rng = np.random.default_rng(21)
+    npl, n_ins = [96, 48, 12], 200
+    w = rng.uniform(-1, 1, 200 * 96 + 96 * 48 + 48 * 12).astype(np.float32)
+    b = rng.uniform(-1, 1, sum(npl)).astype(np.float32)
+    net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_FP32, max_batch=64)
+    net.upload_mlp(w, b)
+    batches = [1, 64, 65, 200, 7, 130, 64, 3, 500]
+    xs = [rng.uniform(-1, 1, (n, n_ins)).astype(np.float32) for n in batches]
+    want = [oracle.mlp_forward(x, w, b, npl, n_ins) for x in xs]
+    # pinned buffers, all nine in flight at once (ring of 4: the older ones are retired by later submits)
+    px = [torch.from_numpy(x).pin_memory() for x in xs]
+    py = [torch.empty((x.shape[0], 12), dtype=torch.float32).pin_memory() for x in xs]
+    tickets = [net.submit(a, o) for a, o in zip(px, py)]
+    assert tickets == list(range(tickets[0], tickets[0] + len(xs)))
+    for i in (8, 2, 5, 0, 1, 3, 4, 6, 7):
+        net.wait(tickets[i])
+        assert net.query(tickets[i])
+        np.testing.assert_array_equal(py[i].numpy(), want[i])
+    net.wait(tickets[4])  # waiting twice is harmless
+    # pageable numpy buffers
+    outs = [np.empty((x.shape[0], 12), dtype=np.float32) for x in xs]
+    tickets = [net.submit(x, o) for x, o in zip(xs[:4], outs[:4])]
+    for t, o, y in zip(tickets, outs, want):
+        net.wait(t)
+        np.testing.assert_array_equal(o, y)
+    # a blocking call between asynchronous ones
+    t = net.submit(px[3], py[3].zero_())
+    np.testing.assert_array_equal(net.forward(xs[5]), want[5])
+    net.wait(t)
+    np.testing.assert_array_equal(py[3].numpy(), want[3])
+    with pytest.raises(netcuda.NetcudaError):
+        net.wait(10 ** 9)
+    with pytest.raises(netcuda.NetcudaError):
+        net.wait(0)
+    assert net.last_forward_us > 0
+    net.close()
+
+
+def test_async_vit_pipeline_matches_blocking(netcuda, torch_cuda):
+    """Two ViT calls in flight (the bench's e2e loop): bit-identical logits to the blocking call."""
+    torch = torch_cuda
+    g = np.load(os.path.join(GOLDEN, "vit_small.npz"))
+    cfg = dict(zip(("image_size", "patch_size", "dim", "depth", "heads", "mlp_dim", "n_classes"), (int(v) for v in g["cfg"])))
+    net = netcuda.Net.vit(cfg, max_batch=8)
+    net.upload_vit(g["flat"])
+    rng = np.random.default_rng(5)
+    xs = [torch.from_numpy(rng.uniform(-1, 1, (n, net.n_in)).astype(np.float32)).pin_memory() for n in (20, 8, 33)]
+    want = [net.forward(x.numpy()) for x in xs]
+    ys = [torch.empty((x.shape[0], net.n_out)).pin_memory() for x in xs]
+    prev = None
+    for rep in range(3):
+        for x, y in zip(xs, ys):
+            t = net.submit(x, y)
+            if prev is not None:
+                net.wait(prev)
+            prev = t
+    net.wait(prev)
+    for y, wnt in zip(ys, want):
+        np.testing.assert_array_equal(y.numpy(), wnt)
+    net.close()

@@ -125,7 +125,10 @@ struct netcuda_net
         int n = 0, variant = 0;
         bool in_is_i8 = false, out_is_i32 = false;
         uint64_t launches = 0; // kernels inside the graph (for the launch counter)
-    } pass_graph;
+    };
+    static constexpr int PASS_GRAPHS = 4; // the host API cycles through 2 input slots x up to 4 output buffers
+    PassGraph pass_graphs[PASS_GRAPHS];
+    int pass_graph_next = 0; // round-robin replacement
 
     // per-kernel profiling (netcuda_profile_enable)
     bool profiling = false;
@@ -142,8 +145,24 @@ struct netcuda_net
     // host-API staging (lazy)
     void *pin_in[2] = {nullptr, nullptr}, *dev_in[2] = {nullptr, nullptr};
     size_t stage_in_bytes = 0;
-    void *dev_out = nullptr, *pin_out = nullptr;
-    size_t out_bytes = 0;
+    uint64_t chunk_seq = 0; // passes staged so far: slot = chunk_seq & 1, across calls
+    // Host-API calls in flight (netcuda_submit / netcuda_wait); netcuda_forward is submit + wait.
+    struct Pending
+    {
+        uint64_t ticket = 0;
+        bool active = false;
+        int status = NETCUDA_OK; // of a retired ticket
+        cudaEvent_t done = nullptr;
+        void *dev_out = nullptr, *pin_out = nullptr;
+        size_t dev_cap = 0, pin_cap = 0;
+        void *user_out = nullptr;
+        size_t out_bytes = 0;
+        bool pinned_out = false;
+        std::chrono::steady_clock::time_point t0;
+    };
+    static constexpr int MAX_IN_FLIGHT = 4;
+    Pending pending[MAX_IN_FLIGHT];
+    uint64_t next_ticket = 1;
 };
 
 static int check_handle(const netcuda_net *h)
@@ -282,10 +301,10 @@ extern "C" int netcuda_destroy(netcuda_net *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     void *dev_ptrs[] = {h->arena, h->act[0], h->act[1], h->acc_out, h->splitk_ws, h->patches, h->ybuf, h->qkv, h->att, h->hid, h->cls_ln, h->x,
-                        h->dev_in[0], h->dev_in[1], h->dev_out};
+                        h->dev_in[0], h->dev_in[1]};
     for (void *p : dev_ptrs)
         if (p) cudaFree(p);
-    void *host_ptrs[] = {h->pin_in[0], h->pin_in[1], h->pin_out, h->h_err};
+    void *host_ptrs[] = {h->pin_in[0], h->pin_in[1], h->h_err};
     for (void *p : host_ptrs)
         if (p) cudaFreeHost(p);
     for (int i = 0; i < 2; i++)
@@ -293,7 +312,14 @@ extern "C" int netcuda_destroy(netcuda_net *h)
         if (h->h2d_done[i]) cudaEventDestroy(h->h2d_done[i]);
         if (h->compute_done[i]) cudaEventDestroy(h->compute_done[i]);
     }
-    if (h->pass_graph.exec) cudaGraphExecDestroy(h->pass_graph.exec);
+    for (auto &g : h->pass_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto &pd : h->pending)
+    {
+        if (pd.done) cudaEventDestroy(pd.done);
+        if (pd.dev_out) cudaFree(pd.dev_out);
+        if (pd.pin_out) cudaFreeHost(pd.pin_out);
+    }
     for (auto &r : h->prof_recs)
     {
         cudaEventDestroy(r.start);
@@ -737,9 +763,18 @@ static int mlp_pass_graphed(netcuda_net *h, const float *in_f32, const int8_t *i
 {
     const void *in = in_i8 ? (const void *)in_i8 : (const void *)in_f32;
     void *out = out_i32 ? (void *)out_i32 : (void *)out_f32;
-    netcuda_net::PassGraph &g = h->pass_graph;
-    const bool hit = g.exec && g.in == in && g.out == out && g.n == n && g.variant == h->gemm_variant && g.in_is_i8 == (in_i8 != nullptr) &&
-                     g.out_is_i32 == (out_i32 != nullptr);
+    netcuda_net::PassGraph *found = nullptr;
+    for (auto &c : h->pass_graphs)
+        if (c.exec && c.in == in && c.out == out && c.n == n && c.variant == h->gemm_variant && c.in_is_i8 == (in_i8 != nullptr) &&
+            c.out_is_i32 == (out_i32 != nullptr))
+            found = &c;
+    const bool hit = found != nullptr;
+    if (!hit)
+    {
+        found = &h->pass_graphs[h->pass_graph_next];
+        h->pass_graph_next = (h->pass_graph_next + 1) % netcuda_net::PASS_GRAPHS;
+    }
+    netcuda_net::PassGraph &g = *found;
     if (!hit)
     {
         if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -839,11 +874,13 @@ static bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
-static int ensure_staging(netcuda_net *h, size_t in_elem, size_t batch, size_t out_elem, bool need_pin_in, bool need_pin_out)
+static int ensure_staging(netcuda_net *h, size_t in_elem, bool need_pin_in)
 {
     const size_t slot_bytes = (size_t)h->max_batch * h->n_in * in_elem;
     if (h->stage_in_bytes < slot_bytes)
     {
+        CK(cudaStreamSynchronize(h->copy_stream)); // (growing the slots: nothing may still be copying into them)
+        CK(cudaStreamSynchronize(h->stream));
         for (int i = 0; i < 2; i++)
         {
             if (h->dev_in[i]) cudaFree(h->dev_in[i]);
@@ -856,60 +893,131 @@ static int ensure_staging(netcuda_net *h, size_t in_elem, size_t batch, size_t o
     }
     if (need_pin_in && !h->pin_in[0])
         for (int i = 0; i < 2; i++) CK(cudaHostAlloc(&h->pin_in[i], h->stage_in_bytes, cudaHostAllocDefault));
-    const size_t ob = batch * h->n_out * out_elem;
-    if (h->out_bytes < ob)
-    {
-        if (h->dev_out) cudaFree(h->dev_out);
-        if (h->pin_out) cudaFreeHost(h->pin_out);
-        h->dev_out = h->pin_out = nullptr;
-        h->out_bytes = 0;
-        CK(cudaMalloc(&h->dev_out, ob));
-        h->out_bytes = ob;
-    }
-    if (need_pin_out && !h->pin_out) CK(cudaHostAlloc(&h->pin_out, h->out_bytes, cudaHostAllocDefault));
     return NETCUDA_OK;
 }
 
-static int forward_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_t batch, void *out, bool out_is_i32)
+// Retire one in-flight call: wait for its D2H, surface kernel errors, hand pageable callers their bytes.
+static int finish_pending(netcuda_net *h, netcuda_net::Pending &pd)
+{
+    if (!pd.active) return pd.status;
+    pd.active = false;
+    const cudaError_t e = cudaEventSynchronize(pd.done);
+    int rc = kernel_error(h);
+    if (rc == NETCUDA_OK && e != cudaSuccess) rc = fail(NETCUDA_ERR_CUDA, "forward failed: %s", cudaGetErrorString(e));
+    if (rc == NETCUDA_OK && !pd.pinned_out) memcpy(pd.user_out, pd.pin_out, pd.out_bytes);
+    h->last_us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - pd.t0).count();
+    pd.status = rc;
+    return rc;
+}
+
+// Enqueue one host-buffer forward: H2D of pass i+1 (copy stream) overlaps the kernels of pass i (compute stream), across
+// calls as well as inside one; the D2H of the outputs follows the last pass on the compute stream.  Returns without waiting.
+static int submit_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_t batch, void *out, bool out_is_i32, uint64_t *ticket)
 {
     if (!h->weights_loaded) return fail(NETCUDA_ERR_INVALID, "forward before weights were uploaded");
-    if (batch == 0) return NETCUDA_OK;
     if (!in || !out) return fail(NETCUDA_ERR_INVALID, "null host buffer");
-    const auto t0 = std::chrono::steady_clock::now();
+    if (batch == 0) return fail(NETCUDA_ERR_INVALID, "empty batch");
+    const uint64_t tk = h->next_ticket;
+    netcuda_net::Pending &pd = h->pending[tk % netcuda_net::MAX_IN_FLIGHT];
+    if (pd.active) (void)finish_pending(h, pd); // ring full: the oldest call is retired first (its status stays readable)
     const size_t in_elem = in_is_i8 ? 1 : 4, out_elem = 4;
-    const bool pinned_in = is_pinned(in), pinned_out = is_pinned(out);
-    if (int rc = ensure_staging(h, in_elem, batch, out_elem, !pinned_in, !pinned_out)) return rc;
-
-    size_t chunk = 0;
-    for (size_t done = 0; done < batch; done += (size_t)h->max_batch, chunk++)
+    const bool pinned_in = is_pinned(in);
+    if (int rc = ensure_staging(h, in_elem, !pinned_in)) return rc;
+    pd.t0 = std::chrono::steady_clock::now();
+    pd.pinned_out = is_pinned(out);
+    pd.user_out = out, pd.out_bytes = batch * h->n_out * out_elem;
+    if (!pd.done) CK(cudaEventCreateWithFlags(&pd.done, cudaEventDisableTiming));
+    if (pd.dev_cap < pd.out_bytes)
     {
-        const int slot = (int)(chunk & 1);
+        if (pd.dev_out) CK(cudaFree(pd.dev_out)); // (cudaFree waits for the device: nothing can still be writing it)
+        pd.dev_out = nullptr, pd.dev_cap = 0;
+        CK(cudaMalloc(&pd.dev_out, pd.out_bytes));
+        pd.dev_cap = pd.out_bytes;
+    }
+    if (!pd.pinned_out && pd.pin_cap < pd.out_bytes)
+    {
+        if (pd.pin_out) CK(cudaFreeHost(pd.pin_out));
+        pd.pin_out = nullptr, pd.pin_cap = 0;
+        CK(cudaHostAlloc(&pd.pin_out, pd.out_bytes, cudaHostAllocDefault));
+        pd.pin_cap = pd.out_bytes;
+    }
+
+    for (size_t done = 0; done < batch; done += (size_t)h->max_batch, h->chunk_seq++)
+    {
+        const int slot = (int)(h->chunk_seq & 1);
         const size_t n = std::min((size_t)h->max_batch, batch - done);
         const size_t bytes = n * h->n_in * in_elem;
         const char *src = (const char *)in + done * h->n_in * in_elem;
-        if (chunk >= 2) CK(cudaStreamWaitEvent(h->copy_stream, h->compute_done[slot], 0)); // device slot free again
+        if (h->chunk_seq >= 2) CK(cudaStreamWaitEvent(h->copy_stream, h->compute_done[slot], 0)); // device slot free again
         if (!pinned_in)
         {
-            if (chunk >= 2) CK(cudaEventSynchronize(h->h2d_done[slot])); // pinned slot drained
+            if (h->chunk_seq >= 2) CK(cudaEventSynchronize(h->h2d_done[slot])); // pinned slot drained
             memcpy(h->pin_in[slot], src, bytes);
             src = (const char *)h->pin_in[slot];
         }
         CK(cudaMemcpyAsync(h->dev_in[slot], src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaEventRecord(h->h2d_done[slot], h->copy_stream));
         CK(cudaStreamWaitEvent(h->stream, h->h2d_done[slot], 0));
-        char *dout = (char *)h->dev_out + done * h->n_out * out_elem;
-        // (a multi-chunk batch alternates between the two staging slots, which would evict the one cached graph every chunk)
+        char *dout = (char *)pd.dev_out + done * h->n_out * out_elem;
+        // (a multi-pass batch walks through fresh (input slot, output offset) pairs: nothing a cached graph could be reused for)
         if (int rc = forward_device_impl(h, h->dev_in[slot], in_is_i8, n, dout, out_is_i32, h->stream, batch <= (size_t)h->max_batch)) return rc;
         CK(cudaEventRecord(h->compute_done[slot], h->stream));
     }
-    const size_t ob = batch * h->n_out * out_elem;
-    void *host_dst = pinned_out ? out : h->pin_out;
-    CK(cudaMemcpyAsync(host_dst, h->dev_out, ob, cudaMemcpyDeviceToHost, h->stream));
-    cudaError_t e = cudaStreamSynchronize(h->stream);
-    if (int rc = kernel_error(h)) return rc;
-    if (e != cudaSuccess) return fail(NETCUDA_ERR_CUDA, "forward failed: %s", cudaGetErrorString(e));
-    if (!pinned_out) memcpy(out, h->pin_out, ob);
-    h->last_us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    CK(cudaMemcpyAsync(pd.pinned_out ? out : pd.pin_out, pd.dev_out, pd.out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(pd.done, h->stream));
+    pd.ticket = tk, pd.active = true, pd.status = NETCUDA_OK;
+    h->next_ticket++;
+    if (ticket) *ticket = tk;
+    return NETCUDA_OK;
+}
+
+static int wait_impl(netcuda_net *h, uint64_t ticket)
+{
+    if (ticket == 0 || ticket >= h->next_ticket) return fail(NETCUDA_ERR_INVALID, "unknown ticket %llu", (unsigned long long)ticket);
+    netcuda_net::Pending &pd = h->pending[ticket % netcuda_net::MAX_IN_FLIGHT];
+    if (pd.ticket != ticket) return NETCUDA_OK; // retired long ago (its slot has been reused since)
+    return finish_pending(h, pd);
+}
+
+static int forward_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_t batch, void *out, bool out_is_i32)
+{
+    if (batch == 0) return h->weights_loaded ? NETCUDA_OK : fail(NETCUDA_ERR_INVALID, "forward before weights were uploaded");
+    uint64_t tk = 0;
+    if (int rc = submit_host_impl(h, in, in_is_i8, batch, out, out_is_i32, &tk)) return rc;
+    return wait_impl(h, tk);
+}
+
+extern "C" int netcuda_submit(netcuda_net *h, const float *in, size_t batch, float *out, uint64_t *ticket)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (!ticket) return fail(NETCUDA_ERR_INVALID, "null ticket");
+    CK(cudaSetDevice(h->device));
+    return submit_host_impl(h, in, false, batch, out, false, ticket);
+}
+
+extern "C" int netcuda_wait(netcuda_net *h, uint64_t ticket)
+{
+    if (int rc = check_handle(h)) return rc;
+    CK(cudaSetDevice(h->device));
+    return wait_impl(h, ticket);
+}
+
+extern "C" int netcuda_query(netcuda_net *h, uint64_t ticket, int *done)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (!done) return fail(NETCUDA_ERR_INVALID, "null done");
+    if (ticket == 0 || ticket >= h->next_ticket) return fail(NETCUDA_ERR_INVALID, "unknown ticket %llu", (unsigned long long)ticket);
+    netcuda_net::Pending &pd = h->pending[ticket % netcuda_net::MAX_IN_FLIGHT];
+    *done = 1;
+    if (pd.ticket == ticket && pd.active)
+    {
+        CK(cudaSetDevice(h->device));
+        const cudaError_t e = cudaEventQuery(pd.done);
+        if (e == cudaErrorNotReady)
+            *done = 0;
+        else if (e != cudaSuccess)
+            return fail(NETCUDA_ERR_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+    }
     return NETCUDA_OK;
 }
 

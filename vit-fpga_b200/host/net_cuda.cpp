@@ -329,6 +329,22 @@ namespace cuda
         if (rc != NETCUDA_OK) throw_last("netcuda_forward", rc);
     }
 
+    std::uint64_t net_cuda::submit(const DATA_TYPE *inputs, std::size_t batch, DATA_TYPE *outputs)
+    {
+        if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        uint64_t ticket = 0;
+        const int rc = netcuda_submit(p_->h, inputs, batch, outputs, &ticket);
+        if (rc != NETCUDA_OK) throw_last("netcuda_submit", rc);
+        return ticket;
+    }
+
+    void net_cuda::wait(std::uint64_t ticket)
+    {
+        if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        const int rc = netcuda_wait(p_->h, ticket);
+        if (rc != NETCUDA_OK) throw_last("netcuda_wait", rc);
+    }
+
     void net_cuda::forward_device(const void *d_inputs, std::size_t batch, void *d_outputs, void *stream)
     {
         if (!p_) throw std::runtime_error("net_cuda: moved-from net");

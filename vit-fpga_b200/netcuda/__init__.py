@@ -291,6 +291,22 @@ class Net:
         _check(lib.netcuda_forward_i8(self._h, _ptr(xq), C.c_size_t(batch), _ptr(out)))
         return out
 
+    def submit(self, x, out) -> int:
+        """netcuda_submit: non-blocking host-buffer forward; `x` / `out` (numpy or CPU torch, ideally pinned) must stay alive
+        until wait(ticket)."""
+        t = C.c_uint64(0)
+        n = (x.size if isinstance(x, np.ndarray) else x.numel()) // self.n_in
+        _check(lib.netcuda_submit(self._h, _ptr(x), C.c_size_t(n), _ptr(out), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int) -> None:
+        _check(lib.netcuda_wait(self._h, C.c_uint64(ticket)))
+
+    def query(self, ticket: int) -> bool:
+        d = C.c_int(0)
+        _check(lib.netcuda_query(self._h, C.c_uint64(ticket), C.byref(d)))
+        return bool(d.value)
+
     def forward_device(self, d_in, d_out, batch: int, stream=None) -> None:
         """Device tensors; asynchronous on `stream` (torch stream or raw handle)."""
         _check(lib.netcuda_forward_device(self._h, _ptr(d_in), C.c_size_t(batch), _ptr(d_out), _stream(stream)))
