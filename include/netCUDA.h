@@ -94,6 +94,12 @@ namespace cuda
         // ---- extensions beyond the abstract interface ----
         // Batched forward on raw host buffers (pinned buffers are DMA'd in place).
         void forward(const DATA_TYPE *inputs, std::size_t batch, DATA_TYPE *outputs);
+        // Vision transformers fed from camera frames, the reference's image carrier (net::image_set, def/defines.h:31-38):
+        // resized_image_data holds H x W x 3 interleaved bytes of one frame (original_h / original_w are checked against the
+        // net's image size when non-zero).  Normalisation v = (u8 / 255 - mean) / stddev on the GPU; default [-1, 1].
+        std::vector<DATA_TYPE> launch_forward(const net::image_set &frame);
+        void forward_u8(const unsigned char *frames, std::size_t batch, DATA_TYPE *outputs);
+        void set_u8_normalization(const float mean[3], const float stddev[3]);
         // Non-blocking forward (netcuda_submit / netcuda_wait): returns a ticket; the buffers must stay valid (and should be
         // page-locked) until wait(ticket) returns.  Up to 4 calls in flight; the copy of call i+1 overlaps the kernels of call i.
         std::uint64_t submit(const DATA_TYPE *inputs, std::size_t batch, DATA_TYPE *outputs);

@@ -180,6 +180,17 @@ int netcuda_forward_device(netcuda_t *h, const void *d_in, size_t batch, void *d
 int netcuda_forward_device_i8(netcuda_t *h, const int8_t *d_in, size_t batch, int32_t *d_out, void *stream);
 int netcuda_forward_i8(netcuda_t *h, const int8_t *in, size_t batch, int32_t *out);
 
+/* ---- u8 frames for vision transformers ---------------------------------- *
+ * The reference moves camera frames as unsigned char vectors (net::image_set::resized_image_data, def/defines.h:31-38,
+ * staged at src/netFPGA.cpp:314-318).  These entry points feed a ViT from such frames directly: `frames` is
+ * batch x H x W x 3 bytes (interleaved RGB, row-major); the first kernel turns them into normalised bf16 patch rows,
+ * v = (u8 / 255 - mean[c]) * (1 / stddev[c]) in fp32 -- a quarter of the PCIe bytes of the float path and no fp32 image
+ * in HBM.  Default mean = stddev = 0.5 (0..255 -> [-1, 1], the reference's MIN_RANGE / MAX_RANGE). */
+int netcuda_set_u8_normalization(netcuda_t *h, const float *mean, const float *stddev); /* 3 values each */
+int netcuda_forward_u8(netcuda_t *h, const uint8_t *frames, size_t batch, float *out);
+int netcuda_submit_u8(netcuda_t *h, const uint8_t *frames, size_t batch, float *out, uint64_t *ticket);
+int netcuda_forward_device_u8(netcuda_t *h, const uint8_t *d_frames, size_t batch, float *d_out, void *stream);
+
 /* ---- introspection ---------------------------------------------------------------------- */
 
 int netcuda_n_in(const netcuda_t *h, size_t *n);  /* floats per input sample  */

@@ -468,3 +468,65 @@ def test_async_vit_pipeline_matches_blocking(netcuda, torch_cuda):
     for y, wnt in zip(ys, want):
         np.testing.assert_array_equal(y.numpy(), wnt)
     net.close()
+
+
+def _frames_to_float(frames, mean, std):
+    """What patchify_u8_kernel computes, in numpy fp32 with the same operation order, as the CHW float images of the float path."""
+    u = frames.astype(np.float32) * np.float32(1.0 / 255.0)
+    inv = (np.float32(1.0) / np.asarray(std, dtype=np.float32)).astype(np.float32)
+    v = (u - np.asarray(mean, dtype=np.float32)) * inv
+    return np.ascontiguousarray(v.astype(np.float32).transpose(0, 3, 1, 2))
+
+
+def test_vit_u8_frames_equal_float_path(netcuda, torch_cuda):
+    """u8 HWC frames (the reference's image carrier, def/defines.h:31-38) through netcuda_forward_u8 give bit for bit the logits of
+    the float path on the identically normalised images: the fused u8 patchify rounds exactly like host fp32 arithmetic."""
+    torch = torch_cuda
+    g = np.load(os.path.join(GOLDEN, "vit_small.npz"))
+    cfg = dict(zip(("image_size", "patch_size", "dim", "depth", "heads", "mlp_dim", "n_classes"), (int(v) for v in g["cfg"])))
+    net = netcuda.Net.vit(cfg, max_batch=16)
+    net.upload_vit(g["flat"])
+    rng = np.random.default_rng(9)
+    frames = rng.integers(0, 256, (37, 32, 32, 3), dtype=np.uint8)  # 37 frames: three passes, the last one ragged
+    frames[0] = 0; frames[1] = 255
+    want = net.forward(_frames_to_float(frames, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)).reshape(37, -1))
+    np.testing.assert_array_equal(net.forward_u8(frames), want)
+    # device-resident and asynchronous forms
+    d_f = torch.from_numpy(frames).cuda(); d_y = torch.empty((37, net.n_out), device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        net.forward_device_u8(d_f, d_y, 37, s)
+    s.synchronize()
+    np.testing.assert_array_equal(d_y.cpu().numpy(), want)
+    pf = torch.from_numpy(frames).pin_memory(); py = torch.empty((37, net.n_out)).pin_memory()
+    net.wait(net.submit_u8(pf, py))
+    np.testing.assert_array_equal(py.numpy(), want)
+    # ImageNet statistics
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    net.set_u8_normalization(mean, std)
+    want2 = net.forward(_frames_to_float(frames, mean, std).reshape(37, -1))
+    np.testing.assert_array_equal(net.forward_u8(frames), want2)
+    assert np.abs(want2 - want).max() > 1e-3
+    with pytest.raises(netcuda.NetcudaError):
+        net.set_u8_normalization(mean, (0.2, 0.0, 0.2))
+    net.close()
+    mlp = netcuda.Net.mlp([4], 3072, precision=netcuda.PREC_FP32)
+    with pytest.raises(netcuda.NetcudaError, match="ViT"):
+        mlp.forward_u8(frames[:1])
+    mlp.close()
+
+
+def test_class_launch_forward_image_set(netcuda, torch_cuda):
+    """cuda::net_cuda::launch_forward(const net::image_set&): one frame in the reference's carrier type."""
+    g = np.load(os.path.join(GOLDEN, "vit_small.npz"))
+    cfg = dict(zip(("image_size", "patch_size", "dim", "depth", "heads", "mlp_dim", "n_classes"), (int(v) for v in g["cfg"])))
+    h = netcuda.HostNet.vit(cfg, g["flat"])
+    frame = np.random.default_rng(4).integers(0, 256, (32, 32, 3), dtype=np.uint8)
+    want = h.launch_forward(_frames_to_float(frame[None], (0.5,) * 3, (0.5,) * 3).ravel()).ravel()
+    np.testing.assert_array_equal(h.launch_forward_frame(frame, 32, 32), want)
+    np.testing.assert_array_equal(h.launch_forward_frame(frame), want)  # original_h / original_w left at 0
+    with pytest.raises(RuntimeError, match="image_size"):
+        h.launch_forward_frame(frame[:16])
+    with pytest.raises(RuntimeError, match="original_h"):
+        h.launch_forward_frame(frame, 64, 32)
+    h.close()

@@ -130,6 +130,65 @@ cudaError_t launch_patchify(const float *img, void *patches, int batch, int imag
                       image_size, patch_size, image_size / patch_size);
 }
 
+// ---- camera frames: u8 HWC -> normalised bf16 patch rows --------------------------------------------------
+// The reference's image side channel carries frames as unsigned char vectors (net::image_set::resized_image_data,
+// def/defines.h:31-38; staged byte by byte at src/netFPGA.cpp:314-315).  Feeding the ViT from such frames directly moves
+// a quarter of the bytes over PCIe and skips the fp32 image in HBM: one thread takes 8 pixels (24 interleaved bytes) and
+// writes 8 bf16 of each colour plane of the patch row.  v = (u8 * (1/255) - mean[c]) * inv_std[c], every step rounded to
+// fp32 on its own (no FMA contraction) so that a host can reproduce the patch matrix bit for bit.
+__global__ void __launch_bounds__(256)
+patchify_u8_kernel(const uint8_t *__restrict__ img, __nv_bfloat16 *__restrict__ patches, long long total8, int S, int P, int g, float3 mean,
+                   float3 inv_std)
+{
+    griddep_launch_dependents();
+    griddep_wait();
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total8) return;
+    const int s8 = S >> 3;
+    const int x = (int)(t % s8) << 3;
+    const long long r = t / s8;
+    const int yy = (int)(r % S);
+    const long long b = r / S;
+    const uint2 *src = reinterpret_cast<const uint2 *>(img + ((b * S + yy) * (long long)S + x) * 3); // 24-byte pixel groups: 8-byte aligned
+    const uint2 q0 = src[0], q1 = src[1], q2 = src[2];
+    const uint32_t w[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
+    const int gy = yy / P, py = yy - gy * P, gx = x / P, px = x - gx * P;
+    const long long prow = (b * g + gy) * g + gx;
+    const float mu[3] = {mean.x, mean.y, mean.z}, is[3] = {inv_std.x, inv_std.y, inv_std.z};
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++)
+    {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+        {
+            const int byte = i * 3 + ch;
+            const float u = (float)((w[byte >> 2] >> (8 * (byte & 3))) & 0xFFu);
+            v[i] = __fmul_rn(__fsub_rn(__fmul_rn(u, 1.0f / 255.0f), mu[ch]), is[ch]);
+        }
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]);
+        o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]);
+        o.w = pack_bf16x2(v[6], v[7]);
+        const int pcol = (ch * P + py) * P + px;
+        *reinterpret_cast<uint4 *>(patches + prow * (long long)(3 * P * P) + pcol) = o;
+    }
+}
+
+cudaError_t launch_patchify_u8(const uint8_t *img, void *patches, int batch, int image_size, int patch_size, const float *mean,
+                               const float *inv_std, cudaStream_t stream)
+{
+    if (batch <= 0) return cudaSuccess;
+    if ((patch_size & 7) || (image_size % patch_size)) return cudaErrorInvalidValue;
+    const long long total8 = (long long)batch * image_size * (image_size >> 3);
+    const int threads = 256;
+    const long long grid = (total8 + threads - 1) / threads;
+    return launch_pdl(patchify_u8_kernel, dim3((unsigned)grid), dim3(threads), 0, stream, 1, img, reinterpret_cast<__nv_bfloat16 *>(patches),
+                      total8, image_size, patch_size, image_size / patch_size, make_float3(mean[0], mean[1], mean[2]),
+                      make_float3(inv_std[0], inv_std[1], inv_std[2]));
+}
+
 // ---- class-token rows of the residual stream ---------------------------------------------------------
 
 __global__ void cls_rows_kernel(float *__restrict__ x, const float *__restrict__ cls, const float *__restrict__ pos, int batch,

@@ -87,6 +87,9 @@ cudaError_t launch_attention(const void *qkv, void *out, int batch, int tokens, 
 
 // fp32 NCHW -> bf16 patch rows [batch * np][3 * p * p].
 cudaError_t launch_patchify(const float *img, void *patches, int batch, int image_size, int patch_size, cudaStream_t stream);
+// u8 HWC frames -> bf16 patch rows of (u8 / 255 - mean[c]) * inv_std[c]
+cudaError_t launch_patchify_u8(const uint8_t *img, void *patches, int batch, int image_size, int patch_size, const float *mean,
+                               const float *inv_std, cudaStream_t stream);
 
 // x[b * tokens][:] = cls + pos[0]  (fp32 residual stream rows of the class token)
 cudaError_t launch_cls_rows(float *x, const float *cls, const float *pos, int batch, int tokens, int dim, cudaStream_t stream);

@@ -145,6 +145,9 @@ struct netcuda_net
     // host-API staging (lazy)
     void *pin_in[2] = {nullptr, nullptr}, *dev_in[2] = {nullptr, nullptr};
     size_t stage_in_bytes = 0;
+    // u8 frame input (netcuda_forward_u8): v = (u8 / 255 - mean) * inv_std; the default maps 0..255 onto [-1, 1], the input range
+    // the reference names (MIN_RANGE / MAX_RANGE, def/defines.h:11-12)
+    float u8_mean[3] = {0.5f, 0.5f, 0.5f}, u8_inv_std[3] = {2.0f, 2.0f, 2.0f};
     uint64_t chunk_seq = 0; // passes staged so far: slot = chunk_seq & 1, across calls
     // Host-API calls in flight (netcuda_submit / netcuda_wait); netcuda_forward is submit + wait.
     struct Pending
@@ -720,13 +723,16 @@ static int run_layernorm(netcuda_net *h, const char *label, const float *x, long
     return NETCUDA_OK;
 }
 
-static int vit_pass(netcuda_net *h, const float *img, int n, float *logits, cudaStream_t s)
+static int vit_pass(netcuda_net *h, const float *img, const uint8_t *img_u8, int n, float *logits, cudaStream_t s)
 {
     const int D = h->desc.dim, F = h->desc.mlp_dim, C = h->desc.n_classes, T = h->T, NP = h->NP, PK = h->PK;
     const int rows = n * T, cap = h->max_batch * T;
     {
-        KernelScope scope(h, s, "patchify", 0.0, (double)n * (double)h->n_in * 6.0);
-        CK(launch_patchify(img, h->patches, n, h->desc.image_size, h->desc.patch_size, s));
+        KernelScope scope(h, s, img_u8 ? "patchify_u8" : "patchify", 0.0, (double)n * (double)h->n_in * (img_u8 ? 3.0 : 6.0));
+        if (img_u8)
+            CK(launch_patchify_u8(img_u8, h->patches, n, h->desc.image_size, h->desc.patch_size, h->u8_mean, h->u8_inv_std, s));
+        else
+            CK(launch_patchify(img, h->patches, n, h->desc.image_size, h->desc.patch_size, s));
     }
     // patch embedding: x[b*T + 1 + t] = patches . patch_w^T + patch_b + pos[1 + t]
     CK(run_gemm(h, "patch_embed", GK_BF16, h->patches, PK, h->max_batch * NP, h->patch_w, PK, h->patch_b, h->x, D, OUT_F32, EPI_PATCH,
@@ -832,7 +838,8 @@ static int forward_device_impl(netcuda_net *h, const void *d_in, bool in_is_i8, 
                 rc = mlp_pass(h, f, q, n, of, oi, s);
         }
         else
-            rc = vit_pass(h, (const float *)d_in + done * h->n_in, n, (float *)d_out + done * h->n_out, s);
+            rc = vit_pass(h, in_is_i8 ? nullptr : (const float *)d_in + done * h->n_in,
+                          in_is_i8 ? (const uint8_t *)d_in + done * h->n_in : nullptr, n, (float *)d_out + done * h->n_out, s);
         if (rc != NETCUDA_OK) return rc;
     }
     return NETCUDA_OK;
@@ -1035,6 +1042,50 @@ extern "C" int netcuda_forward_i8(netcuda_net *h, const int8_t *in, size_t batch
         return fail(NETCUDA_ERR_INVALID, "netcuda_forward_i8 needs an INT8 MLP handle");
     CK(cudaSetDevice(h->device));
     return forward_host_impl(h, in, true, batch, out, true);
+}
+
+// ---- u8 frames (ViT) ---------------------------------------------------------------------------------------
+
+static int check_u8(netcuda_net *h)
+{
+    if (int rc = check_handle(h)) return rc;
+    if (h->desc.kind != NETCUDA_KIND_VIT) return fail(NETCUDA_ERR_INVALID, "u8 frame input is a ViT feature (an MLP takes DATA_TYPE vectors)");
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_set_u8_normalization(netcuda_net *h, const float *mean, const float *stddev)
+{
+    if (int rc = check_u8(h)) return rc;
+    if (!mean || !stddev) return fail(NETCUDA_ERR_INVALID, "null argument");
+    for (int c = 0; c < 3; c++)
+    {
+        if (!(stddev[c] > 0.0f)) return fail(NETCUDA_ERR_INVALID, "stddev[%d] must be positive", c);
+        h->u8_mean[c] = mean[c];
+        h->u8_inv_std[c] = 1.0f / stddev[c];
+    }
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_forward_u8(netcuda_net *h, const uint8_t *frames, size_t batch, float *out)
+{
+    if (int rc = check_u8(h)) return rc;
+    CK(cudaSetDevice(h->device));
+    return forward_host_impl(h, frames, true, batch, out, false);
+}
+
+extern "C" int netcuda_submit_u8(netcuda_net *h, const uint8_t *frames, size_t batch, float *out, uint64_t *ticket)
+{
+    if (int rc = check_u8(h)) return rc;
+    if (!ticket) return fail(NETCUDA_ERR_INVALID, "null ticket");
+    CK(cudaSetDevice(h->device));
+    return submit_host_impl(h, frames, true, batch, out, false, ticket);
+}
+
+extern "C" int netcuda_forward_device_u8(netcuda_net *h, const uint8_t *d_frames, size_t batch, float *d_out, void *stream)
+{
+    if (int rc = check_u8(h)) return rc;
+    CK(cudaSetDevice(h->device));
+    return forward_device_impl(h, d_frames, true, batch, d_out, false, stream ? (cudaStream_t)stream : h->stream);
 }
 
 // ---- introspection -----------------------------------------------------------------------------------------

@@ -151,6 +151,33 @@ long long nch_launch_forward(void *net, const float *in, size_t n_in_floats, flo
     }
 }
 
+// launch_forward(const net::image_set&): one u8 frame through a ViT.  Returns the number of outputs or -1.
+long long nch_launch_forward_frame(void *net, const unsigned char *frame, size_t n_bytes, size_t h, size_t w, float *out, size_t out_capacity)
+{
+    try
+    {
+        cuda::net_cuda *n = dynamic_cast<cuda::net_cuda *>(static_cast<net::net_abstract *>(net));
+        if (!n) return -1;
+        net::image_set set;
+        set.resized_image_data.assign(frame, frame + n_bytes);
+        set.original_x_pos = set.original_y_pos = 0;
+        set.original_h = h, set.original_w = w;
+        std::vector<float> y = n->launch_forward(set);
+        if (y.size() > out_capacity)
+        {
+            set_err("output buffer too small");
+            return -1;
+        }
+        memcpy(out, y.data(), y.size() * sizeof(float));
+        return (long long)y.size();
+    }
+    catch (const std::exception &e)
+    {
+        set_err(e.what());
+        return -1;
+    }
+}
+
 long nch_forward_us(void *net) { return static_cast<net::net_abstract *>(net)->get_forward_performance(); }
 long nch_gradient_us(void *net) { return static_cast<net::net_abstract *>(net)->get_gradient_performance(); }
 

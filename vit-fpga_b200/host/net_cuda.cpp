@@ -329,6 +329,34 @@ namespace cuda
         if (rc != NETCUDA_OK) throw_last("netcuda_forward", rc);
     }
 
+    void net_cuda::forward_u8(const unsigned char *frames, std::size_t batch, DATA_TYPE *outputs)
+    {
+        if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        const int rc = netcuda_forward_u8(p_->h, frames, batch, outputs);
+        if (rc != NETCUDA_OK) throw_last("netcuda_forward_u8", rc);
+    }
+
+    void net_cuda::set_u8_normalization(const float mean[3], const float stddev[3])
+    {
+        if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        const int rc = netcuda_set_u8_normalization(p_->h, mean, stddev);
+        if (rc != NETCUDA_OK) throw_last("netcuda_set_u8_normalization", rc);
+    }
+
+    std::vector<DATA_TYPE> net_cuda::launch_forward(const net::image_set &frame)
+    {
+        if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        if (!p_->is_vit) throw std::invalid_argument("net_cuda::launch_forward(image_set): frames feed vision transformers only");
+        const std::size_t side = p_->vit.image_size;
+        if (frame.resized_image_data.size() != side * side * 3)
+            throw std::invalid_argument("net_cuda::launch_forward(image_set): resized_image_data must hold image_size * image_size * 3 bytes");
+        if ((frame.original_h && frame.original_h != side) || (frame.original_w && frame.original_w != side))
+            throw std::invalid_argument("net_cuda::launch_forward(image_set): original_h / original_w do not match the net's image size");
+        std::vector<DATA_TYPE> out(n_out());
+        forward_u8(frame.resized_image_data.data(), 1, out.data());
+        return out;
+    }
+
     std::uint64_t net_cuda::submit(const DATA_TYPE *inputs, std::size_t batch, DATA_TYPE *outputs)
     {
         if (!p_) throw std::runtime_error("net_cuda: moved-from net");

@@ -74,6 +74,7 @@ hostlib.nch_mlp_create.restype = C.c_void_p
 hostlib.nch_vit_create.restype = C.c_void_p
 hostlib.nch_load.restype = C.c_void_p
 hostlib.nch_launch_forward.restype = C.c_longlong
+hostlib.nch_launch_forward_frame.restype = C.c_longlong
 hostlib.nch_forward_us.restype = C.c_long
 hostlib.nch_gradient_us.restype = C.c_long
 
@@ -291,6 +292,28 @@ class Net:
         _check(lib.netcuda_forward_i8(self._h, _ptr(xq), C.c_size_t(batch), _ptr(out)))
         return out
 
+    # ---- u8 frames (ViT)
+    def set_u8_normalization(self, mean, std) -> None:
+        m = (C.c_float * 3)(*[float(v) for v in mean])
+        sd = (C.c_float * 3)(*[float(v) for v in std])
+        _check(lib.netcuda_set_u8_normalization(self._h, m, sd))
+
+    def forward_u8(self, frames) -> np.ndarray:
+        """frames: uint8 [batch, H, W, 3] (numpy or CPU torch) -> fp32 logits."""
+        f = np.ascontiguousarray(frames, dtype=np.uint8) if isinstance(frames, np.ndarray) else frames
+        batch = int(f.shape[0])
+        out = np.empty((batch, self.n_out), dtype=np.float32)
+        _check(lib.netcuda_forward_u8(self._h, _ptr(f), C.c_size_t(batch), _ptr(out)))
+        return out
+
+    def submit_u8(self, frames, out) -> int:
+        t = C.c_uint64(0)
+        _check(lib.netcuda_submit_u8(self._h, _ptr(frames), C.c_size_t(int(frames.shape[0])), _ptr(out), C.byref(t)))
+        return t.value
+
+    def forward_device_u8(self, d_frames, d_out, batch: int, stream=None) -> None:
+        _check(lib.netcuda_forward_device_u8(self._h, _ptr(d_frames), C.c_size_t(batch), _ptr(d_out), _stream(stream)))
+
     def submit(self, x, out) -> int:
         """netcuda_submit: non-blocking host-buffer forward; `x` / `out` (numpy or CPU torch, ideally pinned) must stay alive
         until wait(ticket)."""
@@ -430,6 +453,15 @@ class HostNet:
         if n < 0:
             raise ValueError(hostlib.nch_last_error().decode())
         return out[:n].reshape(-1, self.n_out)
+
+    def launch_forward_frame(self, frame, h=0, w=0) -> np.ndarray:
+        """launch_forward(const net::image_set&): one uint8 [H, W, 3] frame."""
+        f = np.ascontiguousarray(frame, dtype=np.uint8)
+        out = np.empty(self.n_out, dtype=np.float32)
+        n = hostlib.nch_launch_forward_frame(self._h, _ptr(f), C.c_size_t(f.size), C.c_size_t(h), C.c_size_t(w), _ptr(out), C.c_size_t(out.size))
+        if n < 0:
+            raise RuntimeError("launch_forward(image_set) failed: " + hostlib.nch_last_error().decode())
+        return out[:n]
 
     def get_net_data(self, n_params, n_neurons):
         w = np.empty(n_params, dtype=np.float32)
