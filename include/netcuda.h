@@ -228,6 +228,12 @@ int netcuda_profile_read(netcuda_t *h, netcuda_kernel_stat *stats, int cap, int 
  * 3 = default but with 16 instead of 8 epilogue warps in the GELU GEMM (A/B measurement). */
 int netcuda_set_gemm_variant(netcuda_t *h, int variant);
 
+/* ViT handles: 0 (default) = one LayerNorm kernel per LayerNorm; 1 = LayerNorm folded into the GEMMs around it (no LayerNorm kernel
+ * between the blocks: the GEMM that updates the residual stream also emits its bf16 copy and row sums, the next GEMM applies
+ * mean / rstd / gamma / beta in its epilogue -- DESIGN.md 4.1; passes of <= 128 token rows keep the LayerNorm kernel).  The
+ * environment variable NETCUDA_LN_FUSED=1 sets the default for new handles.  Both forms are held to the same parity bars. */
+int netcuda_set_ln_fusion(netcuda_t *h, int on);
+
 const char *netcuda_last_error(void);
 int netcuda_abi_version(void);
 
