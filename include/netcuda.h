@@ -225,7 +225,8 @@ int netcuda_profile_read(netcuda_t *h, netcuda_kernel_stat *stats, int cap, int 
 /* Select a debugging/measurement variant of the dense kernel for this handle:
  * 0 = default (tcgen05, CTA pairs on large problems), 1 = CUDA-core reference GEMM with the same operand
  * rounding (also selects the mma.sync attention kernel), 2 = tcgen05 with one CTA per tile everywhere,
- * 3 = default but with 16 instead of 8 epilogue warps in the GELU GEMM (A/B measurement). */
+ * 3 = default but with 16 instead of 8 epilogue warps in the GELU GEMM, 4 / 5 = two output slabs per epilogue warp (and a 5-stage
+ * ring) in every / in no CTA-pair GEMM -- the default picks per epilogue (A/B measurements; same bits as 0). */
 int netcuda_set_gemm_variant(netcuda_t *h, int variant);
 
 /* ViT handles: 0 (default) = one LayerNorm kernel per LayerNorm; 1 = LayerNorm folded into the GEMMs around it (no LayerNorm kernel

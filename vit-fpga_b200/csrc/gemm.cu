@@ -52,6 +52,7 @@ constexpr int STAGES_128 = 6;      // 1 CTA per tile, BN = 128: 32 KB per stage
 constexpr int STAGES_256_PAIR = 6; // CTA pair, BN = 256: 16 KB of A + 16 KB of W per CTA and stage
 constexpr int STAGES_256_PAIR_EW16 = 5; // the same with 16 epilogue warps (64 KB of slabs)
 constexpr int STAGES_256_PAIR_RESLN = 5; // MODE_RESLN: two residual slabs per epilogue warp (64 KB)
+constexpr int STAGES_256_PAIR_DS = 5;    // MODE_PLAIN_DS: two output slabs per epilogue warp (64 KB)
 constexpr int STAGES_256_PAIR_LNFOLD = 5; // MODE_LNFOLD: bias + column sums staged in smem (4 KB) do not fit next to 6 stages
 
 // cudaFuncSetAttribute is per device, so the opt-in runs once for every device that is used.
@@ -85,6 +86,8 @@ cudaError_t gemm_global_init()
 #undef NC_OPT
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_EW16, 2, 16>()) != cudaSuccess) return e;
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_LNFOLD, 2, 8, MODE_LNFOLD>()) != cudaSuccess) return e;
+    if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_DS, 2, 8, MODE_PLAIN_DS>()) != cudaSuccess) return e;
+    if ((e = opt_in_smem<KIND_BF16, 256, OUT_F32, STAGES_256_PAIR_DS, 2, 8, MODE_PLAIN_DS>()) != cudaSuccess) return e;
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_F32, STAGES_256_PAIR_RESLN, 2, 8, MODE_RESLN>()) != cudaSuccess) return e;
     if (dev < 64) done[dev] = true;
     return cudaSuccess;
@@ -171,7 +174,7 @@ static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
     else
         map_out = map_a; // never dereferenced
     if (p.k_splits > 1 && !(p.tma_store && OUT == OUT_S32 && c.epi == EPI_SPLITK)) return cudaErrorInvalidValue;
-    if (MODE != MODE_PLAIN)
+    if (MODE == MODE_LNFOLD || MODE == MODE_RESLN)
     {
         // the LayerNorm modes live in the TMA-store epilogue and address `stats` / `colsum` / `xb` with 16-byte accesses
         if (!p.tma_store || !c.stats || (c.n & 63)) return cudaErrorInvalidValue;
@@ -198,6 +201,15 @@ static cudaError_t launch_tc_bn(const GemmCall &c, cudaStream_t stream)
         // 8 warps -- the epilogue is bound by MUFU/FMA work per element, not by the number of warps -- so it is not the default.
         if constexpr (KIND == KIND_BF16 && OUT == OUT_BF16)
             if (c.epi == EPI_GELU && c.variant == 3) return launch_tc<KIND, 256, OUT, STAGES_256_PAIR_EW16, 2, 16>(c, stream);
+        // Two output slabs per epilogue warp (slab i + 1 is filled while the TMA store of slab i drains) at the price of one
+        // pipeline stage: pays where the epilogue or the store path sets the pace -- the GELU epilogue (ViT-B fc1: 10.3 -> 10.0 ms
+        // per step) and the short-K residual update that is bound by the L2 reduce-add (proj: 3.95 -> 3.6 ms) -- and costs where the
+        // mainloop does (qkv 6.75 -> 7.0 ms, fc2 8.4 -> 8.7 ms).  Variant 4 forces it everywhere, variant 5 nowhere (A/B).
+        if constexpr (KIND == KIND_BF16)
+        {
+            const bool pays = c.epi == EPI_GELU || (c.epi == EPI_RESIDUAL && c.k <= 1024);
+            if (c.variant == 4 || (c.variant == 0 && pays)) return launch_tc<KIND, 256, OUT, STAGES_256_PAIR_DS, 2, 8, MODE_PLAIN_DS>(c, stream);
+        }
         return launch_tc<KIND, 256, OUT, STAGES_256_PAIR, 2>(c, stream);
     }
     return launch_tc<KIND, 256, OUT, STAGES_256, 1>(c, stream);

@@ -65,7 +65,8 @@ enum : int
 {
     MODE_PLAIN = 0,
     MODE_LNFOLD = 1,
-    MODE_RESLN = 2
+    MODE_RESLN = 2,
+    MODE_PLAIN_DS = 3 // the plain epilogue with two output slabs per warp: slab i + 1 is filled while the TMA store of slab i drains
 };
 constexpr int LN_STATS_SLOTS = 8; // partial (sum, sum of squares) pairs per row: one per 128-column range, N <= 1024
 constexpr int LN_STATS_PITCH = 2 * LN_STATS_SLOTS; // floats per row
@@ -145,7 +146,7 @@ struct GemmSmem
     static constexpr int B_BYTES = (BN / CG) * GEMM_STAGE_ROW_BYTES; // a CTA of a pair stages half of the W tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OFF_SLABS = STAGES * STAGE_BYTES; // 1024-byte aligned (stage sizes are multiples of 1024)
-    static constexpr int SLABS_PER_WARP = MODE == MODE_RESLN ? 2 : 1; // MODE_RESLN: two residual slabs in flight per warp
+    static constexpr int SLABS_PER_WARP = (MODE == MODE_RESLN || MODE == MODE_PLAIN_DS) ? 2 : 1; // two slabs in flight per warp
     static constexpr int OFF_BIAS = OFF_SLABS + EW * SLABS_PER_WARP * GEMM_SLAB_BYTES;
     // bias slice, double-buffered by tile parity (MODE_LNFOLD: + the column sums of the folded weights, same scheme)
     static constexpr int OFF_BARS = OFF_BIAS + (MODE == MODE_LNFOLD ? 4 : 2) * BN * 4;
@@ -349,7 +350,8 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                        const __grid_constant__ CUtensorMap tma_out, const GemmParams p)
 {
     using L = GemmSmem<BN, STAGES, CG, EW, MODE>;
-    static_assert(MODE == MODE_PLAIN || (KIND == KIND_BF16 && BN == 256 && EW == 8), "the LayerNorm modes exist for the bf16 256-column tiles");
+    static_assert(MODE == MODE_PLAIN || MODE == MODE_PLAIN_DS || (KIND == KIND_BF16 && BN == 256 && EW == 8),
+                  "the LayerNorm modes exist for the bf16 256-column tiles");
     static_assert(MODE != MODE_LNFOLD || OUT == OUT_BF16, "MODE_LNFOLD writes bf16");
     static_assert(MODE != MODE_RESLN || OUT == OUT_F32, "MODE_RESLN updates the fp32 residual stream");
     constexpr int ELEM = KindTraits<KIND>::ELEM;
@@ -559,6 +561,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         const uint32_t slab_addr = base + L::OFF_SLABS + ew * L::SLABS_PER_WARP * GEMM_SLAB_BYTES;
         uint32_t acc = 0, acc_phase = 0, parity = 0;
         [[maybe_unused]] uint32_t xs_phase = 0; // MODE_RESLN: bit b = phase of residual-slab barrier b
+        [[maybe_unused]] uint32_t slab_seq = 0; // MODE_PLAIN_DS: slabs stored so far (parity = buffer)
         for (int work = tile0; work < num_work; work += tile_step, parity ^= 1u)
         {
             const int tile = work / S;
@@ -738,12 +741,20 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                 {
                     const int scol = wcol + sb * SLAB_COLS; // tile column of this slab
                     if (col0 + scol >= p.N) break;          // warp-uniform
-                    // the previous store of this warp must have finished reading the slab
-                    if (lane == 0) tma_store_wait_read();
+                    // the previous store of this warp out of this slab buffer must have finished reading it
+                    const uint32_t buf_off = MODE == MODE_PLAIN_DS ? (slab_seq & 1u) * GEMM_SLAB_BYTES : 0u;
+                    slab_seq++;
+                    if (lane == 0)
+                    {
+                        if constexpr (MODE == MODE_PLAIN_DS)
+                            tma_store_wait_read_1();
+                        else
+                            tma_store_wait_read();
+                    }
                     __syncwarp();
                     const uint32_t t_slab = t_base + sb * SLAB_COLS;
                     const uint32_t *bias_slab = bias_s + scol;
-                    uint8_t *row = slab + lane * SLAB_ROW_BYTES;
+                    uint8_t *row = slab + buf_off + lane * SLAB_ROW_BYTES;
                     uint32_t v0[CHUNK_COLS], v1[CHUNK_COLS], b0[CHUNK_COLS], b1[CHUNK_COLS];
                     tmem_ld_32xN<CHUNK_COLS>(t_slab, v0);
 #pragma unroll 1
@@ -777,9 +788,9 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                     if (lane == 0)
                     {
                         if (epi == EPI_RESIDUAL || epi == EPI_SPLITK)
-                            tma_reduce_add_2d(&tma_out, slab_addr, col0 + scol, row0);
+                            tma_reduce_add_2d(&tma_out, slab_addr + buf_off, col0 + scol, row0);
                         else
-                            tma_store_2d(&tma_out, slab_addr, col0 + scol, row0);
+                            tma_store_2d(&tma_out, slab_addr + buf_off, col0 + scol, row0);
                         tma_store_commit();
                     }
                 }

@@ -135,6 +135,8 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, uint32
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // All committed bulk stores of this thread have finished READING shared memory (the source may be reused).
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent one
+__device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // Named barrier among `nthreads` threads of the CTA (id 0 is __syncthreads).

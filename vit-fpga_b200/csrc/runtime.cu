@@ -1264,7 +1264,7 @@ extern "C" int netcuda_set_ln_fusion(netcuda_net *h, int on)
 extern "C" int netcuda_set_gemm_variant(netcuda_net *h, int variant)
 {
     if (int rc = check_handle(h)) return rc;
-    if (variant < 0 || variant > 3) return fail(NETCUDA_ERR_INVALID, "variant must be 0..3");
+    if (variant < 0 || variant > 5) return fail(NETCUDA_ERR_INVALID, "variant must be 0..5");
     h->gemm_variant = variant;
     return NETCUDA_OK;
 }
