@@ -229,12 +229,6 @@ int netcuda_profile_read(netcuda_t *h, netcuda_kernel_stat *stats, int cap, int 
  * ring) in every / in no CTA-pair GEMM -- the default picks per epilogue (A/B measurements; same bits as 0). */
 int netcuda_set_gemm_variant(netcuda_t *h, int variant);
 
-/* ViT handles: 0 (default) = one LayerNorm kernel per LayerNorm; 1 = LayerNorm folded into the GEMMs around it (no LayerNorm kernel
- * between the blocks: the GEMM that updates the residual stream also emits its bf16 copy and row sums, the next GEMM applies
- * mean / rstd / gamma / beta in its epilogue -- DESIGN.md 4.1; passes of <= 128 token rows keep the LayerNorm kernel).  The
- * environment variable NETCUDA_LN_FUSED=1 sets the default for new handles.  Both forms are held to the same parity bars. */
-int netcuda_set_ln_fusion(netcuda_t *h, int on);
-
 const char *netcuda_last_error(void);
 int netcuda_abi_version(void);
 

@@ -10,12 +10,6 @@ and the GELU output.  This model applies the same roundings to an otherwise fp32
 
 Everything between two rounding points is evaluated in float64, so the model does not depend on which
 matmul kernels (and which reduced-precision fast paths) the host CPU's BLAS picks.
-
-`ln_fused=True` models the opt-in product path (netcuda_set_ln_fusion), where LayerNorm is folded into the GEMMs around it
-(gemm_tcgen05.cuh MODE_RESLN / MODE_LNFOLD): the operand of the qkv / fc1 GEMM is bf16(x) -- the residual
-stream itself, not its normalised form -- against W' = bf16(gamma o W), and the epilogue computes
-rstd * (acc - mean * colsum(W')) + (bias + beta . W).  The rounding points move from LayerNorm's output
-to its input; mean and rstd still come from the fp32 residual stream.
 """
 import numpy as np
 import torch
@@ -25,18 +19,8 @@ def _bf(x):
     return x.float().to(torch.bfloat16).double()
 
 
-def vit_forward_bf16_model(cfg: dict, flat: np.ndarray, images: np.ndarray, rounding: bool = True, ln_fused: bool = False) -> np.ndarray:
+def vit_forward_bf16_model(cfg: dict, flat: np.ndarray, images: np.ndarray, rounding: bool = True) -> np.ndarray:
     r = _bf if rounding else (lambda t: t)
-
-    def ln_gemm(x, gamma, beta, w, bias, eps=1e-6):
-        """LayerNorm(x) @ w.T + bias the way the product path evaluates it."""
-        if not ln_fused:
-            return r(torch.nn.functional.layer_norm(x, (x.shape[-1],), gamma, beta, eps)) @ r(w).T + bias
-        mean = x.mean(-1, keepdim=True)
-        rstd = 1.0 / torch.sqrt(x.var(-1, unbiased=False, keepdim=True) + eps)
-        wf = r((gamma.float() * w.float()).double())  # the fold is an fp32 product, rounded to bf16 on upload
-        return rstd * (r(x) @ wf.T - mean * wf.sum(-1)) + (bias + w @ beta)
-
     flat = torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float64))
     D, F, C, P, S, H = cfg["dim"], cfg["mlp_dim"], cfg["n_classes"], cfg["patch_size"], cfg["image_size"], cfg["heads"]
     g = S // P
@@ -61,13 +45,15 @@ def vit_forward_bf16_model(cfg: dict, flat: np.ndarray, images: np.ndarray, roun
     for _ in range(cfg["depth"]):
         g1, b1, qw, qb, ow, ob = take(D), take(D), take(3 * D, D), take(3 * D), take(D, D), take(D)
         g2, b2, f1w, f1b, f2w, f2b = take(D), take(D), take(F, D), take(F), take(D, F), take(D)
-        qkv = r(ln_gemm(x, g1, b1, qw, qb)).reshape(B, T, 3, H, D // H)
+        y = r(ln(x, (D,), g1, b1, 1e-6))
+        qkv = r(y @ r(qw).T + qb).reshape(B, T, 3, H, D // H)
         q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
         s = (q @ k.transpose(-1, -2)) / float(np.sqrt(D // H))
         pe = torch.exp(s - s.max(-1, keepdim=True).values)
         o = (r(pe) @ v) / pe.sum(-1, keepdim=True)  # the row sum is taken from the fp32 numerators
         x = x + r(o.permute(0, 2, 1, 3).reshape(B, T, D)) @ r(ow).T + ob
-        h = r(torch.nn.functional.gelu(ln_gemm(x, g2, b2, f1w, f1b)))
+        y = r(ln(x, (D,), g2, b2, 1e-6))
+        h = r(torch.nn.functional.gelu(y @ r(f1w).T + f1b))
         x = x + h @ r(f2w).T + f2b
     gf, bfin, hw, hb = take(D), take(D), take(C, D), take(C)
     assert pos_[0] == flat.numel()

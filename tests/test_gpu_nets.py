@@ -253,29 +253,6 @@ def test_vit_golden_torchvision_fixture(netcuda, torch_cuda):
     np.testing.assert_array_equal(got.argmax(1), g["logits"].argmax(1))
 
 
-def test_vit_folded_layernorm_matches_rounding_model(netcuda, oracle, torch_cuda):
-    """Opt-in form with LayerNorm folded into the GEMMs around it (netcuda_set_ln_fusion): the rounding points move from LayerNorm's
-    output to its input; the kernels must reproduce the float64 model of exactly that pipeline, and both forms meet the oracle."""
-    from bf16_pipeline_model import vit_forward_bf16_model
-
-    cfg = dict(image_size=64, patch_size=16, dim=128, depth=2, heads=2, mlp_dim=256, n_classes=10)
-    flat = netcuda.vit_random_params(cfg, seed=21)
-    x = np.random.default_rng(22).uniform(-1, 1, (9, 3 * 64 * 64)).astype(np.float32)  # 9 x 17 = 153 token rows: CTA-pair tiles
-    want = oracle.vit_forward(cfg, flat, x)
-    net = netcuda.Net.vit(cfg, max_batch=16)
-    net.upload_vit(flat)
-    for fused in (True, False):
-        net.set_ln_fusion(fused)
-        got = net.forward(x)
-        model = vit_forward_bf16_model(cfg, flat, x.reshape(9, 3, 64, 64), ln_fused=fused)
-        # 1e-2: on a random 128-wide net one bf16 rounding flip of an intermediate (fp32 accumulation here, float64 in the model)
-        # moves a logit by a few 1e-3; measured 8.2e-3 (folded) and 3.9e-3 (default) against their own models, while the two
-        # models are 1.2e-2 apart (tools/diag_lnfold.py)
-        assert rel_err(got, model) <= 1e-2
-        assert rel_err(got, want) <= 2e-2  # bf16 operand budget of a narrow net
-    net.close()
-
-
 def test_vit_cpp_class(netcuda, torch_cuda):
     g, cfg = _golden_vit()
     net = netcuda.HostNet.vit(cfg, g["flat"])
@@ -297,11 +274,6 @@ def test_vit_real_shapes_vs_oracle(netcuda, oracle, torch_cuda, name, batch, dep
     got = net.forward(x)
     assert rel_err(got, want) <= 1e-2
     np.testing.assert_array_equal(got.argmax(1), want.argmax(1))
-    net.set_ln_fusion(True)  # the same net with LayerNorm folded into the GEMMs around it: same bar, and close to the default form
-    got_fused = net.forward(x)
-    assert rel_err(got_fused, want) <= 1e-2
-    assert rel_err(got, got_fused) <= 1e-2
-    net.set_ln_fusion(False)
     # tcgen05 kernels == CUDA-core GEMM + mma.sync attention with the same operand types (differences: accumulation
     # order, and the flash kernel rounds P relative to a running max) -- both inside the bf16 budget
     net.set_gemm_variant(1)
@@ -318,37 +290,10 @@ def test_vit_large_sequence_577(netcuda, oracle, torch_cuda):
     want = oracle.vit_forward(cfg, flat, x)
     net = netcuda.Net.vit(cfg, max_batch=2)
     net.upload_vit(flat)
-    for fused in (True, False):
-        net.set_ln_fusion(fused)
-        got = net.forward(x)
-        assert rel_err(got, want) <= 1e-2
-        np.testing.assert_array_equal(got.argmax(1), want.argmax(1))
-    net.close()
-
-
-def test_vit_folded_layernorm_handles_offset_rows(netcuda, oracle, torch_cuda):
-    """The folded LayerNorm feeds the GEMM the un-normalised residual stream and subtracts mean * colsum afterwards.  Rows whose mean
-    is large against their spread are the hard case (cancellation, bf16 rounding of x instead of LN(x)): a position embedding with a
-    constant offset of several standard deviations, and non-trivial gamma / beta, must still meet the oracle."""
-    cfg = dict(image_size=32, patch_size=16, dim=192, depth=3, heads=3, mlp_dim=384, n_classes=16)
-    flat = netcuda.vit_random_params(cfg, seed=11)
-    D, pk, T = 192, 3 * 256, 5
-    pos_off = D * pk + D + D
-    flat[pos_off:pos_off + T * D] += 0.75  # |mean| ~ 0.75 against a spread of ~ 0.05 after the patch embedding
-    x = np.random.default_rng(12).uniform(-1, 1, (64, 3 * 32 * 32)).astype(np.float32)  # two passes of 32 x 5 = 160 token rows
-    want = oracle.vit_forward(cfg, flat, x)
-    net = netcuda.Net.vit(cfg, max_batch=32)
-    net.upload_vit(flat)
-    got_unfused = net.forward(x)
-    net.set_ln_fusion(True)
     got = net.forward(x)
     net.close()
-    # narrow net (192 wide): the bf16 operand budget is 2e-2 (1.4e-2 measured for the default path); the folded form must stay
-    # inside it and close to the default form
-    assert rel_err(got_unfused, want) <= 2e-2
-    assert rel_err(got, want) <= 2e-2
-    assert rel_err(got, got_unfused) <= 2e-2
-    assert (got.argmax(1) == want.argmax(1)).mean() >= 0.95
+    assert rel_err(got, want) <= 1e-2
+    np.testing.assert_array_equal(got.argmax(1), want.argmax(1))
 
 
 def test_vit_batch_independence_at_full_batch(netcuda, torch_cuda):

@@ -86,59 +86,6 @@ cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, 
     return cudaGetLastError();
 }
 
-// ---- bf16 copy + row sums of the residual stream (entry point of the LayerNorm-folded GEMMs) -----------------
-// One warp per row: xb = bf16(x), stats[row][0] = (sum x, sum x^2), stats[row][1..7] = 0.  Runs once per pass, after the patch
-// embedding; every later LayerNorm gets the same three things from the epilogue of the GEMM that updates x (MODE_RESLN).
-template <int MAXV>
-__global__ void __launch_bounds__(256)
-cast_stats_kernel(const float *__restrict__ x, long long ldx, __nv_bfloat16 *__restrict__ xb, long long ldxb, float *__restrict__ stats,
-                  int rows, int dim)
-{
-    griddep_launch_dependents();
-    griddep_wait();
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= rows) return;
-    const int nv = dim >> 2;
-    const float4 *xr = reinterpret_cast<const float4 *>(x + (long long)warp * ldx);
-    uint2 *yr = reinterpret_cast<uint2 *>(xb + (long long)warp * ldxb);
-    float s = 0.0f, q = 0.0f;
-#pragma unroll
-    for (int i = 0; i < MAXV; i++)
-    {
-        const int idx = i * 32 + lane;
-        if (idx < nv)
-        {
-            const float4 v = xr[idx];
-            s += (v.x + v.y) + (v.z + v.w);
-            q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-            uint2 o;
-            o.x = pack_bf16x2(v.x, v.y);
-            o.y = pack_bf16x2(v.z, v.w);
-            yr[idx] = o;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-    {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    if (lane < 8) reinterpret_cast<float2 *>(stats + (long long)warp * 16)[lane] = lane == 0 ? make_float2(s, q) : make_float2(0.0f, 0.0f);
-}
-
-cudaError_t launch_cast_stats(const float *x, long long ldx, void *xb, long long ldxb, float *stats, int rows, int dim, cudaStream_t stream)
-{
-    if (rows <= 0) return cudaSuccess;
-    if (dim <= 0 || (dim & 3) || (ldx & 3) || (ldxb & 3) || dim > 4096) return cudaErrorInvalidValue;
-    const int threads = 256, rows_per_block = threads / 32;
-    const int grid = (rows + rows_per_block - 1) / rows_per_block;
-    __nv_bfloat16 *yb = reinterpret_cast<__nv_bfloat16 *>(xb);
-    if (dim <= 256) return launch_pdl(cast_stats_kernel<2>, dim3(grid), dim3(threads), 0, stream, 1, x, ldx, yb, ldxb, stats, rows, dim);
-    if (dim <= 1024) return launch_pdl(cast_stats_kernel<8>, dim3(grid), dim3(threads), 0, stream, 1, x, ldx, yb, ldxb, stats, rows, dim);
-    return launch_pdl(cast_stats_kernel<32>, dim3(grid), dim3(threads), 0, stream, 1, x, ldx, yb, ldxb, stats, rows, dim);
-}
-
 // ---- patch extraction: fp32 NCHW image -> bf16 patch rows (the im2col of a stride==kernel conv) ----
 // One thread converts 8 horizontally adjacent pixels (two float4 loads -> one 16-byte store).
 // Threads walk the image in its own memory order, so loads are fully coalesced; the two threads that

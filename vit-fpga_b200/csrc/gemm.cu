@@ -39,11 +39,11 @@ cudaError_t encode_tma_2d(void *map_out, int dtype_bytes, const void *ptr, long 
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <int KIND, int BN, int OUT, int STAGES, int CG, int EW, int MODE = MODE_PLAIN>
+template <int KIND, int BN, int OUT, int STAGES, int CG, int EW, int DS = 0>
 static cudaError_t opt_in_smem()
 {
-    return cudaFuncSetAttribute(gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES, CG, EW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                GemmSmem<BN, STAGES, CG, EW, MODE>::TOTAL);
+    return cudaFuncSetAttribute(gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES, CG, EW, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmSmem<BN, STAGES, CG, EW, DS>::TOTAL);
 }
 
 // smem ring depth: what fits next to the epilogue slabs (EW x 4 KB) in 227 KB
@@ -51,9 +51,7 @@ constexpr int STAGES_256 = 4;      // 1 CTA per tile, BN = 256: 48 KB per stage
 constexpr int STAGES_128 = 6;      // 1 CTA per tile, BN = 128: 32 KB per stage
 constexpr int STAGES_256_PAIR = 6; // CTA pair, BN = 256: 16 KB of A + 16 KB of W per CTA and stage
 constexpr int STAGES_256_PAIR_EW16 = 5; // the same with 16 epilogue warps (64 KB of slabs)
-constexpr int STAGES_256_PAIR_RESLN = 5; // MODE_RESLN: two residual slabs per epilogue warp (64 KB)
-constexpr int STAGES_256_PAIR_DS = 5;    // MODE_PLAIN_DS: two output slabs per epilogue warp (64 KB)
-constexpr int STAGES_256_PAIR_LNFOLD = 5; // MODE_LNFOLD: bias + column sums staged in smem (4 KB) do not fit next to 6 stages
+constexpr int STAGES_256_PAIR_DS = 5;   // the same with two output slabs per epilogue warp (64 KB of slabs)
 
 // cudaFuncSetAttribute is per device, so the opt-in runs once for every device that is used.
 cudaError_t gemm_global_init()
@@ -85,10 +83,8 @@ cudaError_t gemm_global_init()
     NC_OPT(KIND_I8, OUT_S32)
 #undef NC_OPT
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_EW16, 2, 16>()) != cudaSuccess) return e;
-    if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_LNFOLD, 2, 8, MODE_LNFOLD>()) != cudaSuccess) return e;
-    if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_DS, 2, 8, MODE_PLAIN_DS>()) != cudaSuccess) return e;
-    if ((e = opt_in_smem<KIND_BF16, 256, OUT_F32, STAGES_256_PAIR_DS, 2, 8, MODE_PLAIN_DS>()) != cudaSuccess) return e;
-    if ((e = opt_in_smem<KIND_BF16, 256, OUT_F32, STAGES_256_PAIR_RESLN, 2, 8, MODE_RESLN>()) != cudaSuccess) return e;
+    if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_DS, 2, 8, 1>()) != cudaSuccess) return e;
+    if ((e = opt_in_smem<KIND_BF16, 256, OUT_F32, STAGES_256_PAIR_DS, 2, 8, 1>()) != cudaSuccess) return e;
     if (dev < 64) done[dev] = true;
     return cudaSuccess;
 }
@@ -137,7 +133,7 @@ static cudaError_t make_out_map(CUtensorMap *map, void *ptr, long long n, long l
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <int KIND, int BN, int OUT, int STAGES, int CG, int EW = 8, int MODE = MODE_PLAIN>
+template <int KIND, int BN, int OUT, int STAGES, int CG, int EW = 8, int DS = 0>
 static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
 {
     CUtensorMap map_a, map_w, map_out;
@@ -153,12 +149,10 @@ static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
     p.remap_in = c.remap_in, p.remap_out = c.remap_out, p.pos = c.pos;
     p.error_flag = c.error_flag;
     p.k_splits = c.k_splits > 1 ? c.k_splits : 1;
-    p.stats = c.stats, p.stats_slots = c.stats_slots, p.colsum = c.colsum, p.ln_inv_dim = c.ln_dim > 0 ? 1.0f / (float)c.ln_dim : 0.0f, p.ln_eps = c.ln_eps;
-    p.xb = c.xb, p.ldxb = c.ldxb;
     p.debug = nullptr;
     if (const char *dbg = getenv("NETCUDA_GEMM_DEBUG_PTR")) p.debug = reinterpret_cast<long long *>(strtoull(dbg, nullptr, 0));
-    if (const char *dm = getenv("NETCUDA_GEMM_DEBUG_MODE")) // timeline of one kernel mode only (the last such launch wins)
-        if (atoi(dm) != MODE) p.debug = nullptr;
+    if (const char *de = getenv("NETCUDA_GEMM_DEBUG_EPI")) // timeline of the launches with one epilogue only (the last such launch wins)
+        if (atoi(de) != c.epi) p.debug = nullptr;
     // TMA-store epilogue whenever the output is addressable by a tensor map; otherwise direct stores
     const long long pitch_bytes = c.ldc * OutTraits<OUT>::ELEM;
     // (TMA bounds the innermost dimension in 16-byte units, so N must be a whole number of them as well)
@@ -174,20 +168,11 @@ static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
     else
         map_out = map_a; // never dereferenced
     if (p.k_splits > 1 && !(p.tma_store && OUT == OUT_S32 && c.epi == EPI_SPLITK)) return cudaErrorInvalidValue;
-    if (MODE == MODE_LNFOLD || MODE == MODE_RESLN)
-    {
-        // the LayerNorm modes live in the TMA-store epilogue and address `stats` / `colsum` / `xb` with 16-byte accesses
-        if (!p.tma_store || !c.stats || (c.n & 63)) return cudaErrorInvalidValue;
-        if (MODE == MODE_LNFOLD && (!c.colsum || !c.bias || c.stats_slots < 1 || c.stats_slots > LN_STATS_SLOTS || c.ln_dim <= 0)) return cudaErrorInvalidValue;
-        if (MODE == MODE_RESLN && (c.epi != EPI_RESIDUAL || !c.xb || (c.ldxb & 7) || (reinterpret_cast<uintptr_t>(c.xb) & 15u) ||
-                                   (c.n + 127) / 128 > LN_STATS_SLOTS))
-            return cudaErrorInvalidValue;
-    }
     const int tiles = ((c.m + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * ((c.n + BN - 1) / BN) * p.k_splits;
     const int sms = c.num_sms > 0 ? c.num_sms : 148;
     const int slots = sms / CG; // tiles in flight: one per CTA, or one per CTA pair
-    return launch_pdl(gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES, CG, EW, MODE>, dim3((unsigned)(CG * (tiles < slots ? tiles : slots))),
-                      dim3(gemm_threads(EW)), (size_t)GemmSmem<BN, STAGES, CG, EW, MODE>::TOTAL, stream, CG, map_a, map_w, map_out, p);
+    return launch_pdl(gemm_tn_tcgen05_kernel<KIND, BN, OUT, STAGES, CG, EW, DS>, dim3((unsigned)(CG * (tiles < slots ? tiles : slots))),
+                      dim3(gemm_threads(EW)), (size_t)GemmSmem<BN, STAGES, CG, EW, DS>::TOTAL, stream, CG, map_a, map_w, map_out, p);
 }
 
 template <int KIND, int OUT>
@@ -202,13 +187,13 @@ static cudaError_t launch_tc_bn(const GemmCall &c, cudaStream_t stream)
         if constexpr (KIND == KIND_BF16 && OUT == OUT_BF16)
             if (c.epi == EPI_GELU && c.variant == 3) return launch_tc<KIND, 256, OUT, STAGES_256_PAIR_EW16, 2, 16>(c, stream);
         // Two output slabs per epilogue warp (slab i + 1 is filled while the TMA store of slab i drains) at the price of one
-        // pipeline stage: pays where the epilogue or the store path sets the pace -- the GELU epilogue (ViT-B fc1: 10.3 -> 10.0 ms
+        // pipeline stage: pays where the epilogue or the store path sets the pace -- the GELU epilogue (ViT-B fc1: 10.3 -> 9.9 ms
         // per step) and the short-K residual update that is bound by the L2 reduce-add (proj: 3.95 -> 3.6 ms) -- and costs where the
         // mainloop does (qkv 6.75 -> 7.0 ms, fc2 8.4 -> 8.7 ms).  Variant 4 forces it everywhere, variant 5 nowhere (A/B).
-        if constexpr (KIND == KIND_BF16)
+        if constexpr (KIND == KIND_BF16 && (OUT == OUT_BF16 || OUT == OUT_F32))
         {
             const bool pays = c.epi == EPI_GELU || (c.epi == EPI_RESIDUAL && c.k <= 1024);
-            if (c.variant == 4 || (c.variant == 0 && pays)) return launch_tc<KIND, 256, OUT, STAGES_256_PAIR_DS, 2, 8, MODE_PLAIN_DS>(c, stream);
+            if (c.variant == 4 || (c.variant == 0 && pays)) return launch_tc<KIND, 256, OUT, STAGES_256_PAIR_DS, 2, 8, 1>(c, stream);
         }
         return launch_tc<KIND, 256, OUT, STAGES_256_PAIR, 2>(c, stream);
     }
@@ -373,14 +358,6 @@ cudaError_t launch_gemm(const GemmCall &c, cudaStream_t stream)
         if (c.kind == GK_BF16) return launch_ref<KIND_BF16>(c, stream);
         if (c.kind == GK_TF32) return launch_ref<KIND_TF32>(c, stream);
         return launch_ref<KIND_I8>(c, stream);
-    }
-    if (c.ln_mode != 0)
-    {
-        // LayerNorm folded into the GEMM: bf16 CTA-pair tiles only (every ViT GEMM next to a LayerNorm: M >= 197 rows)
-        if (c.kind != GK_BF16 || c.m <= GEMM_BM) return cudaErrorInvalidValue;
-        if (c.ln_mode == MODE_LNFOLD && c.out_type == OUT_BF16) return launch_tc<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_LNFOLD, 2, 8, MODE_LNFOLD>(c, stream);
-        if (c.ln_mode == MODE_RESLN && c.out_type == OUT_F32) return launch_tc<KIND_BF16, 256, OUT_F32, STAGES_256_PAIR_RESLN, 2, 8, MODE_RESLN>(c, stream);
-        return cudaErrorInvalidValue;
     }
     if (c.kind == GK_BF16)
     {

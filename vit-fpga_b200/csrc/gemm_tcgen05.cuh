@@ -53,24 +53,6 @@ enum : int
     EPI_GELU_X2 = 8 // EPI_GELU evaluated two elements at a time on the packed fp32 pipe (same bits; chosen by the launcher)
 };
 
-// Kernel modes (template parameter MODE): how LayerNorm is folded into the two GEMMs around it.
-//   MODE_RESLN   residual epilogue that PRODUCES what the next LayerNorm needs: x += acc + bias through an explicit read of
-//                the residual tile (TMA load -> smem -> add -> TMA store) instead of the L2 reduce-add, so that the new x is
-//                known here; it is also written as bf16 (`xb`, the next GEMM's A operand) and its per-row partial sums
-//                (sum x, sum x^2 over this warp's 128 columns) go to `stats`.
-//   MODE_LNFOLD  GEMM that CONSUMES them: A = xb (un-normalised), W' = gamma o W folded at upload,
-//                out = rstd_row * (acc - mean_row * colsum_n) + c_n  with  colsum_n = sum_k W'[n][k],  c_n = bias_n + sum_k beta_k W[n][k]
-//                -- LayerNorm(x) . W^T + bias without a LayerNorm kernel and without its 6 bytes per element of HBM traffic.
-enum : int
-{
-    MODE_PLAIN = 0,
-    MODE_LNFOLD = 1,
-    MODE_RESLN = 2,
-    MODE_PLAIN_DS = 3 // the plain epilogue with two output slabs per warp: slab i + 1 is filled while the TMA store of slab i drains
-};
-constexpr int LN_STATS_SLOTS = 8; // partial (sum, sum of squares) pairs per row: one per 128-column range, N <= 1024
-constexpr int LN_STATS_PITCH = 2 * LN_STATS_SLOTS; // floats per row
-
 struct GemmParams
 {
     int M, N, K;       // K in elements of the operand type
@@ -87,15 +69,6 @@ struct GemmParams
     // pos[(1 + t) * N + col] is added (cls token occupies output row b * remap_out).
     int remap_in, remap_out;
     const float *pos;
-    // MODE_LNFOLD: stats (read), stats_slots = valid slots per row, colsum, ln_inv_dim = 1 / row length D, ln_eps.
-    // MODE_RESLN:  stats (written; every slot of a row that this GEMM covers), xb / ldxb = bf16 copy of the new x.
-    float *stats;
-    int stats_slots;
-    const float *colsum;
-    float ln_inv_dim; // 1 / row length D
-    float ln_eps;
-    void *xb;
-    long long ldxb;
     int *error_flag;
     long long *debug; // optional clock64 stamps of cluster 0: [tile < 40][warp 0..11 of CTA 0, 12..23 of CTA 1][4] (profiling aid)
 };
@@ -139,18 +112,17 @@ __host__ __device__ constexpr int slab_cols()
     return (128 / OutTraits<OUT>::ELEM) < (BN / (EW / 4)) ? (128 / OutTraits<OUT>::ELEM) : (BN / (EW / 4));
 }
 
-template <int BN, int STAGES, int CG, int EW, int MODE = MODE_PLAIN>
+template <int BN, int STAGES, int CG, int EW, int DS = 0>
 struct GemmSmem
 {
     static constexpr int A_BYTES = GEMM_BM * GEMM_STAGE_ROW_BYTES;
     static constexpr int B_BYTES = (BN / CG) * GEMM_STAGE_ROW_BYTES; // a CTA of a pair stages half of the W tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OFF_SLABS = STAGES * STAGE_BYTES; // 1024-byte aligned (stage sizes are multiples of 1024)
-    static constexpr int SLABS_PER_WARP = (MODE == MODE_RESLN || MODE == MODE_PLAIN_DS) ? 2 : 1; // two slabs in flight per warp
+    static constexpr int SLABS_PER_WARP = DS ? 2 : 1; // DS: slab i + 1 is filled while the TMA store of slab i drains
     static constexpr int OFF_BIAS = OFF_SLABS + EW * SLABS_PER_WARP * GEMM_SLAB_BYTES;
-    // bias slice, double-buffered by tile parity (MODE_LNFOLD: + the column sums of the folded weights, same scheme)
-    static constexpr int OFF_BARS = OFF_BIAS + (MODE == MODE_LNFOLD ? 4 : 2) * BN * 4;
-    static constexpr int NUM_BARS = 2 * STAGES + 4 + (MODE == MODE_RESLN ? 2 * EW : 0); // + one "slab landed" barrier per residual slab
+    static constexpr int OFF_BARS = OFF_BIAS + 2 * BN * 4; // bias slice, double-buffered by tile parity
+    static constexpr int NUM_BARS = 2 * STAGES + 4;
     static constexpr int OFF_TMEM_PTR = OFF_BARS + NUM_BARS * 8;
     static constexpr int TOTAL = OFF_TMEM_PTR + 16; // the dynamic smem window itself is 1024-byte aligned (checked in the kernel)
     static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
@@ -323,37 +295,12 @@ __device__ __forceinline__ uint4 epi_convert_chunk(const uint32_t *v, const uint
     return w;
 }
 
-// MODE_LNFOLD, 8 accumulator columns of one row -> 8 bf16:  x = rstd * (acc - mean * colsum) + c,  then the activation.
-// `cs` = colsum words, `b` = c words; nmu = -mean of the row, rs = its 1 / sqrt(var + eps).
-__device__ __forceinline__ uint4 epi_convert_chunk_lnfold(const uint32_t *v, const uint32_t *cs, const uint32_t *b, float nmu, float rs, int epi)
-{
-    float f[8];
-    const uint64_t nmu2 = pack_f32x2(nmu, nmu), rs2 = pack_f32x2(rs, rs);
-#pragma unroll
-    for (int e = 0; e < 8; e += 2)
-    {
-        const uint64_t t = fma_f32x2(nmu2, pack_f32x2(__uint_as_float(cs[e]), __uint_as_float(cs[e + 1])),
-                                     pack_f32x2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
-        float x0, x1;
-        unpack_f32x2(fma_f32x2(rs2, t, pack_f32x2(__uint_as_float(b[e]), __uint_as_float(b[e + 1]))), x0, x1);
-        if (epi == EPI_GELU_X2 || epi == EPI_GELU)
-            gelu_erf_x2_of(x0, x1, f[e], f[e + 1]);
-        else
-            f[e] = epi_act_f32(x0, epi), f[e + 1] = epi_act_f32(x1, epi);
-    }
-    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-}
-
-template <int KIND, int BN, int OUT, int STAGES, int CG, int EW, int MODE = MODE_PLAIN>
+template <int KIND, int BN, int OUT, int STAGES, int CG, int EW, int DS = 0>
 __global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                        const __grid_constant__ CUtensorMap tma_out, const GemmParams p)
 {
-    using L = GemmSmem<BN, STAGES, CG, EW, MODE>;
-    static_assert(MODE == MODE_PLAIN || MODE == MODE_PLAIN_DS || (KIND == KIND_BF16 && BN == 256 && EW == 8),
-                  "the LayerNorm modes exist for the bf16 256-column tiles");
-    static_assert(MODE != MODE_LNFOLD || OUT == OUT_BF16, "MODE_LNFOLD writes bf16");
-    static_assert(MODE != MODE_RESLN || OUT == OUT_F32, "MODE_RESLN updates the fp32 residual stream");
+    using L = GemmSmem<BN, STAGES, CG, EW, DS>;
     constexpr int ELEM = KindTraits<KIND>::ELEM;
     constexpr int BK = GEMM_STAGE_ROW_BYTES / ELEM; // elements of K per stage
     constexpr uint32_t TMEM_COLS = 2 * BN;          // two accumulator stages (power of two >= 32)
@@ -421,8 +368,6 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), EW * CG); // one arrive per epilogue warp (of both CTAs of a pair)
         }
-        if constexpr (MODE == MODE_RESLN)
-            for (int i = 0; i < 2 * EW; i++) mbar_init(bars + 8u * (2 * STAGES + 4 + i), 1);
         fence_barrier_init();
     }
     if (warp == W_ALLOC)
@@ -559,19 +504,14 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         uint32_t *bias_all = reinterpret_cast<uint32_t *>(smem + L::OFF_BIAS);
         uint8_t *slab = smem + L::OFF_SLABS + ew * L::SLABS_PER_WARP * GEMM_SLAB_BYTES;
         const uint32_t slab_addr = base + L::OFF_SLABS + ew * L::SLABS_PER_WARP * GEMM_SLAB_BYTES;
+        [[maybe_unused]] uint32_t slab_seq = 0; // DS: slabs stored so far (parity = buffer)
         uint32_t acc = 0, acc_phase = 0, parity = 0;
-        [[maybe_unused]] uint32_t xs_phase = 0; // MODE_RESLN: bit b = phase of residual-slab barrier b
-        [[maybe_unused]] uint32_t slab_seq = 0; // MODE_PLAIN_DS: slabs stored so far (parity = buffer)
         for (int work = tile0; work < num_work; work += tile_step, parity ^= 1u)
         {
             const int tile = work / S;
             const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
             const int col0 = n_blk * BN;
             const int row0 = m_blk * TILE_M + cta_rank * GEMM_BM + q * 32;
-            const int tl = (work - tile0) / tile_step;
-            const bool dbg = p.debug != nullptr && tile0 == 0 && tl < 40 && lane == 0 && warp < 11;
-            long long *dslot = p.debug + (tl * 24 + cta_rank * 12 + warp) * 4;
-            if (dbg) dslot[3] = clock64();
 
             // This tile's bias slice (bit pattern: float or int32).  Every warp fetches the WARP_COLS values of its own column range
             // into registers before it waits for the accumulator and parks them in smem afterwards (the four warps of a column
@@ -586,149 +526,19 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                 bias_r[i] = (p.bias != nullptr && c < p.N) ? __ldg(reinterpret_cast<const uint32_t *>(p.bias) + c) : 0u;
             }
 
-            // MODE_LNFOLD: the column sums of the folded weights travel like the bias (registers now, smem after the wait), and this
-            // thread's row of LayerNorm statistics (lane = row) is fetched with four independent 16-byte loads: all
-            // LN_STATS_SLOTS partial (sum, sum of squares) pairs of the row -- unused slots hold zeros -- combined in a fixed
-            // order (deterministic).
-            [[maybe_unused]] uint32_t *colsum_s = bias_all + 2 * BN + parity * BN;
-            [[maybe_unused]] uint32_t colsum_r[WARP_COLS / 32];
-            float ln_nmu = 0.0f, ln_rs = 0.0f;
-            if constexpr (MODE == MODE_LNFOLD)
-            {
-#pragma unroll
-                for (int i = 0; i < WARP_COLS / 32; i++)
-                {
-                    const int c = col0 + wcol + i * 32 + lane;
-                    colsum_r[i] = c < p.N ? __ldg(reinterpret_cast<const uint32_t *>(p.colsum) + c) : 0u;
-                }
-                const int r = row0 + lane;
-                if (r < p.M)
-                {
-                    static_assert(LN_STATS_SLOTS == 8, "four float4 loads per row");
-                    const float4 *st = reinterpret_cast<const float4 *>(p.stats + (long long)r * LN_STATS_PITCH);
-                    const float4 t0 = __ldg(st), t1 = __ldg(st + 1), t2 = __ldg(st + 2), t3 = __ldg(st + 3);
-                    // fp32 throughout (FP64 instructions cost this epilogue ~7000 cycles per tile when measured): the variance comes
-                    // from sq - sum * mean with one fma; its relative error is ~2^-23 * mean^2 / var, far below the bf16 operands'.
-                    const float sum = ((t0.x + t0.z) + (t1.x + t1.z)) + ((t2.x + t2.z) + (t3.x + t3.z));
-                    const float sq = ((t0.y + t0.w) + (t1.y + t1.w)) + ((t2.y + t2.w) + (t3.y + t3.w));
-                    const float mean = sum * p.ln_inv_dim;
-                    const float var = fmaxf(fmaf(-sum, mean, sq) * p.ln_inv_dim, 0.0f);
-                    ln_nmu = -mean;
-                    ln_rs = rsqrtf(var + p.ln_eps);
-                }
-            }
-            // MODE_RESLN: the first two residual slabs of this tile start their way from HBM now, long before the accumulator
-            // is complete.  (The previous tile's last stores must have finished reading the two buffers.)
-            constexpr int XS_SLABS = WARP_COLS / SLAB_COLS;
-            int xs_n = 0; // slabs of this warp that lie inside the matrix (warp-uniform)
-            [[maybe_unused]] uint32_t xs_bar0 = 0;
-            if constexpr (MODE == MODE_RESLN)
-            {
-                const int cols_left = p.N - (col0 + wcol);
-                xs_n = cols_left <= 0 ? 0 : (cols_left + SLAB_COLS - 1) / SLAB_COLS < XS_SLABS ? (cols_left + SLAB_COLS - 1) / SLAB_COLS : XS_SLABS;
-                xs_bar0 = bars + 8u * (2 * STAGES + 4 + 2 * ew);
-                if (lane == 0)
-                {
-                    tma_store_wait_read();
-                    for (int b = 0; b < 2 && b < xs_n; b++)
-                    {
-                        mbar_arrive_expect_tx(xs_bar0 + 8u * b, GEMM_SLAB_BYTES);
-                        tma_load_2d(slab_addr + b * GEMM_SLAB_BYTES, &tma_out, xs_bar0 + 8u * b, col0 + wcol + b * SLAB_COLS, row0);
-                    }
-                }
-            }
-
+            const int tl = (work - tile0) / tile_step;
+            const bool dbg = p.debug != nullptr && tile0 == 0 && tl < 40 && lane == 0 && warp < 11;
+            long long *dslot = p.debug + (tl * 24 + cta_rank * 12 + warp) * 4;
             if (dbg) dslot[0] = clock64();
             mbar_wait(tfull_bar(acc), acc_phase, p.error_flag, KERR_EPI_TMEM_FULL);
             tcgen05_fence_after();
             if (dbg) dslot[1] = clock64();
 #pragma unroll
             for (int i = 0; i < WARP_COLS / 32; i++) bias_s[wcol + i * 32 + lane] = bias_r[i];
-            if constexpr (MODE == MODE_LNFOLD)
-            {
-#pragma unroll
-                for (int i = 0; i < WARP_COLS / 32; i++) colsum_s[wcol + i * 32 + lane] = colsum_r[i];
-            }
             __syncwarp();
             const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + wcol;
 
-            if constexpr (MODE == MODE_RESLN)
-            {
-                // ---- residual update with explicit read: x slab (TMA load) + acc + bias -> x slab (TMA store), bf16 copy, row sums ----
-                constexpr int CHUNKS = SLAB_ROW_BYTES / 16; // 8 chunks of 4 fp32 columns
-                static_assert(SLAB_COLS == 32 && SLAB_SWIZZLED, "fp32 slabs are 32 columns x 128 bytes");
-                const int r = row0 + lane;
-                const bool row_ok = r < p.M;
-                float sum = 0.0f, sq = 0.0f;
-                for (int sb = 0; sb < xs_n; sb++)
-                {
-                    const int b = sb & 1;
-                    const int scol = wcol + sb * SLAB_COLS;
-                    mbar_wait(xs_bar0 + 8u * b, (xs_phase >> b) & 1u, p.error_flag, KERR_EPI_TMEM_FULL);
-                    xs_phase ^= 1u << b;
-                    const uint32_t t_slab = t_base + sb * SLAB_COLS;
-                    const uint32_t *bias_slab = bias_s + scol;
-                    uint8_t *row = slab + b * GEMM_SLAB_BYTES + lane * SLAB_ROW_BYTES;
-                    uint4 *xb_row = reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(p.xb) + (long long)r * p.ldxb + col0 + scol);
-                    uint32_t v0[4], v1[4], b0[4], b1[4];
-                    tmem_ld_32xN<4>(t_slab, v0);
-#pragma unroll 1
-                    for (int j = 0; j < CHUNKS; j += 2)
-                    {
-                        load_bias_chunk<4>(bias_slab + j * 4, b0);
-                        load_bias_chunk<4>(bias_slab + (j + 1) * 4, b1);
-                        uint4 *c0 = reinterpret_cast<uint4 *>(row + ((j ^ (lane & 7)) << 4));
-                        uint4 *c1 = reinterpret_cast<uint4 *>(row + (((j + 1) ^ (lane & 7)) << 4));
-                        const uint4 x0 = *c0, x1 = *c1;
-                        tmem_ld_wait();
-                        tmem_ld_32xN<4>(t_slab + (j + 1) * 4, v1);
-                        float n0[4], n1[4];
-                        const uint32_t xo0[4] = {x0.x, x0.y, x0.z, x0.w}, xo1[4] = {x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-                        for (int e = 0; e < 4; e++)
-                        {
-                            n0[e] = __uint_as_float(xo0[e]) + (__uint_as_float(v0[e]) + __uint_as_float(b0[e]));
-                            sum += n0[e];
-                            sq = fmaf(n0[e], n0[e], sq);
-                        }
-                        *c0 = make_uint4(__float_as_uint(n0[0]), __float_as_uint(n0[1]), __float_as_uint(n0[2]), __float_as_uint(n0[3]));
-                        tmem_ld_wait();
-                        if (j + 2 < CHUNKS) tmem_ld_32xN<4>(t_slab + (j + 2) * 4, v0);
-#pragma unroll
-                        for (int e = 0; e < 4; e++)
-                        {
-                            n1[e] = __uint_as_float(xo1[e]) + (__uint_as_float(v1[e]) + __uint_as_float(b1[e]));
-                            sum += n1[e];
-                            sq = fmaf(n1[e], n1[e], sq);
-                        }
-                        *c1 = make_uint4(__float_as_uint(n1[0]), __float_as_uint(n1[1]), __float_as_uint(n1[2]), __float_as_uint(n1[3]));
-                        if (row_ok) // 8 bf16 of the new x: the A operand of the GEMM behind the next LayerNorm
-                            xb_row[j >> 1] = make_uint4(pack_bf16x2(n0[0], n0[1]), pack_bf16x2(n0[2], n0[3]), pack_bf16x2(n1[0], n1[1]), pack_bf16x2(n1[2], n1[3]));
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0)
-                    {
-                        tma_store_2d(&tma_out, slab_addr + b * GEMM_SLAB_BYTES, col0 + scol, row0);
-                        tma_store_commit();
-                        if (sb + 2 < xs_n)
-                        {
-                            // this buffer's next occupant: slab sb + 2 of the tile, as soon as the store has read the smem
-                            tma_store_wait_read();
-                            mbar_arrive_expect_tx(xs_bar0 + 8u * b, GEMM_SLAB_BYTES);
-                            tma_load_2d(slab_addr + b * GEMM_SLAB_BYTES, &tma_out, xs_bar0 + 8u * b, col0 + scol + 2 * SLAB_COLS, row0);
-                        }
-                    }
-                }
-                if (row_ok)
-                {
-                    // (a warp whose columns lie outside the matrix still writes its zero partial sums: the consumer adds every slot)
-                    const int slot = n_blk * (EW / 4) + (ew >> 2);
-                    if (slot < LN_STATS_SLOTS)
-                        *reinterpret_cast<float2 *>(p.stats + (long long)r * LN_STATS_PITCH + 2 * slot) = make_float2(sum, sq);
-                }
-            }
-            else if (p.tma_store)
+            if (p.tma_store)
             {
                 // ---- smem slab + TMA store: 32 rows x SLAB_COLS columns per store ----
                 // A slab row is produced 16 bytes at a time in a ROLLED loop (the next chunk's accumulator columns are in
@@ -742,11 +552,11 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                     const int scol = wcol + sb * SLAB_COLS; // tile column of this slab
                     if (col0 + scol >= p.N) break;          // warp-uniform
                     // the previous store of this warp out of this slab buffer must have finished reading it
-                    const uint32_t buf_off = MODE == MODE_PLAIN_DS ? (slab_seq & 1u) * GEMM_SLAB_BYTES : 0u;
+                    const uint32_t buf_off = DS ? (slab_seq & 1u) * GEMM_SLAB_BYTES : 0u;
                     slab_seq++;
                     if (lane == 0)
                     {
-                        if constexpr (MODE == MODE_PLAIN_DS)
+                        if constexpr (DS)
                             tma_store_wait_read_1();
                         else
                             tma_store_wait_read();
@@ -762,26 +572,14 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                     {
                         load_bias_chunk<CHUNK_COLS>(bias_slab + j * CHUNK_COLS, b0);
                         load_bias_chunk<CHUNK_COLS>(bias_slab + (j + 1) * CHUNK_COLS, b1);
-                        [[maybe_unused]] uint32_t s0[CHUNK_COLS], s1[CHUNK_COLS];
-                        if constexpr (MODE == MODE_LNFOLD)
-                        {
-                            load_bias_chunk<CHUNK_COLS>(colsum_s + scol + j * CHUNK_COLS, s0);
-                            load_bias_chunk<CHUNK_COLS>(colsum_s + scol + (j + 1) * CHUNK_COLS, s1);
-                        }
                         tmem_ld_wait();
                         tmem_ld_32xN<CHUNK_COLS>(t_slab + (j + 1) * CHUNK_COLS, v1);
                         // lane = row; 16-byte chunk j of the row goes to chunk (j ^ (row & 7)) (128B swizzle)
-                        if constexpr (MODE == MODE_LNFOLD)
-                            *reinterpret_cast<uint4 *>(row + ((j ^ (lane & 7)) << 4)) = epi_convert_chunk_lnfold(v0, s0, b0, ln_nmu, ln_rs, epi);
-                        else
-                            *reinterpret_cast<uint4 *>(row + ((SLAB_SWIZZLED ? (j ^ (lane & 7)) : j) << 4)) = epi_convert_chunk<OUT>(v0, b0, epi);
+                        *reinterpret_cast<uint4 *>(row + ((SLAB_SWIZZLED ? (j ^ (lane & 7)) : j) << 4)) = epi_convert_chunk<OUT>(v0, b0, epi);
                         tmem_ld_wait();
                         if (j + 2 < CHUNKS_PER_ROW) tmem_ld_32xN<CHUNK_COLS>(t_slab + (j + 2) * CHUNK_COLS, v0);
-                        if constexpr (MODE == MODE_LNFOLD)
-                            *reinterpret_cast<uint4 *>(row + (((j + 1) ^ (lane & 7)) << 4)) = epi_convert_chunk_lnfold(v1, s1, b1, ln_nmu, ln_rs, epi);
-                        else
-                            *reinterpret_cast<uint4 *>(row + ((SLAB_SWIZZLED ? ((j + 1) ^ (lane & 7)) : (j + 1)) << 4)) =
-                                epi_convert_chunk<OUT>(v1, b1, epi);
+                        *reinterpret_cast<uint4 *>(row + ((SLAB_SWIZZLED ? ((j + 1) ^ (lane & 7)) : (j + 1)) << 4)) =
+                            epi_convert_chunk<OUT>(v1, b1, epi);
                     }
                     fence_proxy_async_smem();
                     __syncwarp();

@@ -64,17 +64,6 @@ struct GemmCall
     const float *pos;
     int *error_flag;
     int num_sms;
-    // LayerNorm folded into the GEMMs around it (gemm_tcgen05.cuh, MODE_*): 0 = plain, 1 = MODE_LNFOLD (bf16 out; `a` is the
-    // un-normalised bf16 residual copy, `bias` = c, `colsum`, `stats` read), 2 = MODE_RESLN (epi must be EPI_RESIDUAL; `stats` and
-    // the bf16 copy `xb` of the updated residual stream are written).
-    int ln_mode = 0;
-    float *stats = nullptr;
-    int stats_slots = 0;
-    const float *colsum = nullptr;
-    int ln_dim = 0;
-    float ln_eps = 0.0f;
-    void *xb = nullptr;
-    long long ldxb = 0;
 };
 
 // out = epilogue(A . W^T + bias) -- tcgen05 path or reference path depending on call.variant / kind.
@@ -88,9 +77,6 @@ cudaError_t encode_tma_2d(void *map_out, int dtype_bytes, const void *ptr, long 
                           int box0, int box1, bool swizzle128);
 
 // y = LayerNorm(x) * gamma + beta; x fp32 rows (pitch ldx), y bf16 rows (pitch ldy).
-// xb = bf16(x) and the row sums (sum x, sum x^2) in slot 0 of `stats` ([rows][16] floats, remaining slots zeroed): what
-// MODE_LNFOLD needs when the residual stream was not produced by a MODE_RESLN GEMM (after the patch embedding).
-cudaError_t launch_cast_stats(const float *x, long long ldx, void *xb, long long ldxb, float *stats, int rows, int dim, cudaStream_t stream);
 cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, const float *beta, void *y, long long ldy,
                              int rows, int dim, float eps, cudaStream_t stream);
 

@@ -411,9 +411,11 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
-// GELU of two pre-activations at once
-__device__ __forceinline__ void gelu_erf_x2_of(float x0, float x1, float &g0, float &g1)
+// (acc0 + bias0, acc1 + bias1) -> GELU of both
+__device__ __forceinline__ void gelu_erf_x2(float acc0, float acc1, float bias0, float bias1, float &g0, float &g1)
 {
+    float x0, x1;
+    unpack_f32x2(add_f32x2(pack_f32x2(acc0, acc1), pack_f32x2(bias0, bias1)), x0, x1);
     const float a0 = fminf(fabsf(x0), 6.0f), a1 = fminf(fabsf(x1), 6.0f);
     const uint64_t a = pack_f32x2(a0, a1);
     uint64_t p = fma_f32x2(pack_f32x2(3.3361295209033415e-05f, 3.3361295209033415e-05f), a,
@@ -428,13 +430,6 @@ __device__ __forceinline__ void gelu_erf_x2_of(float x0, float x1, float &g0, fl
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h0) : "f"(p0));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(p1));
     unpack_f32x2(fma_f32x2(pack_f32x2(-a0, -a1), pack_f32x2(h0, h1), pack_f32x2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f))), g0, g1);
-}
-// (acc0 + bias0, acc1 + bias1) -> GELU of both
-__device__ __forceinline__ void gelu_erf_x2(float acc0, float acc1, float bias0, float bias1, float &g0, float &g1)
-{
-    float x0, x1;
-    unpack_f32x2(add_f32x2(pack_f32x2(acc0, acc1), pack_f32x2(bias0, bias1)), x0, x1);
-    gelu_erf_x2_of(x0, x1, g0, g1);
 }
 
 } // namespace nc

@@ -75,10 +75,6 @@ struct VitBlock
 {
     float *ln1_g, *ln1_b, *qkv_b, *proj_b, *ln2_g, *ln2_b, *fc1_b, *fc2_b;
     void *qkv_w, *proj_w, *fc1_w, *fc2_w; // bf16
-    // LayerNorm folded into the GEMM behind it (gemm_tcgen05.cuh MODE_LNFOLD): W' = bf16(gamma o W), colsum_n = sum_k W'[n][k],
-    // c_n = bias_n + sum_k beta_k W[n][k]
-    void *qkv_wf, *fc1_wf;
-    float *qkv_c, *qkv_s, *fc1_c, *fc1_s;
 };
 
 struct netcuda_net
@@ -88,7 +84,6 @@ struct netcuda_net
     int device = 0, num_sms = 148;
     int max_batch = 0;
     int gemm_variant = 0;
-    bool ln_fused = false;  // ViT: LayerNorm folded into the GEMMs around it (opt-in: NETCUDA_LN_FUSED=1 / netcuda_set_ln_fusion)
     bool use_graphs = true; // NETCUDA_GRAPHS=0 disables the CUDA-graph replay of small MLP passes
     bool weights_loaded = false;
     size_t n_in = 0, n_out = 0;
@@ -120,7 +115,6 @@ struct netcuda_net
     int32_t *splitk_ws = nullptr;          // INT8 small batch: [128][widest layer] int32 partial sums, all zero between layers
     void *patches = nullptr, *ybuf = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *cls_ln = nullptr;
     float *x = nullptr;
-    float *ln_stats = nullptr; // [max_batch * T][16]: per-row partial (sum, sum of squares) pairs for the folded LayerNorm
 
     // CUDA graph of the last small MLP pass (launch-bound regime): replayed while the buffers, the batch and the variant repeat
     struct PassGraph
@@ -309,7 +303,7 @@ extern "C" int netcuda_destroy(netcuda_net *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-    void *dev_ptrs[] = {h->arena, h->act[0], h->act[1], h->acc_out, h->splitk_ws, h->patches, h->ybuf, h->qkv, h->att, h->hid, h->cls_ln, h->x, h->ln_stats,
+    void *dev_ptrs[] = {h->arena, h->act[0], h->act[1], h->acc_out, h->splitk_ws, h->patches, h->ybuf, h->qkv, h->att, h->hid, h->cls_ln, h->x,
                         h->dev_in[0], h->dev_in[1]};
     for (void *p : dev_ptrs)
         if (p) cudaFree(p);
@@ -436,9 +430,7 @@ static int create_impl(const netcuda_desc *desc, netcuda_net *h)
         h->flops_per_sample = 2.0 * ((double)h->NP * h->PK * D +
                                      desc->depth * (N * (4.0 * D * D + 2.0 * D * F) + 2.0 * N * N * D) + (double)D * C);
         const size_t nparams = vit_param_count(desc);
-        const size_t vpad = 256; // folded-LayerNorm vectors are read in 16-byte groups up to the tile edge: pad to whole tiles
-        const size_t fold_bytes = (size_t)desc->depth * (((size_t)3 * D * D + (size_t)F * D) * 2 + 2 * ((size_t)3 * D + F + 2 * vpad) * 4 + 6 * 256);
-        h->arena_bytes = nparams * 4 + (size_t)(desc->depth * 12 + 16) * 256 + fold_bytes; // generous: every tensor as fp32 + alignment
+        h->arena_bytes = nparams * 4 + (size_t)(desc->depth * 12 + 16) * 256; // generous: every tensor as fp32 + alignment
         CK(cudaMalloc((void **)&h->arena, h->arena_bytes));
         auto take = [&](size_t bytes) { return arena_take(h, bytes); };
         h->patch_w = take((size_t)D * h->PK * 2);
@@ -454,9 +446,6 @@ static int create_impl(const netcuda_desc *desc, netcuda_net *h)
             b.ln2_g = (float *)take((size_t)D * 4), b.ln2_b = (float *)take((size_t)D * 4);
             b.fc1_w = take((size_t)F * D * 2), b.fc1_b = (float *)take((size_t)F * 4);
             b.fc2_w = take((size_t)D * F * 2), b.fc2_b = (float *)take((size_t)D * 4);
-            b.qkv_wf = take((size_t)3 * D * D * 2), b.fc1_wf = take((size_t)F * D * 2);
-            b.qkv_c = (float *)take(((size_t)3 * D + vpad) * 4), b.qkv_s = (float *)take(((size_t)3 * D + vpad) * 4);
-            b.fc1_c = (float *)take(((size_t)F + vpad) * 4), b.fc1_s = (float *)take(((size_t)F + vpad) * 4);
         }
         h->lnf_g = (float *)take((size_t)D * 4), h->lnf_b = (float *)take((size_t)D * 4);
         h->head_w = take((size_t)C * D * 2), h->head_b = (float *)take((size_t)C * 4);
@@ -470,11 +459,6 @@ static int create_impl(const netcuda_desc *desc, netcuda_net *h)
         CK(cudaMalloc(&h->att, rows * D * 2));
         CK(cudaMalloc(&h->hid, rows * F * 2));
         CK(cudaMalloc(&h->cls_ln, mb * D * 2));
-        CK(cudaMalloc((void **)&h->ln_stats, rows * LN_STATS_PITCH * 4));
-        CK(cudaMemset(h->arena, 0, h->arena_bytes));
-        if (const char *e = getenv("NETCUDA_LN_FUSED")) h->ln_fused = atoi(e) != 0;
-        // the folded form needs the 256-column CTA-pair tiles and one stats slot per 128 columns of the residual stream
-        if ((D + 127) / 128 > LN_STATS_SLOTS || (D & 63) || (F & 63)) h->ln_fused = false;
     }
     return NETCUDA_OK;
 }
@@ -602,52 +586,15 @@ extern "C" int netcuda_upload_vit(netcuda_net *h, const float *flat, size_t coun
             rc = fail(NETCUDA_ERR_CUDA, "ViT vector upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         p += n;
     };
-    // LayerNorm folded into the GEMM behind it: W' = gamma o W (rounded to bf16 on upload like every operand), and the two
-    // per-column vectors the epilogue needs; colsum is taken over the ROUNDED W' so that a constant row normalises to exactly beta.W
-    std::vector<float> wf, cvec, svec;
-    auto bf16_rn = [](float f) {
-        uint32_t u;
-        memcpy(&u, &f, 4);
-        u += 0x7FFFu + ((u >> 16) & 1u);
-        u &= 0xFFFF0000u;
-        memcpy(&f, &u, 4);
-        return f;
-    };
-    auto fold = [&](const float *gamma, const float *beta, const float *w, const float *bias, long long rows, int cols, void *dst_w, float *dst_c,
-                    float *dst_s) {
-        if (rc != NETCUDA_OK) return;
-        wf.resize((size_t)rows * cols), cvec.resize((size_t)rows), svec.resize((size_t)rows);
-        for (long long n = 0; n < rows; n++)
-        {
-            double cs = 0.0, cb = 0.0;
-            for (int k = 0; k < cols; k++)
-            {
-                const float v = gamma[k] * w[n * cols + k];
-                wf[(size_t)(n * cols + k)] = v;
-                cs += (double)bf16_rn(v);
-                cb += (double)beta[k] * (double)w[n * cols + k];
-            }
-            svec[(size_t)n] = (float)cs;
-            cvec[(size_t)n] = (float)((double)bias[n] + cb);
-        }
-        rc = upload_matrix(h, wf.data(), rows, cols, cols, GK_BF16, dst_w, scratch);
-        if (rc == NETCUDA_OK && (cudaMemcpy(dst_c, cvec.data(), (size_t)rows * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-                                 cudaMemcpy(dst_s, svec.data(), (size_t)rows * 4, cudaMemcpyHostToDevice) != cudaSuccess))
-            rc = fail(NETCUDA_ERR_CUDA, "ViT folded-LayerNorm upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-    };
     mat(h->patch_w, D, h->PK);
     vec(h->patch_b, D);
     vec(h->cls, D);
     vec(h->pos, (size_t)h->T * D);
     for (auto &b : h->blocks)
     {
-        const float *g1 = p, *b1 = p + D, *qw = p + 2 * (size_t)D, *qb = qw + (size_t)3 * D * D;
-        fold(g1, b1, qw, qb, 3LL * D, D, b.qkv_wf, b.qkv_c, b.qkv_s);
         vec(b.ln1_g, D), vec(b.ln1_b, D);
         mat(b.qkv_w, 3LL * D, D), vec(b.qkv_b, 3 * (size_t)D);
         mat(b.proj_w, D, D), vec(b.proj_b, D);
-        const float *g2 = p, *b2 = p + D, *f1w = p + 2 * (size_t)D, *f1b = f1w + (size_t)F * D;
-        fold(g2, b2, f1w, f1b, F, D, b.fc1_wf, b.fc1_c, b.fc1_s);
         vec(b.ln2_g, D), vec(b.ln2_b, D);
         mat(b.fc1_w, F, D), vec(b.fc1_b, F);
         mat(b.fc2_w, D, F), vec(b.fc2_b, D);
@@ -665,11 +612,9 @@ static int out_elem_size(int out_type) { return out_type == OUT_BF16 ? 2 : out_t
 
 static cudaError_t run_gemm(netcuda_net *h, const char *label, int kind, const void *a, long long lda, int a_rows, const void *w,
                             long long ldw, const void *bias, void *out, long long ldc, int out_type, int epi, int m, int n, int k,
-                            cudaStream_t s, int remap_in = 0, int remap_out = 0, const float *pos = nullptr, int k_splits = 1,
-                            const GemmCall *ln = nullptr)
+                            cudaStream_t s, int remap_in = 0, int remap_out = 0, const float *pos = nullptr, int k_splits = 1)
 {
     GemmCall c;
-    if (ln) c = *ln; // the LayerNorm-mode fields; everything else is filled in below
     c.k_splits = k_splits;
     c.kind = kind, c.variant = h->gemm_variant;
     c.a = a, c.lda = lda, c.a_rows = a_rows, c.w = w, c.ldw = ldw, c.bias = bias;
@@ -680,8 +625,6 @@ static cudaError_t run_gemm(netcuda_net *h, const char *label, int kind, const v
     const double es = kind == GK_BF16 ? 2 : kind == GK_I8 ? 1 : 4;
     double bytes = ((double)m * k + (double)n * k) * es + (double)m * n * out_elem_size(out_type) + (double)n * 4;
     if (epi == EPI_RESIDUAL) bytes += (double)m * n * 4;
-    if (ln && ln->ln_mode == MODE_RESLN) bytes += (double)m * n * 2 + (double)m * 8 * ((n + 127) / 128); // bf16 copy + row sums
-    if (ln && ln->ln_mode == MODE_LNFOLD) bytes += (double)n * 4 + (double)m * 8 * ln->stats_slots;
     if (epi == EPI_PATCH) bytes += (double)remap_in * n * 4;
     KernelScope scope(h, s, label, 2.0 * m * n * k, bytes);
     return launch_gemm(c, s);
@@ -798,40 +741,6 @@ static int vit_pass(netcuda_net *h, const float *img, const uint8_t *img_u8, int
         KernelScope scope(h, s, "cls_rows", 0.0, (double)n * D * 4.0 + (double)D * 8.0);
         CK(launch_cls_rows(h->x, h->cls, h->pos, n, T, D, s));
     }
-    if (h->ln_fused && h->gemm_variant == 0 && rows > GEMM_BM) // (the folded form lives in the CTA-pair tiles: more than 128 token rows)
-    {
-        // LayerNorm folded into the GEMMs around it: no LayerNorm kernel between the blocks.  ybuf holds bf16(x) (un-normalised),
-        // ln_stats the row sums; both are refreshed by the epilogue of every GEMM that updates x (MODE_RESLN).
-        GemmCall fold, res;
-        fold.ln_mode = MODE_LNFOLD, fold.stats = h->ln_stats, fold.ln_dim = D, fold.ln_eps = 1e-6f;
-        res.ln_mode = MODE_RESLN, res.stats = h->ln_stats, res.xb = h->ybuf, res.ldxb = D;
-        const int slots = 2 * ((D + 255) / 256); // what a MODE_RESLN GEMM with N = D writes per row
-        {
-            KernelScope scope(h, s, "cast_stats", 0.0, (double)rows * D * 6.0 + (double)rows * 64.0);
-            CK(launch_cast_stats(h->x, D, h->ybuf, D, h->ln_stats, rows, D, s));
-        }
-        for (size_t i = 0; i < h->blocks.size(); i++)
-        {
-            VitBlock &b = h->blocks[i];
-            fold.stats_slots = i == 0 ? 1 : slots;
-            fold.colsum = b.qkv_s;
-            CK(run_gemm(h, "qkv", GK_BF16, h->ybuf, D, cap, b.qkv_wf, D, b.qkv_c, h->qkv, 3LL * D, OUT_BF16, EPI_NONE, rows, 3 * D, D, s, 0, 0, nullptr, 1,
-                        &fold));
-            {
-                KernelScope scope(h, s, "attention", 4.0 * n * (double)T * T * D, (double)rows * D * 8.0);
-                CK(launch_attention(h->qkv, h->att, n, T, h->desc.heads, s, h->d_err, h->num_sms, 0));
-            }
-            CK(run_gemm(h, "proj", GK_BF16, h->att, D, cap, b.proj_w, D, b.proj_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, D, s, 0, 0, nullptr, 1, &res));
-            fold.stats_slots = slots;
-            fold.colsum = b.fc1_s;
-            CK(run_gemm(h, "fc1", GK_BF16, h->ybuf, D, cap, b.fc1_wf, D, b.fc1_c, h->hid, F, OUT_BF16, EPI_GELU, rows, F, D, s, 0, 0, nullptr, 1, &fold));
-            // (the last block's output is only read by the final LayerNorm on the class tokens: plain residual epilogue)
-            const bool last = i + 1 == h->blocks.size();
-            CK(run_gemm(h, "fc2", GK_BF16, h->hid, F, cap, b.fc2_w, F, b.fc2_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, F, s, 0, 0, nullptr, 1,
-                        last ? nullptr : &res));
-        }
-    }
-    else
     for (auto &b : h->blocks)
     {
         if (int rc = run_layernorm(h, "layernorm", h->x, D, b.ln1_g, b.ln1_b, h->ybuf, D, rows, D, s)) return rc;
@@ -1248,17 +1157,6 @@ extern "C" int netcuda_profile_read(netcuda_net *h, netcuda_kernel_stat *stats, 
     for (int i = 0; i < cap && i < (int)acc.size(); i++) stats[i] = acc[i];
     h->prof_labels.clear();
     return rc;
-}
-
-extern "C" int netcuda_set_ln_fusion(netcuda_net *h, int on)
-{
-    if (int rc = check_handle(h)) return rc;
-    if (h->desc.kind != NETCUDA_KIND_VIT) return fail(NETCUDA_ERR_INVALID, "LayerNorm fusion is a ViT setting");
-    const int D = h->desc.dim, F = h->desc.mlp_dim;
-    if (on && ((D + 127) / 128 > LN_STATS_SLOTS || (D & 63) || (F & 63)))
-        return fail(NETCUDA_ERR_UNSUPPORTED, "the folded LayerNorm needs dim <= 1024 and dim, mlp_dim multiples of 64");
-    h->ln_fused = on != 0;
-    return NETCUDA_OK;
 }
 
 extern "C" int netcuda_set_gemm_variant(netcuda_net *h, int variant)

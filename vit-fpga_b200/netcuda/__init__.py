@@ -367,9 +367,6 @@ class Net:
         return {buf[i].label.decode(): dict(launches=int(buf[i].launches), ms=buf[i].ms, flops=buf[i].flops, bytes=buf[i].bytes)
                 for i in range(min(n.value, 64))}
 
-    def set_ln_fusion(self, on: bool) -> None:
-        _check(lib.netcuda_set_ln_fusion(self._h, C.c_int(int(on))))
-
     def set_gemm_variant(self, variant: int) -> None:
         _check(lib.netcuda_set_gemm_variant(self._h, C.c_int(variant)))
 
