@@ -55,12 +55,15 @@ for name, batch, mb in (("vit_tiny_16_224", 256, 256), ("vit_large_16_384", 64, 
 # C5: 8 x 4096 INT8, batch sweep
 npl, n_ins = [4096] * 8, 4096
 wq = rng.integers(-8, 9, 8 * 4096 * 4096, dtype=np.int8); bq = rng.integers(-2000, 2000, 8 * 4096, dtype=np.int32)
-net = nc.Net.mlp(npl, n_ins, precision=nc.PREC_INT8, max_batch=16384); net.upload_mlp_i8(wq, bq)
-for batch in (1, 16, 128, 1024, 4096, 16384):
-    x = torch.randint(-128, 128, (batch, n_ins), dtype=torch.int8, device="cuda"); y = torch.empty((batch, 4096), dtype=torch.int32, device="cuda")
-    for _ in range(3): net.forward_device_i8(x, y, batch, s)
-    ms = timeit(lambda: net.forward_device_i8(x, y, batch, s), s, inner=5)
-    ops = 2.0 * 8 * 4096 * 4096 * batch
-    out[f"C5 int8 batch {batch}"] = dict(ms=ms, samples_per_s=batch / ms * 1e3, tops=ops / ms / 1e9, weight_stream_gbs=8 * 4096 * 4096 / ms / 1e6)
-net.close()
+for path in ("default", "gemm_only"):  # default: <= 16 samples run the persistent weight-streaming kernel (mlp_stream.cu)
+    if path == "gemm_only": os.environ["NETCUDA_MLP_STREAM"] = "0"
+    net = nc.Net.mlp(npl, n_ins, precision=nc.PREC_INT8, max_batch=16384); net.upload_mlp_i8(wq, bq)
+    for batch in (1, 4, 16, 128, 1024, 4096, 16384) if path == "default" else (1, 4, 16):
+        x = torch.randint(-128, 128, (batch, n_ins), dtype=torch.int8, device="cuda"); y = torch.empty((batch, 4096), dtype=torch.int32, device="cuda")
+        for _ in range(3): net.forward_device_i8(x, y, batch, s)
+        ms = timeit(lambda: net.forward_device_i8(x, y, batch, s), s, inner=5)
+        ops = 2.0 * 8 * 4096 * 4096 * batch
+        out[f"C5 int8 batch {batch}" + ("" if path == "default" else " (split-K GEMM path)")] = dict(
+            ms=ms, samples_per_s=batch / ms * 1e3, tops=ops / ms / 1e9, weight_stream_gbs=8 * 4096 * 4096 / ms / 1e6)
+    net.close()
 print(json.dumps(out, indent=1))

@@ -27,7 +27,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("NETCUDA_CXX", "/usr/bin/g++")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-ccbin", CXX]
-CU_SOURCES = ["gemm.cu", "elementwise.cu", "attention.cu", "runtime.cu", "weights_io.cu"]
+CU_SOURCES = ["gemm.cu", "elementwise.cu", "attention.cu", "mlp_stream.cu", "runtime.cu", "weights_io.cu"]
 CU_HEADERS = ["ptx.cuh", "gemm_tcgen05.cuh", "kernels.h"]
 HOST_SOURCES = ["net_cuda.cpp", "host_capi.cpp"]
 

@@ -76,6 +76,31 @@ cudaError_t gemm_global_init();
 cudaError_t encode_tma_2d(void *map_out, int dtype_bytes, const void *ptr, long long dim0, long long dim1, long long pitch_bytes,
                           int box0, int box1, bool swizzle128);
 
+// ---- INT8 MLP forward for 1..16 samples in one persistent weight-streaming kernel (mlp_stream.cu) ----
+constexpr int MLP_STREAM_MAX_LAYERS = 16;
+struct MlpStreamLayer
+{
+    const int8_t *w;     // [fan_out][fan_in], fan_in a multiple of 16, at most 4096
+    const int32_t *bias; // [fan_out]
+    int fan_in, fan_out;
+};
+struct MlpStreamParams
+{
+    MlpStreamLayer layers[MLP_STREAM_MAX_LAYERS];
+    int n_layers, batch;
+    int max_fan_in;      // widest fan-in of the net (sizes the ring slots)
+    unsigned relu_mask;  // bit l: ReLU after layer l
+    const int8_t *in;    // [batch][fan_in of layer 0]
+    int8_t *act[2];      // hidden activations: layer l writes act[(l + 1) & 1] with pitch fan_out, layer l + 1 reads it
+    int32_t *out;        // [batch][fan_out of the last layer]: raw accumulators (+ bias, ReLU if flagged)
+    unsigned *barrier;   // two zero-initialised counters in device memory (left at zero by every launch)
+    long long *debug = nullptr; // optional [n_layers][6] globaltimer stamps of CTA debug_cta (NETCUDA_STREAM_DEBUG_PTR)
+    int debug_cta = 0;
+    int *error_flag;
+};
+bool mlp_stream_supported(const MlpStreamParams &p, int grid);
+cudaError_t launch_mlp_i8_stream(const MlpStreamParams &p, int grid, cudaStream_t stream);
+
 // y = LayerNorm(x) * gamma + beta; x fp32 rows (pitch ldx), y bf16 rows (pitch ldy).
 cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, const float *beta, void *y, long long ldy,
                              int rows, int dim, float eps, cudaStream_t stream);

@@ -113,6 +113,8 @@ struct netcuda_net
     void *act[2] = {nullptr, nullptr};     // MLP ping-pong
     int32_t *acc_out = nullptr;            // INT8 float API: last layer accumulators
     int32_t *splitk_ws = nullptr;          // INT8 small batch: [128][widest layer] int32 partial sums, all zero between layers
+    unsigned *stream_bar = nullptr;        // INT8, <= 16 samples: the two counters of the weight-streaming kernel's grid barrier
+    bool use_stream = true;                // NETCUDA_MLP_STREAM=0 keeps such batches on the split-K GEMM path
     void *patches = nullptr, *ybuf = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *cls_ln = nullptr;
     float *x = nullptr;
 
@@ -303,7 +305,7 @@ extern "C" int netcuda_destroy(netcuda_net *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-    void *dev_ptrs[] = {h->arena, h->act[0], h->act[1], h->acc_out, h->splitk_ws, h->patches, h->ybuf, h->qkv, h->att, h->hid, h->cls_ln, h->x,
+    void *dev_ptrs[] = {h->arena, h->act[0], h->act[1], h->acc_out, h->splitk_ws, h->stream_bar, h->patches, h->ybuf, h->qkv, h->att, h->hid, h->cls_ln, h->x,
                         h->dev_in[0], h->dev_in[1]};
     for (void *p : dev_ptrs)
         if (p) cudaFree(p);
@@ -415,6 +417,9 @@ static int create_impl(const netcuda_desc *desc, netcuda_net *h)
             for (auto &L : h->layers) widest = std::max(widest, L.fan_out);
             CK(cudaMalloc((void **)&h->splitk_ws, (size_t)SPLITK_MAX_M * widest * 4));
             CK(cudaMemset(h->splitk_ws, 0, (size_t)SPLITK_MAX_M * widest * 4));
+            CK(cudaMalloc((void **)&h->stream_bar, 2 * sizeof(unsigned)));
+            CK(cudaMemset(h->stream_bar, 0, 2 * sizeof(unsigned)));
+            if (const char *e = getenv("NETCUDA_MLP_STREAM")) h->use_stream = atoi(e) != 0;
         }
     }
     else
@@ -630,6 +635,33 @@ static cudaError_t run_gemm(netcuda_net *h, const char *label, int kind, const v
     return launch_gemm(c, s);
 }
 
+// INT8 nets, up to 16 samples: the whole forward is one persistent weight-streaming kernel (mlp_stream.cu) when every layer's
+// fan-in is a multiple of 16 bytes (no row padding anywhere) and the per-CTA output slices fit its shared memory.
+static bool mlp_stream_params(netcuda_net *h, int n, const int8_t *in, int32_t *out, MlpStreamParams &p)
+{
+    if (h->desc.kind != NETCUDA_KIND_MLP || h->desc.precision != NETCUDA_PREC_INT8 || !h->use_stream || h->gemm_variant != 0 || !h->stream_bar)
+        return false;
+    const int L = (int)h->layers.size();
+    if (n < 1 || n > 16 || L > MLP_STREAM_MAX_LAYERS) return false;
+    p.n_layers = L, p.batch = n, p.relu_mask = 0, p.max_fan_in = 0;
+    for (int l = 0; l < L; l++)
+    {
+        const MlpLayer &ly = h->layers[l];
+        if (ly.ldw != ly.fan_in) return false;
+        p.layers[l].w = (const int8_t *)ly.w, p.layers[l].bias = (const int32_t *)ly.bias;
+        p.layers[l].fan_in = ly.fan_in, p.layers[l].fan_out = ly.fan_out;
+        p.max_fan_in = std::max(p.max_fan_in, ly.fan_in);
+        const bool last = l == L - 1;
+        if (h->desc.activation == NETCUDA_ACT_RELU_ALL || (h->desc.activation == NETCUDA_ACT_RELU_HIDDEN && !last)) p.relu_mask |= 1u << l;
+    }
+    p.in = in, p.act[0] = (int8_t *)h->act[0], p.act[1] = (int8_t *)h->act[1], p.out = out;
+    p.barrier = h->stream_bar, p.error_flag = h->d_err;
+    p.debug = nullptr, p.debug_cta = 0;
+    if (const char *dbg = getenv("NETCUDA_STREAM_DEBUG_PTR")) p.debug = reinterpret_cast<long long *>(strtoull(dbg, nullptr, 0));
+    if (const char *dc = getenv("NETCUDA_STREAM_DEBUG_CTA")) p.debug_cta = atoi(dc);
+    return mlp_stream_supported(p, h->num_sms);
+}
+
 // MLP pass.  `in_f32` (fp32 [n][n_in]) or `in_i8` (int8 [n][n_in]); writes fp32 `out_f32` or int32 `out_i32`.
 static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, int n, float *out_f32, int32_t *out_i32, cudaStream_t s)
 {
@@ -638,10 +670,15 @@ static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, in
     const long long ld0 = h->layers[0].ldw;
     const void *cur;
     long long cur_ld;
+    MlpStreamParams sp;
+    // (an int8 input of a streamed pass is read in place: its rows are unpadded)
+    const bool stream_in_place = in_i8 && n <= 16 && mlp_stream_params(h, n, in_i8, out_i32 ? out_i32 : h->acc_out, sp);
     if (prec == NETCUDA_PREC_FP32)
     {
         cur = in_f32, cur_ld = (long long)h->n_in; // CUDA-core path reads the caller's matrix in place
     }
+    else if (stream_in_place)
+        cur = in_i8, cur_ld = ld0;
     else
     {
         KernelScope scope(h, s, "convert_in", 0.0, (double)n * ((double)h->n_in * (in_i8 ? 1 : 4) + (double)ld0 * h->elem));
@@ -658,7 +695,19 @@ static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, in
         cur = h->act[0], cur_ld = ld0;
     }
     int slot = 1;
-    for (int l = 0; l < L; l++)
+    bool streamed = false;
+    if (prec == NETCUDA_PREC_INT8 && n <= 16)
+    {
+        if (mlp_stream_params(h, n, (const int8_t *)cur, out_i32 ? out_i32 : h->acc_out, sp))
+        {
+            double bytes = 0.0, ops = 0.0;
+            for (auto &ly : h->layers) bytes += (double)ly.fan_in * ly.fan_out + 4.0 * ly.fan_out, ops += 2.0 * n * (double)ly.fan_in * ly.fan_out;
+            KernelScope scope(h, s, "mlp_stream", ops, bytes);
+            CK(launch_mlp_i8_stream(sp, h->num_sms, s));
+            streamed = true;
+        }
+    }
+    for (int l = 0; l < L && !streamed; l++)
     {
         const MlpLayer &ly = h->layers[l];
         const bool last = (l == L - 1);
@@ -831,8 +880,10 @@ static int forward_device_impl(netcuda_net *h, const void *d_in, bool in_is_i8, 
             int32_t *oi = out_is_i32 ? (int32_t *)d_out + done * h->n_out : nullptr;
             // single small pass, not being profiled (the profile brackets individual launches): graph replay
             // (worth it from about eight kernels up: a 3-layer net was measured faster with plain launches, 71 vs 86 us per call)
-            if (allow_graph && h->layers.size() >= 4 && batch <= (size_t)GRAPH_MAX_SAMPLES && batch <= (size_t)h->max_batch && !h->profiling &&
-                h->use_graphs)
+            MlpStreamParams sp;
+            const bool streamed = mlp_stream_params(h, n, q ? q : (const int8_t *)h->act[0], oi ? oi : h->acc_out, sp); // (three launches at most)
+            if (allow_graph && !streamed && h->layers.size() >= 4 && batch <= (size_t)GRAPH_MAX_SAMPLES && batch <= (size_t)h->max_batch &&
+                !h->profiling && h->use_graphs)
                 rc = mlp_pass_graphed(h, f, q, n, of, oi, s);
             else
                 rc = mlp_pass(h, f, q, n, of, oi, s);
