@@ -225,6 +225,35 @@ def test_attention_vs_oracle(netcuda, oracle, torch_cuda, batch, tokens, heads):
     assert _max_rel(got, want) <= 1e-2
 
 
+def test_attention_late_peaks_take_the_rescale_path(netcuda, oracle, torch_cuda):
+    """The tcgen05 kernel reads S once: p = 2^((s - m) * scale) with m = the first 32 keys' maximum, raised only when a later chunk
+    exceeds it by more than 8 binades -- then the P chunks written so far are rescaled in tensor memory.  Rows built to do that twice
+    (keys 100 and 180 beat everything before them by 8.7 and 9 binades) while the first 32 keys still carry ~8 % of the weight before
+    the second peak: a wrong or missing rescale shows up far above the tolerance."""
+    torch = torch_cuda
+    rng = np.random.default_rng(99)
+    batch, tokens, heads = 3, 197, 2
+    qkv = (rng.standard_normal((batch, tokens, 3, heads, 64)) * 0.25).astype(np.float32)
+    u = np.full(64, 0.125, np.float32)  # unit vector; all products below are exact in bf16
+    qkv[:, :, 0, 0, :] = 8.0 * u                       # every query of head 0
+    qkv[:, :32, 1, 0, :] = 3.0 * u                     # raw score 24 for the first chunk of keys
+    qkv[:, 100, 1, 0, :] = 9.0 * u                     # 72: +48 raw = +8.7 binades -> first raise
+    qkv[0, 180, 1, 0, :] = 15.25 * u                   # image 0 only: 122 = +9 binades -> second raise
+    qkv[:, :32, 2, 0, :] = 1.0                         # values that tell the three groups apart
+    qkv[:, 100, 2, 0, :] = -1.0
+    qkv[:, 180, 2, 0, :] = 3.0
+    qkv = _bf16_round(torch, qkv.reshape(batch * tokens, 3 * heads * 64))
+    dq = torch.from_numpy(qkv).cuda().to(torch.bfloat16)
+    out = torch.full((batch * tokens, heads * 64), 55.0, dtype=torch.bfloat16, device="cuda")
+    netcuda.op_attention(dq, out, batch, tokens, heads)
+    torch.cuda.synchronize()
+    want = oracle.attention(qkv, batch, tokens, heads)
+    got = out.float().cpu().numpy()
+    assert -0.9 < want[tokens + 5, 0] < -0.75  # image 1: mostly key 100 (-1), visibly pulled towards the first chunk's +1
+    assert want[5, 0] > 2.9                    # image 0: key 180 (3) after the second raise
+    assert _max_rel(got, want) <= 1e-2
+
+
 def test_attention_tcgen05_matches_mma_sync_kernel(netcuda, torch_cuda, monkeypatch):
     """Both attention kernels on a full ViT-B pass worth of heads (256 images x 12 heads x 197 tokens)."""
     torch = torch_cuda

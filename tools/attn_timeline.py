@@ -19,8 +19,8 @@ print("producer issue (rel):", (d[:21, 0, 0] - t0))
 print("mma S0,S1,PV0,PV1 per item:")
 print(d[:21, 1, :4] - t0)
 for w in (4, 8):
-    print(f"warp {w}: wait_start, S ready, pass1 done, pass2 done(arrive), O ready, stores done")
-    print(d[:21, w, :6] - t0)
+    print(f"warp {w}: wait_start, S ready, softmax start, softmax done(arrive), O ready, O in registers, stores done")
+    print(d[:21, w, [0, 1, 2, 3, 4, 6, 5]] - t0)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(20):

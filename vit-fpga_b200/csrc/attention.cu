@@ -254,7 +254,9 @@ constexpr int ATC_W_PRODUCER = 0, ATC_W_MMA = 1, ATC_W_ALLOC = 2;
 constexpr int ATC_Q_BYTES = 128 * 128;  // one query tile: 128 rows x 64 bf16
 constexpr int ATC_KV_BYTES = 256 * 128; // up to 256 keys x 64 bf16
 constexpr int ATC_BUF_BYTES = 2 * ATC_Q_BYTES + 2 * ATC_KV_BYTES;
-constexpr int ATC_OFF_BARS = 2 * ATC_BUF_BYTES;
+constexpr int ATC_OSLAB_BYTES = 32 * 128;         // one softmax warp's 32 output rows x 64 bf16 (128B-swizzled TMA-store source)
+constexpr int ATC_OFF_OSLAB = 2 * ATC_BUF_BYTES; // 1024-byte aligned
+constexpr int ATC_OFF_BARS = ATC_OFF_OSLAB + 8 * ATC_OSLAB_BYTES;
 constexpr int ATC_NUM_BARS = 4 + 8;
 constexpr int ATC_OFF_TMEM_PTR = ATC_OFF_BARS + ATC_NUM_BARS * 8;
 constexpr int ATC_SMEM = ATC_OFF_TMEM_PTR + 16;
@@ -277,12 +279,14 @@ struct AttnTcParams
     int batch, tokens, heads;
     int n_pad;    // keys padded to a multiple of 16 (UMMA N of the S tile, UMMA K extent of P.V)
     int n_mtiles; // 1 or 2 query tiles of 128 rows
+    int stagger;  // hold the first S of tile 1 back until tile 0 has finished its first softmax (the two warpgroups then alternate)
     int *error_flag;
     long long *debug; // optional [32 items][12 warps][8] clock64 stamps of CTA 0 (profiling aid; null in production)
 };
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const AttnTcParams p)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
+                    const __grid_constant__ CUtensorMap tma_out, const AttnTcParams p)
 {
     extern __shared__ __align__(1024) uint8_t atc_smem[];
     const uint32_t base = smem_u32(atc_smem);
@@ -383,7 +387,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                     // The very first S_1 is held back until tile 0 has finished its first softmax: the two warpgroups then
                     // stay half a period apart, so that one is in its exp2 (MUFU-bound) pass while the other one waits for
                     // its MMAs, reduces the row max or stores O, instead of both fighting for the MUFU at the same time.
-                    if (it_s[t] < n_it && it_pv[t] == it_s[t] && !(t == 1 && it_s[1] == 0 && it_pv[0] == 0))
+                    if (it_s[t] < n_it && it_pv[t] == it_s[t] && !(p.stagger && t == 1 && it_s[1] == 0 && it_pv[0] == 0))
                     {
                         const int i = it_s[t], buf = i & 1;
                         if (mbar_test_wait(full_bar(buf), (uint32_t)(i >> 1) & 1u) && mbar_test_wait(sfree_bar(t), ((uint32_t)i & 1u) ^ 1u))
@@ -440,6 +444,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         const int qrow = t * 128 + q * 32 + lane; // query row within the image
         const uint32_t region = tmem_base + ((uint32_t)(q * 32) << 16) + t * ATC_REGION_COLS;
         const float sl = 0.125f * 1.4426950408889634f; // 1/sqrt(64) * log2(e)
+        uint8_t *oslab = atc_smem + ATC_OFF_OSLAB + (warp - 4) * ATC_OSLAB_BYTES;
+        const uint32_t oslab_addr = base + ATC_OFF_OSLAB + (warp - 4) * ATC_OSLAB_BYTES;
         const int nfull = p.tokens >> 5, tail = p.tokens & 31; // full 32-key chunks, keys in the ragged last chunk
         const int nchunks = nfull + (tail ? 1 : 0);
         int it = 0;
@@ -455,11 +461,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             tcgen05_fence_after();
             stamp(1);
 
-            // ---- pass 1: exact row maximum over the valid keys (chunk c + 1 is in flight while c is reduced) ----
-            float mx = -INFINITY;
+            // ---- single pass over S (32-key chunks; chunk c + 1 is in flight while c is processed) ----
+            // p = 2^((s - m) * scale) with a reference maximum m that is the maximum of the FIRST chunk and is only raised when a
+            // later chunk exceeds it by more than 8 binades: softmax does not care which constant is subtracted, p <= 2^8 is as
+            // exact in bf16 / fp32 as p <= 1, and S is read from tensor memory once instead of twice (the kernel is paced by
+            // the TMEM read port: 2 x 208 + 64 columns per row before, 208 + 64 now).  When a row does exceed the margin, the
+            // whole warp takes the slow path: the P chunks written so far and the running sums are rescaled to the new maximum
+            // (rows that did not ask for it multiply by 1).  P (bf16) overwrites the first half of the S columns it came from.
+            stamp(2);
+            float mref = 0.0f, msc = 0.0f;
+            float sum0 = 0.0f, sum1 = 0.0f;
             {
                 uint32_t va[32], vb[32];
-                auto reduce = [&](const uint32_t *v, int c) {
+                const float margin = 8.0f / sl; // 8 binades in raw-score units
+                auto chunk_max = [&](const uint32_t *v, int c) {
+                    float mx;
                     if (c < nfull)
                     {
                         float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
@@ -469,37 +485,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                             m0 = fmaxf(m0, __uint_as_float(v[j])), m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
                             m2 = fmaxf(m2, __uint_as_float(v[j + 2])), m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
                         }
-                        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+                        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                     }
                     else
                     {
+                        mx = __uint_as_float(v[0]); // (a ragged chunk holds at least one key)
 #pragma unroll
-                        for (int j = 0; j < 32; j++)
+                        for (int j = 1; j < 32; j++)
                             if (j < tail) mx = fmaxf(mx, __uint_as_float(v[j]));
                     }
+                    return mx;
                 };
-                tmem_ld_32x32(region, va);
-                for (int c = 0; c < nchunks; c += 2)
-                {
-                    tmem_ld_wait();
-                    if (c + 1 < nchunks) tmem_ld_32x32(region + (c + 1) * 32, vb);
-                    reduce(va, c);
-                    if (c + 1 < nchunks)
-                    {
-                        tmem_ld_wait();
-                        if (c + 2 < nchunks) tmem_ld_32x32(region + (c + 2) * 32, va);
-                        reduce(vb, c + 1);
-                    }
-                }
-            }
-
-            stamp(2);
-            // ---- pass 2: p = 2^((s - max) * scale); P (bf16) overwrites the first half of the S columns it came from ----
-            const float msc = mx * sl;
-            float sum0 = 0.0f, sum1 = 0.0f;
-            {
-                uint32_t va[32], vb[32];
                 auto expo = [&](const uint32_t *v, int c) {
+                    const float cm = chunk_max(v, c);
+                    if (c == 0)
+                        mref = cm, msc = cm * sl;
+                    else
+                    {
+                        const bool raise = cm > mref + margin;
+                        if (__any_sync(0xffffffffu, raise))
+                        {
+                            const float f = raise ? ex2_approx((mref - cm) * sl) : 1.0f;
+                            tmem_st_wait(); // the chunks written so far are read back
+                            for (int cc = 0; cc < c; cc++)
+                            {
+                                uint32_t w[16];
+                                tmem_ld_32xN<16>(region + cc * 16, w);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int j = 0; j < 16; j++)
+                                    w[j] = pack_bf16x2(__uint_as_float(w[j] << 16) * f, __uint_as_float(w[j] & 0xFFFF0000u) * f);
+                                tmem_st_32x16(region + cc * 16, w);
+                            }
+                            sum0 *= f, sum1 *= f;
+                            if (raise) mref = cm, msc = cm * sl;
+                        }
+                    }
                     uint32_t w[16];
                     if (c < nfull)
                     {
@@ -557,10 +578,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(sfree_bar(t)); // region t may be overwritten by the next item's S
-            if (qrow < p.tokens)
+            stamp(6);
+            // O / rowsum as bf16 into this warp's 128B-swizzled slab, then ONE 3-D TMA store of 32 rows x 128 bytes (rows past the
+            // image's last token are clipped by the tensor map).  Per-lane-row global stores -- 8 x 16 bytes to 32 different
+            // lines per instruction -- kept the warp in this phase for ~1700 cycles of its ~8700-cycle chain per item.
             {
                 const float inv = 1.0f / sum;
-                uint4 *dst = reinterpret_cast<uint4 *>(p.out + ((long long)b * p.tokens + qrow) * D + h * ATT_HD);
+                if (lane == 0) tma_store_wait_read(); // the previous item's store has finished reading the slab
+                __syncwarp();
+                uint8_t *orow = oslab + lane * 128;
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                 {
@@ -569,11 +595,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                     pk.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
                     pk.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
                     pk.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
-                    dst[j] = pk;
+                    *reinterpret_cast<uint4 *>(orow + ((j ^ (lane & 7)) << 4)) = pk;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0)
+                {
+                    tma_store_3d(&tma_out, oslab_addr, h * ATT_HD, t * 128 + q * 32, b);
+                    tma_store_commit();
                 }
             }
             stamp(5);
         }
+        if (lane == 0) tma_store_wait_all(); // the slab is read, and the rows are written, before the CTA goes away
     }
 
     tcgen05_fence_before();
@@ -930,6 +964,7 @@ static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, in
     p.batch = batch, p.tokens = tokens, p.heads = heads;
     p.n_pad = (tokens + 15) & ~15;
     p.n_mtiles = tokens > 128 ? 2 : 1;
+    p.stagger = getenv("NETCUDA_ATT_NOSTAGGER") == nullptr;
     p.error_flag = error_flag;
     p.debug = nullptr;
     if (const char *dbg = getenv("NETCUDA_ATTENTION_DEBUG_PTR")) p.debug = reinterpret_cast<long long *>(strtoull(dbg, nullptr, 0));
@@ -941,9 +976,13 @@ static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, in
     if (e != cudaSuccess) return e;
     e = encode_tma_2d(&map_kv, 2, qkv, 3 * D, rows, 3 * D * 2, ATT_HD, p.n_pad, true);
     if (e != cudaSuccess) return e;
+    // output [batch][tokens][D] as a 3-D map: a 32-row store box never spills into the next image
+    CUtensorMap map_out;
+    e = encode_tma_3d(&map_out, 2, out, D, tokens, batch, D * 2, (long long)tokens * D * 2, ATT_HD, 32, true);
+    if (e != cudaSuccess) return e;
     const int items = batch * heads;
     const int sms = num_sms > 0 ? num_sms : 148;
-    return launch_pdl(attention_tc_kernel, dim3(items < sms ? items : sms), dim3(ATC_THREADS), (size_t)ATC_SMEM, stream, 1, map_q, map_kv, p);
+    return launch_pdl(attention_tc_kernel, dim3(items < sms ? items : sms), dim3(ATC_THREADS), (size_t)ATC_SMEM, stream, 1, map_q, map_kv, map_out, p);
 }
 
 cudaError_t launch_attention(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag, int num_sms,

@@ -39,6 +39,27 @@ cudaError_t encode_tma_2d(void *map_out, int dtype_bytes, const void *ptr, long 
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// 3-D map over a [dim2][dim1][dim0] array (dim0 contiguous), box = box0 x box1 x 1: a TMA store clips the rows of a box that lie
+// beyond dim1, so tiles that straddle the end of one image never touch the next one.
+cudaError_t encode_tma_3d(void *map_out, int dtype_bytes, const void *ptr, long long dim0, long long dim1, long long dim2, long long stride1_bytes,
+                          long long stride2_bytes, int box0, int box1, bool swizzle128)
+{
+    if (!g_encode_tiled) return cudaErrorNotReady;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (stride1_bytes & 15) != 0 || (stride2_bytes & 15) != 0 || dim0 <= 0 || dim1 <= 0 || dim2 <= 0)
+        return cudaErrorInvalidValue;
+    const CUtensorMapDataType dt = dtype_bytes == 2   ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                   : dtype_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                                      : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    cuuint64_t gdim[3] = {(cuuint64_t)dim0, (cuuint64_t)dim1, (cuuint64_t)dim2};
+    cuuint64_t gstride[2] = {(cuuint64_t)stride1_bytes, (cuuint64_t)stride2_bytes};
+    cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
+    cuuint32_t estride[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(reinterpret_cast<CUtensorMap *>(map_out), dt, 3, const_cast<void *>(ptr), gdim, gstride, box, estride,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <int KIND, int BN, int OUT, int STAGES, int CG, int EW, int DS = 0>
 static cudaError_t opt_in_smem()
 {

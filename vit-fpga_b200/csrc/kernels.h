@@ -75,6 +75,8 @@ cudaError_t gemm_global_init();
 // 128 bytes and `swizzle128` is set.  dtype_bytes selects the element type (1: u8, 2: bf16, 4: f32).
 cudaError_t encode_tma_2d(void *map_out, int dtype_bytes, const void *ptr, long long dim0, long long dim1, long long pitch_bytes,
                           int box0, int box1, bool swizzle128);
+cudaError_t encode_tma_3d(void *map_out, int dtype_bytes, const void *ptr, long long dim0, long long dim1, long long dim2, long long stride1_bytes,
+                          long long stride2_bytes, int box0, int box1, bool swizzle128);
 
 // ---- INT8 MLP forward for 1..16 samples in one persistent weight-streaming kernel (mlp_stream.cu) ----
 constexpr int MLP_STREAM_MAX_LAYERS = 16;

@@ -125,6 +125,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t sr
                  ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src_smem, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 // Same, but global += shared (element-wise add performed at L2, type taken from the tensor map).
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, uint32_t src_smem, int c0, int c1)
 {
