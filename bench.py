@@ -56,14 +56,17 @@ def load_peaks():
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
-def ncu_traffic_per_launch(prof, prof_steps):
+def ncu_traffic_per_launch(prof, prof_steps, pass_images):
     """dram__bytes_read + dram__bytes_write per GEMM launch from the committed ncu --set full capture (profiles/ncu_traffic.json),
     averaged over the GEMM launches of a step with the same weighting as roofline.achieved; None when no capture is committed or the
     capture was taken at another pass size."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(path):
         return None
-    per = json.load(open(path)).get("per_launch_bytes", {})
+    cap = json.load(open(path))
+    if cap.get("pass_images") != pass_images:
+        return None
+    per = cap.get("per_launch_bytes", {})
     num = den = 0.0
     for k in ("qkv", "proj", "fc1", "fc2"):
         if k in per and k in prof:
@@ -353,7 +356,7 @@ def main():
         "flops_per_launch": gemm_flops / max(gemm_launches, 1), "ms_per_launch": gemm_ms / max(gemm_launches, 1),
         "algorithmic_bytes_per_launch": sum(v["bytes"] for k, v in prof.items() if k in GEMM_LABELS) / max(gemm_launches, 1),
         "share_of_step": round(gemm_ms / all_ms, 4) if all_ms > 0 else None,
-        "traffic": ncu_traffic_per_launch(prof, prof_steps),
+        "traffic": ncu_traffic_per_launch(prof, prof_steps, min(max_batch, per_gpu)),
         "whole_step_tflops": round(value / world * flops_per_image / 1e12, 2),
         "whole_step_frac_of_burst_peak": round(value / world * flops_per_image / 1e12 / peaks["burst"], 4),
         "per_kernel": per_kernel,

@@ -504,6 +504,29 @@ def test_async_vit_pipeline_matches_blocking(netcuda, torch_cuda):
     net.close()
 
 
+def test_host_call_quarter_first_chunk_is_bit_equal(netcuda, torch_cuda):
+    """A large ViT batch handed to an idle GPU starts with a quarter-size first chunk (its H2D copy is the only exposed one); chunking
+    never changes a logit: blocking call, two calls in flight and the device-resident path agree bit for bit."""
+    torch = torch_cuda
+    cfg = dict(image_size=32, patch_size=16, dim=128, depth=1, heads=2, mlp_dim=256, n_classes=10)
+    net = netcuda.Net.vit(cfg, max_batch=512)
+    net.upload_vit(netcuda.vit_random_params(cfg, seed=3))
+    rng = np.random.default_rng(6)
+    x = torch.from_numpy(rng.uniform(-1, 1, (600, net.n_in)).astype(np.float32)).pin_memory()  # chunks of 128 + 472 (idle) or 512 + 88
+    dx, dy = x.cuda(), torch.empty((600, net.n_out), device="cuda")
+    net.forward_device(dx, dy, 600)
+    torch.cuda.synchronize()
+    want = dy.cpu().numpy()
+    np.testing.assert_array_equal(net.forward(x.numpy()), want)
+    ys = [torch.empty((600, net.n_out)).pin_memory() for _ in range(2)]
+    t0 = net.submit(x, ys[0])
+    t1 = net.submit(x, ys[1])  # the GPU is busy with t0: full-size first chunk
+    net.wait(t0), net.wait(t1)
+    np.testing.assert_array_equal(ys[0].numpy(), want)
+    np.testing.assert_array_equal(ys[1].numpy(), want)
+    net.close()
+
+
 def _frames_to_float(frames, mean, std):
     """What patchify_u8_kernel computes, in numpy fp32 with the same operation order, as the CHW float images of the float path."""
     u = frames.astype(np.float32) * np.float32(1.0 / 255.0)

@@ -2,7 +2,7 @@
 # ncu evidence for profiles/: launch list of one bench step + --set full captures of the hot kernels.
 # Each ncu run is preceded by the same command without ncu (B200_PROFILING.md).
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 3 --batch 256 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --steps 1 --warmup 3 --batch 512 --no-cpu-baseline --no-e2e"  # one pass of the bench's pass size (512 images)
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches rc=$?"

@@ -44,8 +44,8 @@ def launch_list():
         csv.writer(f).writerows(out)
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(P, f"{tag}_launch_shares.md"), "w") as f:
-        f.write(f"# Launch list summary ({tag})\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over `python bench.py --steps 1 --warmup 3 --batch 256 "
-                "--no-cpu-baseline --no-e2e` (weight upload + 4 warm-up + 1 timed + 1 profiled pass of 256 images).  Per-launch times are cold-cache and serialised: "
+        f.write(f"# Launch list summary ({tag})\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over `python bench.py --steps 1 --warmup 3 --batch 512 "
+                "--no-cpu-baseline --no-e2e` (weight upload + 4 warm-up + 1 timed + 1 profiled pass of 512 images).  Per-launch times are cold-cache and serialised: "
                 "compare SHARES with `roofline.per_kernel` of the bench line, not absolutes.\n\n| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {a[0]} | {a[1] / 1e6:.3f} | {a[1] / tot * 100:.1f} % |\n")
@@ -83,7 +83,7 @@ def traffic_json():
     ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     labels = ["qkv", "proj", "fc1", "fc2"]
-    out = {"source": f"profiles/{tag}_prof_gemm.md (ncu --set full, 256-image pass of ViT-B/16-224)", "per_launch_bytes": {}}
+    out = {"source": f"profiles/{tag}_prof_gemm.md (ncu --set full, 512-image pass of ViT-B/16-224)", "pass_images": 512, "per_launch_bytes": {}}
     for lab, r in zip(labels, rows[2:]):
         out["per_launch_bytes"][lab] = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
     json.dump(out, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
