@@ -11,7 +11,18 @@
 namespace nc
 {
 
-// Launch with an optional cluster size and, when NETCUDA_PDL is set, programmatic stream serialization (ptx.cuh, griddep_wait).
+// Programmatic dependent launch (ptx.cuh, griddep_wait): the next kernel's launch and prologue overlap the tail of the running one.
+// Measured: nothing at the bench's pass size (kernel boundaries are not where the time goes: 22,999 vs 23,283 images/s, inside the
+// noise) but a quarter of the time of a single-sample ViT pass (ViT-Tiny: 831 -> 627 us, ~90 kernels of a few microseconds).  So the
+// runtime switches it on for small passes (g_pdl_small_pass); NETCUDA_PDL=0 / 1 forces it off / on everywhere.
+extern thread_local bool g_pdl_small_pass;
+inline bool pdl_enabled()
+{
+    static const int forced = getenv("NETCUDA_PDL") ? atoi(getenv("NETCUDA_PDL")) : -1;
+    return forced >= 0 ? forced != 0 : g_pdl_small_pass;
+}
+
+// Launch with an optional cluster size and, when pdl_enabled(), programmatic stream serialization.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster, Args &&...args)
 {
@@ -19,9 +30,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int n = 0;
-    // Measured on ViT-B/16 (round 1): no gain over plain stream order (22,999 vs 23,283 images/s, within run-to-run noise) --
-    // kernel boundaries are not where the time goes -- so the overlap is opt-in: NETCUDA_PDL=1.
-    static const int pdl = getenv("NETCUDA_PDL") != nullptr;
+    const int pdl = pdl_enabled() ? 1 : 0;
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = pdl;
     n++;

@@ -60,6 +60,8 @@ static inline long long round_up(long long v, long long m) { return (v + m - 1) 
 
 // INT8 layers at small batch are weight streaming: up to this many samples a layer is split along K over the whole GPU
 constexpr int SPLITK_MAX_M = 128;
+constexpr int GRAPH_MAX_SAMPLES = 4096;   // MLP passes up to this many samples are launch-latency bound (graph replay, PDL)
+constexpr int VIT_GRAPH_MAX_ROWS = 8192; // ViT passes up to this many token rows are launch-latency bound (graph replay, PDL)
 
 // ---- handle --------------------------------------------------------------------------------------
 
@@ -128,8 +130,10 @@ struct netcuda_net
         bool in_is_i8 = false, out_is_i32 = false;
         uint64_t launches = 0; // kernels inside the graph (for the launch counter)
     };
-    static constexpr int PASS_GRAPHS = 4; // the host API cycles through 2 input slots x up to 4 output buffers
+    static constexpr int PASS_GRAPHS = 8; // the host API cycles through 2 input slots x up to 4 output buffers
     PassGraph pass_graphs[PASS_GRAPHS];
+    PassGraph graph_candidates[PASS_GRAPHS]; // ViT: a (buffers, batch) combination is captured the second time it shows up
+    int graph_candidate_next = 0;
     int pass_graph_next = 0; // round-robin replacement
 
     // per-kernel profiling (netcuda_profile_enable)
@@ -662,12 +666,24 @@ static bool mlp_stream_params(netcuda_net *h, int n, const int8_t *in, int32_t *
     return mlp_stream_supported(p, h->num_sms);
 }
 
+namespace nc
+{
+thread_local bool g_pdl_small_pass = false;
+}
+struct SmallPassPdl // programmatic dependent launch for the kernels of a small (launch-latency bound) pass
+{
+    bool prev;
+    explicit SmallPassPdl(bool on) : prev(nc::g_pdl_small_pass) { nc::g_pdl_small_pass = on; }
+    ~SmallPassPdl() { nc::g_pdl_small_pass = prev; }
+};
+
 // MLP pass.  `in_f32` (fp32 [n][n_in]) or `in_i8` (int8 [n][n_in]); writes fp32 `out_f32` or int32 `out_i32`.
 static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, int n, float *out_f32, int32_t *out_i32, cudaStream_t s)
 {
     const int prec = h->desc.precision, kind = operand_kind(prec);
     const int L = (int)h->layers.size();
     const long long ld0 = h->layers[0].ldw;
+    SmallPassPdl pdl(n <= GRAPH_MAX_SAMPLES);
     const void *cur;
     long long cur_ld;
     MlpStreamParams sp;
@@ -776,6 +792,7 @@ static int vit_pass(netcuda_net *h, const float *img, const uint8_t *img_u8, int
 {
     const int D = h->desc.dim, F = h->desc.mlp_dim, C = h->desc.n_classes, T = h->T, NP = h->NP, PK = h->PK;
     const int rows = n * T, cap = h->max_batch * T;
+    SmallPassPdl pdl(rows <= VIT_GRAPH_MAX_ROWS);
     {
         KernelScope scope(h, s, img_u8 ? "patchify_u8" : "patchify", 0.0, (double)n * (double)h->n_in * (img_u8 ? 3.0 : 6.0));
         if (img_u8)
@@ -812,18 +829,31 @@ static int vit_pass(netcuda_net *h, const float *img, const uint8_t *img_u8, int
 // MLP passes of a few thousand samples are a handful of microsecond kernels: the host cannot enqueue them (three tensor-map
 // encodes + a launch each) as fast as the GPU runs them.  Such a pass is captured into a CUDA graph once and replayed while the
 // caller keeps presenting the same buffers (what a serving loop and the host API's staging slots do).
-constexpr int GRAPH_MAX_SAMPLES = 4096;
 
-static int mlp_pass_graphed(netcuda_net *h, const float *in_f32, const int8_t *in_i8, int n, float *out_f32, int32_t *out_i32, cudaStream_t s)
+// `body` enqueues the pass on `s`.  `second_sight`: capture only when the same (buffers, batch) combination has been seen before --
+// capturing and instantiating ~90 kernel nodes costs more than a plain pass, so callers with ever-changing batch sizes never pay it.
+template <class Body>
+static int pass_graphed(netcuda_net *h, const void *in, void *out, int n, bool in_is_i8, bool out_is_i32, cudaStream_t s, bool second_sight,
+                        Body body)
 {
-    const void *in = in_i8 ? (const void *)in_i8 : (const void *)in_f32;
-    void *out = out_i32 ? (void *)out_i32 : (void *)out_f32;
     netcuda_net::PassGraph *found = nullptr;
     for (auto &c : h->pass_graphs)
-        if (c.exec && c.in == in && c.out == out && c.n == n && c.variant == h->gemm_variant && c.in_is_i8 == (in_i8 != nullptr) &&
-            c.out_is_i32 == (out_i32 != nullptr))
+        if (c.exec && c.in == in && c.out == out && c.n == n && c.variant == h->gemm_variant && c.in_is_i8 == in_is_i8 && c.out_is_i32 == out_is_i32)
             found = &c;
     const bool hit = found != nullptr;
+    if (!hit && second_sight)
+    {
+        bool again = false;
+        for (auto &cand : h->graph_candidates)
+            again = again || (cand.n == n && cand.in == in && cand.out == out && cand.variant == h->gemm_variant && cand.in_is_i8 == in_is_i8);
+        if (!again)
+        {
+            netcuda_net::PassGraph &cand = h->graph_candidates[h->graph_candidate_next];
+            h->graph_candidate_next = (h->graph_candidate_next + 1) % netcuda_net::PASS_GRAPHS;
+            cand.in = in, cand.out = out, cand.n = n, cand.variant = h->gemm_variant, cand.in_is_i8 = in_is_i8;
+            return body();
+        }
+    }
     if (!hit)
     {
         found = &h->pass_graphs[h->pass_graph_next];
@@ -840,9 +870,9 @@ static int mlp_pass_graphed(netcuda_net *h, const float *in_f32, const int8_t *i
         {
             // the default stream cannot be captured, and neither can a stream the caller is capturing already: plain launches
             (void)cudaGetLastError();
-            return mlp_pass(h, in_f32, in_i8, n, out_f32, out_i32, s);
+            return body();
         }
-        const int rc = mlp_pass(h, in_f32, in_i8, n, out_f32, out_i32, s);
+        const int rc = body();
         const cudaError_t e = cudaStreamEndCapture(s, &graph);
         if (rc != NETCUDA_OK)
         {
@@ -853,7 +883,7 @@ static int mlp_pass_graphed(netcuda_net *h, const float *in_f32, const int8_t *i
         const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ei != cudaSuccess) return fail(NETCUDA_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ei));
-        g.in = in, g.out = out, g.n = n, g.variant = h->gemm_variant, g.in_is_i8 = in_i8 != nullptr, g.out_is_i32 = out_i32 != nullptr;
+        g.in = in, g.out = out, g.n = n, g.variant = h->gemm_variant, g.in_is_i8 = in_is_i8, g.out_is_i32 = out_is_i32;
         g.launches = h->launches - l0;
         h->launches = l0;
     }
@@ -861,6 +891,18 @@ static int mlp_pass_graphed(netcuda_net *h, const float *in_f32, const int8_t *i
     h->launches += g.launches;
     return NETCUDA_OK;
 }
+
+static int mlp_pass_graphed(netcuda_net *h, const float *in_f32, const int8_t *in_i8, int n, float *out_f32, int32_t *out_i32, cudaStream_t s)
+{
+    const void *in = in_i8 ? (const void *)in_i8 : (const void *)in_f32;
+    void *out = out_i32 ? (void *)out_i32 : (void *)out_f32;
+    return pass_graphed(h, in, out, n, in_i8 != nullptr, out_i32 != nullptr, s, false,
+                        [&]() { return mlp_pass(h, in_f32, in_i8, n, out_f32, out_i32, s); });
+}
+
+// A ViT pass of a few samples is ~90 kernels of a few microseconds each: what a caller sees is the host's launch rate (three tensor-map
+// encodes and a launch per GEMM: ViT-B, one sample: 1.18 ms per call).  The reference's own contract is one sample per launch_forward
+// (src/netFPGA.cpp:266-289), so this is the drop-in's latency: such passes are replayed from a CUDA graph.
 
 static int forward_device_impl(netcuda_net *h, const void *d_in, bool in_is_i8, size_t batch, void *d_out, bool out_is_i32, cudaStream_t s,
                                bool allow_graph = true)
@@ -889,8 +931,16 @@ static int forward_device_impl(netcuda_net *h, const void *d_in, bool in_is_i8, 
                 rc = mlp_pass(h, f, q, n, of, oi, s);
         }
         else
-            rc = vit_pass(h, in_is_i8 ? nullptr : (const float *)d_in + done * h->n_in,
-                          in_is_i8 ? (const uint8_t *)d_in + done * h->n_in : nullptr, n, (float *)d_out + done * h->n_out, s);
+        {
+            const float *img = in_is_i8 ? nullptr : (const float *)d_in + done * h->n_in;
+            const uint8_t *img_u8 = in_is_i8 ? (const uint8_t *)d_in + done * h->n_in : nullptr;
+            float *logits = (float *)d_out + done * h->n_out;
+            if (allow_graph && n * h->T <= VIT_GRAPH_MAX_ROWS && batch <= (size_t)h->max_batch && !h->profiling && h->use_graphs)
+                rc = pass_graphed(h, in_is_i8 ? (const void *)img_u8 : (const void *)img, logits, n, in_is_i8, false, s, true,
+                                  [&]() { return vit_pass(h, img, img_u8, n, logits, s); });
+            else
+                rc = vit_pass(h, img, img_u8, n, logits, s);
+        }
         if (rc != NETCUDA_OK) return rc;
     }
     return NETCUDA_OK;
