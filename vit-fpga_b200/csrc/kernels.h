@@ -12,9 +12,9 @@ namespace nc
 {
 
 // Programmatic dependent launch (ptx.cuh, griddep_wait): the next kernel's launch and prologue overlap the tail of the running one.
-// Measured: nothing at the bench's pass size (kernel boundaries are not where the time goes: 22,999 vs 23,283 images/s, inside the
-// noise) but a quarter of the time of a single-sample ViT pass (ViT-Tiny: 831 -> 627 us, ~90 kernels of a few microseconds).  So the
-// runtime switches it on for small passes (g_pdl_small_pass); NETCUDA_PDL=0 / 1 forces it off / on everywhere.
+// Measured: a loss at the bench's pass size (ViT-B, 512 images: 24.8 -> 24.2 k images/s; kernel boundaries are not where the time goes)
+// but 9 % on ViT-Tiny at 256 images and a quarter of the time of a single-sample ViT pass (831 -> 627 us, ~90 kernels of a few
+// microseconds).  So the runtime switches it on for passes of short kernels (g_pdl_small_pass); NETCUDA_PDL=0 / 1 forces it off / on.
 extern thread_local bool g_pdl_small_pass;
 inline bool pdl_enabled()
 {
