@@ -205,8 +205,9 @@ static cudaError_t launch_tc_bn(const GemmCall &c, cudaStream_t stream)
     {
         // variant 3: 16 epilogue warps for the GELU epilogue.  Measured on ViT-B fc1 (ncu, round 1): 212.5 us vs 203.5 us with
         // 8 warps -- the epilogue is bound by MUFU/FMA work per element, not by the number of warps -- so it is not the default.
+        // ... but it is the default where K is so short that the GELU epilogue is all there is (ViT-Tiny fc1, K = 192: 40.7 -> 34.7 us).
         if constexpr (KIND == KIND_BF16 && OUT == OUT_BF16)
-            if (c.epi == EPI_GELU && c.variant == 3) return launch_tc<KIND, 256, OUT, STAGES_256_PAIR_EW16, 2, 16>(c, stream);
+            if (c.epi == EPI_GELU && (c.variant == 3 || (c.variant == 0 && c.k <= 256))) return launch_tc<KIND, 256, OUT, STAGES_256_PAIR_EW16, 2, 16>(c, stream);
         // Two output slabs per epilogue warp (slab i + 1 is filled while the TMA store of slab i drains) at the price of one
         // pipeline stage: pays where the epilogue or the store path sets the pace -- the GELU epilogue (ViT-B fc1: 10.3 -> 9.9 ms
         // per step) and the short-K residual update that is bound by the L2 reduce-add (proj: 3.95 -> 3.6 ms) -- and costs where the
