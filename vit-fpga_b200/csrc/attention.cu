@@ -629,7 +629,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
 // (double-buffered across items), K / V blocks stream through a two-slot ring.
 
 constexpr int ATL_OFF_KV = 4 * ATC_Q_BYTES;                  // after 2 item slots x 2 query tiles
-constexpr int ATL_OFF_BARS = ATL_OFF_KV + 4 * ATC_KV_BYTES;  // 2 step slots x (K + V)
+constexpr int ATL_OFF_OSLAB = ATL_OFF_KV + 4 * ATC_KV_BYTES; // 2 step slots x (K + V); then one output slab per softmax warp
+constexpr int ATL_OFF_BARS = ATL_OFF_OSLAB + 8 * ATC_OSLAB_BYTES;
 constexpr int ATL_NUM_BARS = 16;
 constexpr int ATL_OFF_TMEM_PTR = ATL_OFF_BARS + ATL_NUM_BARS * 8;
 constexpr int ATL_SMEM = ATL_OFF_TMEM_PTR + 16;
@@ -647,7 +648,8 @@ struct AttnLongParams
 };
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
-attention_tc_long_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv, const AttnLongParams p)
+attention_tc_long_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
+                         const __grid_constant__ CUtensorMap tma_out, const AttnLongParams p)
 {
     extern __shared__ __align__(1024) uint8_t atl_smem[];
     const uint32_t base = smem_u32(atl_smem);
@@ -901,10 +903,15 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
 #pragma unroll
                 for (int j = 0; j < 64; j++) o[j] = fmaf(o[j], alpha, __uint_as_float(ob[j]));
             }
-            if (qrow < p.tokens)
+            // O / rowsum through this warp's swizzled slab and one 3-D TMA store (rows past the image's last token are clipped),
+            // as in attention_tc_kernel
+            if (qrow - lane < p.tokens) // (warp-uniform: the box starts inside the image)
             {
                 const float inv = 1.0f / l_run;
-                uint4 *dst = reinterpret_cast<uint4 *>(p.out + ((long long)b * p.tokens + qrow) * D + h * ATT_HD);
+                uint8_t *oslab = atl_smem + ATL_OFF_OSLAB + (warp - 4) * ATC_OSLAB_BYTES;
+                if (lane == 0) tma_store_wait_read(); // the previous item's store has finished reading the slab
+                __syncwarp();
+                uint8_t *orow = oslab + lane * 128;
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                 {
@@ -913,10 +920,18 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
                     pk.y = pack_bf16x2(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
                     pk.z = pack_bf16x2(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
                     pk.w = pack_bf16x2(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
-                    dst[j] = pk;
+                    *reinterpret_cast<uint4 *>(orow + ((j ^ (lane & 7)) << 4)) = pk;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0)
+                {
+                    tma_store_3d(&tma_out, base + ATL_OFF_OSLAB + (warp - 4) * ATC_OSLAB_BYTES, h * ATT_HD, qrow - lane, b);
+                    tma_store_commit();
                 }
             }
         }
+        if (lane == 0) tma_store_wait_all(); // the slab is read, and the rows are written, before the CTA goes away
     }
 
     tcgen05_fence_before();
@@ -950,8 +965,12 @@ static cudaError_t launch_attention_tc_long(const void *qkv, void *out, int batc
     if (e != cudaSuccess) return e;
     const long long items = (long long)batch * heads * p.n_qpairs;
     const int sms = num_sms > 0 ? num_sms : 148;
+    CUtensorMap map_out; // [batch][tokens][D]: a 32-row store box never spills into the next image
+    e = encode_tma_3d(&map_out, 2, out, (long long)heads * ATT_HD, tokens, batch, (long long)heads * ATT_HD * 2, (long long)tokens * heads * ATT_HD * 2,
+                      ATT_HD, 32, true);
+    if (e != cudaSuccess) return e;
     return launch_pdl(attention_tc_long_kernel, dim3((unsigned)(items < sms ? items : sms)), dim3(ATC_THREADS), (size_t)ATL_SMEM, stream, 1, map_q,
-                      map_kv, p);
+                      map_kv, map_out, p);
 }
 
 static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag,
