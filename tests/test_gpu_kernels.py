@@ -225,14 +225,15 @@ def test_attention_vs_oracle(netcuda, oracle, torch_cuda, batch, tokens, heads):
     assert _max_rel(got, want) <= 1e-2
 
 
-def test_attention_late_peaks_take_the_rescale_path(netcuda, oracle, torch_cuda):
-    """The tcgen05 kernel reads S once: p = 2^((s - m) * scale) with m = the first 32 keys' maximum, raised only when a later chunk
+@pytest.mark.parametrize("tokens", [197, 577])
+def test_attention_late_peaks_take_the_rescale_path(netcuda, oracle, torch_cuda, tokens):
+    """The tcgen05 kernel for up to 256 tokens reads S once: p = 2^((s - m) * scale) with m = the first 32 keys' maximum, raised only when a later chunk
     exceeds it by more than 8 binades -- then the P chunks written so far are rescaled in tensor memory.  Rows built to do that twice
     (keys 100 and 180 beat everything before them by 8.7 and 9 binades) while the first 32 keys still carry ~8 % of the weight before
     the second peak: a wrong or missing rescale shows up far above the tolerance."""
     torch = torch_cuda
     rng = np.random.default_rng(99)
-    batch, tokens, heads = 3, 197, 2
+    batch, heads = 3, 2
     qkv = (rng.standard_normal((batch, tokens, 3, heads, 64)) * 0.25).astype(np.float32)
     u = np.full(64, 0.125, np.float32)  # unit vector; all products below are exact in bf16
     qkv[:, :, 0, 0, :] = 8.0 * u                       # every query of head 0
@@ -242,6 +243,9 @@ def test_attention_late_peaks_take_the_rescale_path(netcuda, oracle, torch_cuda)
     qkv[:, :32, 2, 0, :] = 1.0                         # values that tell the three groups apart
     qkv[:, 100, 2, 0, :] = -1.0
     qkv[:, 180, 2, 0, :] = 3.0
+    if tokens > 256:  # key-blocked kernel (online softmax across key blocks): image 2 gets a new maximum in a LATER key block
+        qkv[2, 400, 1, 0, :] = 15.25 * u
+        qkv[2, 400, 2, 0, :] = 5.0
     qkv = _bf16_round(torch, qkv.reshape(batch * tokens, 3 * heads * 64))
     dq = torch.from_numpy(qkv).cuda().to(torch.bfloat16)
     out = torch.full((batch * tokens, heads * 64), 55.0, dtype=torch.bfloat16, device="cuda")
