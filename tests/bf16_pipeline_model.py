@@ -19,17 +19,6 @@ def _bf(x):
     return x.float().to(torch.bfloat16).double()
 
 
-def _reference_max(s, chunk=32, margin=8.0 / 1.4426950408889634):
-    """The constant the tcgen05 attention kernel subtracts before exp (attention.cu, single pass over S): the maximum of the first
-    32 keys, raised to a later chunk's maximum only when that exceeds it by more than 8 binades.  Any constant gives the same
-    softmax; it only decides where the bf16 rounding of P falls."""
-    m = s[..., :chunk].max(-1, keepdim=True).values
-    for c in range(chunk, s.shape[-1], chunk):
-        cm = s[..., c:c + chunk].max(-1, keepdim=True).values
-        m = torch.where(cm > m + margin, cm, m)
-    return m
-
-
 def vit_forward_bf16_model(cfg: dict, flat: np.ndarray, images: np.ndarray, rounding: bool = True) -> np.ndarray:
     r = _bf if rounding else (lambda t: t)
     flat = torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float64))
@@ -60,7 +49,7 @@ def vit_forward_bf16_model(cfg: dict, flat: np.ndarray, images: np.ndarray, roun
         qkv = r(y @ r(qw).T + qb).reshape(B, T, 3, H, D // H)
         q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
         s = (q @ k.transpose(-1, -2)) / float(np.sqrt(D // H))
-        pe = torch.exp(s - _reference_max(s))
+        pe = torch.exp(s - s.max(-1, keepdim=True).values)
         o = (r(pe) @ v) / pe.sum(-1, keepdim=True)  # the row sum is taken from the fp32 numerators
         x = x + r(o.permute(0, 2, 1, 3).reshape(B, T, D)) @ r(ow).T + ob
         y = r(ln(x, (D,), g2, b2, 1e-6))

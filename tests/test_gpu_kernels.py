@@ -226,11 +226,11 @@ def test_attention_vs_oracle(netcuda, oracle, torch_cuda, batch, tokens, heads):
 
 
 @pytest.mark.parametrize("tokens", [197, 577])
-def test_attention_late_peaks_take_the_rescale_path(netcuda, oracle, torch_cuda, tokens):
-    """The tcgen05 kernel for up to 256 tokens reads S once: p = 2^((s - m) * scale) with m = the first 32 keys' maximum, raised only when a later chunk
-    exceeds it by more than 8 binades -- then the P chunks written so far are rescaled in tensor memory.  Rows built to do that twice
-    (keys 100 and 180 beat everything before them by 8.7 and 9 binades) while the first 32 keys still carry ~8 % of the weight before
-    the second peak: a wrong or missing rescale shows up far above the tolerance."""
+def test_attention_late_peaks(netcuda, oracle, torch_cuda, tokens):
+    """Rows whose maximum arrives late -- keys 100 and 180 beat everything before them by 8.7 and 9 binades (and, in the key-blocked
+    kernel, key 400 of a later block does so again) while the first 32 keys still carry ~8 % of the weight before the second peak:
+    any shortcut around the exact row maximum, or a wrong rescale of the running output across key blocks, shows up far above the
+    tolerance."""
     torch = torch_cuda
     rng = np.random.default_rng(99)
     batch, heads = 3, 2

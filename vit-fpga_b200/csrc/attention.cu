@@ -461,21 +461,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             tcgen05_fence_after();
             stamp(1);
 
-            // ---- single pass over S (32-key chunks; chunk c + 1 is in flight while c is processed) ----
-            // p = 2^((s - m) * scale) with a reference maximum m that is the maximum of the FIRST chunk and is only raised when a
-            // later chunk exceeds it by more than 8 binades: softmax does not care which constant is subtracted, p <= 2^8 is as
-            // exact in bf16 / fp32 as p <= 1, and S is read from tensor memory once instead of twice (the kernel is paced by
-            // the TMEM read port: 2 x 208 + 64 columns per row before, 208 + 64 now).  When a row does exceed the margin, the
-            // whole warp takes the slow path: the P chunks written so far and the running sums are rescaled to the new maximum
-            // (rows that did not ask for it multiply by 1).  P (bf16) overwrites the first half of the S columns it came from.
-            stamp(2);
-            float mref = 0.0f, msc = 0.0f;
-            float sum0 = 0.0f, sum1 = 0.0f;
+            // ---- pass 1: exact row maximum over the valid keys (chunk c + 1 is in flight while c is reduced) ----
+            float mx = -INFINITY;
             {
                 uint32_t va[32], vb[32];
-                const float margin = 8.0f / sl; // 8 binades in raw-score units
-                auto chunk_max = [&](const uint32_t *v, int c) {
-                    float mx;
+                auto reduce = [&](const uint32_t *v, int c) {
                     if (c < nfull)
                     {
                         float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
@@ -485,42 +475,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                             m0 = fmaxf(m0, __uint_as_float(v[j])), m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
                             m2 = fmaxf(m2, __uint_as_float(v[j + 2])), m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
                         }
-                        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
                     }
                     else
                     {
-                        mx = __uint_as_float(v[0]); // (a ragged chunk holds at least one key)
 #pragma unroll
-                        for (int j = 1; j < 32; j++)
+                        for (int j = 0; j < 32; j++)
                             if (j < tail) mx = fmaxf(mx, __uint_as_float(v[j]));
                     }
-                    return mx;
                 };
-                auto expo = [&](const uint32_t *v, int c) {
-                    const float cm = chunk_max(v, c);
-                    if (c == 0)
-                        mref = cm, msc = cm * sl;
-                    else
+                tmem_ld_32x32(region, va);
+                for (int c = 0; c < nchunks; c += 2)
+                {
+                    tmem_ld_wait();
+                    if (c + 1 < nchunks) tmem_ld_32x32(region + (c + 1) * 32, vb);
+                    reduce(va, c);
+                    if (c + 1 < nchunks)
                     {
-                        const bool raise = cm > mref + margin;
-                        if (__any_sync(0xffffffffu, raise))
-                        {
-                            const float f = raise ? ex2_approx((mref - cm) * sl) : 1.0f;
-                            tmem_st_wait(); // the chunks written so far are read back
-                            for (int cc = 0; cc < c; cc++)
-                            {
-                                uint32_t w[16];
-                                tmem_ld_32xN<16>(region + cc * 16, w);
-                                tmem_ld_wait();
-#pragma unroll
-                                for (int j = 0; j < 16; j++)
-                                    w[j] = pack_bf16x2(__uint_as_float(w[j] << 16) * f, __uint_as_float(w[j] & 0xFFFF0000u) * f);
-                                tmem_st_32x16(region + cc * 16, w);
-                            }
-                            sum0 *= f, sum1 *= f;
-                            if (raise) mref = cm, msc = cm * sl;
-                        }
+                        tmem_ld_wait();
+                        if (c + 2 < nchunks) tmem_ld_32x32(region + (c + 2) * 32, va);
+                        reduce(vb, c + 1);
                     }
+                }
+            }
+
+            stamp(2);
+            // ---- pass 2: p = 2^((s - max) * scale); P (bf16) overwrites the first half of the S columns it came from ----
+            const float msc = mx * sl;
+            float sum0 = 0.0f, sum1 = 0.0f;
+            {
+                uint32_t va[32], vb[32];
+                auto expo = [&](const uint32_t *v, int c) {
                     uint32_t w[16];
                     if (c < nfull)
                     {
