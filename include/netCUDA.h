@@ -14,7 +14,10 @@
 //   * launch_forward accepts B * n_ins inputs and returns B * n_out outputs (B = 1 is the
 //     reference contract), validates sizes and throws instead of reading out of bounds / exit()ing;
 //   * get_net_data() really is the inverse of the constructor's flatten;
-//   * a second family of nets (vision transformers) can be built from cuda::vit_data.
+//   * a second family of nets (vision transformers) can be built from cuda::vit_data;
+//   * one object can drive several GPUs of the box (net_cuda_options::n_devices / NETCUDA_DEVICES): the weights are replicated,
+//     every batched forward is cut into contiguous slices, one per GPU, each fed by its own host thread -- samples are independent
+//     (src/netFPGA.cpp:266-277: one sample in, one out), so the outputs are the single-GPU bits.
 #ifndef NETCUDA_CLASS_H
 #define NETCUDA_CLASS_H
 
@@ -47,7 +50,8 @@ namespace cuda
         int device;     // CUDA ordinal; -1 = NETCUDA_DEVICE from the environment, else 0
         int activation; // activation_t
         int max_batch;  // samples per internal pass, 0 = library default
-        net_cuda_options() : precision(-1), device(-1), activation(ACT_RELU_HIDDEN), max_batch(0) {}
+        int n_devices;  // GPUs [device, device + n_devices) share every batched forward; -1 = NETCUDA_DEVICES from the environment, else 1
+        net_cuda_options() : precision(-1), device(-1), activation(ACT_RELU_HIDDEN), max_batch(0), n_devices(-1) {}
     };
 
     // Vision-transformer description (net::net_data can only express an MLP, def/defines.h:14-23).

@@ -140,6 +140,32 @@ def test_cpp_class_random_init_matches_reference_rule(netcuda, oracle, torch_cud
     net.close()
 
 
+def test_cpp_class_shards_over_gpus(netcuda, oracle, torch_cuda, monkeypatch):
+    """net_cuda_options::n_devices / NETCUDA_DEVICES: one net_cuda object drives several GPUs -- weights replicated, every batched
+    forward cut into contiguous slices, one host thread per GPU.  Samples are independent, so the outputs are the single-GPU bits
+    (MLP fp32 path: the oracle's bits; ViT: the same kernels on another device)."""
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    npl, n_ins, w, b = c1_net(oracle)
+    x = np.random.default_rng(2).uniform(-1, 1, (301, n_ins)).astype(np.float32)  # ragged slices: 151 + 150
+    monkeypatch.setenv("NETCUDA_DEVICES", "2")
+    net2 = netcuda.HostNet.mlp(npl, n_ins, w, b, precision=netcuda.PREC_FP32)
+    np.testing.assert_array_equal(net2.launch_forward(x), oracle.mlp_forward(x, w, b, npl, n_ins))
+    np.testing.assert_array_equal(net2.launch_forward(x[:1]), oracle.mlp_forward(x[:1], w, b, npl, n_ins))  # one sample: one GPU
+    assert net2.forward_us() > 0
+    net2.close()
+    g = np.load(os.path.join(GOLDEN, "vit_small.npz"))
+    cfg = dict(zip(("image_size", "patch_size", "dim", "depth", "heads", "mlp_dim", "n_classes"), (int(v) for v in g["cfg"])))
+    imgs = np.random.default_rng(3).uniform(-1, 1, (37, 3 * cfg["image_size"] ** 2)).astype(np.float32)
+    vit2 = netcuda.HostNet.vit(cfg, g["flat"], max_batch=8)
+    got2 = vit2.launch_forward(imgs)
+    vit2.close()
+    monkeypatch.setenv("NETCUDA_DEVICES", "1")
+    vit1 = netcuda.HostNet.vit(cfg, g["flat"], max_batch=8)
+    np.testing.assert_array_equal(got2, vit1.launch_forward(imgs))
+    vit1.close()
+
+
 def test_cpp_class_move_and_copy(netcuda, oracle, torch_cuda):
     npl, n_ins, w, b = c1_net(oracle)
     net = netcuda.HostNet.mlp(npl, n_ins, w, b, precision=-1)  # the reference-shaped 3-argument constructor

@@ -70,7 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> dict:
     if force or _newer(lib_host, host_deps):
         # gnu++14: the only language level the reference states (.vscode/c_cpp_properties.json:13)
         _run([CXX, "-std=gnu++14", "-O2", "-fPIC", "-Wall", "-shared", "-I", INCLUDE, "-o", lib_host] + host_srcs +
-             ["-L", LIB, "-lnetcuda", "-Wl,-rpath,$ORIGIN", "-Wl,-z,defs"])
+             ["-L", LIB, "-lnetcuda", "-pthread", "-Wl,-rpath,$ORIGIN", "-Wl,-z,defs"])
     if verbose:
         print("built", lib_cuda, "and", lib_host)
     return {"libnetcuda": lib_cuda, "libnetcuda_host": lib_host}

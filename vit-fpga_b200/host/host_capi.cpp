@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <exception>
 #include <vector>
@@ -148,6 +149,28 @@ long long nch_launch_forward(void *net, const float *in, size_t n_in_floats, flo
     {
         set_err(e.what());
         return -1;
+    }
+}
+
+// Seconds per launch_forward call as a C++ application sees it: the input std::vector exists before the clock starts (the
+// application owns it), every call returns its outputs by value through the vtable.  -1 on error.
+double nch_time_launch_forward(void *net, const float *in, size_t n_in_floats, int reps, float *last_out, size_t out_capacity)
+{
+    try
+    {
+        net::net_abstract *n = static_cast<net::net_abstract *>(net);
+        const std::vector<float> x(in, in + n_in_floats);
+        std::vector<float> y = n->launch_forward(x); // warm-up (staging buffers, first-touch of the output pages)
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < reps; i++) y = n->launch_forward(x);
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / (reps > 0 ? reps : 1);
+        if (last_out && y.size() <= out_capacity) memcpy(last_out, y.data(), y.size() * sizeof(float));
+        return s;
+    }
+    catch (const std::exception &e)
+    {
+        set_err(e.what());
+        return -1.0;
     }
 }
 

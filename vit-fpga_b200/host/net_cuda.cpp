@@ -14,14 +14,21 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <vector>
 
 namespace cuda
 {
     struct net_cuda::impl
     {
         netcuda_t *h = nullptr;
+        std::vector<netcuda_t *> replicas; // the same net on devices device + 1 ... (net_cuda_options::n_devices)
+        long long last_sharded_us = -1;    // wall time of the last multi-GPU forward (-1: the last forward used one GPU)
         bool is_vit = false;
         net_cuda_options opt;
         // MLP host copy in the reference's flat layout (src/netFPGA.cpp:78-107)
@@ -34,8 +41,13 @@ namespace cuda
 
         ~impl()
         {
+            for (netcuda_t *r : replicas)
+                if (r) netcuda_destroy(r);
             if (h) netcuda_destroy(h);
         }
+        // Batched forward over every GPU of this net: contiguous slices, one host thread per extra GPU (slice 0 runs on the caller's).
+        template <class In, class Call>
+        void forward_sharded(const In *inputs, std::size_t in_per_sample, std::size_t batch, DATA_TYPE *outputs, std::size_t out_per_sample, Call call);
         void instantiate(); // build the device net from the host copies above
     };
 
@@ -68,6 +80,15 @@ namespace cuda
                 o.device = 0;
                 if (const char *e = std::getenv("NETCUDA_DEVICE")) o.device = std::atoi(e);
             }
+            if (o.n_devices < 0)
+            {
+                o.n_devices = 1;
+                if (const char *e = std::getenv("NETCUDA_DEVICES")) o.n_devices = std::atoi(e);
+            }
+            if (o.n_devices < 1) o.n_devices = 1;
+            int visible = 0;
+            if (o.n_devices > 1 && netcuda_device_count(&visible) == NETCUDA_OK && o.device + o.n_devices > visible)
+                throw std::invalid_argument("net_cuda: n_devices asks for more GPUs than are visible");
             return o;
         }
     }
@@ -150,32 +171,80 @@ namespace cuda
     void net_cuda::impl::instantiate()
     {
         impl *p = this;
-        netcuda_desc d;
-        std::memset(&d, 0, sizeof(d));
-        d.precision = p->opt.precision;
-        d.device = p->opt.device;
-        d.activation = p->opt.activation;
-        d.max_batch = p->opt.max_batch;
-        int rc;
-        if (p->is_vit)
-        {
-            d.kind = NETCUDA_KIND_VIT;
-            d.image_size = (int32_t)p->vit.image_size, d.patch_size = (int32_t)p->vit.patch_size;
-            d.dim = (int32_t)p->vit.dim, d.depth = (int32_t)p->vit.depth, d.heads = (int32_t)p->vit.heads;
-            d.mlp_dim = (int32_t)p->vit.mlp_dim, d.n_classes = (int32_t)p->vit.n_classes;
-            if ((rc = netcuda_create(&d, &p->h)) != NETCUDA_OK) throw_last("netcuda_create", rc);
-            if ((rc = netcuda_upload_vit(p->h, p->vit.params.data(), p->vit.params.size())) != NETCUDA_OK)
-                throw_last("netcuda_upload_vit", rc);
-        }
-        else
-        {
-            d.kind = NETCUDA_KIND_MLP;
-            d.n_ins = (int32_t)p->n_ins;
-            d.n_layers = (int32_t)p->n_p_l.size();
-            d.n_p_l = p->n_p_l.data();
-            if ((rc = netcuda_create(&d, &p->h)) != NETCUDA_OK) throw_last("netcuda_create", rc);
-            if ((rc = netcuda_upload_mlp(p->h, p->params.data(), p->bias.data())) != NETCUDA_OK) throw_last("netcuda_upload_mlp", rc);
-        }
+        auto build = [p](int device) {
+            netcuda_t *h = nullptr;
+            netcuda_desc d;
+            std::memset(&d, 0, sizeof(d));
+            d.precision = p->opt.precision;
+            d.device = device;
+            d.activation = p->opt.activation;
+            d.max_batch = p->opt.max_batch;
+            int rc;
+            if (p->is_vit)
+            {
+                d.kind = NETCUDA_KIND_VIT;
+                d.image_size = (int32_t)p->vit.image_size, d.patch_size = (int32_t)p->vit.patch_size;
+                d.dim = (int32_t)p->vit.dim, d.depth = (int32_t)p->vit.depth, d.heads = (int32_t)p->vit.heads;
+                d.mlp_dim = (int32_t)p->vit.mlp_dim, d.n_classes = (int32_t)p->vit.n_classes;
+                if ((rc = netcuda_create(&d, &h)) != NETCUDA_OK) throw_last("netcuda_create", rc);
+                if ((rc = netcuda_upload_vit(h, p->vit.params.data(), p->vit.params.size())) != NETCUDA_OK)
+                {
+                    netcuda_destroy(h);
+                    throw_last("netcuda_upload_vit", rc);
+                }
+            }
+            else
+            {
+                d.kind = NETCUDA_KIND_MLP;
+                d.n_ins = (int32_t)p->n_ins;
+                d.n_layers = (int32_t)p->n_p_l.size();
+                d.n_p_l = p->n_p_l.data();
+                if ((rc = netcuda_create(&d, &h)) != NETCUDA_OK) throw_last("netcuda_create", rc);
+                if ((rc = netcuda_upload_mlp(h, p->params.data(), p->bias.data())) != NETCUDA_OK)
+                {
+                    netcuda_destroy(h);
+                    throw_last("netcuda_upload_mlp", rc);
+                }
+            }
+            return h;
+        };
+        p->h = build(p->opt.device);
+        for (int g = 1; g < p->opt.n_devices; g++) p->replicas.push_back(build(p->opt.device + g)); // weights replicated per GPU
+    }
+
+    template <class In, class Call>
+    void net_cuda::impl::forward_sharded(const In *inputs, std::size_t in_per_sample, std::size_t batch, DATA_TYPE *outputs,
+                                         std::size_t out_per_sample, Call call)
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        const std::size_t gpus = std::min(replicas.size() + 1, batch); // no empty slices
+        const std::size_t per = (batch + gpus - 1) / gpus;             // GPU g takes samples [g * per, min(batch, (g + 1) * per))
+        std::vector<std::string> errors(gpus);
+        std::vector<int> codes(gpus, NETCUDA_OK);
+        auto run = [&](std::size_t g) {
+            const std::size_t lo = g * per, hi = std::min(batch, lo + per);
+            if (lo >= hi) return;
+            netcuda_t *hg = g == 0 ? h : replicas[g - 1];
+            const auto s0 = std::chrono::steady_clock::now();
+            codes[g] = call(hg, inputs + lo * in_per_sample, hi - lo, outputs + lo * out_per_sample);
+            if (std::getenv("NETCUDA_SHARD_DEBUG"))
+                std::fprintf(stderr, "slice %zu: %zu samples, started %+lld us after the call, took %lld us\n", g, hi - lo,
+                             (long long)std::chrono::duration_cast<std::chrono::microseconds>(s0 - t0).count(),
+                             (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - s0).count());
+            if (codes[g] != NETCUDA_OK) errors[g] = netcuda_last_error(); // (the message is thread-local: fetched where it was set)
+        };
+        std::vector<std::thread> workers;
+        for (std::size_t g = 1; g < gpus; g++) workers.emplace_back(run, g);
+        run(0);
+        for (auto &w : workers) w.join();
+        last_sharded_us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        for (std::size_t g = 0; g < gpus; g++)
+            if (codes[g] != NETCUDA_OK)
+            {
+                const std::string msg = "net_cuda: forward on GPU slice " + std::to_string(g) + ": " + errors[g];
+                if (codes[g] == NETCUDA_ERR_INVALID) throw std::invalid_argument(msg);
+                throw std::runtime_error(msg);
+            }
     }
 
     void net_cuda::save(const char *path) const
@@ -325,6 +394,13 @@ namespace cuda
     void net_cuda::forward(const DATA_TYPE *inputs, std::size_t batch, DATA_TYPE *outputs)
     {
         if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        if (!p_->replicas.empty() && batch > 1)
+        {
+            p_->forward_sharded(inputs, n_in(), batch, outputs, n_out(),
+                                [](netcuda_t *h, const DATA_TYPE *in, std::size_t n, DATA_TYPE *out) { return netcuda_forward(h, in, n, out); });
+            return;
+        }
+        p_->last_sharded_us = -1;
         const int rc = netcuda_forward(p_->h, inputs, batch, outputs);
         if (rc != NETCUDA_OK) throw_last("netcuda_forward", rc);
     }
@@ -332,6 +408,14 @@ namespace cuda
     void net_cuda::forward_u8(const unsigned char *frames, std::size_t batch, DATA_TYPE *outputs)
     {
         if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        if (!p_->replicas.empty() && batch > 1)
+        {
+            p_->forward_sharded(frames, n_in(), batch, outputs, n_out(), [](netcuda_t *h, const unsigned char *in, std::size_t n, DATA_TYPE *out) {
+                return netcuda_forward_u8(h, in, n, out);
+            });
+            return;
+        }
+        p_->last_sharded_us = -1;
         const int rc = netcuda_forward_u8(p_->h, frames, batch, outputs);
         if (rc != NETCUDA_OK) throw_last("netcuda_forward_u8", rc);
     }
@@ -339,6 +423,8 @@ namespace cuda
     void net_cuda::set_u8_normalization(const float mean[3], const float stddev[3])
     {
         if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        for (netcuda_t *r : p_->replicas)
+            if (netcuda_set_u8_normalization(r, mean, stddev) != NETCUDA_OK) throw_last("netcuda_set_u8_normalization", NETCUDA_ERR_CUDA);
         const int rc = netcuda_set_u8_normalization(p_->h, mean, stddev);
         if (rc != NETCUDA_OK) throw_last("netcuda_set_u8_normalization", rc);
     }
@@ -411,6 +497,7 @@ namespace cuda
     {
         int64_t us = 0;
         if (p_ && p_->h) netcuda_last_forward_us(p_->h, &us);
+        if (p_ && p_->last_sharded_us >= 0) us = p_->last_sharded_us; // the last forward ran on several GPUs: the whole call
         return (signed long)us;
     }
 

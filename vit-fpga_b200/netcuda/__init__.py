@@ -454,6 +454,16 @@ class HostNet:
             raise ValueError(hostlib.nch_last_error().decode())
         return out[:n].reshape(-1, self.n_out)
 
+    def time_launch_forward(self, x, reps=3):
+        """(seconds per call, outputs of the last call) of launch_forward(std::vector) with the input vector built beforehand."""
+        x = np.ascontiguousarray(x, dtype=np.float32).ravel()
+        out = np.empty((x.size // self.n_in) * self.n_out, dtype=np.float32)
+        hostlib.nch_time_launch_forward.restype = C.c_double
+        s = hostlib.nch_time_launch_forward(self._h, _ptr(x), C.c_size_t(x.size), C.c_int(reps), _ptr(out), C.c_size_t(out.size))
+        if s < 0:
+            raise RuntimeError(hostlib.nch_last_error().decode())
+        return s, out.reshape(-1, self.n_out)
+
     def launch_forward_frame(self, frame, h=0, w=0) -> np.ndarray:
         """launch_forward(const net::image_set&): one uint8 [H, W, 3] frame."""
         f = np.ascontiguousarray(frame, dtype=np.uint8)
