@@ -200,6 +200,14 @@ template <int KIND, int OUT>
 static cudaError_t launch_tc_bn(const GemmCall &c, cudaStream_t stream)
 {
     if (c.n <= 128) return launch_tc<KIND, 128, OUT, STAGES_128, 1>(c, stream);
+    // A few hundred rows (a single image of a ViT: M = 197) make a handful of 256 x 256 pair tiles, each a long serial K loop on two
+    // SMs while the rest of the GPU idles (ViT-B fc2, one image: 3 tiles, 23 us).  128 x 128 single-CTA tiles spread the same work
+    // over four times as many SMs; same k order per output element, same bits.
+    {
+        const int sms = c.num_sms > 0 ? c.num_sms : 148;
+        const long long pair_tiles = (long long)((c.m + 255) / 256) * ((c.n + 255) / 256);
+        if (c.variant == 0 && c.k_splits <= 1 && pair_tiles * 4 <= sms) return launch_tc<KIND, 128, OUT, STAGES_128, 1>(c, stream);
+    }
     // more than one 128-row block: pair the SMs (256-row tiles, half the W traffic per SM); variant 2 forces single CTAs
     if (c.m > GEMM_BM && c.variant != 2)
     {
