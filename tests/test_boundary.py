@@ -161,3 +161,30 @@ def test_descriptor_validation(netcuda):
     with pytest.raises(netcuda.NetcudaError) as e:
         netcuda.Net(netcuda.Desc(kind=7))
     assert e.value.code == netcuda.ERR_INVALID
+
+
+EXAMPLE = os.path.join(ROOT, "examples", "drop_in_app.cpp")
+
+
+def build_example_app(out_dir):
+    """Compile the consumer application of examples/ against the public headers and the two shared libraries (gnu++14, like the
+    reference's only stated language level)."""
+    lib = os.path.join(ROOT, "vit-fpga_b200", "lib")
+    exe = os.path.join(out_dir, "drop_in_app")
+    r = subprocess.run(["g++", "-std=gnu++14", "-O2", "-Wall", "-Werror", "-I", INCLUDE, EXAMPLE, "-L", lib, "-lnetcuda_host", "-lnetcuda",
+                        "-Wl,-rpath," + lib, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_example_consumer_application_builds_and_fails_loudly_without_gpu(netcuda):
+    """A host application written against net::net_abstract only (examples/drop_in_app.cpp: the reference consumer's shape) builds
+    against include/ + the two libraries; without a GPU it stops with the library's error instead of computing anything on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible: the GPU suite runs the application")
+    with tempfile.TemporaryDirectory() as d:
+        exe = build_example_app(d)
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode != 0
+        assert "no CUDA device" in r.stderr

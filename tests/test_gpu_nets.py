@@ -140,6 +140,26 @@ def test_cpp_class_random_init_matches_reference_rule(netcuda, oracle, torch_cud
     net.close()
 
 
+def test_example_consumer_application(netcuda, oracle, torch_cuda, tmp_path):
+    """examples/drop_in_app.cpp -- a C++ host application in the shape of the reference's consumer (backend header, backend class,
+    then only net::net_abstract*): built with g++ -std=gnu++14, run with NETCUDA_PRECISION=fp32, its printed outputs are the CPU
+    oracle's bits for the reference's own random initialisation (srand(1); src/netFPGA.cpp:82-88)."""
+    import subprocess
+    from test_boundary import build_example_app
+    exe = build_example_app(str(tmp_path))
+    r = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, NETCUDA_PRECISION="fp32"), timeout=120)
+    assert r.returncode == 0, r.stderr
+    line = next(l for l in r.stdout.splitlines() if l.startswith("outputs"))
+    got = np.array([float(v) for v in line.split()[1:]], dtype=np.float32)
+    npl, n_ins = [128, 64, 10], 784
+    w, b = oracle.rand_init(1, 784 * 128 + 128 * 64 + 64 * 10, sum(npl))
+    i = np.arange(n_ins, dtype=np.uint64)
+    x = (((i * 2654435761) & 0xFFFFFFFF) >> 8 & 0xFFFF).astype(np.float32) / np.float32(32768.0) - np.float32(1.0)
+    want = oracle.mlp_forward(x[None], w, b, npl, n_ins)[0]
+    np.testing.assert_array_equal(got, want)
+    assert "one sample per call" in r.stdout and "64 samples per call" in r.stdout
+
+
 def test_cpp_class_shards_over_gpus(netcuda, oracle, torch_cuda, monkeypatch):
     """net_cuda_options::n_devices / NETCUDA_DEVICES: one net_cuda object drives several GPUs -- weights replicated, every batched
     forward cut into contiguous slices, one host thread per GPU.  Samples are independent, so the outputs are the single-GPU bits
