@@ -15,7 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
-LIB_DIR = os.path.join(PKG, "lib")
+LIB_DIR = os.environ.get("NETCUDA_LIB_DIR") or os.path.join(PKG, "lib")  # (override: A/B of two builds inside one GPU call)
 HEADER = os.path.join(ROOT, "include", "netcuda.h")
 
 KIND_MLP, KIND_VIT = 0, 1
