@@ -9,7 +9,7 @@ s = torch.cuda.Stream(); torch.cuda.set_stream(s)
 for variant in (0, 5):
     net = nc.Net.mlp(npl, n_ins, precision=nc.PREC_INT8, max_batch=2048); net.upload_mlp_i8(wq, bq)
     net.set_gemm_variant(variant)
-    for batch in (160, 256, 512, 1024):
+    for batch in (16, 24, 32, 48, 160, 256, 512, 1024):
         x = torch.randint(-128, 128, (batch, n_ins), dtype=torch.int8, device="cuda"); y = torch.empty((batch, 4096), dtype=torch.int32, device="cuda")
         for _ in range(5): net.forward_device_i8(x, y, batch, s)
         s.synchronize()

@@ -87,8 +87,9 @@ cudaError_t encode_tma_2d(void *map_out, int dtype_bytes, const void *ptr, long 
 cudaError_t encode_tma_3d(void *map_out, int dtype_bytes, const void *ptr, long long dim0, long long dim1, long long dim2, long long stride1_bytes,
                           long long stride2_bytes, int box0, int box1, bool swizzle128);
 
-// ---- INT8 MLP forward for 1..16 samples in one persistent weight-streaming kernel (mlp_stream.cu) ----
+// ---- INT8 MLP forward for 1..32 samples in one persistent weight-streaming kernel (mlp_stream.cu) ----
 constexpr int MLP_STREAM_MAX_LAYERS = 16;
+constexpr int MLP_STREAM_MAX_BATCH = 32;
 struct MlpStreamLayer
 {
     const int8_t *w;     // [fan_out][fan_in], fan_in a multiple of 16, at most 4096

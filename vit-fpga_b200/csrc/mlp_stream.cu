@@ -1,7 +1,7 @@
 // mlp_stream.cu -- whole INT8 MLP forward for a handful of samples in ONE persistent kernel: weight streaming at HBM pace.
 //
 // Reference counterpart: the single-work-item task `network_v1` that walks all layers of the net for one sample
-// (src/netFPGA.cpp:250,275; argument list :427-436,499-502).  For 1..16 samples of config C5 (8 x 4096 x 4096 int8) the forward is
+// (src/netFPGA.cpp:250,275; argument list :427-436,499-502).  For 1..32 samples of config C5 (8 x 4096 x 4096 int8) the forward is
 // 128 MiB of weights against a few KB of activations: HBM-bound integer work, ~2 int-ops per weight byte and sample.  Padding such a
 // batch to a 128-row tcgen05 tile and launching two kernels per layer (split-K GEMM + finalize) runs at ~1.5 TB/s; this kernel
 // keeps the byte stream going instead:
@@ -9,7 +9,7 @@
 //     pulls its weight rows, 16 at a time, through a shared-memory ring with 1-D bulk copies (cp.async.bulk + mbarrier
 //     complete_tx; row pitch = 64 mod 128 bytes so that the fragment loads below are bank-conflict free).  Weights do not depend
 //     on activations, so the ring keeps filling across the grid barrier between layers -- the stream does not drain;
-//   * the 8 consumer warps split K: warp w keeps its K slice of all (<= 16) activation rows in REGISTERS for the whole layer, laid
+//   * the 8 consumer warps split K: warp w keeps its K slice of all (<= 32) activation rows in REGISTERS for the whole layer, laid
 //     out as the B fragments of mma.sync.m16n8k32.s8 (the CUDA-core dp4a form of this kernel needed as many shuffles as multiply-
 //     adds to reduce over the lanes and was instruction-bound from 8 samples up); K is permuted so that every activation and
 //     weight load is 16 bytes wide: 16 weight rows cost 2 shared-memory loads and 2-4 MMAs per 64 bytes of K.  The legacy
@@ -31,8 +31,8 @@ constexpr int MS_RING_BYTES = 199680;  // 3 slots at fan_in 4096 (pitch 4160); m
 constexpr int MS_MAX_SLOTS = 8;
 constexpr int MS_MAX_K = 4096;
 constexpr int MS_DSTEPS = MS_MAX_K / 64 / MS_CONSUMER_WARPS; // 64-byte K steps (two MMAs) per warp: 8
-constexpr int MS_MAX_PARTIAL = 512;    // (rows per CTA, padded to 16) x (samples, padded to 8 or 16) int32 per consumer warp
-constexpr int MS_OFF_PARTIAL = MS_RING_BYTES + 128;
+constexpr int MS_MAX_PARTIAL = 1008;   // (rows per CTA) x (samples, padded to 8 / 16 / 32) int32 per consumer warp: what is left of 227 KB
+constexpr int MS_OFF_PARTIAL = MS_RING_BYTES + 64;
 constexpr int MS_OFF_BARS = MS_OFF_PARTIAL + MS_CONSUMER_WARPS * MS_MAX_PARTIAL * 4;
 constexpr int MS_SMEM = MS_OFF_BARS + 2 * MS_MAX_SLOTS * 8;
 
@@ -88,7 +88,7 @@ __device__ __forceinline__ void mma_s8_16832(int *d, const unsigned *a, unsigned
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// NT: 8-sample groups (1: up to 8 samples, 2: up to 16)
+// NT: 8-sample groups (1: up to 8 samples, 2: up to 16, 4: up to 32)
 template <int NT>
 __global__ void __launch_bounds__(MS_THREADS, 1)
 mlp_i8_stream_kernel(const MlpStreamParams p)
@@ -210,7 +210,7 @@ mlp_i8_stream_kernel(const MlpStreamParams p)
         stamp(l, 2);
         // bias of the (up to two) outputs this thread finalises below: fetched now, needed after the last tile
         const int nvals = (r1 - r0) * BTP;
-        constexpr int FIN = MS_MAX_PARTIAL / (MS_CONSUMER_WARPS * 32); // values per thread
+        constexpr int FIN = (MS_MAX_PARTIAL + MS_CONSUMER_WARPS * 32 - 1) / (MS_CONSUMER_WARPS * 32); // values per thread
         int bias_r[FIN];
 #pragma unroll
         for (int j = 0; j < FIN; j++)
@@ -228,7 +228,8 @@ mlp_i8_stream_kernel(const MlpStreamParams p)
             // (rows past the CTA's slice and 16-byte chunks past a row's end are stale ring content: they are never stored, or
             //  meet zero activations)
             const uint8_t *w = ms_smem + slot * slot_bytes + gid * pitch + ds0 * 64 + tig * 16;
-            int acc[2][NT][4]; // two independent accumulation chains
+            constexpr int CH = NT >= 4 ? 1 : 2; // independent accumulation chains per sample group (four groups are chains enough)
+            int acc[2][NT][4];
 #pragma unroll
             for (int c = 0; c < 2; c++)
 #pragma unroll
@@ -246,17 +247,20 @@ mlp_i8_stream_kernel(const MlpStreamParams p)
                     for (int nt = 0; nt < NT; nt++)
                     {
                         mma_s8_16832(acc[0][nt], a1, (unsigned)bf[s][nt].x, (unsigned)bf[s][nt].y);
-                        mma_s8_16832(acc[1][nt], a2, (unsigned)bf[s][nt].z, (unsigned)bf[s][nt].w);
+                        mma_s8_16832(acc[CH - 1][nt], a2, (unsigned)bf[s][nt].z, (unsigned)bf[s][nt].w);
                     }
                 }
             }
             // accumulator fragment: c0 / c1 = row gid, samples tig*2, +1; c2 / c3 = row gid + 8
             int32_t *dst = my_partial + (r - r0) * BTP;
+            const int rows_left = r1 - r; // (rows of the tile past the CTA's slice are stale ring content: not stored)
 #pragma unroll
             for (int nt = 0; nt < NT; nt++)
             {
-                *reinterpret_cast<int2 *>(dst + gid * BTP + nt * 8 + tig * 2) = make_int2(acc[0][nt][0] + acc[1][nt][0], acc[0][nt][1] + acc[1][nt][1]);
-                *reinterpret_cast<int2 *>(dst + (gid + 8) * BTP + nt * 8 + tig * 2) = make_int2(acc[0][nt][2] + acc[1][nt][2], acc[0][nt][3] + acc[1][nt][3]);
+                if (gid < rows_left)
+                    *reinterpret_cast<int2 *>(dst + gid * BTP + nt * 8 + tig * 2) = make_int2(acc[0][nt][0] + acc[1][nt][0], acc[0][nt][1] + acc[1][nt][1]);
+                if (gid + 8 < rows_left)
+                    *reinterpret_cast<int2 *>(dst + (gid + 8) * BTP + nt * 8 + tig * 2) = make_int2(acc[0][nt][2] + acc[1][nt][2], acc[0][nt][3] + acc[1][nt][3]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty_bar(slot));
@@ -323,15 +327,15 @@ static cudaError_t launch_one(const MlpStreamParams &p, int grid, cudaStream_t s
 
 bool mlp_stream_supported(const MlpStreamParams &p, int grid)
 {
-    if (p.n_layers < 1 || p.n_layers > MLP_STREAM_MAX_LAYERS || p.batch < 1 || p.batch > 16 || grid < 1) return false;
-    const int btp = p.batch <= 8 ? 8 : 16;
+    if (p.n_layers < 1 || p.n_layers > MLP_STREAM_MAX_LAYERS || p.batch < 1 || p.batch > MLP_STREAM_MAX_BATCH || grid < 1) return false;
+    const int btp = p.batch <= 8 ? 8 : p.batch <= 16 ? 16 : 32;
     int max_k = 0;
     for (int l = 0; l < p.n_layers; l++)
     {
         const MlpStreamLayer &ly = p.layers[l];
         if (ly.fan_in < 16 || (ly.fan_in & 15) || ly.fan_in > MS_MAX_K || ly.fan_out < 1) return false;
         const int rpc = (ly.fan_out + grid - 1) / grid;
-        if (((rpc + MS_TILE_ROWS - 1) / MS_TILE_ROWS) * MS_TILE_ROWS * btp > MS_MAX_PARTIAL) return false;
+        if (rpc * btp > MS_MAX_PARTIAL) return false;
         if ((reinterpret_cast<uintptr_t>(ly.w) & 15u) != 0) return false;
         max_k = ly.fan_in > max_k ? ly.fan_in : max_k;
     }
@@ -341,7 +345,7 @@ bool mlp_stream_supported(const MlpStreamParams &p, int grid)
 cudaError_t launch_mlp_i8_stream(const MlpStreamParams &p, int grid, cudaStream_t stream)
 {
     if (!mlp_stream_supported(p, grid)) return cudaErrorInvalidValue;
-    return p.batch <= 8 ? launch_one<1>(p, grid, stream) : launch_one<2>(p, grid, stream);
+    return p.batch <= 8 ? launch_one<1>(p, grid, stream) : p.batch <= 16 ? launch_one<2>(p, grid, stream) : launch_one<4>(p, grid, stream);
 }
 
 } // namespace nc

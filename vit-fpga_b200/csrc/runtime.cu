@@ -116,7 +116,7 @@ struct netcuda_net
     void *act[2] = {nullptr, nullptr};     // MLP ping-pong
     int32_t *acc_out = nullptr;            // INT8 float API: last layer accumulators
     int32_t *splitk_ws = nullptr;          // INT8 small batch: [128][widest layer] int32 partial sums, all zero between layers
-    unsigned *stream_bar = nullptr;        // INT8, <= 16 samples: the two counters of the weight-streaming kernel's grid barrier
+    unsigned *stream_bar = nullptr;        // INT8, <= 32 samples: the two counters of the weight-streaming kernel's grid barrier
     bool use_stream = true;                // NETCUDA_MLP_STREAM=0 keeps such batches on the split-K GEMM path
     void *patches = nullptr, *ybuf = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *cls_ln = nullptr;
     float *x = nullptr;
@@ -640,14 +640,14 @@ static cudaError_t run_gemm(netcuda_net *h, const char *label, int kind, const v
     return launch_gemm(c, s);
 }
 
-// INT8 nets, up to 16 samples: the whole forward is one persistent weight-streaming kernel (mlp_stream.cu) when every layer's
+// INT8 nets, up to 32 samples: the whole forward is one persistent weight-streaming kernel (mlp_stream.cu) when every layer's
 // fan-in is a multiple of 16 bytes (no row padding anywhere) and the per-CTA output slices fit its shared memory.
 static bool mlp_stream_params(netcuda_net *h, int n, const int8_t *in, int32_t *out, MlpStreamParams &p)
 {
     if (h->desc.kind != NETCUDA_KIND_MLP || h->desc.precision != NETCUDA_PREC_INT8 || !h->use_stream || h->gemm_variant != 0 || !h->stream_bar)
         return false;
     const int L = (int)h->layers.size();
-    if (n < 1 || n > 16 || L > MLP_STREAM_MAX_LAYERS) return false;
+    if (n < 1 || n > MLP_STREAM_MAX_BATCH || L > MLP_STREAM_MAX_LAYERS) return false;
     p.n_layers = L, p.batch = n, p.relu_mask = 0, p.max_fan_in = 0;
     for (int l = 0; l < L; l++)
     {
@@ -689,7 +689,7 @@ static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, in
     long long cur_ld;
     MlpStreamParams sp;
     // (an int8 input of a streamed pass is read in place: its rows are unpadded)
-    const bool stream_in_place = in_i8 && n <= 16 && mlp_stream_params(h, n, in_i8, out_i32 ? out_i32 : h->acc_out, sp);
+    const bool stream_in_place = in_i8 && n <= MLP_STREAM_MAX_BATCH && mlp_stream_params(h, n, in_i8, out_i32 ? out_i32 : h->acc_out, sp);
     if (prec == NETCUDA_PREC_FP32)
     {
         cur = in_f32, cur_ld = (long long)h->n_in; // CUDA-core path reads the caller's matrix in place
@@ -713,7 +713,7 @@ static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, in
     }
     int slot = 1;
     bool streamed = false;
-    if (prec == NETCUDA_PREC_INT8 && n <= 16)
+    if (prec == NETCUDA_PREC_INT8 && n <= MLP_STREAM_MAX_BATCH)
     {
         if (mlp_stream_params(h, n, (const int8_t *)cur, out_i32 ? out_i32 : h->acc_out, sp))
         {
