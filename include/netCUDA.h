@@ -32,9 +32,9 @@ namespace cuda
     // Values mirror NETCUDA_PREC_* / NETCUDA_ACT_* in netcuda.h.
     enum precision_t
     {
-        PREC_FP32 = 0, // CUDA-core fp32, bit-equal to the CPU oracle
-        PREC_TF32 = 1, // default for nets built from net::net_data (the reference's DATA_TYPE is float)
-        PREC_BF16 = 2, // default (and only) precision of vision transformers
+        PREC_FP32 = 0, // CUDA-core fp32, bit-equal to the CPU oracle: the default for nets built from net::net_data (DATA_TYPE is float)
+        PREC_TF32 = 1, // tcgen05 kind::tf32 (opt-in for MLPs: ~1e-3 relative; vision transformers: every linear layer in tf32)
+        PREC_BF16 = 2, // default precision of vision transformers
         PREC_INT8 = 3  // Q1.7 fixed point, bit-exact
     };
     enum activation_t
@@ -46,7 +46,7 @@ namespace cuda
 
     struct net_cuda_options
     {
-        int precision;  // precision_t; -1 = take NETCUDA_PRECISION from the environment, else TF32 (MLP) / BF16 (ViT)
+        int precision;  // precision_t; -1 = take NETCUDA_PRECISION from the environment, else FP32 (MLP) / BF16 (ViT)
         int device;     // CUDA ordinal; -1 = NETCUDA_DEVICE from the environment, else 0
         int activation; // activation_t
         int max_batch;  // samples per internal pass, 0 = library default
@@ -92,7 +92,7 @@ namespace cuda
         // Writes this net (the fp32 values it was constructed from) to `path`.
         void save(const char *path) const;
         // Builds the net a file describes.  options.precision < 0 = the file's natural precision
-        // (TF32 for an fp32 MLP file unless NETCUDA_PRECISION says otherwise, BF16 for a ViT).
+        // (FP32 for an fp32 MLP file unless NETCUDA_PRECISION says otherwise, BF16 for a ViT).
         static net_cuda load(const char *path, const net_cuda_options &options = net_cuda_options());
 
         // ---- extensions beyond the abstract interface ----

@@ -43,7 +43,7 @@ extern "C" {
 
 /* arithmetic */
 #define NETCUDA_PREC_FP32 0 /* CUDA-core fp32, k-ascending fmaf: bit-equal to the oracle   */
-#define NETCUDA_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate (MLP only)               */
+#define NETCUDA_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate (MLPs; ViT linear layers) */
 #define NETCUDA_PREC_BF16 2 /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate           */
 #define NETCUDA_PREC_INT8 3 /* tcgen05 kind::i8, Q1.7 operands, int32 accumulate (MLP only) */
 
@@ -131,7 +131,7 @@ int netcuda_upload_vit(netcuda_t *h, const float *flat, size_t count);
 typedef struct netcuda_file_info
 {
     netcuda_desc desc; /* kind, activation, n_ins, n_layers, ViT dims; precision = the file's natural one
-                          (INT8 for Q17, BF16 for a ViT, TF32 for an fp32 MLP); n_p_l points at n_p_l below */
+                          (INT8 for Q17, BF16 for a ViT, FP32 for an fp32 MLP); n_p_l points at n_p_l below */
     int32_t n_p_l[NETCUDA_FILE_MAX_LAYERS];
     int32_t dtype; /* NETCUDA_FILE_* */
     uint64_t n_weights, n_biases;
@@ -147,7 +147,7 @@ int netcuda_file_info_read(const char *path, netcuda_file_info *info);
 /* Payload into caller buffers of exactly n_weights / n_biases elements of the file's dtype; checks the CRC. */
 int netcuda_file_read(const char *path, void *weights, size_t weight_bytes, void *biases, size_t bias_bytes);
 /* netcuda_create + upload from a file.  precision < 0 = the file's natural precision (an fp32 MLP file can be
- * opened as FP32 / TF32 / BF16 / INT8, a Q17 file only as INT8, a ViT only as BF16); max_batch 0 = default. */
+ * opened as FP32 / TF32 / BF16 / INT8, a Q17 file only as INT8, a ViT as BF16 or TF32); max_batch 0 = default. */
 int netcuda_create_from_file(const char *path, int precision, int device, int max_batch, netcuda_t **out);
 
 /* ---- forward ---------------------------------------------------------------------------- */

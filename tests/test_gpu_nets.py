@@ -342,14 +342,17 @@ def test_vit_cpp_class(netcuda, torch_cuda):
     np.testing.assert_array_equal(got.argmax(1), g["logits"].argmax(1))
 
 
-@pytest.mark.parametrize("name,batch,depth", [("vit_tiny_16_224", 5, 12), ("vit_base_16_224", 3, 2)])
-def test_vit_real_shapes_vs_oracle(netcuda, oracle, torch_cuda, name, batch, depth):
-    """197-token configurations (ViT-Tiny in full; ViT-B at reduced depth so the CPU oracle stays in seconds)."""
-    cfg = dict(netcuda.VIT_PRESETS[name], depth=depth)
+@pytest.mark.parametrize("name,batch,max_batch", [("vit_tiny_16_224", 5, 2), ("vit_base_16_224", 5, 3)])
+def test_vit_real_shapes_vs_oracle(netcuda, oracle, torch_cuda, name, batch, max_batch):
+    """197-token configurations at FULL depth (12 blocks): ViT-Tiny (config C2) and ViT-B/16-224 (config C3, the headline) against
+    the CPU oracle, with max_batch forcing several internal passes, the last one partial.  The rounding of 12 blocks compounds in
+    the fp32 residual stream; the bar stays the north_star's: <= 1e-2 of max |logit| per image and identical top-1."""
+    cfg = dict(netcuda.VIT_PRESETS[name])
+    assert cfg["depth"] == 12
     flat = netcuda.vit_random_params(cfg, seed=2)
     x = np.random.default_rng(6).uniform(-1, 1, (batch, 3 * cfg["image_size"] ** 2)).astype(np.float32)
     want = oracle.vit_forward(cfg, flat, x)
-    net = netcuda.Net.vit(cfg, max_batch=2)  # several internal passes, last one partial
+    net = netcuda.Net.vit(cfg, max_batch=max_batch)
     net.upload_vit(flat)
     got = net.forward(x)
     assert rel_err(got, want) <= 1e-2
@@ -360,15 +363,18 @@ def test_vit_real_shapes_vs_oracle(netcuda, oracle, torch_cuda, name, batch, dep
     got_ref = net.forward(x)
     net.close()
     assert rel_err(got, got_ref) <= 1e-2
+    np.testing.assert_array_equal(got.argmax(1), got_ref.argmax(1))
 
 
-def test_vit_large_sequence_577(netcuda, oracle, torch_cuda):
-    """ViT-L/16-384 geometry (577 tokens, 16 heads) at depth 1."""
-    cfg = dict(netcuda.VIT_PRESETS["vit_large_16_384"], depth=1)
+@pytest.mark.parametrize("depth,batch", [(1, 2), (24, 2)])
+def test_vit_large_sequence_577(netcuda, oracle, torch_cuda, depth, batch):
+    """ViT-L/16-384 (config C4: 577 tokens, 16 heads, D = 1024) at depth 1 (fast) and at its FULL depth of 24 blocks, one image per
+    internal pass, against the CPU oracle (about a minute of host time at depth 24): <= 1e-2 and identical top-1."""
+    cfg = dict(netcuda.VIT_PRESETS["vit_large_16_384"], depth=depth)
     flat = netcuda.vit_random_params(cfg, seed=4)
-    x = np.random.default_rng(7).uniform(-1, 1, (2, 3 * 384 * 384)).astype(np.float32)
+    x = np.random.default_rng(7).uniform(-1, 1, (batch, 3 * 384 * 384)).astype(np.float32)
     want = oracle.vit_forward(cfg, flat, x)
-    net = netcuda.Net.vit(cfg, max_batch=2)
+    net = netcuda.Net.vit(cfg, max_batch=1 if depth > 1 else 2)
     net.upload_vit(flat)
     got = net.forward(x)
     net.close()

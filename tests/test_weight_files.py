@@ -20,7 +20,7 @@ def test_mlp_file_round_trip(netcuda, oracle, tmp_path):
     path = tmp_path / "c1.ncw"
     netcuda.file_write_mlp(path, npl, n_ins, w, b, activation=netcuda.ACT_RELU_ALL)
     info = netcuda.file_info(path)
-    assert info["kind"] == netcuda.KIND_MLP and info["dtype"] == netcuda.FILE_F32 and info["precision"] == netcuda.PREC_TF32
+    assert info["kind"] == netcuda.KIND_MLP and info["dtype"] == netcuda.FILE_F32 and info["precision"] == netcuda.PREC_FP32
     assert info["npl"] == npl and info["n_ins"] == n_ins and info["activation"] == netcuda.ACT_RELU_ALL
     assert info["n_weights"] == w.size and info["n_biases"] == b.size
     # header 96 + n_p_l padded to 16 + payload sections padded to 16 (the documented layout)
@@ -73,6 +73,10 @@ def test_damaged_files_are_rejected(netcuda, oracle, tmp_path):
     with pytest.raises(netcuda.NetcudaError, match="checksum"):
         netcuda.file_read(variant("flip.ncw", flipped))
     netcuda.file_info(variant("flip2.ncw", flipped))  # the header alone is still fine
+    act = bytearray(raw); act[20] ^= 1  # header field `activation` (offset 20): sizes still agree, only the checksum can tell
+    netcuda.file_info(variant("act.ncw", act))
+    with pytest.raises(netcuda.NetcudaError, match="checksum"):
+        netcuda.file_read(variant("act2.ncw", act))
     with pytest.raises(netcuda.NetcudaError, match="bytes on disk"):
         netcuda.file_info(variant("short.ncw", raw[:-16]))
     with pytest.raises(netcuda.NetcudaError, match="bytes on disk"):
@@ -161,8 +165,8 @@ def test_net_from_file_equals_net_from_arrays(netcuda, oracle, torch_cuda, tmp_p
         assert f.n_in == n_ins and f.n_out == npl[-1]
         assert np.array_equal(a.forward(x), f.forward(x))
         a.close(); f.close()
-    f = netcuda.Net.from_file(path)  # natural precision of an fp32 MLP file: TF32
-    a = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_TF32); a.upload_mlp(w, b)
+    f = netcuda.Net.from_file(path)  # natural precision of an fp32 MLP file: FP32 (DATA_TYPE is float; bit-equal to the oracle)
+    a = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_FP32); a.upload_mlp(w, b)
     assert np.array_equal(a.forward(x), f.forward(x))
     golden = np.load(os.path.join(GOLDEN, "mlp_c1.npz"))
     f32 = netcuda.Net.from_file(path, precision=netcuda.PREC_FP32)

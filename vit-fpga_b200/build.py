@@ -4,7 +4,8 @@
 
 Produces
     vit-fpga_b200/lib/libnetcuda.so        CUDA kernels (sm_100a SASS) + host runtime + the extern "C" ABI
-    vit-fpga_b200/lib/libnetcuda_host.so   cuda::net_cuda (the net::net_abstract implementation) + test driver
+    vit-fpga_b200/lib/libnetcuda_host.so   cuda::net_cuda (the net::net_abstract implementation): what an application links
+    vit-fpga_b200/lib/libnetcuda_hostdrv.so  C entry points that drive net_cuda through net::net_abstract* (tests/ and bench.py only)
 
 nvcc cross-compiles for sm_100a without a GPU; the .so files travel to the GPU box with the repo snapshot.
 """
@@ -27,9 +28,12 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("NETCUDA_CXX", "/usr/bin/g++")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-ccbin", CXX]
+if os.environ.get("NETCUDA_DEBUG_TIMELINE"):  # clock64 timeline hooks for tools/*_timeline.py (never in the shipped build)
+    NVCC_FLAGS += ["-DNETCUDA_DEBUG_TIMELINE"]
 CU_SOURCES = ["gemm.cu", "elementwise.cu", "attention.cu", "mlp_stream.cu", "runtime.cu", "weights_io.cu"]
 CU_HEADERS = ["ptx.cuh", "gemm_tcgen05.cuh", "kernels.h"]
-HOST_SOURCES = ["net_cuda.cpp", "host_capi.cpp"]
+HOST_SOURCES = ["net_cuda.cpp"]
+HOST_DRIVER_SOURCES = ["host_capi.cpp"]  # ctypes driver for tests/ and bench.py: NOT part of the shipped host library
 
 
 def _newer(target: str, deps: list[str]) -> bool:
@@ -71,9 +75,14 @@ def build(force: bool = False, verbose: bool = False) -> dict:
         # gnu++14: the only language level the reference states (.vscode/c_cpp_properties.json:13)
         _run([CXX, "-std=gnu++14", "-O2", "-fPIC", "-Wall", "-shared", "-I", INCLUDE, "-o", lib_host] + host_srcs +
              ["-L", LIB, "-lnetcuda", "-pthread", "-Wl,-rpath,$ORIGIN", "-Wl,-z,defs"])
+    lib_drv = os.path.join(LIB, "libnetcuda_hostdrv.so")
+    drv_srcs = [os.path.join(HOST, s) for s in HOST_DRIVER_SOURCES]
+    if force or _newer(lib_drv, drv_srcs + [os.path.join(INCLUDE, h) for h in ("netCUDA.h", "netAbstract.h", "defines.h")] + [lib_host]):
+        _run([CXX, "-std=gnu++14", "-O2", "-fPIC", "-Wall", "-shared", "-I", INCLUDE, "-o", lib_drv] + drv_srcs +
+             ["-L", LIB, "-lnetcuda_host", "-lnetcuda", "-pthread", "-Wl,-rpath,$ORIGIN", "-Wl,-z,defs"])
     if verbose:
-        print("built", lib_cuda, "and", lib_host)
-    return {"libnetcuda": lib_cuda, "libnetcuda_host": lib_host}
+        print("built", lib_cuda, ",", lib_host, "and", lib_drv)
+    return {"libnetcuda": lib_cuda, "libnetcuda_host": lib_host, "libnetcuda_hostdrv": lib_drv}
 
 
 if __name__ == "__main__":

@@ -5,30 +5,28 @@
 // rows [q | k | v] of 3*heads*64 columns per token, so no re-layout kernel runs between the GEMM and
 // attention, and the output [token][heads*64] is directly the A operand of the output projection.
 //
-// Two kernels:
+// Three kernels:
 //  (1) attention_tc_kernel (tokens <= 256, i.e. every 224-pixel ViT): tcgen05.  One persistent CTA per SM
 //      walks over (image, head) items.  Per item: TMA loads Q (two 128-row tiles), K and V of the head
 //      (128B-swizzled, double-buffered across items); S = Q.K^T with UMMA 128 x n_pad x 16 into tensor
 //      memory; two softmax warpgroups (one per query tile, thread = query row) read S from TMEM, take the
 //      exact row max, write the un-normalised bf16 P back into the same TMEM columns; O = P.V is a UMMA
 //      with the A operand in TMEM and V consumed MN-major straight from its row-major [key][64] tile;
-//      the warpgroup scales O by 1/rowsum and writes 128-byte rows.  S and P never touch smem or HBM.
-//      Measured alternatives (round 1, 256 x 12 x 197, us per launch): this two-pass softmax 126; a single-read
-//      softmax that keeps the row as fp16 differences in registers (setmaxnreg 232) 134; P through shared
-//      memory with an SS-mode P.V (single-buffered V) 171.  The kernel is paced by the TMEM read port and by
-//      the serial S -> softmax -> P.V -> O chain of each warpgroup, see tools/attn_timeline.py.  Issuing P.V in
-//      64-key groups while the softmax is still running (O moved to columns [192, 256)) was slower as well
-//      (147 us): the A-from-TMEM MMAs and the softmax's tcgen05.ld then compete for the TMEM read port.
-//  (2) attention_kernel (longer sequences, e.g. 577 tokens at 384 pixels): flash-style single pass with
-//      mma.sync m16n8k16 (bf16 in, fp32 accumulate), described below.
-//
-// mma.sync kernel:
+//      the warpgroup scales O by 1/rowsum and stores its rows with TMA.  S and P never touch smem or HBM.
+//      One MMA-issuing thread per query tile (blocking waits); the two softmax warps of an SM sub-partition
+//      take turns in their exp2 pass (template parameter MODE), part of the exponentials can run on the FMA
+//      pipe (POLY).  Measured alternatives of round 1 (256 x 12 x 197, us per launch): two-pass softmax 126; a
+//      single-read softmax that keeps the row as fp16 differences in registers 134; P through shared memory
+//      with an SS-mode P.V 171; P.V issued in 64-key groups while the softmax is still running 147.
+//  (2) attention_tc_long_kernel (tokens > 256, e.g. 577 tokens at 384 pixels): the key-blocked variant of the
+//      same building blocks (online softmax across key blocks of <= 256 keys, O accumulated in registers).
+//  (3) attention_kernel: flash-style single pass with mma.sync m16n8k16 (bf16 in, fp32 accumulate) -- NOT on
+//      the product path; it is the cross-check variant (netcuda_set_gemm_variant(1)) the tests compare with:
 //   - one CTA per (query block, head, image); K and V of the head live in shared memory once
 //     (197 keys: 2 x 26 KB; 577 keys: 2 x 74 KB), XOR-swizzled in 16-byte chunks so ldmatrix is
 //     bank-conflict free; rows >= tokens are zero-filled and masked to -inf before the softmax;
 //   - each warp owns 16 query rows; S and P never leave registers (online softmax over 64-key
-//     chunks, exp2 with the 1/sqrt(64)*log2(e) scale folded in, warp-shuffle row reductions);
-//   - the attention core is ~4 % of ViT-B's FLOPs; moving it to tcgen05 is listed in DESIGN.md.
+//     chunks, exp2 with the 1/sqrt(64)*log2(e) scale folded in, warp-shuffle row reductions).
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -70,9 +68,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 constexpr int ATT_HD = 64;
 
-template <int NW>
+template <int NW, typename OutT>
 __global__ void __launch_bounds__(NW * 32)
-attention_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restrict__ out, int tokens, int heads, int tpad)
+attention_kernel(const __nv_bfloat16 *__restrict__ qkv, OutT *__restrict__ out, int tokens, int heads, int tpad)
 {
     extern __shared__ __align__(128) uint8_t att_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,25 +218,32 @@ attention_kernel(const __nv_bfloat16 *__restrict__ qkv, __nv_bfloat16 *__restric
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-    __nv_bfloat16 *obase = out + b * tokens * (long long)D + h * ATT_HD + tg * 2;
+    OutT *obase = out + b * tokens * (long long)D + h * ATT_HD + tg * 2;
     const int r0 = q0 + g, r1 = q0 + g + 8;
 #pragma unroll
     for (int i = 0; i < 8; i++)
     {
-        if (r0 < tokens) *reinterpret_cast<uint32_t *>(obase + (long long)r0 * D + i * 8) = pack_bf16x2(o[i][0] * i0, o[i][1] * i0);
-        if (r1 < tokens) *reinterpret_cast<uint32_t *>(obase + (long long)r1 * D + i * 8) = pack_bf16x2(o[i][2] * i1, o[i][3] * i1);
+        if constexpr (sizeof(OutT) == 2)
+        {
+            if (r0 < tokens) *reinterpret_cast<uint32_t *>(obase + (long long)r0 * D + i * 8) = pack_bf16x2(o[i][0] * i0, o[i][1] * i0);
+            if (r1 < tokens) *reinterpret_cast<uint32_t *>(obase + (long long)r1 * D + i * 8) = pack_bf16x2(o[i][2] * i1, o[i][3] * i1);
+        }
+        else
+        {
+            if (r0 < tokens) *reinterpret_cast<float2 *>(obase + (long long)r0 * D + i * 8) = make_float2(o[i][0] * i0, o[i][1] * i0);
+            if (r1 < tokens) *reinterpret_cast<float2 *>(obase + (long long)r1 * D + i * 8) = make_float2(o[i][2] * i1, o[i][3] * i1);
+        }
     }
 }
 
-template <int NW>
-static cudaError_t launch_attention_nw(const __nv_bfloat16 *q, __nv_bfloat16 *o, int batch, int tokens, int heads, int tpad,
-                                       size_t smem, cudaStream_t stream)
+template <int NW, typename OutT>
+static cudaError_t launch_attention_nw(const __nv_bfloat16 *q, OutT *o, int batch, int tokens, int heads, int tpad, size_t smem, cudaStream_t stream)
 {
     // per-device attribute; setting it on every launch costs ~1 us and keeps multi-GPU processes correct
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<NW, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     dim3 grid((tokens + 16 * NW - 1) / (16 * NW), heads, batch);
-    attention_kernel<NW><<<grid, NW * 32, smem, stream>>>(q, o, tokens, heads, tpad);
+    attention_kernel<NW, OutT><<<grid, NW * 32, smem, stream>>>(q, o, tokens, heads, tpad);
     return cudaGetLastError();
 }
 
@@ -247,17 +252,18 @@ static cudaError_t launch_attention_nw(const __nv_bfloat16 *q, __nv_bfloat16 *o,
 // =====================================================================================================
 
 constexpr int ATC_THREADS = 384;
-// Warp roles: producer, MMA issuer, TMEM allocator = warps 0-2; softmax warpgroups = warps 4-7 (query tile 0) and 8-11 (tile 1).
+// Warp roles: producer = warp 0; MMA issuers = warp 1 (query tile 0) and warp 3 (query tile 1); TMEM allocator = warp 2; softmax
+// warpgroups = warps 4-7 (query tile 0) and 8-11 (tile 1).
 // (The opposite order -- softmax on the low warp ids so that the scheduler favours the MMA / TMA issue -- was measured: 129.5
 // vs 126 us per launch, 7.9 vs 7.0 ms per ViT-B step.)
-constexpr int ATC_W_PRODUCER = 0, ATC_W_MMA = 1, ATC_W_ALLOC = 2;
+constexpr int ATC_W_PRODUCER = 0, ATC_W_MMA = 1, ATC_W_ALLOC = 2, ATC_W_MMA1 = 3;
 constexpr int ATC_Q_BYTES = 128 * 128;  // one query tile: 128 rows x 64 bf16
 constexpr int ATC_KV_BYTES = 256 * 128; // up to 256 keys x 64 bf16
 constexpr int ATC_BUF_BYTES = 2 * ATC_Q_BYTES + 2 * ATC_KV_BYTES;
-constexpr int ATC_OSLAB_BYTES = 32 * 128;         // one softmax warp's 32 output rows x 64 bf16 (128B-swizzled TMA-store source)
+constexpr int ATC_OSLAB_BYTES = 32 * 128;         // one softmax warp's 32 output rows x 128 bytes (128B-swizzled TMA-store source)
 constexpr int ATC_OFF_OSLAB = 2 * ATC_BUF_BYTES; // 1024-byte aligned
 constexpr int ATC_OFF_BARS = ATC_OFF_OSLAB + 8 * ATC_OSLAB_BYTES;
-constexpr int ATC_NUM_BARS = 4 + 8;
+constexpr int ATC_NUM_BARS = 4 + 8 + 8;
 constexpr int ATC_OFF_TMEM_PTR = ATC_OFF_BARS + ATC_NUM_BARS * 8;
 constexpr int ATC_SMEM = ATC_OFF_TMEM_PTR + 16;
 constexpr int ATC_REGION_COLS = 256; // TMEM columns per query tile: S at [0, n_pad), P over [0, n_pad/2), O at [128, 192)
@@ -271,19 +277,112 @@ enum : int
     KERR_ATT_MMA_PFULL = 14,
     KERR_ATT_WG_SFULL = 15,
     KERR_ATT_WG_OFULL = 16,
+    KERR_ATT_WG_TURN = 17,
 };
 
 struct AttnTcParams
 {
-    __nv_bfloat16 *out; // [batch * tokens][heads * 64]
+    void *out;    // [batch * tokens][heads * 64], bf16 or (out_f32) fp32
     int batch, tokens, heads;
     int n_pad;    // keys padded to a multiple of 16 (UMMA N of the S tile, UMMA K extent of P.V)
     int n_mtiles; // 1 or 2 query tiles of 128 rows
-    int stagger;  // hold the first S of tile 1 back until tile 0 has finished its first softmax (the two warpgroups then alternate)
+    int stagger;  // MODE 0: hold the first S of tile 1 back until tile 0 has finished its first softmax
+    int out_f32;  // output rows are fp32 (tf32 nets): two 32-column store boxes per warp instead of one 64-column bf16 box
     int *error_flag;
-    long long *debug; // optional [32 items][12 warps][8] clock64 stamps of CTA 0 (profiling aid; null in production)
+    long long *debug; // optional [32 items][12 warps][8] clock64 stamps of CTA 0 (NETCUDA_DEBUG_TIMELINE builds; null otherwise)
 };
 
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); // FMNMX3: one issue slot for two comparisons
+    return d;
+}
+
+// 2^x for two arguments x <= 0 on the FMA / ALU pipes instead of the MUFU (which, at 4 results per cycle and SM sub-partition, is
+// the busiest unit of this kernel: one exponential per score against 1/32 of a tensor-core cycle of MMA work for it).
+// Cody-Waite: n = round(x) through the 1.5 * 2^23 magic add, f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial
+// (relative error 7.5e-5; P is rounded to bf16, 2e-3, right after), 2^n by adding n to the exponent field.
+__device__ __forceinline__ void exp2_poly_x2(float xa, float xb, float &ra, float &rb)
+{
+    const float MAGIC = 12582912.0f; // 1.5 * 2^23: as_int(x + MAGIC) = as_int(MAGIC) + round(x), and as_int(MAGIC) << 23 == 0
+    const uint64_t x2 = pack_f32x2(fmaxf(xa, -125.0f), fmaxf(xb, -125.0f));
+    const uint64_t t2 = add_f32x2(x2, pack_f32x2(MAGIC, MAGIC));
+    const uint64_t n2 = add_f32x2(t2, pack_f32x2(-MAGIC, -MAGIC));
+    const uint64_t f2 = fma_f32x2(n2, pack_f32x2(-1.0f, -1.0f), x2);
+    uint64_t p2 = fma_f32x2(pack_f32x2(0.055171459913253784f, 0.055171459913253784f), f2, pack_f32x2(0.2426108568906784f, 0.2426108568906784f));
+    p2 = fma_f32x2(p2, f2, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+    p2 = fma_f32x2(p2, f2, pack_f32x2(0.9999281167984009f, 0.9999281167984009f));
+    float pa, pb, ta, tb;
+    unpack_f32x2(p2, pa, pb);
+    unpack_f32x2(t2, ta, tb);
+    ra = __uint_as_float(__float_as_uint(pa) + (__float_as_uint(ta) << 23));
+    rb = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(tb) << 23));
+}
+
+// O rows of one softmax warp (lane = row, 64 fp32 columns each, scaled by inv) -> global memory through the warp's 128B-swizzled
+// slab and 3-D TMA stores (rows past the image's last token are clipped by the tensor map): one 64-column bf16 box, or two
+// 32-column fp32 boxes.  Per-lane-row global stores -- 8 x 16 bytes to 32 different lines per instruction -- kept the warp in
+// this phase for ~1700 cycles of its ~8700-cycle chain per item.
+__device__ __forceinline__ void store_o_rows(const uint32_t *o, float inv, uint8_t *oslab, uint32_t oslab_addr, const CUtensorMap *map, bool f32,
+                                             int col0, int row0, int img, int lane)
+{
+    uint8_t *orow = oslab + lane * 128;
+    if (!f32)
+    {
+        if (lane == 0) tma_store_wait_read(); // the previous item's store has finished reading the slab
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+        {
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
+            pk.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
+            pk.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
+            pk.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
+            *reinterpret_cast<uint4 *>(orow + ((j ^ (lane & 7)) << 4)) = pk;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0)
+        {
+            tma_store_3d(map, oslab_addr, col0, row0, img);
+            tma_store_commit();
+        }
+        return;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; half++)
+    {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+        {
+            const uint32_t *v = o + half * 32 + 4 * j;
+            const uint4 pk = make_uint4(__float_as_uint(__uint_as_float(v[0]) * inv), __float_as_uint(__uint_as_float(v[1]) * inv),
+                                        __float_as_uint(__uint_as_float(v[2]) * inv), __float_as_uint(__uint_as_float(v[3]) * inv));
+            *reinterpret_cast<uint4 *>(orow + ((j ^ (lane & 7)) << 4)) = pk;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0)
+        {
+            tma_store_3d(map, oslab_addr, col0 + half * 32, row0, img);
+            tma_store_commit();
+        }
+    }
+}
+
+// MODE 0: one MMA-issuing thread polls both query tiles (round-1 kernel).
+// MODE 1: one issuing thread per query tile (warps 1 and 3), each in blocking mbarrier waits: no polling round (six test_waits of
+//         ~150 cycles each) between "P is ready" and the P.V issue, or between "O has been read" and the next S.
+// MODE 2: MODE 1 + the two softmax warps of one SM sub-partition (query tile 0 / tile 1, same TMEM lane quarter) take turns in
+//         their exponential pass: a warp alone runs it at the MUFU's pace; two at once both take twice as long, which lengthens
+//         BOTH serial chains (S -> softmax -> P.V -> O).  Turn-taking keeps one warp in exp2 while the other one waits for its
+//         MMAs, reduces the row maximum or stores O.
+// POLY: how many of every four exponentials run on the FMA pipe (exp2_poly_x2) instead of the MUFU: 0, 1 or 2.
+template <int POLY, int MODE>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
                     const __grid_constant__ CUtensorMap tma_out, const AttnTcParams p)
@@ -302,11 +401,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     auto pfull_bar = [&](int t) { return bars + 8u * (6 + t); };
     auto ofull_bar = [&](int t) { return bars + 8u * (8 + t); };
     auto sfree_bar = [&](int t) { return bars + 8u * (10 + t); };
+    auto turn_bar = [&](int t, int q) { return bars + 8u * (12 + t * 4 + q); }; // MODE 2: "tile t's warp of lane quarter q may run its exp2 pass"
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(atc_smem + ATC_OFF_TMEM_PTR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = p.batch * p.heads;
     const int D = p.heads * ATT_HD;
+#ifdef NETCUDA_DEBUG_TIMELINE
+    long long *const dbg = p.debug;
+#else
+    constexpr long long *dbg = nullptr;
+#endif
 
     if (warp == ATC_W_PRODUCER && lane == 0)
     {
@@ -318,13 +423,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         for (int b = 0; b < 2; b++)
         {
             mbar_init(full_bar(b), 1);
-            mbar_init(empty_bar(b), 1);
+            mbar_init(empty_bar(b), MODE == 0 ? 1 : p.n_mtiles); // MODE >= 1: one commit per tile's issuer
             mbar_init(sfull_bar(b), 1);
             // one arrive per softmax warp that owns at least one real query row (197 tokens: 4 warps for tile 0, 3 for tile 1)
             const int rows_b = min(max(p.tokens - b * 128, 1), 128);
             mbar_init(pfull_bar(b), (rows_b + 31) / 32);
             mbar_init(ofull_bar(b), 1);
             mbar_init(sfree_bar(b), (rows_b + 31) / 32);
+            for (int q = 0; q < 4; q++) mbar_init(turn_bar(b, q), 1);
         }
         fence_barrier_init();
     }
@@ -352,7 +458,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                 const int buf = it & 1;
                 const int b = item / p.heads, h = item - b * p.heads;
                 mbar_wait(empty_bar(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u, p.error_flag, KERR_ATT_PRODUCER);
-                if (p.debug && blockIdx.x == 0 && it < 32) p.debug[(it * 12 + ATC_W_PRODUCER) * 8] = clock64();
+                if (dbg && blockIdx.x == 0 && it < 32) dbg[(it * 12 + ATC_W_PRODUCER) * 8] = clock64();
                 mbar_arrive_expect_tx(full_bar(buf), tx);
                 const uint32_t dst = base + buf * ATC_BUF_BYTES;
                 const int row = b * p.tokens;
@@ -362,9 +468,50 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             }
         }
     }
-    else if (warp == ATC_W_MMA)
+    else if (MODE >= 1 && (warp == ATC_W_MMA || warp == ATC_W_MMA1))
     {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer of one query tile (blocking waits) =====================
+        const int t = warp == ATC_W_MMA ? 0 : 1;
+        if (lane == 0 && t < p.n_mtiles)
+        {
+            const uint32_t idesc_s = umma_idesc(1, 1, 128, (uint32_t)p.n_pad);
+            const uint32_t idesc_o = umma_idesc(1, 1, 128, ATT_HD) | UMMA_IDESC_B_MN_MAJOR;
+            const int ksteps = p.n_pad / 16;
+            const uint32_t region = tmem_base + t * ATC_REGION_COLS;
+            int it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, it++)
+            {
+                const int buf = it & 1;
+                const uint32_t sm = base + buf * ATC_BUF_BYTES;
+                // S_t = Q_t . K^T: K / Q landed, and the previous item's O (same TMEM region) has been read
+                mbar_wait(full_bar(buf), (uint32_t)(it >> 1) & 1u, p.error_flag, KERR_ATT_MMA_FULL);
+                mbar_wait(sfree_bar(t), ((uint32_t)it & 1u) ^ 1u, p.error_flag, KERR_ATT_MMA_SFREE);
+                tcgen05_fence_after();
+                {
+                    const uint64_t q_desc = umma_smem_desc_sw128(sm + t * ATC_Q_BYTES);
+                    const uint64_t k_desc = umma_smem_desc_sw128(sm + 2 * ATC_Q_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) umma_ss<KIND_BF16>(region, q_desc + 2u * k, k_desc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+                    tcgen05_commit(sfull_bar(t));
+                }
+                if (dbg && blockIdx.x == 0 && it < 32) dbg[(it * 12 + warp) * 8 + 0] = clock64();
+                // O_t = P_t . V.  V tile [key][64] read MN-major: one UMMA K step = 16 keys = 2048 bytes
+                mbar_wait(pfull_bar(t), (uint32_t)it & 1u, p.error_flag, KERR_ATT_MMA_PFULL);
+                tcgen05_fence_after();
+                {
+                    const uint64_t v_desc = umma_smem_desc_sw128(sm + 2 * ATC_Q_BYTES + ATC_KV_BYTES);
+                    for (int k = 0; k < ksteps; k++)
+                        umma_ts_bf16(region + ATC_O_COL, region + 8u * k, v_desc + (uint64_t)(128u * k), idesc_o, k != 0 ? 1u : 0u);
+                    tcgen05_commit(ofull_bar(t));
+                    tcgen05_commit(empty_bar(buf)); // this tile is done with the smem buffer (the producer waits for every tile's commit)
+                }
+                if (dbg && blockIdx.x == 0 && it < 32) dbg[(it * 12 + warp) * 8 + 2] = clock64();
+            }
+        }
+    }
+    else if (MODE == 0 && warp == ATC_W_MMA)
+    {
+        // ===================== MMA issuer (polling both tiles) =====================
         // One thread serves both query tiles.  The two softmax warpgroups run independently of each other, so the
         // issuer does not follow a fixed order: it polls, per tile, "S of the next item may start" (K/Q landed,
         // previous O of this tile drained) and "P of the current item is ready" and issues whichever is.
@@ -400,7 +547,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                             for (int k = 0; k < 4; k++)
                                 umma_ss<KIND_BF16>(tmem_base + t * ATC_REGION_COLS, q_desc + 2u * k, k_desc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
                             tcgen05_commit(sfull_bar(t));
-                            if (p.debug && blockIdx.x == 0 && i < 32) p.debug[(i * 12 + ATC_W_MMA) * 8 + t] = clock64();
+                            if (dbg && blockIdx.x == 0 && i < 32) dbg[(i * 12 + ATC_W_MMA) * 8 + t] = clock64();
                             it_s[t]++;
                             progress = true;
                         }
@@ -417,7 +564,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                             for (int k = 0; k < ksteps; k++)
                                 umma_ts_bf16(region + ATC_O_COL, region + 8u * k, v_desc + (uint64_t)(128u * k), idesc_o, k != 0 ? 1u : 0u);
                             tcgen05_commit(ofull_bar(t));
-                            if (p.debug && blockIdx.x == 0 && i < 32) p.debug[(i * 12 + ATC_W_MMA) * 8 + 2 + t] = clock64();
+                            if (dbg && blockIdx.x == 0 && i < 32) dbg[(i * 12 + ATC_W_MMA) * 8 + 2 + t] = clock64();
                             it_pv[t]++;
                             // both tiles are past item i: every MMA that reads its smem buffer has been issued
                             if (it_pv[t ^ 1] > i) tcgen05_commit(empty_bar(buf));
@@ -441,20 +588,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         // ===================== softmax + output warpgroups (one per query tile) =====================
         const int t = (warp - 4) >> 2; // query tile
         const int q = warp & 3;        // TMEM lane quarter
-        const int qrow = t * 128 + q * 32 + lane; // query row within the image
         const uint32_t region = tmem_base + ((uint32_t)(q * 32) << 16) + t * ATC_REGION_COLS;
         const float sl = 0.125f * 1.4426950408889634f; // 1/sqrt(64) * log2(e)
         uint8_t *oslab = atc_smem + ATC_OFF_OSLAB + (warp - 4) * ATC_OSLAB_BYTES;
         const uint32_t oslab_addr = base + ATC_OFF_OSLAB + (warp - 4) * ATC_OSLAB_BYTES;
         const int nfull = p.tokens >> 5, tail = p.tokens & 31; // full 32-key chunks, keys in the ragged last chunk
         const int nchunks = nfull + (tail ? 1 : 0);
+        // MODE 2: the other tile's warp on this SM sub-partition exists (it owns at least one query row)
+        const bool partner = MODE == 2 && p.n_mtiles == 2 && (t ^ 1) * 128 + q * 32 < p.tokens;
         int it = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, it++)
         {
             const uint32_t ph = (uint32_t)it & 1u;
             const int b = item / p.heads, h = item - b * p.heads;
             auto stamp = [&](int slot) {
-                if (p.debug && blockIdx.x == 0 && lane == 0 && it < 32) p.debug[(it * 12 + warp) * 8 + slot] = clock64();
+                if (dbg && blockIdx.x == 0 && lane == 0 && it < 32) dbg[(it * 12 + warp) * 8 + slot] = clock64();
             };
             stamp(0);
             mbar_wait(sfull_bar(t), ph, p.error_flag, KERR_ATT_WG_SFULL);
@@ -468,14 +616,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                 auto reduce = [&](const uint32_t *v, int c) {
                     if (c < nfull)
                     {
-                        float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+                        float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+                        float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+                        float m2 = fmax3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
+                        float m3 = fmax3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
 #pragma unroll
-                        for (int j = 4; j < 32; j += 4)
+                        for (int j = 12; j < 28; j += 8)
                         {
-                            m0 = fmaxf(m0, __uint_as_float(v[j])), m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
-                            m2 = fmaxf(m2, __uint_as_float(v[j + 2])), m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+                            m0 = fmax3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                            m1 = fmax3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                            m2 = fmax3(m2, __uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                            m3 = fmax3(m3, __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
                         }
-                        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+                        m0 = fmax3(m0, __uint_as_float(v[28]), __uint_as_float(v[29]));
+                        m1 = fmax3(m1, __uint_as_float(v[30]), __uint_as_float(v[31]));
+                        mx = fmax3(mx, fmaxf(m0, m1), fmaxf(m2, m3));
                     }
                     else
                     {
@@ -500,6 +655,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             }
 
             stamp(2);
+            // MODE 2: wait for this warp's turn on the MUFU (tile 0 goes first; the very first wait of a fresh barrier passes)
+            if (partner) mbar_wait(turn_bar(t, q), t == 0 ? (ph ^ 1u) : ph, p.error_flag, KERR_ATT_WG_TURN);
+            stamp(7);
             // ---- pass 2: p = 2^((s - max) * scale); P (bf16) overwrites the first half of the S columns it came from ----
             const float msc = mx * sl;
             float sum0 = 0.0f, sum1 = 0.0f;
@@ -512,8 +670,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
 #pragma unroll
                         for (int j = 0; j < 16; j++)
                         {
-                            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl, -msc));
-                            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl, -msc));
+                            const float x0 = fmaf(__uint_as_float(v[2 * j]), sl, -msc), x1 = fmaf(__uint_as_float(v[2 * j + 1]), sl, -msc);
+                            float p0, p1;
+                            // POLY of every 4 element PAIRS go to the FMA pipe (1 of 4 / 2 of 4 exponentials)
+                            if ((POLY == 1 && (j & 3) == 3) || (POLY == 2 && (j & 1) == 1))
+                                exp2_poly_x2(x0, x1, p0, p1);
+                            else
+                                p0 = ex2_approx(x0), p1 = ex2_approx(x1);
                             sum0 += p0, sum1 += p1;
                             w[j] = pack_bf16x2(p0, p1);
                         }
@@ -546,6 +709,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                 }
             }
             const float sum = sum0 + sum1;
+            if (partner)
+            {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(turn_bar(t ^ 1, q)); // the partner's turn
+            }
             tmem_st_wait();
             tcgen05_fence_before();
             __syncwarp();
@@ -564,32 +732,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(sfree_bar(t)); // region t may be overwritten by the next item's S
             stamp(6);
-            // O / rowsum as bf16 into this warp's 128B-swizzled slab, then ONE 3-D TMA store of 32 rows x 128 bytes (rows past the
-            // image's last token are clipped by the tensor map).  Per-lane-row global stores -- 8 x 16 bytes to 32 different
-            // lines per instruction -- kept the warp in this phase for ~1700 cycles of its ~8700-cycle chain per item.
-            {
-                const float inv = 1.0f / sum;
-                if (lane == 0) tma_store_wait_read(); // the previous item's store has finished reading the slab
-                __syncwarp();
-                uint8_t *orow = oslab + lane * 128;
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                {
-                    uint4 pk;
-                    pk.x = pack_bf16x2(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
-                    pk.y = pack_bf16x2(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
-                    pk.z = pack_bf16x2(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
-                    pk.w = pack_bf16x2(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
-                    *reinterpret_cast<uint4 *>(orow + ((j ^ (lane & 7)) << 4)) = pk;
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0)
-                {
-                    tma_store_3d(&tma_out, oslab_addr, h * ATT_HD, t * 128 + q * 32, b);
-                    tma_store_commit();
-                }
-            }
+            store_o_rows(o, 1.0f / sum, oslab, oslab_addr, &tma_out, p.out_f32 != 0, h * ATT_HD, t * 128 + q * 32, b, lane);
             stamp(5);
         }
         if (lane == 0) tma_store_wait_all(); // the slab is read, and the rows are written, before the CTA goes away
@@ -623,7 +766,8 @@ static_assert(ATL_SMEM <= 232448, "exceeds the 227 KB of shared memory a CTA can
 
 struct AttnLongParams
 {
-    __nv_bfloat16 *out; // [batch * tokens][heads * 64]
+    void *out; // [batch * tokens][heads * 64], bf16 or (out_f32) fp32
+    int out_f32;
     int batch, tokens, heads;
     int kb;       // keys per block: multiple of 16, <= 256
     int n_kb;     // key blocks per item
@@ -888,32 +1032,12 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
 #pragma unroll
                 for (int j = 0; j < 64; j++) o[j] = fmaf(o[j], alpha, __uint_as_float(ob[j]));
             }
-            // O / rowsum through this warp's swizzled slab and one 3-D TMA store (rows past the image's last token are clipped),
-            // as in attention_tc_kernel
+            // O / rowsum through this warp's swizzled slab and 3-D TMA stores, as in attention_tc_kernel
             if (qrow - lane < p.tokens) // (warp-uniform: the box starts inside the image)
             {
-                const float inv = 1.0f / l_run;
                 uint8_t *oslab = atl_smem + ATL_OFF_OSLAB + (warp - 4) * ATC_OSLAB_BYTES;
-                if (lane == 0) tma_store_wait_read(); // the previous item's store has finished reading the slab
-                __syncwarp();
-                uint8_t *orow = oslab + lane * 128;
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                {
-                    uint4 pk;
-                    pk.x = pack_bf16x2(o[8 * j + 0] * inv, o[8 * j + 1] * inv);
-                    pk.y = pack_bf16x2(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
-                    pk.z = pack_bf16x2(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
-                    pk.w = pack_bf16x2(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
-                    *reinterpret_cast<uint4 *>(orow + ((j ^ (lane & 7)) << 4)) = pk;
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0)
-                {
-                    tma_store_3d(&tma_out, base + ATL_OFF_OSLAB + (warp - 4) * ATC_OSLAB_BYTES, h * ATT_HD, qrow - lane, b);
-                    tma_store_commit();
-                }
+                store_o_rows(reinterpret_cast<const uint32_t *>(o), 1.0f / l_run, oslab, base + ATL_OFF_OSLAB + (warp - 4) * ATC_OSLAB_BYTES, &tma_out,
+                             p.out_f32 != 0, h * ATT_HD, qrow - lane, b, lane);
             }
         }
         if (lane == 0) tma_store_wait_all(); // the slab is read, and the rows are written, before the CTA goes away
@@ -929,12 +1053,12 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
 }
 
 static cudaError_t launch_attention_tc_long(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag,
-                                            int num_sms)
+                                            int num_sms, bool out_f32)
 {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATL_SMEM);
     if (e != cudaSuccess) return e;
     AttnLongParams p;
-    p.out = reinterpret_cast<__nv_bfloat16 *>(out);
+    p.out = out, p.out_f32 = out_f32 ? 1 : 0;
     p.batch = batch, p.tokens = tokens, p.heads = heads;
     p.n_kb = (tokens + 255) / 256;                            // fewest blocks of at most 256 keys ...
     p.kb = (((tokens + p.n_kb - 1) / p.n_kb) + 15) & ~15;     // ... of equal size, rounded up to the UMMA granularity
@@ -951,60 +1075,91 @@ static cudaError_t launch_attention_tc_long(const void *qkv, void *out, int batc
     const long long items = (long long)batch * heads * p.n_qpairs;
     const int sms = num_sms > 0 ? num_sms : 148;
     CUtensorMap map_out; // [batch][tokens][D]: a 32-row store box never spills into the next image
-    e = encode_tma_3d(&map_out, 2, out, (long long)heads * ATT_HD, tokens, batch, (long long)heads * ATT_HD * 2, (long long)tokens * heads * ATT_HD * 2,
-                      ATT_HD, 32, true);
+    const int oe = out_f32 ? 4 : 2;
+    e = encode_tma_3d(&map_out, oe, out, D, tokens, batch, D * oe, (long long)tokens * D * oe, out_f32 ? 32 : ATT_HD, 32, true);
     if (e != cudaSuccess) return e;
     return launch_pdl(attention_tc_long_kernel, dim3((unsigned)(items < sms ? items : sms)), dim3(ATC_THREADS), (size_t)ATL_SMEM, stream, 1, map_q,
                       map_kv, map_out, p);
 }
 
-static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag,
-                                       int num_sms)
+template <int POLY, int MODE>
+static cudaError_t launch_attention_tc_v(const CUtensorMap &map_q, const CUtensorMap &map_kv, const CUtensorMap &map_out, const AttnTcParams &p,
+                                         int grid, cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<POLY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
     if (e != cudaSuccess) return e;
+    return launch_pdl(attention_tc_kernel<POLY, MODE>, dim3(grid), dim3(ATC_THREADS), (size_t)ATC_SMEM, stream, 1, map_q, map_kv, map_out, p);
+}
+
+// Kernel variant = 10 * POLY + MODE (see attention_tc_kernel).  The default is the measured best; NETCUDA_ATT_TC_VARIANT (read once)
+// selects another one for A/B runs.
+constexpr int ATT_TC_DEFAULT_VARIANT = 2;
+static int att_tc_variant()
+{
+    static const int v = getenv("NETCUDA_ATT_TC_VARIANT") ? atoi(getenv("NETCUDA_ATT_TC_VARIANT")) : ATT_TC_DEFAULT_VARIANT;
+    return v;
+}
+
+static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag,
+                                       int num_sms, bool out_f32)
+{
     AttnTcParams p;
-    p.out = reinterpret_cast<__nv_bfloat16 *>(out);
+    p.out = out, p.out_f32 = out_f32 ? 1 : 0;
     p.batch = batch, p.tokens = tokens, p.heads = heads;
     p.n_pad = (tokens + 15) & ~15;
     p.n_mtiles = tokens > 128 ? 2 : 1;
-    p.stagger = getenv("NETCUDA_ATT_NOSTAGGER") == nullptr;
+    p.stagger = 1;
     p.error_flag = error_flag;
     p.debug = nullptr;
+#ifdef NETCUDA_DEBUG_TIMELINE
     if (const char *dbg = getenv("NETCUDA_ATTENTION_DEBUG_PTR")) p.debug = reinterpret_cast<long long *>(strtoull(dbg, nullptr, 0));
+#endif
     const long long D = (long long)heads * ATT_HD, rows = (long long)batch * tokens;
     // rows past the last token of the last image are zero-filled by TMA; a tile that runs into the next image reads
     // that image's (finite) rows: extra keys are masked in the softmax, extra query rows are never stored
     CUtensorMap map_q, map_kv;
-    e = encode_tma_2d(&map_q, 2, qkv, 3 * D, rows, 3 * D * 2, ATT_HD, 128, true);
+    cudaError_t e = encode_tma_2d(&map_q, 2, qkv, 3 * D, rows, 3 * D * 2, ATT_HD, 128, true);
     if (e != cudaSuccess) return e;
     e = encode_tma_2d(&map_kv, 2, qkv, 3 * D, rows, 3 * D * 2, ATT_HD, p.n_pad, true);
     if (e != cudaSuccess) return e;
     // output [batch][tokens][D] as a 3-D map: a 32-row store box never spills into the next image
     CUtensorMap map_out;
-    e = encode_tma_3d(&map_out, 2, out, D, tokens, batch, D * 2, (long long)tokens * D * 2, ATT_HD, 32, true);
+    const int oe = out_f32 ? 4 : 2;
+    e = encode_tma_3d(&map_out, oe, out, D, tokens, batch, D * oe, (long long)tokens * D * oe, out_f32 ? 32 : ATT_HD, 32, true);
     if (e != cudaSuccess) return e;
     const int items = batch * heads;
     const int sms = num_sms > 0 ? num_sms : 148;
-    return launch_pdl(attention_tc_kernel, dim3(items < sms ? items : sms), dim3(ATC_THREADS), (size_t)ATC_SMEM, stream, 1, map_q, map_kv, map_out, p);
+    const int grid = items < sms ? items : sms;
+    switch (att_tc_variant())
+    {
+    case 0: return launch_attention_tc_v<0, 0>(map_q, map_kv, map_out, p, grid, stream);
+    case 1: return launch_attention_tc_v<0, 1>(map_q, map_kv, map_out, p, grid, stream);
+    case 2: return launch_attention_tc_v<0, 2>(map_q, map_kv, map_out, p, grid, stream);
+    case 11: return launch_attention_tc_v<1, 1>(map_q, map_kv, map_out, p, grid, stream);
+    case 12: return launch_attention_tc_v<1, 2>(map_q, map_kv, map_out, p, grid, stream);
+    case 21: return launch_attention_tc_v<2, 1>(map_q, map_kv, map_out, p, grid, stream);
+    case 22: return launch_attention_tc_v<2, 2>(map_q, map_kv, map_out, p, grid, stream);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_attention(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag, int num_sms,
-                             int variant)
+                             int variant, bool out_f32)
 {
     if (batch <= 0) return cudaSuccess;
     if (tokens <= 0 || heads <= 0 || heads > 65535 || batch > 65535) return cudaErrorInvalidValue;
-    if (tokens <= 256 && variant == 0) return launch_attention_tc(qkv, out, batch, tokens, heads, stream, error_flag, num_sms);
-    if (variant == 0) return launch_attention_tc_long(qkv, out, batch, tokens, heads, stream, error_flag, num_sms);
+    if (tokens <= 256 && variant == 0) return launch_attention_tc(qkv, out, batch, tokens, heads, stream, error_flag, num_sms, out_f32);
+    if (variant == 0) return launch_attention_tc_long(qkv, out, batch, tokens, heads, stream, error_flag, num_sms, out_f32);
     const int tpad = (tokens + 15) & ~15;
     const size_t smem = (size_t)tpad * 128 * 2;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     // 197 tokens: 7 warps x 2 CTAs = 224 rows (12 % padding); general case: 4 warps per CTA.
     const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16 *>(qkv);
-    __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(out);
     if (tokens > 112 && tokens <= 224)
-        return launch_attention_nw<7>(q, o, batch, tokens, heads, tpad, smem, stream);
-    return launch_attention_nw<4>(q, o, batch, tokens, heads, tpad, smem, stream);
+        return out_f32 ? launch_attention_nw<7, float>(q, reinterpret_cast<float *>(out), batch, tokens, heads, tpad, smem, stream)
+                       : launch_attention_nw<7, __nv_bfloat16>(q, reinterpret_cast<__nv_bfloat16 *>(out), batch, tokens, heads, tpad, smem, stream);
+    return out_f32 ? launch_attention_nw<4, float>(q, reinterpret_cast<float *>(out), batch, tokens, heads, tpad, smem, stream)
+                   : launch_attention_nw<4, __nv_bfloat16>(q, reinterpret_cast<__nv_bfloat16 *>(out), batch, tokens, heads, tpad, smem, stream);
 }
 
 } // namespace nc

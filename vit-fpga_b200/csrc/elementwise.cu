@@ -10,10 +10,10 @@ namespace nc
 
 // ---- LayerNorm: one warp per row, row cached in registers, two-pass (mean, then variance) --------
 
-template <int MAXV> // MAXV float4 per lane -> dim <= 128 * MAXV
+template <int MAXV, typename OutT> // MAXV float4 per lane -> dim <= 128 * MAXV; OutT = bf16 (bf16 nets) or float (tf32 nets)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float *__restrict__ x, long long ldx, const float *__restrict__ gamma, const float *__restrict__ beta,
-                 __nv_bfloat16 *__restrict__ y, long long ldy, int rows, int dim, float eps)
+                 OutT *__restrict__ y, long long ldy, int rows, int dim, float eps)
 {
     griddep_launch_dependents();
     griddep_wait(); // x is the previous kernel's output, y the previous-but-one's input
@@ -53,7 +53,7 @@ layernorm_kernel(const float *__restrict__ x, long long ldx, const float *__rest
     const float rstd = rsqrtf(q / (float)dim + eps);
     const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
     const float4 *b4 = reinterpret_cast<const float4 *>(beta);
-    uint2 *yr = reinterpret_cast<uint2 *>(y + (long long)warp * ldy);
+    OutT *yrow = y + (long long)warp * ldy;
 #pragma unroll
     for (int i = 0; i < MAXV; i++)
     {
@@ -61,29 +61,36 @@ layernorm_kernel(const float *__restrict__ x, long long ldx, const float *__rest
         if (idx < nv)
         {
             const float4 g = g4[idx], b = b4[idx];
-            uint2 o;
-            o.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
-            o.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
-            yr[idx] = o;
+            const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
+            const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
+            if constexpr (sizeof(OutT) == 2)
+                reinterpret_cast<uint2 *>(yrow)[idx] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+            else
+                reinterpret_cast<float4 *>(yrow)[idx] = make_float4(o0, o1, o2, o3);
         }
     }
 }
 
+template <typename OutT>
+static cudaError_t launch_layernorm_t(const float *x, long long ldx, const float *gamma, const float *beta, OutT *y, long long ldy, int rows,
+                                      int dim, float eps, cudaStream_t stream)
+{
+    const int threads = 256, rows_per_block = threads / 32;
+    const int grid = (rows + rows_per_block - 1) / rows_per_block;
+    if (dim <= 256)
+        return launch_pdl(layernorm_kernel<2, OutT>, dim3(grid), dim3(threads), 0, stream, 1, x, ldx, gamma, beta, y, ldy, rows, dim, eps);
+    else if (dim <= 1024)
+        return launch_pdl(layernorm_kernel<8, OutT>, dim3(grid), dim3(threads), 0, stream, 1, x, ldx, gamma, beta, y, ldy, rows, dim, eps);
+    return launch_pdl(layernorm_kernel<32, OutT>, dim3(grid), dim3(threads), 0, stream, 1, x, ldx, gamma, beta, y, ldy, rows, dim, eps);
+}
+
 cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, const float *beta, void *y, long long ldy,
-                             int rows, int dim, float eps, cudaStream_t stream)
+                             int rows, int dim, float eps, cudaStream_t stream, bool out_f32)
 {
     if (rows <= 0) return cudaSuccess;
     if (dim <= 0 || (dim & 3) || (ldx & 3) || (ldy & 3) || dim > 4096) return cudaErrorInvalidValue;
-    const int threads = 256, rows_per_block = threads / 32;
-    const int grid = (rows + rows_per_block - 1) / rows_per_block;
-    __nv_bfloat16 *yb = reinterpret_cast<__nv_bfloat16 *>(y);
-    if (dim <= 256)
-        return launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(threads), 0, stream, 1, x, ldx, gamma, beta, yb, ldy, rows, dim, eps);
-    else if (dim <= 1024)
-        return launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(threads), 0, stream, 1, x, ldx, gamma, beta, yb, ldy, rows, dim, eps);
-    else
-        return launch_pdl(layernorm_kernel<32>, dim3(grid), dim3(threads), 0, stream, 1, x, ldx, gamma, beta, yb, ldy, rows, dim, eps);
-    return cudaGetLastError();
+    if (out_f32) return launch_layernorm_t(x, ldx, gamma, beta, reinterpret_cast<float *>(y), ldy, rows, dim, eps, stream);
+    return launch_layernorm_t(x, ldx, gamma, beta, reinterpret_cast<__nv_bfloat16 *>(y), ldy, rows, dim, eps, stream);
 }
 
 // ---- patch extraction: fp32 NCHW image -> bf16 patch rows (the im2col of a stride==kernel conv) ----
@@ -91,8 +98,22 @@ cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, 
 // Threads walk the image in its own memory order, so loads are fully coalesced; the two threads that
 // cover one 16-pixel patch row write adjacent 16-byte halves of the same 32-byte sector.
 
+// 8 values of one patch row, as bf16 (one 16-byte store) or unchanged as fp32 (tf32 nets: two 16-byte stores)
+template <typename OutT>
+__device__ __forceinline__ void store_patch8(OutT *dst, const float *v)
+{
+    if constexpr (sizeof(OutT) == 2)
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    else
+    {
+        reinterpret_cast<float4 *>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4 *>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+template <typename OutT>
 __global__ void __launch_bounds__(256)
-patchify_kernel(const float *__restrict__ img, __nv_bfloat16 *__restrict__ patches, long long total8, int S, int P, int g)
+patchify_kernel(const float *__restrict__ img, OutT *__restrict__ patches, long long total8, int S, int P, int g)
 {
     griddep_launch_dependents();
     griddep_wait();
@@ -109,25 +130,24 @@ patchify_kernel(const float *__restrict__ img, __nv_bfloat16 *__restrict__ patch
     const int gy = yy / P, py = yy - gy * P, gx = x / P, px = x - gx * P;
     const float4 *src = reinterpret_cast<const float4 *>(img + (((b * 3 + ch) * S + yy) * (long long)S + x));
     const float4 a = src[0], c = src[1];
-    uint4 o;
-    o.x = pack_bf16x2(a.x, a.y);
-    o.y = pack_bf16x2(a.z, a.w);
-    o.z = pack_bf16x2(c.x, c.y);
-    o.w = pack_bf16x2(c.z, c.w);
+    const float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
     const long long prow = (b * g + gy) * g + gx;
     const int pcol = (ch * P + py) * P + px;
-    *reinterpret_cast<uint4 *>(patches + prow * (long long)(3 * P * P) + pcol) = o;
+    store_patch8(patches + prow * (long long)(3 * P * P) + pcol, v);
 }
 
-cudaError_t launch_patchify(const float *img, void *patches, int batch, int image_size, int patch_size, cudaStream_t stream)
+cudaError_t launch_patchify(const float *img, void *patches, int batch, int image_size, int patch_size, cudaStream_t stream, bool out_f32)
 {
     if (batch <= 0) return cudaSuccess;
     if ((patch_size & 7) || (image_size % patch_size)) return cudaErrorInvalidValue;
     const long long total8 = (long long)batch * 3 * image_size * (image_size >> 3);
     const int threads = 256;
     const long long grid = (total8 + threads - 1) / threads;
-    return launch_pdl(patchify_kernel, dim3((unsigned)grid), dim3(threads), 0, stream, 1, img, reinterpret_cast<__nv_bfloat16 *>(patches), total8,
-                      image_size, patch_size, image_size / patch_size);
+    if (out_f32)
+        return launch_pdl(patchify_kernel<float>, dim3((unsigned)grid), dim3(threads), 0, stream, 1, img, reinterpret_cast<float *>(patches), total8,
+                          image_size, patch_size, image_size / patch_size);
+    return launch_pdl(patchify_kernel<__nv_bfloat16>, dim3((unsigned)grid), dim3(threads), 0, stream, 1, img,
+                      reinterpret_cast<__nv_bfloat16 *>(patches), total8, image_size, patch_size, image_size / patch_size);
 }
 
 // ---- camera frames: u8 HWC -> normalised bf16 patch rows --------------------------------------------------
@@ -136,8 +156,9 @@ cudaError_t launch_patchify(const float *img, void *patches, int batch, int imag
 // a quarter of the bytes over PCIe and skips the fp32 image in HBM: one thread takes 8 pixels (24 interleaved bytes) and
 // writes 8 bf16 of each colour plane of the patch row.  v = (u8 * (1/255) - mean[c]) * inv_std[c], every step rounded to
 // fp32 on its own (no FMA contraction) so that a host can reproduce the patch matrix bit for bit.
+template <typename OutT>
 __global__ void __launch_bounds__(256)
-patchify_u8_kernel(const uint8_t *__restrict__ img, __nv_bfloat16 *__restrict__ patches, long long total8, int S, int P, int g, float3 mean,
+patchify_u8_kernel(const uint8_t *__restrict__ img, OutT *__restrict__ patches, long long total8, int S, int P, int g, float3 mean,
                    float3 inv_std)
 {
     griddep_launch_dependents();
@@ -166,27 +187,25 @@ patchify_u8_kernel(const uint8_t *__restrict__ img, __nv_bfloat16 *__restrict__ 
             const float u = (float)((w[byte >> 2] >> (8 * (byte & 3))) & 0xFFu);
             v[i] = __fmul_rn(__fsub_rn(__fmul_rn(u, 1.0f / 255.0f), mu[ch]), is[ch]);
         }
-        uint4 o;
-        o.x = pack_bf16x2(v[0], v[1]);
-        o.y = pack_bf16x2(v[2], v[3]);
-        o.z = pack_bf16x2(v[4], v[5]);
-        o.w = pack_bf16x2(v[6], v[7]);
         const int pcol = (ch * P + py) * P + px;
-        *reinterpret_cast<uint4 *>(patches + prow * (long long)(3 * P * P) + pcol) = o;
+        store_patch8(patches + prow * (long long)(3 * P * P) + pcol, v);
     }
 }
 
 cudaError_t launch_patchify_u8(const uint8_t *img, void *patches, int batch, int image_size, int patch_size, const float *mean,
-                               const float *inv_std, cudaStream_t stream)
+                               const float *inv_std, cudaStream_t stream, bool out_f32)
 {
     if (batch <= 0) return cudaSuccess;
     if ((patch_size & 7) || (image_size % patch_size)) return cudaErrorInvalidValue;
     const long long total8 = (long long)batch * image_size * (image_size >> 3);
     const int threads = 256;
     const long long grid = (total8 + threads - 1) / threads;
-    return launch_pdl(patchify_u8_kernel, dim3((unsigned)grid), dim3(threads), 0, stream, 1, img, reinterpret_cast<__nv_bfloat16 *>(patches),
-                      total8, image_size, patch_size, image_size / patch_size, make_float3(mean[0], mean[1], mean[2]),
-                      make_float3(inv_std[0], inv_std[1], inv_std[2]));
+    const float3 mu = make_float3(mean[0], mean[1], mean[2]), is = make_float3(inv_std[0], inv_std[1], inv_std[2]);
+    if (out_f32)
+        return launch_pdl(patchify_u8_kernel<float>, dim3((unsigned)grid), dim3(threads), 0, stream, 1, img, reinterpret_cast<float *>(patches),
+                          total8, image_size, patch_size, image_size / patch_size, mu, is);
+    return launch_pdl(patchify_u8_kernel<__nv_bfloat16>, dim3((unsigned)grid), dim3(threads), 0, stream, 1, img,
+                      reinterpret_cast<__nv_bfloat16 *>(patches), total8, image_size, patch_size, image_size / patch_size, mu, is);
 }
 
 // ---- class-token rows of the residual stream ---------------------------------------------------------

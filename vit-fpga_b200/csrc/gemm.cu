@@ -100,6 +100,7 @@ cudaError_t gemm_global_init()
     NC_OPT(KIND_BF16, OUT_BF16)
     NC_OPT(KIND_BF16, OUT_F32)
     NC_OPT(KIND_TF32, OUT_F32)
+    NC_OPT(KIND_TF32, OUT_BF16) // tf32 ViTs: the qkv projection feeds the bf16 attention core
     NC_OPT(KIND_I8, OUT_S8)
     NC_OPT(KIND_I8, OUT_S32)
 #undef NC_OPT
@@ -171,9 +172,11 @@ static cudaError_t launch_tc(const GemmCall &c, cudaStream_t stream)
     p.error_flag = c.error_flag;
     p.k_splits = c.k_splits > 1 ? c.k_splits : 1;
     p.debug = nullptr;
+#ifdef NETCUDA_DEBUG_TIMELINE // clock-stamp hooks of tools/gemm_timeline.py: compiled out of release builds
     if (const char *dbg = getenv("NETCUDA_GEMM_DEBUG_PTR")) p.debug = reinterpret_cast<long long *>(strtoull(dbg, nullptr, 0));
     if (const char *de = getenv("NETCUDA_GEMM_DEBUG_EPI")) // timeline of the launches with one epilogue only (the last such launch wins)
         if (atoi(de) != c.epi) p.debug = nullptr;
+#endif
     // TMA-store epilogue whenever the output is addressable by a tensor map; otherwise direct stores
     const long long pitch_bytes = c.ldc * OutTraits<OUT>::ELEM;
     // (TMA bounds the innermost dimension in 16-byte units, so N must be a whole number of them as well)
@@ -398,6 +401,7 @@ cudaError_t launch_gemm(const GemmCall &c, cudaStream_t stream)
     else if (c.kind == GK_TF32)
     {
         if (c.out_type == OUT_F32) return launch_tc_bn<KIND_TF32, OUT_F32>(c, stream);
+        if (c.out_type == OUT_BF16) return launch_tc_bn<KIND_TF32, OUT_BF16>(c, stream);
     }
     else if (c.kind == GK_I8)
     {

@@ -113,20 +113,21 @@ struct MlpStreamParams
 bool mlp_stream_supported(const MlpStreamParams &p, int grid);
 cudaError_t launch_mlp_i8_stream(const MlpStreamParams &p, int grid, cudaStream_t stream);
 
-// y = LayerNorm(x) * gamma + beta; x fp32 rows (pitch ldx), y bf16 rows (pitch ldy).
+// y = LayerNorm(x) * gamma + beta; x fp32 rows (pitch ldx), y bf16 rows (pitch ldy) -- or fp32 rows for the tf32 nets.
 cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, const float *beta, void *y, long long ldy,
-                             int rows, int dim, float eps, cudaStream_t stream);
+                             int rows, int dim, float eps, cudaStream_t stream, bool out_f32 = false);
 
 // softmax(q k^T / sqrt(64)) v per (image, head) on packed bf16 qkv rows; head_dim fixed at 64.
 // tokens <= 256: tcgen05 kernel (S and P in tensor memory); longer sequences: mma.sync flash kernel.
+// `out` is bf16 [batch * tokens][heads * 64], or fp32 of the same shape when out_f32 is set (the A operand of a tf32 projection).
 cudaError_t launch_attention(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag = nullptr,
-                             int num_sms = 0, int variant = 0);
+                             int num_sms = 0, int variant = 0, bool out_f32 = false);
 
-// fp32 NCHW -> bf16 patch rows [batch * np][3 * p * p].
-cudaError_t launch_patchify(const float *img, void *patches, int batch, int image_size, int patch_size, cudaStream_t stream);
-// u8 HWC frames -> bf16 patch rows of (u8 / 255 - mean[c]) * inv_std[c]
+// fp32 NCHW -> bf16 (or, out_f32, fp32) patch rows [batch * np][3 * p * p].
+cudaError_t launch_patchify(const float *img, void *patches, int batch, int image_size, int patch_size, cudaStream_t stream, bool out_f32 = false);
+// u8 HWC frames -> patch rows of (u8 / 255 - mean[c]) * inv_std[c]
 cudaError_t launch_patchify_u8(const uint8_t *img, void *patches, int batch, int image_size, int patch_size, const float *mean,
-                               const float *inv_std, cudaStream_t stream);
+                               const float *inv_std, cudaStream_t stream, bool out_f32 = false);
 
 // x[b * tokens][:] = cls + pos[0]  (fp32 residual stream rows of the class token)
 cudaError_t launch_cls_rows(float *x, const float *cls, const float *pos, int batch, int tokens, int dim, cudaStream_t stream);

@@ -77,7 +77,7 @@ struct MlpLayer
 struct VitBlock
 {
     float *ln1_g, *ln1_b, *qkv_b, *proj_b, *ln2_g, *ln2_b, *fc1_b, *fc2_b;
-    void *qkv_w, *proj_w, *fc1_w, *fc2_w; // bf16
+    void *qkv_w, *proj_w, *fc1_w, *fc2_w; // operand type: bf16, or fp32 (tf32 nets)
 };
 
 struct netcuda_net
@@ -107,6 +107,7 @@ struct netcuda_net
     int elem = 4;        // operand element size (MLP)
     long long max_ld = 0; // widest padded activation row (MLP)
     // ViT
+    int vit_kind = GK_BF16; // operand kind of the linear layers: GK_BF16 or GK_TF32 (attention core: bf16 operands either way)
     int T = 0, NP = 0, PK = 0;
     void *patch_w = nullptr, *head_w = nullptr;
     float *patch_b = nullptr, *cls = nullptr, *pos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr, *head_b = nullptr;
@@ -271,8 +272,8 @@ static int validate_desc(const netcuda_desc *d)
     }
     if (d->kind == NETCUDA_KIND_VIT)
     {
-        if (d->precision != NETCUDA_PREC_BF16)
-            return fail(NETCUDA_ERR_UNSUPPORTED, "ViT nets run in NETCUDA_PREC_BF16 (got precision %d)", d->precision);
+        if (d->precision != NETCUDA_PREC_BF16 && d->precision != NETCUDA_PREC_TF32)
+            return fail(NETCUDA_ERR_UNSUPPORTED, "ViT nets run in NETCUDA_PREC_BF16 or NETCUDA_PREC_TF32 (got precision %d)", d->precision);
         if (d->image_size <= 0 || d->patch_size <= 0 || d->image_size % d->patch_size || d->patch_size % 8)
             return fail(NETCUDA_ERR_INVALID, "image_size must be a multiple of patch_size, patch_size a multiple of 8");
         if (d->dim <= 0 || d->heads <= 0 || d->dim != d->heads * 64)
@@ -443,7 +444,11 @@ static int create_impl(const netcuda_desc *desc, netcuda_net *h)
         h->arena_bytes = nparams * 4 + (size_t)(desc->depth * 12 + 16) * 256; // generous: every tensor as fp32 + alignment
         CK(cudaMalloc((void **)&h->arena, h->arena_bytes));
         auto take = [&](size_t bytes) { return arena_take(h, bytes); };
-        h->patch_w = take((size_t)D * h->PK * 2);
+        // TF32 nets (the reference's DATA_TYPE is float, def/defines.h:10): fp32 weights and activations feed kind::tf32 MMAs in every
+        // linear layer; only the attention core keeps bf16 operands (q, k, v and P are rounded to bf16, fp32 accumulate).
+        h->vit_kind = desc->precision == NETCUDA_PREC_TF32 ? GK_TF32 : GK_BF16;
+        const size_t es = h->vit_kind == GK_TF32 ? 4 : 2;
+        h->patch_w = take((size_t)D * h->PK * es);
         h->patch_b = (float *)take((size_t)D * 4);
         h->cls = (float *)take((size_t)D * 4);
         h->pos = (float *)take((size_t)h->T * D * 4);
@@ -451,24 +456,24 @@ static int create_impl(const netcuda_desc *desc, netcuda_net *h)
         for (auto &b : h->blocks)
         {
             b.ln1_g = (float *)take((size_t)D * 4), b.ln1_b = (float *)take((size_t)D * 4);
-            b.qkv_w = take((size_t)3 * D * D * 2), b.qkv_b = (float *)take((size_t)3 * D * 4);
-            b.proj_w = take((size_t)D * D * 2), b.proj_b = (float *)take((size_t)D * 4);
+            b.qkv_w = take((size_t)3 * D * D * es), b.qkv_b = (float *)take((size_t)3 * D * 4);
+            b.proj_w = take((size_t)D * D * es), b.proj_b = (float *)take((size_t)D * 4);
             b.ln2_g = (float *)take((size_t)D * 4), b.ln2_b = (float *)take((size_t)D * 4);
-            b.fc1_w = take((size_t)F * D * 2), b.fc1_b = (float *)take((size_t)F * 4);
-            b.fc2_w = take((size_t)D * F * 2), b.fc2_b = (float *)take((size_t)D * 4);
+            b.fc1_w = take((size_t)F * D * es), b.fc1_b = (float *)take((size_t)F * 4);
+            b.fc2_w = take((size_t)D * F * es), b.fc2_b = (float *)take((size_t)D * 4);
         }
         h->lnf_g = (float *)take((size_t)D * 4), h->lnf_b = (float *)take((size_t)D * 4);
-        h->head_w = take((size_t)C * D * 2), h->head_b = (float *)take((size_t)C * 4);
+        h->head_w = take((size_t)C * D * es), h->head_b = (float *)take((size_t)C * 4);
         if (!h->head_b) return fail(NETCUDA_ERR_CUDA, "weight arena overflow");
 
         const size_t mb = (size_t)h->max_batch, rows = mb * h->T;
-        CK(cudaMalloc(&h->patches, mb * h->NP * h->PK * 2));
+        CK(cudaMalloc(&h->patches, mb * h->NP * h->PK * es));
         CK(cudaMalloc((void **)&h->x, rows * D * 4));
-        CK(cudaMalloc(&h->ybuf, rows * D * 2));
-        CK(cudaMalloc(&h->qkv, rows * 3 * D * 2));
-        CK(cudaMalloc(&h->att, rows * D * 2));
-        CK(cudaMalloc(&h->hid, rows * F * 2));
-        CK(cudaMalloc(&h->cls_ln, mb * D * 2));
+        CK(cudaMalloc(&h->ybuf, rows * D * es));
+        CK(cudaMalloc(&h->qkv, rows * 3 * D * 2)); // always bf16: the attention kernels' TMA source
+        CK(cudaMalloc(&h->att, rows * D * es));
+        CK(cudaMalloc(&h->hid, rows * F * es));
+        CK(cudaMalloc(&h->cls_ln, mb * D * es));
     }
     return NETCUDA_OK;
 }
@@ -588,7 +593,7 @@ extern "C" int netcuda_upload_vit(netcuda_net *h, const float *flat, size_t coun
     const float *p = flat;
     int rc = NETCUDA_OK;
     auto mat = [&](void *dst, long long rows, int cols) {
-        if (rc == NETCUDA_OK) rc = upload_matrix(h, p, rows, cols, cols, GK_BF16, dst, scratch);
+        if (rc == NETCUDA_OK) rc = upload_matrix(h, p, rows, cols, cols, h->vit_kind, dst, scratch);
         p += (size_t)rows * cols;
     };
     auto vec = [&](float *dst, size_t n) {
@@ -662,8 +667,10 @@ static bool mlp_stream_params(netcuda_net *h, int n, const int8_t *in, int32_t *
     p.in = in, p.act[0] = (int8_t *)h->act[0], p.act[1] = (int8_t *)h->act[1], p.out = out;
     p.barrier = h->stream_bar, p.error_flag = h->d_err;
     p.debug = nullptr, p.debug_cta = 0;
+#ifdef NETCUDA_DEBUG_TIMELINE // clock-stamp hooks of tools/*_timeline.py: compiled out of release builds (NETCUDA_DEBUG_TIMELINE=1 python build.py)
     if (const char *dbg = getenv("NETCUDA_STREAM_DEBUG_PTR")) p.debug = reinterpret_cast<long long *>(strtoull(dbg, nullptr, 0));
     if (const char *dc = getenv("NETCUDA_STREAM_DEBUG_CTA")) p.debug_cta = atoi(dc);
+#endif
     return mlp_stream_supported(p, h->num_sms);
 }
 
@@ -784,27 +791,44 @@ static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, in
 static int run_layernorm(netcuda_net *h, const char *label, const float *x, long long ldx, const float *g, const float *b, void *y,
                          long long ldy, int rows, int dim, cudaStream_t s)
 {
-    KernelScope scope(h, s, label, 0.0, (double)rows * dim * 6.0 + (double)dim * 8.0);
-    CK(launch_layernorm(x, ldx, g, b, y, ldy, rows, dim, 1e-6f, s));
+    const bool f32 = h->vit_kind == GK_TF32;
+    KernelScope scope(h, s, label, 0.0, (double)rows * dim * (f32 ? 8.0 : 6.0) + (double)dim * 8.0);
+    CK(launch_layernorm(x, ldx, g, b, y, ldy, rows, dim, 1e-6f, s, f32));
     return NETCUDA_OK;
+}
+
+// ViT passes up to this many token rows run with programmatic dependent launch / are replayed from CUDA graphs (NETCUDA_VIT_PDL_ELEMS,
+// NETCUDA_VIT_GRAPH_ROWS override the thresholds for A/B measurements; read once)
+static long long vit_pdl_max_elems()
+{
+    static const long long v = getenv("NETCUDA_VIT_PDL_ELEMS") ? atoll(getenv("NETCUDA_VIT_PDL_ELEMS")) : (16LL << 20);
+    return v;
+}
+static long long vit_graph_max_rows()
+{
+    static const long long v = getenv("NETCUDA_VIT_GRAPH_ROWS") ? atoll(getenv("NETCUDA_VIT_GRAPH_ROWS")) : (long long)VIT_GRAPH_MAX_ROWS;
+    return v;
 }
 
 static int vit_pass(netcuda_net *h, const float *img, const uint8_t *img_u8, int n, float *logits, cudaStream_t s)
 {
     const int D = h->desc.dim, F = h->desc.mlp_dim, C = h->desc.n_classes, T = h->T, NP = h->NP, PK = h->PK;
     const int rows = n * T, cap = h->max_batch * T;
+    const int kind = h->vit_kind;
+    const bool f32 = kind == GK_TF32;
+    const int act_out = f32 ? OUT_F32 : OUT_BF16; // activations that feed the next GEMM's A operand
     // programmatic dependent launch pays while the kernels are short: ViT-Tiny, 256 images (50 k rows x 192): 112.8 -> 122.6 k images/s;
     // ViT-B, 512 images (101 k rows x 768): 24.8 -> 24.2 k images/s -- so it follows the size of the residual stream
-    SmallPassPdl pdl((long long)rows * D <= (16LL << 20));
+    SmallPassPdl pdl((long long)rows * D <= vit_pdl_max_elems());
     {
-        KernelScope scope(h, s, img_u8 ? "patchify_u8" : "patchify", 0.0, (double)n * (double)h->n_in * (img_u8 ? 3.0 : 6.0));
+        KernelScope scope(h, s, img_u8 ? "patchify_u8" : "patchify", 0.0, (double)n * (double)h->n_in * ((img_u8 ? 1.0 : 4.0) + (f32 ? 4.0 : 2.0)));
         if (img_u8)
-            CK(launch_patchify_u8(img_u8, h->patches, n, h->desc.image_size, h->desc.patch_size, h->u8_mean, h->u8_inv_std, s));
+            CK(launch_patchify_u8(img_u8, h->patches, n, h->desc.image_size, h->desc.patch_size, h->u8_mean, h->u8_inv_std, s, f32));
         else
-            CK(launch_patchify(img, h->patches, n, h->desc.image_size, h->desc.patch_size, s));
+            CK(launch_patchify(img, h->patches, n, h->desc.image_size, h->desc.patch_size, s, f32));
     }
     // patch embedding: x[b*T + 1 + t] = patches . patch_w^T + patch_b + pos[1 + t]
-    CK(run_gemm(h, "patch_embed", GK_BF16, h->patches, PK, h->max_batch * NP, h->patch_w, PK, h->patch_b, h->x, D, OUT_F32, EPI_PATCH,
+    CK(run_gemm(h, "patch_embed", kind, h->patches, PK, h->max_batch * NP, h->patch_w, PK, h->patch_b, h->x, D, OUT_F32, EPI_PATCH,
                 n * NP, D, PK, s, NP, T, h->pos));
     {
         KernelScope scope(h, s, "cls_rows", 0.0, (double)n * D * 4.0 + (double)D * 8.0);
@@ -813,19 +837,19 @@ static int vit_pass(netcuda_net *h, const float *img, const uint8_t *img_u8, int
     for (auto &b : h->blocks)
     {
         if (int rc = run_layernorm(h, "layernorm", h->x, D, b.ln1_g, b.ln1_b, h->ybuf, D, rows, D, s)) return rc;
-        CK(run_gemm(h, "qkv", GK_BF16, h->ybuf, D, cap, b.qkv_w, D, b.qkv_b, h->qkv, 3LL * D, OUT_BF16, EPI_NONE, rows, 3 * D, D, s));
+        CK(run_gemm(h, "qkv", kind, h->ybuf, D, cap, b.qkv_w, D, b.qkv_b, h->qkv, 3LL * D, OUT_BF16, EPI_NONE, rows, 3 * D, D, s));
         {
-            KernelScope scope(h, s, "attention", 4.0 * n * (double)T * T * D, (double)rows * D * 8.0);
-            CK(launch_attention(h->qkv, h->att, n, T, h->desc.heads, s, h->d_err, h->num_sms, h->gemm_variant == 1 ? 1 : 0));
+            KernelScope scope(h, s, "attention", 4.0 * n * (double)T * T * D, (double)rows * D * (f32 ? 10.0 : 8.0));
+            CK(launch_attention(h->qkv, h->att, n, T, h->desc.heads, s, h->d_err, h->num_sms, h->gemm_variant == 1 ? 1 : 0, f32));
         }
-        CK(run_gemm(h, "proj", GK_BF16, h->att, D, cap, b.proj_w, D, b.proj_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, D, s));
+        CK(run_gemm(h, "proj", kind, h->att, D, cap, b.proj_w, D, b.proj_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, D, s));
         if (int rc = run_layernorm(h, "layernorm", h->x, D, b.ln2_g, b.ln2_b, h->ybuf, D, rows, D, s)) return rc;
-        CK(run_gemm(h, "fc1", GK_BF16, h->ybuf, D, cap, b.fc1_w, D, b.fc1_b, h->hid, F, OUT_BF16, EPI_GELU, rows, F, D, s));
-        CK(run_gemm(h, "fc2", GK_BF16, h->hid, F, cap, b.fc2_w, F, b.fc2_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, F, s));
+        CK(run_gemm(h, "fc1", kind, h->ybuf, D, cap, b.fc1_w, D, b.fc1_b, h->hid, F, act_out, EPI_GELU, rows, F, D, s));
+        CK(run_gemm(h, "fc2", kind, h->hid, F, cap, b.fc2_w, F, b.fc2_b, h->x, D, OUT_F32, EPI_RESIDUAL, rows, D, F, s));
     }
     // final LayerNorm on the class-token rows only (row pitch T*D), then the head
     if (int rc = run_layernorm(h, "layernorm_cls", h->x, (long long)T * D, h->lnf_g, h->lnf_b, h->cls_ln, D, n, D, s)) return rc;
-    CK(run_gemm(h, "head", GK_BF16, h->cls_ln, D, h->max_batch, h->head_w, D, h->head_b, logits, C, OUT_F32, EPI_NONE, n, C, D, s));
+    CK(run_gemm(h, "head", kind, h->cls_ln, D, h->max_batch, h->head_w, D, h->head_b, logits, C, OUT_F32, EPI_NONE, n, C, D, s));
     return NETCUDA_OK;
 }
 
@@ -938,7 +962,7 @@ static int forward_device_impl(netcuda_net *h, const void *d_in, bool in_is_i8, 
             const float *img = in_is_i8 ? nullptr : (const float *)d_in + done * h->n_in;
             const uint8_t *img_u8 = in_is_i8 ? (const uint8_t *)d_in + done * h->n_in : nullptr;
             float *logits = (float *)d_out + done * h->n_out;
-            if (allow_graph && n * h->T <= VIT_GRAPH_MAX_ROWS && batch <= (size_t)h->max_batch && !h->profiling && h->use_graphs)
+            if (allow_graph && (long long)n * h->T <= vit_graph_max_rows() && batch <= (size_t)h->max_batch && !h->profiling && h->use_graphs)
                 rc = pass_graphed(h, in_is_i8 ? (const void *)img_u8 : (const void *)img, logits, n, in_is_i8, false, s, true,
                                   [&]() { return vit_pass(h, img, img_u8, n, logits, s); });
             else
@@ -967,11 +991,19 @@ extern "C" int netcuda_forward_device_i8(netcuda_net *h, const int8_t *d_in, siz
 
 // ---- forward: host buffers, pipelined staging ------------------------------------------------------------
 
+// A device-side wait that ran out of its budget (~4 s: a pipeline bug, never a slow GPU) records its site code in the mapped flag and
+// traps; the trap poisons the CUDA context, so the handle -- like every other handle of the process -- is unusable afterwards.  The
+// code is decoded per kernel and the flag cleared once reported, so that a later call does not report a stale site.
 static int kernel_error(netcuda_net *h)
 {
     const int code = h->h_err ? *h->h_err : 0;
-    if (code != 0) return fail(NETCUDA_ERR_KERNEL, "tcgen05 pipeline time-out in the dense kernel (wait site %d)", code);
-    return NETCUDA_OK;
+    if (code == 0) return NETCUDA_OK;
+    *h->h_err = 0;
+    const char *where = code == KERR_SMEM_ALIGN ? "misaligned dynamic shared memory window"
+                        : code < 10               ? "tcgen05 GEMM pipeline"
+                        : code < 20               ? "attention kernel pipeline"
+                                                  : "INT8 weight-streaming kernel (grid barrier / weight ring)";
+    return fail(NETCUDA_ERR_KERNEL, "device-side wait timed out in the %s (wait site %d); the CUDA context is poisoned by the trap", where, code);
 }
 
 // Pageable host inputs are staged through pinned slots; one thread moves ~8-10 GB/s, a 1024-image ViT batch is 616 MB: the copy
@@ -1188,6 +1220,19 @@ extern "C" int netcuda_forward_i8(netcuda_net *h, const int8_t *in, size_t batch
 
 // ---- u8 frames (ViT) ---------------------------------------------------------------------------------------
 
+// Forget every captured pass (their kernel arguments are frozen at capture time).
+static void invalidate_pass_graphs(netcuda_net *h)
+{
+    if (h->stream) cudaStreamSynchronize(h->stream); // a replay may still be running on the handle's stream
+    for (auto &g : h->pass_graphs)
+    {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g = netcuda_net::PassGraph();
+    }
+    for (auto &c : h->graph_candidates) c = netcuda_net::PassGraph();
+    (void)cudaGetLastError();
+}
+
 static int check_u8(netcuda_net *h)
 {
     if (int rc = check_handle(h)) return rc;
@@ -1200,11 +1245,16 @@ extern "C" int netcuda_set_u8_normalization(netcuda_net *h, const float *mean, c
     if (int rc = check_u8(h)) return rc;
     if (!mean || !stddev) return fail(NETCUDA_ERR_INVALID, "null argument");
     for (int c = 0; c < 3; c++)
-    {
         if (!(stddev[c] > 0.0f)) return fail(NETCUDA_ERR_INVALID, "stddev[%d] must be positive", c);
+    for (int c = 0; c < 3; c++)
+    {
         h->u8_mean[c] = mean[c];
         h->u8_inv_std[c] = 1.0f / stddev[c];
     }
+    // mean / inv_std are kernel arguments passed by value, so every captured pass has the old ones baked in: drop the graphs
+    // (and the candidates, so that the next capture starts from a pass that ran with the new values)
+    CK(cudaSetDevice(h->device));
+    invalidate_pass_graphs(h);
     return NETCUDA_OK;
 }
 

@@ -26,7 +26,7 @@ int fail(int code, const char *fmt, ...)
 }
 
 constexpr char MAGIC[8] = {'N', 'E', 'T', 'C', 'U', 'D', 'A', 'W'};
-constexpr uint32_t VERSION = 1;
+constexpr uint32_t VERSION = 2; // 2: the checksum covers the header fields as well (with the crc field itself read as zero)
 constexpr size_t HEADER_BYTES = 96;
 
 struct Header // 96 bytes, little endian, no implicit padding
@@ -93,7 +93,7 @@ int write_file(const char *path, Header hd, const int32_t *npl, const void *w, s
     hd.version = VERSION, hd.reserved = 0, hd.crc = 0;
     memset(hd.pad, 0, sizeof(hd.pad));
     if (fwrite(&hd, 1, sizeof(hd), f.get()) != sizeof(hd)) return fail(NETCUDA_ERR_INVALID, "short write to %s", path);
-    uint32_t crc = 0;
+    uint32_t crc = crc32_update(0, &hd, sizeof(hd)); // header with crc = 0: a flipped dimension or activation is caught like a flipped weight
     if (int rc = write_section(f.get(), npl, (size_t)hd.n_layers * 4, crc, path)) return rc;
     if (int rc = write_section(f.get(), w, (size_t)hd.n_weights * w_elem, crc, path)) return rc;
     if (int rc = write_section(f.get(), b, (size_t)hd.n_biases * b_elem, crc, path)) return rc;
@@ -111,8 +111,10 @@ int mlp_counts(const int32_t *npl, int n_layers, int n_ins, uint64_t *nw, uint64
     for (int l = 0; l < n_layers; l++)
     {
         if (npl[l] <= 0) return fail(NETCUDA_ERR_INVALID, "n_p_l[%d] must be positive", l);
-        w += fan_in * (uint64_t)npl[l]; // W_l[out][in], src/netFPGA.cpp:91-106
+        w += fan_in * (uint64_t)npl[l]; // W_l[out][in], src/netFPGA.cpp:91-106 (each product < 2^62, the sum is bounded right below)
         b += (uint64_t)npl[l];
+        // a crafted layer table must not wrap the 64-bit sum: no net this library can hold comes near 2^40 weights
+        if (w > (1ull << 40)) return fail(NETCUDA_ERR_INVALID, "layer table describes more than 2^40 weights");
         fan_in = (uint64_t)npl[l];
     }
     *nw = w, *nb = b;
@@ -158,7 +160,7 @@ void fill_info(const Header &hd, const int32_t *npl, netcuda_file_info *info)
     d.n_ins = (int32_t)hd.n_ins, d.n_layers = (int32_t)hd.n_layers, d.n_p_l = info->n_p_l;
     d.image_size = (int32_t)hd.vit[0], d.patch_size = (int32_t)hd.vit[1], d.dim = (int32_t)hd.vit[2], d.depth = (int32_t)hd.vit[3];
     d.heads = (int32_t)hd.vit[4], d.mlp_dim = (int32_t)hd.vit[5], d.n_classes = (int32_t)hd.vit[6];
-    d.precision = hd.kind == NETCUDA_KIND_VIT ? NETCUDA_PREC_BF16 : hd.dtype == NETCUDA_FILE_Q17 ? NETCUDA_PREC_INT8 : NETCUDA_PREC_TF32;
+    d.precision = hd.kind == NETCUDA_KIND_VIT ? NETCUDA_PREC_BF16 : hd.dtype == NETCUDA_FILE_Q17 ? NETCUDA_PREC_INT8 : NETCUDA_PREC_FP32;
     info->dtype = (int32_t)hd.dtype, info->n_weights = hd.n_weights, info->n_biases = hd.n_biases;
 }
 
@@ -230,7 +232,9 @@ extern "C" int netcuda_file_read(const char *path, void *weights, size_t weight_
     const size_t npl_bytes = pad16((size_t)hd.n_layers * 4);
     if (fseek(f.get(), (long)HEADER_BYTES, SEEK_SET) != 0) return fail(NETCUDA_ERR_INVALID, "%s: cannot seek", path);
     uint8_t scratch[NETCUDA_FILE_MAX_LAYERS * 4 + 16];
-    uint32_t crc = 0;
+    Header hz = hd;
+    hz.crc = 0;
+    uint32_t crc = crc32_update(0, &hz, sizeof(hz));
     if (fread(scratch, 1, npl_bytes, f.get()) != npl_bytes) return fail(NETCUDA_ERR_INVALID, "%s: truncated", path);
     crc = crc32_update(crc, scratch, npl_bytes);
     auto section = [&](void *dst, size_t bytes) -> int {

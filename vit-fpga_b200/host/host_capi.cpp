@@ -77,7 +77,7 @@ void *nch_mlp_create(const int *npl, int n_layers, int n_ins, const float *w, co
 }
 
 void *nch_vit_create(int image_size, int patch_size, int dim, int depth, int heads, int mlp_dim, int n_classes, const float *flat,
-                     size_t count, int device, int max_batch)
+                     size_t count, int device, int max_batch, int precision)
 {
     try
     {
@@ -85,7 +85,7 @@ void *nch_vit_create(int image_size, int patch_size, int dim, int depth, int hea
         v.image_size = image_size, v.patch_size = patch_size, v.dim = dim, v.depth = depth, v.heads = heads;
         v.mlp_dim = mlp_dim, v.n_classes = n_classes;
         v.params.assign(flat, flat + count);
-        net::net_abstract *n = new cuda::net_cuda(v, make_opt(cuda::PREC_BF16, device, 0, max_batch));
+        net::net_abstract *n = new cuda::net_cuda(v, make_opt(precision, device, 0, max_batch));
         return n;
     }
     catch (const std::exception &e)

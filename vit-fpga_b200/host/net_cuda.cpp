@@ -102,7 +102,9 @@ namespace cuda
     {
         try
         {
-            p_->opt = resolve(options, PREC_TF32);
+            // fp32 by default: the reference's DATA_TYPE is float (def/defines.h:10), and NETCUDA_PREC_FP32 reproduces the CPU oracle's
+            // k-ordered fmaf sequence bit for bit.  The tensor-core precisions are opt-in (options.precision / NETCUDA_PRECISION).
+            p_->opt = resolve(options, PREC_FP32);
             // depth comes from n_p_l.size(); data.n_layers is informational (src/netFPGA.cpp:59)
             if (data.n_p_l.empty() || data.n_ins == 0) throw std::invalid_argument("net_cuda: empty net description");
             p_->n_ins = data.n_ins;
@@ -299,6 +301,7 @@ namespace cuda
             data.bias.emplace_back();
             for (std::size_t j = 0; j < fan_out; j++)
             {
+                if (pc + fan_in > w.size() || nc >= b.size()) throw std::invalid_argument("net_cuda::load: layer table exceeds the file's payload");
                 data.params[l].emplace_back(w.begin() + pc, w.begin() + pc + fan_in);
                 pc += fan_in;
                 data.bias[l].push_back(b[nc++]);

@@ -68,7 +68,8 @@ def _load(name: str) -> C.CDLL:
 
 lib = _load("libnetcuda.so")
 lib.netcuda_last_error.restype = C.c_char_p
-hostlib = _load("libnetcuda_host.so")
+_hostcls = _load("libnetcuda_host.so")   # cuda::net_cuda (the shipped class library)
+hostlib = _load("libnetcuda_hostdrv.so")  # its ctypes driver (test / bench plumbing only)
 hostlib.nch_last_error.restype = C.c_char_p
 hostlib.nch_mlp_create.restype = C.c_void_p
 hostlib.nch_vit_create.restype = C.c_void_p
@@ -111,11 +112,12 @@ def _stream(stream) -> C.c_void_p:
     return C.c_void_p(raw if raw != 0 else CUDA_STREAM_LEGACY)
 
 
-VIT_PRESETS = {
-    "vit_tiny_16_224": dict(image_size=224, patch_size=16, dim=192, depth=12, heads=3, mlp_dim=768, n_classes=1000),
-    "vit_base_16_224": dict(image_size=224, patch_size=16, dim=768, depth=12, heads=12, mlp_dim=3072, n_classes=1000),
-    "vit_large_16_384": dict(image_size=384, patch_size=16, dim=1024, depth=24, heads=16, mlp_dim=4096, n_classes=1000),
-}
+import sys as _sys
+
+if PKG not in _sys.path:
+    _sys.path.insert(0, PKG)
+import vit_presets as _presets  # pure Python (no dlopen): shared with bench.py's reference arm
+from vit_presets import VIT_PRESETS  # noqa: E402,F401
 
 
 def vit_param_count(cfg: dict) -> int:
@@ -126,32 +128,8 @@ def vit_param_count(cfg: dict) -> int:
 
 
 def vit_random_params(cfg: dict, seed: int = 0) -> np.ndarray:
-    """Random-init weights of the named architecture in the flat layout (synthetic benchmark weights).
-    Matrices ~ N(0, 0.02) like torchvision's trunc-normal init, LN gamma 1 +- 0.05, small biases."""
-    rng = np.random.default_rng(seed)
-    D, F, Cn = cfg["dim"], cfg["mlp_dim"], cfg["n_classes"]
-    g = cfg["image_size"] // cfg["patch_size"]
-    N, pk = g * g + 1, 3 * cfg["patch_size"] ** 2
-    parts = []
-
-    def mat(r, c, std=0.02):
-        parts.append((rng.standard_normal((r, c), dtype=np.float32) * std).ravel())
-
-    def vec(n, mean=0.0, std=0.02):
-        parts.append(mean + rng.standard_normal(n, dtype=np.float32) * std)
-
-    mat(D, pk, std=(1.0 / pk) ** 0.5)
-    vec(D), vec(D), mat(N, D)
-    for _ in range(cfg["depth"]):
-        vec(D, 1.0, 0.05), vec(D)
-        mat(3 * D, D, std=D ** -0.5), vec(3 * D)
-        mat(D, D, std=D ** -0.5), vec(D)
-        vec(D, 1.0, 0.05), vec(D)
-        mat(F, D, std=D ** -0.5), vec(F)
-        mat(D, F, std=F ** -0.5), vec(D)
-    vec(D, 1.0, 0.05), vec(D)
-    mat(Cn, D, std=0.05), vec(Cn)
-    flat = np.concatenate(parts).astype(np.float32)
+    """vit_presets.vit_random_params, with the size checked against the library's own count."""
+    flat = _presets.vit_random_params(cfg, seed)
     assert flat.size == vit_param_count(cfg)
     return flat
 
@@ -229,8 +207,9 @@ class Net:
         return cls(d, keepalive=arr)
 
     @classmethod
-    def vit(cls, cfg: dict, device=0, max_batch=0) -> "Net":
-        d = Desc(kind=KIND_VIT, precision=PREC_BF16, device=device, max_batch=max_batch, **cfg)
+    def vit(cls, cfg: dict, device=0, max_batch=0, precision=PREC_BF16) -> "Net":
+        """precision: PREC_BF16 (default) or PREC_TF32 (fp32 weights / activations, kind::tf32 MMAs in every linear layer)."""
+        d = Desc(kind=KIND_VIT, precision=precision, device=device, max_batch=max_batch, **cfg)
         return cls(d)
 
     @classmethod
@@ -427,11 +406,11 @@ class HostNet:
         return cls(h, int(n_ins), int(arr[-1]))
 
     @classmethod
-    def vit(cls, cfg: dict, flat, device=0, max_batch=0) -> "HostNet":
+    def vit(cls, cfg: dict, flat, device=0, max_batch=0, precision=PREC_BF16) -> "HostNet":
         f = np.ascontiguousarray(flat, dtype=np.float32)
         h = hostlib.nch_vit_create(C.c_int(cfg["image_size"]), C.c_int(cfg["patch_size"]), C.c_int(cfg["dim"]), C.c_int(cfg["depth"]),
                                    C.c_int(cfg["heads"]), C.c_int(cfg["mlp_dim"]), C.c_int(cfg["n_classes"]), _ptr(f),
-                                   C.c_size_t(f.size), C.c_int(device), C.c_int(max_batch))
+                                   C.c_size_t(f.size), C.c_int(device), C.c_int(max_batch), C.c_int(precision))
         return cls(h, 3 * cfg["image_size"] ** 2, cfg["n_classes"])
 
     @classmethod
