@@ -260,6 +260,14 @@ int netcuda_op_layernorm(int device, const float *d_x, int ldx, const float *d_g
 /* Multi-head attention core on packed qkv: d_qkv bf16 [batch*tokens][3*heads*64] (q|k|v blocks,
  * head-major inside each), d_out bf16 [batch*tokens][heads*64] = softmax(q k^T / 8) v per head. */
 int netcuda_op_attention(int device, const void *d_qkv, void *d_out, int batch, int tokens, int heads, void *stream);
+/* The same with an explicit kernel choice and output type (tests and A/B measurements):
+ *   kernel < 0: the product default;  NETCUDA_ATT_KERNEL_MMA_SYNC: the mma.sync cross-check kernel;
+ *   otherwise 10 * POLY + MODE of the short-sequence tcgen05 kernel (csrc/attention.cu: MODE 0 = one polling MMA issuer,
+ *   1 = one blocking issuer per query tile, 2 = 1 + exp2 turn-taking; POLY 0..2 = exponentials per four on the FMA pipe).
+ *   out_f32 != 0: d_out is fp32 [batch*tokens][heads*64] (what a TF32 ViT's output projection reads). */
+#define NETCUDA_ATT_KERNEL_MMA_SYNC 100
+int netcuda_op_attention_ex(int device, const void *d_qkv, void *d_out, int batch, int tokens, int heads, int kernel, int out_f32,
+                            void *stream);
 
 /* fp32 NCHW images -> bf16 patch matrix [batch*np][3*p*p] (column = c*p*p + py*p + px). */
 int netcuda_op_patchify(int device, const float *d_img, void *d_patches, int batch, int image_size, int patch_size, void *stream);

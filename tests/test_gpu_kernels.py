@@ -274,6 +274,42 @@ def test_attention_tcgen05_matches_mma_sync_kernel(netcuda, torch_cuda, monkeypa
     assert err <= 1e-2, err
 
 
+@pytest.mark.parametrize("kernel", [0, 1, 2, 11, 12, 21, 22])
+@pytest.mark.parametrize("batch,tokens,heads", [(40, 197, 12), (3, 37, 2), (2, 129, 2), (2, 256, 1), (1, 128, 1), (5, 200, 3)])
+def test_attention_kernel_variants_vs_oracle(netcuda, oracle, torch_cuda, kernel, batch, tokens, heads):
+    """Every build variant of the short-sequence tcgen05 kernel (10 * POLY + MODE: polling / per-tile MMA issuers, exp2 turn-taking,
+    exponentials on the FMA pipe), bf16 and fp32 outputs, against the oracle; several items per CTA (40 x 12 heads over 148 SMs),
+    one and two query tiles, ragged last tile.  The polynomial exp2 is within 7.5e-5 of 2^x: far inside P's bf16 rounding."""
+    torch = torch_cuda
+    rng = np.random.default_rng(tokens * 7 + heads + kernel)
+    qkv = _bf16_round(torch, (rng.standard_normal((batch * tokens, 3 * heads * 64)) * 1.5).astype(np.float32))
+    dq = torch.from_numpy(qkv).cuda().to(torch.bfloat16)
+    want = oracle.attention(qkv, batch, tokens, heads)
+    for f32 in (False, True):
+        out = torch.full((batch * tokens, heads * 64), 55.0, dtype=torch.float32 if f32 else torch.bfloat16, device="cuda")
+        netcuda.op_attention_ex(dq, out, batch, tokens, heads, kernel=kernel, out_f32=f32)
+        torch.cuda.synchronize()
+        assert _max_rel(out.float().cpu().numpy(), want) <= 1e-2, (kernel, f32)
+
+
+@pytest.mark.parametrize("batch,tokens,heads", [(2, 577, 3), (1, 300, 1), (2, 197, 2)])
+def test_attention_fp32_output(netcuda, oracle, torch_cuda, batch, tokens, heads):
+    """fp32 output rows (two 32-column TMA store boxes per warp) of the key-blocked kernel, the short-sequence kernel and the
+    mma.sync cross-check kernel: the bf16 output of the same kernel, before its final rounding."""
+    torch = torch_cuda
+    rng = np.random.default_rng(tokens)
+    qkv = torch.from_numpy(rng.standard_normal((batch * tokens, 3 * heads * 64)).astype(np.float32)).cuda().to(torch.bfloat16)
+    for kernel in (-1, netcuda.ATT_KERNEL_MMA_SYNC):
+        o16 = torch.full((batch * tokens, heads * 64), 7.0, dtype=torch.bfloat16, device="cuda")
+        o32 = torch.full((batch * tokens, heads * 64), 7.0, dtype=torch.float32, device="cuda")
+        netcuda.op_attention_ex(qkv, o16, batch, tokens, heads, kernel=kernel, out_f32=False)
+        netcuda.op_attention_ex(qkv, o32, batch, tokens, heads, kernel=kernel, out_f32=True)
+        torch.cuda.synchronize()
+        assert torch.equal(o32.to(torch.bfloat16), o16), kernel
+    want = oracle.attention(qkv.float().cpu().numpy(), batch, tokens, heads)
+    assert _max_rel(o32.cpu().numpy(), want) <= 1e-2
+
+
 def test_patchify_exact(netcuda, torch_cuda):
     torch = torch_cuda
     rng = np.random.default_rng(4)

@@ -165,7 +165,9 @@ def test_cpp_class_shards_over_gpus(netcuda, oracle, torch_cuda, monkeypatch):
     forward cut into contiguous slices, one host thread per GPU.  Samples are independent, so the outputs are the single-GPU bits
     (MLP fp32 path: the oracle's bits; ViT: the same kernels on another device)."""
     if torch_cuda.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+        if int(os.environ.get("NETCUDA_REQUIRE_GPUS", "0")) >= 2:
+            pytest.fail("NETCUDA_REQUIRE_GPUS >= 2 but fewer than two CUDA devices are visible")
+        pytest.skip("needs two GPUs (NETCUDA_REQUIRE_GPUS=2 turns this skip into a failure)")
     npl, n_ins, w, b = c1_net(oracle)
     x = np.random.default_rng(2).uniform(-1, 1, (301, n_ins)).astype(np.float32)  # ragged slices: 151 + 150
     monkeypatch.setenv("NETCUDA_DEVICES", "2")
@@ -380,6 +382,44 @@ def test_vit_large_sequence_577(netcuda, oracle, torch_cuda, depth, batch):
     net.close()
     assert rel_err(got, want) <= 1e-2
     np.testing.assert_array_equal(got.argmax(1), want.argmax(1))
+
+
+@pytest.mark.parametrize("name,batch,depth", [("vit_tiny_16_224", 5, 12), ("vit_base_16_224", 3, 12)])
+def test_vit_tf32_vs_oracle(netcuda, oracle, torch_cuda, name, batch, depth):
+    """NETCUDA_PREC_TF32 vision transformers (config C2: "FP32 reference vs TF32/BF16 netCUDA"; the reference's DATA_TYPE is float,
+    def/defines.h:10): fp32 weights and activations, kind::tf32 MMAs in every linear layer, bf16 operands in the attention core
+    only.  Same bar as bf16 -- <= 1e-2 of max |logit| and identical top-1 -- and measurably closer to the fp32 oracle than bf16."""
+    cfg = dict(netcuda.VIT_PRESETS[name], depth=depth)
+    flat = netcuda.vit_random_params(cfg, seed=2)
+    x = np.random.default_rng(6).uniform(-1, 1, (batch, 3 * cfg["image_size"] ** 2)).astype(np.float32)
+    want = oracle.vit_forward(cfg, flat, x)
+    errs = {}
+    for prec in ("tf32", "bf16"):
+        net = netcuda.Net.vit(cfg, max_batch=2, precision=netcuda.PRECISIONS[prec])
+        net.upload_vit(flat)
+        got = net.forward(x)
+        errs[prec] = rel_err(got, want)
+        np.testing.assert_array_equal(got.argmax(1), want.argmax(1))
+        if prec == "tf32":
+            net.set_gemm_variant(1)  # CUDA-core GEMMs with tf32-truncated operands + mma.sync attention writing fp32
+            assert rel_err(net.forward(x), want) <= 1e-2
+        net.close()
+    assert errs["tf32"] <= 1e-2 and errs["bf16"] <= 1e-2
+    assert errs["tf32"] < errs["bf16"], errs  # the linear layers keep 3 more mantissa bits per operand
+
+
+def test_vit_tf32_cpp_class_and_u8(netcuda, torch_cuda):
+    """The C++ class with net_cuda_options::precision = PREC_TF32 on the golden ViT: u8 frames and float images agree bit for bit,
+    and the 128-wide fixture that costs bf16 1.14e-2 of operand rounding stays well inside 1e-2."""
+    g, cfg = _golden_vit()
+    h = netcuda.HostNet.vit(cfg, g["flat"], precision=netcuda.PREC_TF32)
+    got = h.launch_forward(g["images"])
+    assert rel_err(got, g["logits"]) <= 1e-2
+    np.testing.assert_array_equal(got.argmax(1), g["logits"].argmax(1))
+    frame = np.random.default_rng(4).integers(0, 256, (32, 32, 3), dtype=np.uint8)
+    want = h.launch_forward(_frames_to_float(frame[None], (0.5,) * 3, (0.5,) * 3).ravel()).ravel()
+    np.testing.assert_array_equal(h.launch_forward_frame(frame, 32, 32), want)
+    h.close()
 
 
 def test_vit_batch_independence_at_full_batch(netcuda, torch_cuda):
@@ -660,6 +700,36 @@ def test_vit_u8_frames_equal_float_path(netcuda, torch_cuda):
     with pytest.raises(netcuda.NetcudaError, match="ViT"):
         mlp.forward_u8(frames[:1])
     mlp.close()
+
+
+def test_u8_normalization_change_invalidates_captured_graphs(netcuda, torch_cuda):
+    """Regression: mean / inv_std are by-value kernel arguments, so a captured pass has them baked in.  With
+    batch <= max_batch the same (staging slot, output) pair repeats and the pass is replayed from a CUDA graph; a later
+    netcuda_set_u8_normalization must drop those graphs or the new statistics are silently ignored."""
+    torch = torch_cuda
+    g, cfg = _golden_vit()
+    net = netcuda.Net.vit(cfg, max_batch=16)
+    net.upload_vit(g["flat"])
+    frames = np.random.default_rng(10).integers(0, 256, (8, 32, 32, 3), dtype=np.uint8)
+    want1 = net.forward(_frames_to_float(frames, (0.5,) * 3, (0.5,) * 3).reshape(8, -1))
+    d_f = torch.from_numpy(frames).cuda()
+    d_y = torch.empty((8, net.n_out), device="cuda")
+    s = torch.cuda.Stream()
+    for _ in range(6):  # plain, capture, replays
+        np.testing.assert_array_equal(net.forward_u8(frames), want1)
+        net.forward_device_u8(d_f, d_y, 8, s)
+        s.synchronize()
+        np.testing.assert_array_equal(d_y.cpu().numpy(), want1)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    net.set_u8_normalization(mean, std)
+    want2 = net.forward(_frames_to_float(frames, mean, std).reshape(8, -1))
+    assert np.abs(want2 - want1).max() > 1e-3
+    for _ in range(6):
+        np.testing.assert_array_equal(net.forward_u8(frames), want2)
+        net.forward_device_u8(d_f, d_y, 8, s)
+        s.synchronize()
+        np.testing.assert_array_equal(d_y.cpu().numpy(), want2)
+    net.close()
 
 
 def test_class_launch_forward_image_set(netcuda, torch_cuda):

@@ -1101,7 +1101,7 @@ static int att_tc_variant()
 }
 
 static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag,
-                                       int num_sms, bool out_f32)
+                                       int num_sms, bool out_f32, int tc_variant)
 {
     AttnTcParams p;
     p.out = out, p.out_f32 = out_f32 ? 1 : 0;
@@ -1130,7 +1130,7 @@ static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, in
     const int items = batch * heads;
     const int sms = num_sms > 0 ? num_sms : 148;
     const int grid = items < sms ? items : sms;
-    switch (att_tc_variant())
+    switch (tc_variant >= 0 ? tc_variant : att_tc_variant())
     {
     case 0: return launch_attention_tc_v<0, 0>(map_q, map_kv, map_out, p, grid, stream);
     case 1: return launch_attention_tc_v<0, 1>(map_q, map_kv, map_out, p, grid, stream);
@@ -1144,11 +1144,11 @@ static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, in
 }
 
 cudaError_t launch_attention(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag, int num_sms,
-                             int variant, bool out_f32)
+                             int variant, bool out_f32, int tc_variant)
 {
     if (batch <= 0) return cudaSuccess;
     if (tokens <= 0 || heads <= 0 || heads > 65535 || batch > 65535) return cudaErrorInvalidValue;
-    if (tokens <= 256 && variant == 0) return launch_attention_tc(qkv, out, batch, tokens, heads, stream, error_flag, num_sms, out_f32);
+    if (tokens <= 256 && variant == 0) return launch_attention_tc(qkv, out, batch, tokens, heads, stream, error_flag, num_sms, out_f32, tc_variant);
     if (variant == 0) return launch_attention_tc_long(qkv, out, batch, tokens, heads, stream, error_flag, num_sms, out_f32);
     const int tpad = (tokens + 15) & ~15;
     const size_t smem = (size_t)tpad * 128 * 2;

@@ -120,8 +120,9 @@ cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, 
 // softmax(q k^T / sqrt(64)) v per (image, head) on packed bf16 qkv rows; head_dim fixed at 64.
 // tokens <= 256: tcgen05 kernel (S and P in tensor memory); longer sequences: mma.sync flash kernel.
 // `out` is bf16 [batch * tokens][heads * 64], or fp32 of the same shape when out_f32 is set (the A operand of a tf32 projection).
+// variant 1 = the mma.sync cross-check kernel; tc_variant >= 0 picks a build variant of the short-sequence tcgen05 kernel (A/B, tests).
 cudaError_t launch_attention(const void *qkv, void *out, int batch, int tokens, int heads, cudaStream_t stream, int *error_flag = nullptr,
-                             int num_sms = 0, int variant = 0, bool out_f32 = false);
+                             int num_sms = 0, int variant = 0, bool out_f32 = false, int tc_variant = -1);
 
 // fp32 NCHW -> bf16 (or, out_f32, fp32) patch rows [batch * np][3 * p * p].
 cudaError_t launch_patchify(const float *img, void *patches, int batch, int image_size, int patch_size, cudaStream_t stream, bool out_f32 = false);

@@ -1415,6 +1415,16 @@ extern "C" int netcuda_op_attention(int device, const void *d_qkv, void *d_out, 
     return NETCUDA_OK;
 }
 
+extern "C" int netcuda_op_attention_ex(int device, const void *d_qkv, void *d_out, int batch, int tokens, int heads, int kernel, int out_f32,
+                                       void *stream)
+{
+    if (int rc = op_prologue(device)) return rc;
+    const cudaError_t e = launch_attention(d_qkv, d_out, batch, tokens, heads, (cudaStream_t)stream, nullptr, 0, kernel == NETCUDA_ATT_KERNEL_MMA_SYNC ? 1 : 0,
+                                           out_f32 != 0, kernel >= 0 ? kernel : -1);
+    if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? NETCUDA_ERR_INVALID : NETCUDA_ERR_CUDA, "netcuda_op_attention_ex: %s", cudaGetErrorString(e));
+    return NETCUDA_OK;
+}
+
 extern "C" int netcuda_op_patchify(int device, const float *d_img, void *d_patches, int batch, int image_size, int patch_size, void *stream)
 {
     if (int rc = op_prologue(device)) return rc;

@@ -264,10 +264,12 @@ class Net:
         batch = x.numel() // self.n_in
         _check(lib.netcuda_forward(self._h, _ptr(x), C.c_size_t(batch), _ptr(out)))
 
-    def forward_i8(self, xq) -> np.ndarray:
+    def forward_i8(self, xq, out=None) -> np.ndarray:
         xq = np.ascontiguousarray(xq, dtype=np.int8)
         batch = xq.size // self.n_in
-        out = np.empty((batch, self.n_out), dtype=np.int32)
+        if out is None:
+            out = np.empty((batch, self.n_out), dtype=np.int32)
+        assert out.dtype == np.int32 and out.size == batch * self.n_out and out.flags.c_contiguous
         _check(lib.netcuda_forward_i8(self._h, _ptr(xq), C.c_size_t(batch), _ptr(out)))
         return out
 
@@ -377,6 +379,14 @@ def op_layernorm(x, gamma, beta, y, eps=1e-6, rows=None, dim=None, ldx=None, ldy
 def op_attention(qkv, out, batch, tokens, heads, device=0, stream=None) -> None:
     _check(lib.netcuda_op_attention(C.c_int(device), _ptr(qkv), _ptr(out), C.c_int(batch), C.c_int(tokens), C.c_int(heads),
                                     _stream(stream)))
+
+
+ATT_KERNEL_MMA_SYNC = 100
+
+
+def op_attention_ex(qkv, out, batch, tokens, heads, kernel=-1, out_f32=False, device=0, stream=None) -> None:
+    _check(lib.netcuda_op_attention_ex(C.c_int(device), _ptr(qkv), _ptr(out), C.c_int(batch), C.c_int(tokens), C.c_int(heads),
+                                       C.c_int(kernel), C.c_int(int(out_f32)), _stream(stream)))
 
 
 def op_patchify(img, patches, batch, image_size, patch_size, device=0, stream=None) -> None:
