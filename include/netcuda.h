@@ -36,6 +36,8 @@ extern "C" {
 #define NETCUDA_ERR_UNSUPPORTED 3 /* valid request this build cannot serve   */
 #define NETCUDA_ERR_NO_DEVICE 4   /* no sm_100 device visible                */
 #define NETCUDA_ERR_KERNEL 5      /* a kernel reported a pipeline time-out   */
+#define NETCUDA_ERR_RING_FULL 6   /* frame ring: every slot is in flight     */
+#define NETCUDA_ERR_RING_EMPTY 7  /* frame ring: nothing to pop              */
 
 /* net kinds */
 #define NETCUDA_KIND_MLP 0 /* what net::net_data describes (def/defines.h:14-23) */
@@ -271,6 +273,23 @@ int netcuda_op_attention_ex(int device, const void *d_qkv, void *d_out, int batc
 
 /* fp32 NCHW images -> bf16 patch matrix [batch*np][3*p*p] (column = c*p*p + py*p + px). */
 int netcuda_op_patchify(int device, const float *d_img, void *d_patches, int batch, int image_size, int patch_size, void *stream);
+
+/* ---- frame ring: the image side channel (net_abstract::filter_image / get_filtered_image) ------------- *
+ * Replaces the 24-slot event-chained ring of src/netFPGA.cpp:292-365 (BATCH_SIZE, :12): push = filter_image (copy the
+ * frame, H2D, `image_process`, non-blocking D2H; NETCUDA_ERR_RING_FULL when every slot is in flight -- the reference's
+ * "PILA LLENA", :333), pop = get_filtered_image (wait for the oldest slot, :349; NETCUDA_ERR_RING_EMPTY = "PILA VACIA",
+ * :359).  Frames are single-channel u8, h * w <= max_pixels.  `image_process` is absent from the reference; the filter
+ * here is a 3 x 3 binomial smoothing with replicated borders in integer arithmetic (csrc/frame_ring.cu). */
+typedef struct netcuda_ring netcuda_ring_t;
+#define NETCUDA_RING_DEPTH 24 /* BATCH_SIZE, src/netFPGA.cpp:12 */
+int netcuda_ring_create(int device, int depth, size_t max_pixels, netcuda_ring_t **out);
+int netcuda_ring_push(netcuda_ring_t *r, const uint8_t *pixels, size_t h, size_t w);
+int netcuda_ring_pop(netcuda_ring_t *r, uint8_t *pixels_out, size_t capacity, size_t *h, size_t *w);
+int netcuda_ring_peek(netcuda_ring_t *r, size_t *h, size_t *w); /* dimensions of the oldest frame in flight */
+int netcuda_ring_in_flight(const netcuda_ring_t *r, int *count, uint64_t *dropped);
+int netcuda_ring_destroy(netcuda_ring_t *r);
+/* The filter alone on device buffers (h x w bytes each). */
+int netcuda_op_filter3x3(int device, const uint8_t *d_in, uint8_t *d_out, int h, int w, void *stream);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,9 @@ void oracle_layernorm(const float *x, size_t rows, int dim, const float *gamma, 
 void oracle_attention(const float *qkv, size_t batch, int tokens, int heads, int head_dim, float *out, int threads);
 float oracle_gelu(float x);
 
+/* ---- image side channel: the ring's device stage (oracle_image.c; builder-defined filter) ---- */
+void oracle_filter3x3(const uint8_t *in, uint8_t *out, int h, int w);
+
 int oracle_max_threads(void);
 
 #ifdef __cplusplus

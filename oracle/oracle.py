@@ -127,6 +127,14 @@ class Oracle:
         x = _f32(x)
         return np.array([self.lib.oracle_gelu(float(v)) for v in x.ravel()], dtype=np.float32).reshape(x.shape)
 
+    # ---- image side channel ------------------------------------------------------------------
+    def filter3x3(self, img):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        out = np.empty_like(img)
+        self.lib.oracle_filter3x3(_p(img, C.c_uint8), _p(out, C.c_uint8), C.c_int(h), C.c_int(w))
+        return out
+
     # ---- ViT --------------------------------------------------------------------------------
     def vit_param_count(self, cfg: dict) -> int:
         c = VitCfg(**cfg)

@@ -274,7 +274,7 @@ def test_attention_tcgen05_matches_mma_sync_kernel(netcuda, torch_cuda, monkeypa
     assert err <= 1e-2, err
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 2, 11, 12, 21, 22])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 12, 22, 3, 13, 23, 4, 14, 24, 34, 104])
 @pytest.mark.parametrize("batch,tokens,heads", [(40, 197, 12), (3, 37, 2), (2, 129, 2), (2, 256, 1), (1, 128, 1), (5, 200, 3)])
 def test_attention_kernel_variants_vs_oracle(netcuda, oracle, torch_cuda, kernel, batch, tokens, heads):
     """Every build variant of the short-sequence tcgen05 kernel (10 * POLY + MODE: polling / per-tile MMA issuers, exp2 turn-taking,

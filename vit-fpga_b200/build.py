@@ -20,8 +20,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
-LIB = os.path.join(HERE, "lib")
-OBJ = os.path.join(HERE, "build")
+# NETCUDA_BUILD_TAG=<tag>: a second build beside the product one (lib_<tag>/, build_<tag>/), selected at run time with
+# NETCUDA_LIB_DIR -- for A/B runs of two kernel versions inside one GPU call and for NETCUDA_DEBUG_TIMELINE builds
+_TAG = os.environ.get("NETCUDA_BUILD_TAG", "")
+LIB = os.path.join(HERE, "lib" + ("_" + _TAG if _TAG else ""))
+OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
 INCLUDE = os.path.join(ROOT, "include")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -30,7 +33,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-ccbin", CXX]
 if os.environ.get("NETCUDA_DEBUG_TIMELINE"):  # clock64 timeline hooks for tools/*_timeline.py (never in the shipped build)
     NVCC_FLAGS += ["-DNETCUDA_DEBUG_TIMELINE"]
-CU_SOURCES = ["gemm.cu", "elementwise.cu", "attention.cu", "mlp_stream.cu", "runtime.cu", "weights_io.cu"]
+CU_SOURCES = ["gemm.cu", "elementwise.cu", "attention.cu", "mlp_stream.cu", "runtime.cu", "weights_io.cu", "frame_ring.cu", "staging.cpp"]
 CU_HEADERS = ["ptx.cuh", "gemm_tcgen05.cuh", "kernels.h"]
 HOST_SOURCES = ["net_cuda.cpp"]
 HOST_DRIVER_SOURCES = ["host_capi.cpp"]  # ctypes driver for tests/ and bench.py: NOT part of the shipped host library
@@ -58,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> dict:
     objs = []
     for src in CU_SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _newer(o, [s] + headers):
             jobs.append([NVCC] + NVCC_FLAGS + ["-I", INCLUDE, "-c", s, "-o", o])

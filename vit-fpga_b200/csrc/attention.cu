@@ -288,6 +288,7 @@ struct AttnTcParams
     int n_mtiles; // 1 or 2 query tiles of 128 rows
     int stagger;  // MODE 0: hold the first S of tile 1 back until tile 0 has finished its first softmax
     int out_f32;  // output rows are fp32 (tf32 nets): two 32-column store boxes per warp instead of one 64-column bf16 box
+    int split, p1_col, o_col; // attention_tc16_kernel: first key chunk of half 1; TMEM columns of half 1's P and of O | row sums (80 columns)
     int *error_flag;
     long long *debug; // optional [32 items][12 warps][8] clock64 stamps of CTA 0 (NETCUDA_DEBUG_TIMELINE builds; null otherwise)
 };
@@ -381,6 +382,14 @@ __device__ __forceinline__ void store_o_rows(const uint32_t *o, float inv, uint8
 //         their exponential pass: a warp alone runs it at the MUFU's pace; two at once both take twice as long, which lengthens
 //         BOTH serial chains (S -> softmax -> P.V -> O).  Turn-taking keeps one warp in exp2 while the other one waits for its
 //         MMAs, reduces the row maximum or stores O.
+// MODE 3: MODE 1 + register re-balancing (setmaxnreg: 232 per softmax thread, 40 for the other warps) that buys a deeper TMEM
+//         load pipeline and a re-ordered exponential pass.  Measured on the MODE 0..2 kernels (tools/attn_timeline.py): the period
+//         of a CTA (~7.5 k cycles per item) IS the serial chain of one query tile -- S issue 0.7 k, max pass 1.35 k, exp2 pass 3.35 k,
+//         P.V 1.45 k, O 0.1 k -- and the two tiles hardly slow each other down.  The max pass was one tcgen05.ld (~80 cycles, all-or-
+//         nothing wait::ld) ahead of 17 FMNMX3; the exp2 pass ran at ~420 cycles per 32 keys where the MUFU needs 256, because
+//         every FADD / F2FP sat two MUFU issues behind the MUFU whose result it consumes (in-order issue stalls on the scoreboard).
+//         Here both passes keep two 32-column loads in flight (four 32-register buffers) and the exp2 pass issues the 32 MUFUs of
+//         a chunk back to back before anything consumes them.
 // POLY: how many of every four exponentials run on the FMA pipe (exp2_poly_x2) instead of the MUFU: 0, 1 or 2.
 template <int POLY, int MODE>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
@@ -445,7 +454,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     const uint32_t tmem_base = *tmem_ptr;
     griddep_launch_dependents();
     griddep_wait(); // the qkv matrix is the previous kernel's output
-
+    if (warp < 4)
+    {
+    // MODE 3: whole warpgroups (warps 0-3 | 4-7 | 8-11) re-balance their registers: 128 x 40 + 256 x 232 = 384 x 168
+    if constexpr (MODE == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == ATC_W_PRODUCER)
     {
         // ===================== TMA producer =====================
@@ -487,6 +499,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                 mbar_wait(full_bar(buf), (uint32_t)(it >> 1) & 1u, p.error_flag, KERR_ATT_MMA_FULL);
                 mbar_wait(sfree_bar(t), ((uint32_t)it & 1u) ^ 1u, p.error_flag, KERR_ATT_MMA_SFREE);
                 tcgen05_fence_after();
+                if (dbg && blockIdx.x == 0 && it < 32) dbg[(it * 12 + warp) * 8 + 3] = clock64();
                 {
                     const uint64_t q_desc = umma_smem_desc_sw128(sm + t * ATC_Q_BYTES);
                     const uint64_t k_desc = umma_smem_desc_sw128(sm + 2 * ATC_Q_BYTES);
@@ -498,6 +511,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                 // O_t = P_t . V.  V tile [key][64] read MN-major: one UMMA K step = 16 keys = 2048 bytes
                 mbar_wait(pfull_bar(t), (uint32_t)it & 1u, p.error_flag, KERR_ATT_MMA_PFULL);
                 tcgen05_fence_after();
+                if (dbg && blockIdx.x == 0 && it < 32) dbg[(it * 12 + warp) * 8 + 1] = clock64();
                 {
                     const uint64_t v_desc = umma_smem_desc_sw128(sm + 2 * ATC_Q_BYTES + ATC_KV_BYTES);
                     for (int k = 0; k < ksteps; k++)
@@ -583,7 +597,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             }
         }
     }
-    else if (warp >= 4 && ((warp - 4) >> 2) < p.n_mtiles && ((warp - 4) >> 2) * 128 + (warp & 3) * 32 < p.tokens)
+    }
+    else
+    {
+    if constexpr (MODE == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    if (((warp - 4) >> 2) < p.n_mtiles && ((warp - 4) >> 2) * 128 + (warp & 3) * 32 < p.tokens)
     {
         // ===================== softmax + output warpgroups (one per query tile) =====================
         const int t = (warp - 4) >> 2; // query tile
@@ -609,36 +627,82 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             tcgen05_fence_after();
             stamp(1);
 
-            // ---- pass 1: exact row maximum over the valid keys (chunk c + 1 is in flight while c is reduced) ----
+            // ---- pass 1: exact row maximum over the valid keys ----
             float mx = -INFINITY;
+            auto reduce = [&](const uint32_t *v, int c) {
+                if (c < nfull)
+                {
+                    float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+                    float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+                    float m2 = fmax3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
+                    float m3 = fmax3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+#pragma unroll
+                    for (int j = 12; j < 28; j += 8)
+                    {
+                        m0 = fmax3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                        m1 = fmax3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        m2 = fmax3(m2, __uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                        m3 = fmax3(m3, __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                    }
+                    m0 = fmax3(m0, __uint_as_float(v[28]), __uint_as_float(v[29]));
+                    m1 = fmax3(m1, __uint_as_float(v[30]), __uint_as_float(v[31]));
+                    mx = fmax3(mx, fmaxf(m0, m1), fmaxf(m2, m3));
+                }
+                else
+                {
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (j < tail) mx = fmaxf(mx, __uint_as_float(v[j]));
+                }
+            };
+            // two 32-column loads (chunks c, c + 1) into x / y; tcgen05.wait::ld is all-or-nothing, so loads travel in pairs
+            // (both loads are unconditional: chunk c + 1 <= 7 stays inside the tile's 256-column region even when it is not a full one)
+            auto ld2 = [&](uint32_t *x, uint32_t *y, int c) {
+                tmem_ld_32x32(region + c * 32, x);
+                tmem_ld_32x32(region + (c + 1) * 32, y);
+            };
+            if constexpr (MODE == 3)
             {
-                uint32_t va[32], vb[32];
-                auto reduce = [&](const uint32_t *v, int c) {
-                    if (c < nfull)
-                    {
-                        float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
-                        float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
-                        float m2 = fmax3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
-                        float m3 = fmax3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
-#pragma unroll
-                        for (int j = 12; j < 28; j += 8)
-                        {
-                            m0 = fmax3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-                            m1 = fmax3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                            m2 = fmax3(m2, __uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                            m3 = fmax3(m3, __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                        }
-                        m0 = fmax3(m0, __uint_as_float(v[28]), __uint_as_float(v[29]));
-                        m1 = fmax3(m1, __uint_as_float(v[30]), __uint_as_float(v[31]));
-                        mx = fmax3(mx, fmaxf(m0, m1), fmaxf(m2, m3));
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            if (j < tail) mx = fmaxf(mx, __uint_as_float(v[j]));
-                    }
+                uint32_t a0[32], a1[32], b0[32], b1[32];
+                const int npairs = (nfull + 1) >> 1; // pairs of FULL chunks; the ragged last chunk is reduced on its own below
+                auto red2 = [&](const uint32_t *lo, const uint32_t *hi, int pr) {
+                    reduce(lo, 2 * pr);
+                    if (2 * pr + 1 < nfull) reduce(hi, 2 * pr + 1);
                 };
+                if (npairs > 0)
+                {
+                    ld2(a0, a1, 0);
+                    for (int pr = 0;; pr += 2) // every load dominates its uses on every path (no conditionally written buffers)
+                    {
+                        tmem_ld_wait();
+                        if (pr + 1 >= npairs)
+                        {
+                            red2(a0, a1, pr);
+                            break;
+                        }
+                        ld2(b0, b1, 2 * (pr + 1)); // in flight while the pair pr is reduced
+                        red2(a0, a1, pr);
+                        tmem_ld_wait();
+                        if (pr + 2 >= npairs)
+                        {
+                            red2(b0, b1, pr + 1);
+                            break;
+                        }
+                        ld2(a0, a1, 2 * (pr + 2));
+                        red2(b0, b1, pr + 1);
+                    }
+                }
+                if (tail)
+                {
+                    tmem_ld_32x32(region + nfull * 32, a0);
+                    tmem_ld_wait();
+                    reduce(a0, nfull);
+                }
+            }
+            else
+            {
+                // (chunk c + 1 is in flight while c is reduced)
+                uint32_t va[32], vb[32];
                 tmem_ld_32x32(region, va);
                 for (int c = 0; c < nchunks; c += 2)
                 {
@@ -661,6 +725,82 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             // ---- pass 2: p = 2^((s - max) * scale); P (bf16) overwrites the first half of the S columns it came from ----
             const float msc = mx * sl;
             float sum0 = 0.0f, sum1 = 0.0f;
+            if constexpr (MODE == 3)
+            {
+                // One chunk: every exponent first, then the 32 exponentials back to back (MUFU, or exp2_poly_x2 for POLY of every 4
+                // pairs: FMA-pipe work that fills the issue slots between MUFUs), and only then the sums and the bf16 packing -- no
+                // instruction waits on a MUFU result that was issued a couple of slots earlier.
+                auto expo_full = [&](uint32_t *v, int c) {
+                    uint32_t w[16];
+                    float x[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) x[j] = fmaf(__uint_as_float(v[j]), sl, -msc);
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                    {
+                        if ((POLY == 1 && (j & 3) == 3) || (POLY == 2 && (j & 1) == 1))
+                            exp2_poly_x2(x[2 * j], x[2 * j + 1], x[2 * j], x[2 * j + 1]);
+                        else
+                            x[2 * j] = ex2_approx(x[2 * j]), x[2 * j + 1] = ex2_approx(x[2 * j + 1]);
+                    }
+                    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f; // four chains of eight adds
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                    {
+                        s0 += x[4 * j], s1 += x[4 * j + 1], s2 += x[4 * j + 2], s3 += x[4 * j + 3];
+                        w[2 * j] = pack_bf16x2(x[4 * j], x[4 * j + 1]);
+                        w[2 * j + 1] = pack_bf16x2(x[4 * j + 2], x[4 * j + 3]);
+                    }
+                    sum0 += s0 + s2, sum1 += s1 + s3;
+                    tmem_st_32x16(region + c * 16, w);
+                };
+                auto expo2 = [&](uint32_t *lo, uint32_t *hi, int pr) {
+                    expo_full(lo, 2 * pr);
+                    if (2 * pr + 1 < nfull) expo_full(hi, 2 * pr + 1);
+                };
+                uint32_t a0[32], a1[32], b0[32], b1[32];
+                const int npairs = (nfull + 1) >> 1;
+                if (npairs > 0)
+                {
+                    ld2(a0, a1, 0);
+                    for (int pr = 0;; pr += 2)
+                    {
+                        tmem_ld_wait();
+                        if (pr + 1 >= npairs)
+                        {
+                            expo2(a0, a1, pr);
+                            break;
+                        }
+                        ld2(b0, b1, 2 * (pr + 1));
+                        expo2(a0, a1, pr);
+                        tmem_ld_wait();
+                        if (pr + 2 >= npairs)
+                        {
+                            expo2(b0, b1, pr + 1);
+                            break;
+                        }
+                        ld2(a0, a1, 2 * (pr + 2));
+                        expo2(b0, b1, pr + 1);
+                    }
+                }
+                if (tail)
+                {
+                    // ragged last chunk: keys beyond the image are written as zeros (they are rows of the next image, or TMA zero fill)
+                    tmem_ld_32x32(region + nfull * 32, a0);
+                    tmem_ld_wait();
+                    uint32_t w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                    {
+                        const float p0 = (2 * j < tail) ? ex2_approx(fmaf(__uint_as_float(a0[2 * j]), sl, -msc)) : 0.0f;
+                        const float p1 = (2 * j + 1 < tail) ? ex2_approx(fmaf(__uint_as_float(a0[2 * j + 1]), sl, -msc)) : 0.0f;
+                        sum0 += p0, sum1 += p1;
+                        w[j] = pack_bf16x2(p0, p1);
+                    }
+                    tmem_st_32x16(region + nfull * 16, w);
+                }
+            }
+            else
             {
                 uint32_t va[32], vb[32];
                 auto expo = [&](const uint32_t *v, int c) {
@@ -736,6 +876,397 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             stamp(5);
         }
         if (lane == 0) tma_store_wait_all(); // the slab is read, and the rows are written, before the CTA goes away
+    }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == ATC_W_ALLOC)
+    {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// =====================================================================================================
+// tcgen05 kernel, tokens <= 256, SIXTEEN softmax warps (attention_tc16_kernel)
+// =====================================================================================================
+// Measured on the kernel above (tools/attn_timeline.py, tools/micro/mufu_bw.cu, B200): a CTA's period (~7.3 k cycles per item) is
+// the instruction time of ONE softmax warp per query row block, and an SM sub-partition runs only two such warps.  A single warp
+// cannot overlap its MUFU work with its FMA-pipe work -- 32 EX2 alone take 298 cycles, the 112 FFMA / FADD / F2FP of a 32-key
+// chunk 215, both together 510 -- while two warps of a sub-partition in the same phase get through a chunk each in 616 (308 per
+// chunk and sub-partition), three in 276, four in 267: the MUFU's 256.  So the softmax needs more warps per sub-partition, not
+// fewer instructions per warp:
+//   * 20 warps: producer, one MMA issuer per query tile, TMEM allocator, and 16 softmax warps -- two per (query tile, TMEM lane
+//     quarter): "half 0" owns keys [0, 128), "half 1" keys [128, n_pad).  Four softmax warps per sub-partition.
+//   * The two warps of a row block exchange their partial row maxima once per item through 256 bytes of shared memory and a
+//     64-thread named barrier; nothing else is exchanged:
+//   * the row sums come out of the tensor core: next to O = P.V (N = 64) the issuer runs P.1 (N = 16) against a tile of bf16 ones,
+//     so the 32 FADDs per chunk disappear and the sum is the sum of exactly the bf16 values that multiply V;
+//   * the half-1 warp (three key chunks of a 197-token image against four) also reads O, divides by the row sum and stores the
+//     rows; the half-0 warp goes straight on to the next item;
+//   * the two query tiles take turns in the exponential pass (per lane quarter): with four warps of a sub-partition in it at once
+//     the pass takes 4 x 256 cycles per chunk for everybody, and every other phase of BOTH tiles -- S, the max pass, P.V, O -- is then
+//     exposed (measured: period 8.7 k cycles); alternating, one tile's MMAs and max pass run under the other tile's exponentials.
+// TMEM per query tile (256 columns): S at [0, n_pad); P of half 0 over [0, 64), of half 1 over [128, 128 + 16 chunks) -- each over
+// S columns its own warp has already consumed; O at [64, 128) and the row sums at [192, 208): written by the MMAs only after both
+// halves have arrived.
+constexpr int A16_THREADS = 640;
+constexpr int A16_OFF_OSLAB = 2 * ATC_BUF_BYTES;    // 1024-byte aligned; one 32 x 128-byte slab per half-1 warp (as in attention_tc_kernel)
+constexpr int A16_OFF_ONES = A16_OFF_OSLAB + 8 * ATC_OSLAB_BYTES; // 16 rows x 128 bytes of bf16 1.0 (1024-byte aligned)
+constexpr int A16_OFF_BARS = A16_OFF_ONES + 2048;
+constexpr int A16_NUM_BARS = 12 + 8;
+constexpr int A16_OFF_TMEM_PTR = A16_OFF_BARS + A16_NUM_BARS * 8;
+constexpr int A16_SMEM = A16_OFF_TMEM_PTR + 16;
+static_assert(A16_SMEM <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
+// Key split and TMEM columns (AttnTcParams::split / p1_col / o_col, chosen by the launcher): P of half 0 over [0, 16 split), P of half 1
+// from p1_col on, O at [o_col, o_col + 64) and the row sums at [o_col + 64, o_col + 80).  Up to 224 keys: split 3 (three full chunks
+// against three full chunks + the ragged one for 197 tokens), p1_col 112, o_col 176; 225..256 keys: split 4, p1_col 144, o_col 64.
+
+template <bool DB> // DB: keep the next chunk's tcgen05.ld in flight while the current one is processed
+__global__ void __launch_bounds__(A16_THREADS, 1)
+attention_tc16_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
+                      const __grid_constant__ CUtensorMap tma_out, const AttnTcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t a16_smem[];
+    const uint32_t base = smem_u32(a16_smem);
+    if ((base & 1023u) != 0)
+    {
+        if (threadIdx.x == 0 && p.error_flag) atomicExch(p.error_flag, KERR_SMEM_ALIGN);
+        return;
+    }
+    const uint32_t bars = base + A16_OFF_BARS;
+    auto full_bar = [&](int b) { return bars + 8u * b; };
+    auto empty_bar = [&](int b) { return bars + 8u * (2 + b); };
+    auto sfull_bar = [&](int t) { return bars + 8u * (4 + t); };
+    auto pfull_bar = [&](int t) { return bars + 8u * (6 + t); };
+    auto ofull_bar = [&](int t) { return bars + 8u * (8 + t); };
+    auto sfree_bar = [&](int t) { return bars + 8u * (10 + t); };
+    auto turn_bar = [&](int t, int q) { return bars + 8u * (12 + t * 4 + q); }; // "tile t's warps of lane quarter q may run their exp2 pass"
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(a16_smem + A16_OFF_TMEM_PTR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items = p.batch * p.heads;
+    const int D = p.heads * ATT_HD;
+    const int nfull = p.tokens >> 5, tail = p.tokens & 31; // full 32-key chunks, keys in the ragged last chunk
+    const int nchunks = nfull + (tail ? 1 : 0);
+    const bool two_halves = nchunks > p.split;              // does half 1 own any keys?
+#ifdef NETCUDA_DEBUG_TIMELINE
+    long long *const dbg = p.debug; // [32 items][20 warps][8] clock64 stamps of CTA 0
+#else
+    constexpr long long *dbg = nullptr;
+#endif
+
+    if (warp == ATC_W_PRODUCER && lane == 0)
+    {
+        tma_prefetch_desc(&tma_q);
+        tma_prefetch_desc(&tma_kv);
+    }
+    if (warp == ATC_W_MMA && lane == 0)
+    {
+        for (int b = 0; b < 2; b++)
+        {
+            mbar_init(full_bar(b), 1);
+            mbar_init(empty_bar(b), p.n_mtiles); // one commit per tile's issuer
+            mbar_init(sfull_bar(b), 1);
+            // one arrive per softmax warp that owns at least one real query row (and, for half 1, at least one key)
+            const int rows_b = min(max(p.tokens - b * 128, 1), 128);
+            const uint32_t blocks = (uint32_t)((rows_b + 31) / 32);
+            mbar_init(pfull_bar(b), blocks * (two_halves ? 2u : 1u));
+            mbar_init(ofull_bar(b), 1);
+            mbar_init(sfree_bar(b), blocks); // the half-1 warps read O
+            for (int q = 0; q < 4; q++) mbar_init(turn_bar(b, q), two_halves ? 2u : 1u);
+        }
+        fence_barrier_init();
+    }
+    if (warp == ATC_W_ALLOC)
+    {
+        tmem_alloc(base + A16_OFF_TMEM_PTR, 512);
+        tmem_relinquish();
+    }
+    // the tile of ones behind the row-sum MMA: every element is 1.0, so swizzle and majorness of the descriptor do not matter
+    for (int i = threadIdx.x; i < 2048 / 4; i += A16_THREADS) reinterpret_cast<uint32_t *>(a16_smem + A16_OFF_ONES)[i] = 0x3F803F80u;
+    fence_proxy_async_smem(); // generic-proxy writes -> visible to the tensor core's async-proxy reads
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    griddep_launch_dependents();
+    griddep_wait(); // the qkv matrix is the previous kernel's output
+
+    if (warp < 4)
+    {
+        // 640 x 96 registers at launch; the four service warps keep 40 each, the 16 softmax warps grow to 104
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == ATC_W_PRODUCER)
+        {
+            // ===================== TMA producer =====================
+            if (lane == 0)
+            {
+                const uint32_t tx = (uint32_t)(p.n_mtiles * ATC_Q_BYTES + 2 * p.n_pad * 128);
+                int it = 0;
+                for (int item = blockIdx.x; item < items; item += gridDim.x, it++)
+                {
+                    const int buf = it & 1;
+                    const int b = item / p.heads, h = item - b * p.heads;
+                    mbar_wait(empty_bar(buf), ((uint32_t)(it >> 1) & 1u) ^ 1u, p.error_flag, KERR_ATT_PRODUCER);
+                    mbar_arrive_expect_tx(full_bar(buf), tx);
+                    const uint32_t dst = base + buf * ATC_BUF_BYTES;
+                    const int row = b * p.tokens;
+                    for (int t = 0; t < p.n_mtiles; t++) tma_load_2d(dst + t * ATC_Q_BYTES, &tma_q, full_bar(buf), h * ATT_HD, row + t * 128);
+                    tma_load_2d(dst + 2 * ATC_Q_BYTES, &tma_kv, full_bar(buf), D + h * ATT_HD, row);
+                    tma_load_2d(dst + 2 * ATC_Q_BYTES + ATC_KV_BYTES, &tma_kv, full_bar(buf), 2 * D + h * ATT_HD, row);
+                }
+            }
+        }
+        else if (warp == ATC_W_MMA || warp == ATC_W_MMA1)
+        {
+            // ===================== MMA issuer of one query tile (blocking waits) =====================
+            const int t = warp == ATC_W_MMA ? 0 : 1;
+            if (lane == 0 && t < p.n_mtiles)
+            {
+                const uint32_t idesc_s = umma_idesc(1, 1, 128, (uint32_t)p.n_pad);
+                // O and the row sums in ONE MMA per 16 keys (the A operand, P, is read from tensor memory once): B is MN-major with
+                // N = 80 = the 64 columns of V plus a second MN atom whose 16 used columns are ones.  The second atom is addressed through
+                // the descriptor's leading-dimension byte offset, set per step so that it always lands on the tile of ones.
+                const uint32_t idesc_o = umma_idesc(1, 1, 128, ATT_HD + 16) | UMMA_IDESC_B_MN_MAJOR;
+                const int ksteps = p.n_pad / 16;
+                const uint32_t region = tmem_base + t * ATC_REGION_COLS;
+                int it = 0;
+                for (int item = blockIdx.x; item < items; item += gridDim.x, it++)
+                {
+                    const int buf = it & 1;
+                    const uint32_t sm = base + buf * ATC_BUF_BYTES;
+                    // S_t = Q_t . K^T: K / Q landed, and the previous item's O and row sums (same TMEM region) have been read
+                    mbar_wait(full_bar(buf), (uint32_t)(it >> 1) & 1u, p.error_flag, KERR_ATT_MMA_FULL);
+                    mbar_wait(sfree_bar(t), ((uint32_t)it & 1u) ^ 1u, p.error_flag, KERR_ATT_MMA_SFREE);
+                    tcgen05_fence_after();
+                    if (dbg && blockIdx.x == 0 && it < 32) dbg[(it * 20 + warp) * 8 + 3] = clock64();
+                    {
+                        const uint64_t q_desc = umma_smem_desc_sw128(sm + t * ATC_Q_BYTES);
+                        const uint64_t k_desc = umma_smem_desc_sw128(sm + 2 * ATC_Q_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) umma_ss<KIND_BF16>(region, q_desc + 2u * k, k_desc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+                        tcgen05_commit(sfull_bar(t));
+                        if (dbg && blockIdx.x == 0 && it < 32) dbg[(it * 20 + warp) * 8 + 0] = clock64();
+                    }
+                    // O_t = P_t . V and rowsum_t = P_t . 1, 16 keys per step; P of keys >= 128 lives at column A16_P1_COL
+                    mbar_wait(pfull_bar(t), (uint32_t)it & 1u, p.error_flag, KERR_ATT_MMA_PFULL);
+                    tcgen05_fence_after();
+                    {
+                        const uint32_t v_addr = sm + 2 * ATC_Q_BYTES + ATC_KV_BYTES;
+                        if (dbg && blockIdx.x == 0 && it < 32) dbg[(it * 20 + warp) * 8 + 1] = clock64();
+                        for (int k = 0; k < ksteps; k++)
+                        {
+                            const uint32_t a_col = region + (k < 2 * p.split ? 8u * k : (uint32_t)p.p1_col + 8u * (k - 2 * p.split));
+                            const uint32_t vk = v_addr + 2048u * k; // 16 keys x 128 bytes per step
+                            uint64_t v_desc = umma_smem_desc_sw128(vk) & ~((uint64_t)0x3FFF << 16);
+                            v_desc |= (uint64_t)(((base + A16_OFF_ONES - vk) >> 4) & 0x3FFFu) << 16; // LBO: V's MN atom -> the atom of ones
+                            umma_ts_bf16(region + p.o_col, a_col, v_desc, idesc_o, k != 0 ? 1u : 0u);
+                        }
+                        tcgen05_commit(ofull_bar(t));
+                        tcgen05_commit(empty_bar(buf)); // this tile is done with the smem buffer
+                        if (dbg && blockIdx.x == 0 && it < 32) dbg[(it * 20 + warp) * 8 + 2] = clock64();
+                    }
+                }
+            }
+        }
+    }
+    else
+    {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const int idx = warp - 4;
+        const int q = idx & 3;           // TMEM lane quarter (= warp % 4)
+        const int half = (idx >> 2) & 1; // key half
+        const int t = idx >> 3;          // query tile
+        if (t < p.n_mtiles && t * 128 + q * 32 < p.tokens)
+        {
+            // ===================== softmax + output: one warp per (query tile, lane quarter, key half) =====================
+            const uint32_t region = tmem_base + ((uint32_t)(q * 32) << 16) + t * ATC_REGION_COLS;
+            const float sl = 0.125f * 1.4426950408889634f; // 1/sqrt(64) * log2(e)
+            const int slab = t * 4 + q; // (used by the half-1 warp)
+            uint8_t *oslab = a16_smem + A16_OFF_OSLAB + slab * ATC_OSLAB_BYTES;
+            const uint32_t oslab_addr = base + A16_OFF_OSLAB + slab * ATC_OSLAB_BYTES;
+            const bool works = half == 0 || two_halves; // does this warp own keys?
+            const bool partner = p.n_mtiles == 2 && (t ^ 1) * 128 + q * 32 < p.tokens; // the other tile has warps on this sub-partition
+            const int c_lo = half ? p.split : 0;
+            const int c_hi = half ? nchunks : min(nchunks, p.split);
+            const uint32_t p_col = half ? (uint32_t)p.p1_col : 0u; // where this half's P goes: chunk c -> p_col + 16 (c - c_lo)
+            const uint32_t pair_bar = 1u + (uint32_t)(t * 4 + q);    // named barrier of this row block's two warps
+            int it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, it++)
+            {
+                const uint32_t ph = (uint32_t)it & 1u;
+                const int buf = it & 1;
+                const int b = item / p.heads, h = item - b * p.heads;
+                auto stamp = [&](int slot) {
+                    if (dbg && blockIdx.x == 0 && lane == 0 && it < 32) dbg[(it * 20 + warp) * 8 + slot] = clock64();
+                };
+                stamp(0);
+                if (works)
+                {
+                mbar_wait(sfull_bar(t), ph, p.error_flag, KERR_ATT_WG_SFULL);
+                tcgen05_fence_after();
+                stamp(1);
+
+                // ---- pass 1: row maximum over this half's keys (chunk c + 1 in flight while c is reduced), then the exact maximum
+                // through the partner ----
+                float mx = -INFINITY;
+                {
+                    uint32_t va[32], vb[32];
+                    auto reduce = [&](const uint32_t *v, int c) {
+                        if (c < nfull)
+                        {
+                            float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+                            float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+                            float m2 = fmax3(__uint_as_float(v[6]), __uint_as_float(v[7]), __uint_as_float(v[8]));
+                            float m3 = fmax3(__uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+#pragma unroll
+                            for (int j = 12; j < 28; j += 8)
+                            {
+                                m0 = fmax3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                                m1 = fmax3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                                m2 = fmax3(m2, __uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                                m3 = fmax3(m3, __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                            }
+                            m0 = fmax3(m0, __uint_as_float(v[28]), __uint_as_float(v[29]));
+                            m1 = fmax3(m1, __uint_as_float(v[30]), __uint_as_float(v[31]));
+                            mx = fmax3(mx, fmaxf(m0, m1), fmaxf(m2, m3));
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                if (j < tail) mx = fmaxf(mx, __uint_as_float(v[j]));
+                        }
+                    };
+                    // (loads are unconditional -- chunk c + 1 <= 7 stays inside the tile's 256 columns -- so that no buffer is
+                    // written on one path only: ptxas spills conditionally loaded tcgen05.ld destinations)
+                    if constexpr (DB)
+                    {
+                        tmem_ld_32x32(region + c_lo * 32, va);
+                        for (int c = c_lo; c < c_hi; c += 2)
+                        {
+                            tmem_ld_wait();
+                            tmem_ld_32x32(region + min(c + 1, 7) * 32, vb);
+                            reduce(va, c);
+                            if (c + 1 >= c_hi) break;
+                            tmem_ld_wait();
+                            tmem_ld_32x32(region + min(c + 2, 7) * 32, va);
+                            reduce(vb, c + 1);
+                        }
+                        tmem_ld_wait(); // (the last prefetch)
+                    }
+                    else
+                    {
+                        for (int c = c_lo; c < c_hi; c++)
+                        {
+                            tmem_ld_32x32(region + c * 32, va);
+                            tmem_ld_wait();
+                            reduce(va, c);
+                        }
+                    }
+                }
+                stamp(2);
+                if (two_halves)
+                {
+                    // the Q tile of this item is dead once S has been computed (and is not reloaded before both issuers have passed
+                    // this item): its first kilobyte carries the 2 x 128 partial maxima of the tile
+                    float *ex = reinterpret_cast<float *>(a16_smem + buf * ATC_BUF_BYTES + t * ATC_Q_BYTES);
+                    ex[half * 128 + q * 32 + lane] = mx;
+                    named_bar_sync(pair_bar, 64);
+                    mx = fmaxf(mx, ex[(half ^ 1) * 128 + q * 32 + lane]);
+                    fence_proxy_async_smem(); // these generic-proxy accesses precede the TMA reload of the buffer (ordered through pfull -> empty)
+                }
+
+                // the exponential pass belongs to one query tile at a time (tile 0 first; the very first wait of a fresh barrier passes)
+                if (partner && p.stagger) mbar_wait(turn_bar(t, q), t == 0 ? (ph ^ 1u) : ph, p.error_flag, KERR_ATT_WG_TURN);
+                stamp(7);
+                // ---- pass 2: p = 2^((s - max) * scale) as bf16, over S columns this warp has already consumed ----
+                const float msc = mx * sl;
+                {
+                    uint32_t va[32], vb[32];
+                    auto expo = [&](const uint32_t *v, int c) {
+                        uint32_t w[16];
+                        if (c < nfull)
+                        {
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                            {
+                                const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl, -msc));
+                                const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl, -msc));
+                                w[j] = pack_bf16x2(p0, p1);
+                            }
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                            {
+                                const float p0 = (2 * j < tail) ? ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl, -msc)) : 0.0f;
+                                const float p1 = (2 * j + 1 < tail) ? ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl, -msc)) : 0.0f;
+                                w[j] = pack_bf16x2(p0, p1);
+                            }
+                        }
+                        tmem_st_32x16(region + p_col + (c - c_lo) * 16, w);
+                    };
+                    // P of chunk c lands on S columns of chunks <= c of this half: the prefetched chunk c + 1 is never overwritten early
+                    if constexpr (DB)
+                    {
+                        tmem_ld_32x32(region + c_lo * 32, va);
+                        for (int c = c_lo; c < c_hi; c += 2)
+                        {
+                            tmem_ld_wait();
+                            tmem_ld_32x32(region + min(c + 1, 7) * 32, vb);
+                            expo(va, c);
+                            if (c + 1 >= c_hi) break;
+                            tmem_ld_wait();
+                            tmem_ld_32x32(region + min(c + 2, 7) * 32, va);
+                            expo(vb, c + 1);
+                        }
+                        tmem_ld_wait(); // (the last prefetch)
+                    }
+                    else
+                    {
+                        for (int c = c_lo; c < c_hi; c++)
+                        {
+                            tmem_ld_32x32(region + c * 32, va);
+                            tmem_ld_wait();
+                            expo(va, c);
+                        }
+                    }
+                }
+                if (partner && p.stagger)
+                {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(turn_bar(t ^ 1, q)); // the other tile's turn
+                }
+                tmem_st_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pfull_bar(t));
+                }
+                stamp(3);
+                if (half == 0) continue; // the half-1 warp finishes the row block
+
+                // ---- O = P.V divided by the row sum P.1 ----
+                mbar_wait(ofull_bar(t), ph, p.error_flag, KERR_ATT_WG_OFULL);
+                tcgen05_fence_after();
+                stamp(4);
+                uint32_t o[64], rs[4];
+                tmem_ld_32x32(region + p.o_col, o);
+                tmem_ld_32x32(region + p.o_col + 32, o + 32);
+                tmem_ld_32xN<4>(region + p.o_col + 64, rs);
+                tmem_ld_wait();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sfree_bar(t)); // region t may be overwritten by the next item's S
+                stamp(6);
+                store_o_rows(o, 1.0f / __uint_as_float(rs[0]), oslab, oslab_addr, &tma_out, p.out_f32 != 0, h * ATT_HD, t * 128 + q * 32, b, lane);
+                stamp(5);
+            }
+            if (lane == 0) tma_store_wait_all(); // the slab is read, and the rows are written, before the CTA goes away
+        }
     }
 
     tcgen05_fence_before();
@@ -1093,7 +1624,7 @@ static cudaError_t launch_attention_tc_v(const CUtensorMap &map_q, const CUtenso
 
 // Kernel variant = 10 * POLY + MODE (see attention_tc_kernel).  The default is the measured best; NETCUDA_ATT_TC_VARIANT (read once)
 // selects another one for A/B runs.
-constexpr int ATT_TC_DEFAULT_VARIANT = 2;
+constexpr int ATT_TC_DEFAULT_VARIANT = 4; // the 16-softmax-warp kernel (177 us per 512 x 12 x 197 launch in isolation; round-1 kernel = variant 0: 200 us)
 static int att_tc_variant()
 {
     static const int v = getenv("NETCUDA_ATT_TC_VARIANT") ? atoi(getenv("NETCUDA_ATT_TC_VARIANT")) : ATT_TC_DEFAULT_VARIANT;
@@ -1130,15 +1661,34 @@ static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, in
     const int items = batch * heads;
     const int sms = num_sms > 0 ? num_sms : 148;
     const int grid = items < sms ? items : sms;
-    switch (tc_variant >= 0 ? tc_variant : att_tc_variant())
+    const int vcode = tc_variant >= 0 ? tc_variant : att_tc_variant();
+    const int variant = vcode % 100;
+    if (variant % 10 == 4)
+    {
+        // 4: single-buffered loads, keys split 128 | rest;  14: double-buffered;  24 / 34: the same with the balanced split (96 | rest,
+        // up to 224 keys);  + 100: no turn-taking between the two query tiles
+        const int nchunks = (tokens + 31) / 32;
+        const bool balanced = variant >= 20 && nchunks <= 7;
+        p.split = balanced ? 3 : 4;
+        p.p1_col = balanced ? 112 : 144;
+        p.o_col = balanced ? 176 : 64;
+        p.stagger = vcode < 100 ? 1 : 0;
+        const bool db = (variant / 10) & 1;
+        auto kern = db ? attention_tc16_kernel<true> : attention_tc16_kernel<false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A16_SMEM);
+        if (e != cudaSuccess) return e;
+        return launch_pdl(kern, dim3(grid), dim3(A16_THREADS), (size_t)A16_SMEM, stream, 1, map_q, map_kv, map_out, p);
+    }
+    switch (variant)
     {
     case 0: return launch_attention_tc_v<0, 0>(map_q, map_kv, map_out, p, grid, stream);
     case 1: return launch_attention_tc_v<0, 1>(map_q, map_kv, map_out, p, grid, stream);
     case 2: return launch_attention_tc_v<0, 2>(map_q, map_kv, map_out, p, grid, stream);
-    case 11: return launch_attention_tc_v<1, 1>(map_q, map_kv, map_out, p, grid, stream);
     case 12: return launch_attention_tc_v<1, 2>(map_q, map_kv, map_out, p, grid, stream);
-    case 21: return launch_attention_tc_v<2, 1>(map_q, map_kv, map_out, p, grid, stream);
     case 22: return launch_attention_tc_v<2, 2>(map_q, map_kv, map_out, p, grid, stream);
+    case 3: return launch_attention_tc_v<0, 3>(map_q, map_kv, map_out, p, grid, stream);
+    case 13: return launch_attention_tc_v<1, 3>(map_q, map_kv, map_out, p, grid, stream);
+    case 23: return launch_attention_tc_v<2, 3>(map_q, map_kv, map_out, p, grid, stream);
     default: return cudaErrorInvalidValue;
     }
 }

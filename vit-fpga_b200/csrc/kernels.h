@@ -145,6 +145,11 @@ cudaError_t launch_splitk_finalize(int32_t *ws, const int32_t *bias, void *out, 
 // out_f32 = (float)acc * 2^-14   (INT8 nets through the float API)
 cudaError_t launch_dequant_q214(const int32_t *in, float *out, long long count, cudaStream_t stream);
 
+// Host-side staging copy (staging.cpp): pageable caller memory -> page-locked slot, on the process-wide copy-thread pool with
+// non-temporal stores.  Returns when every byte has landed.
+void staging_copy(void *dst, const void *src, size_t bytes);
+int staging_threads();
+
 // Sets the calling thread's netcuda_last_error() text and returns `code` (runtime.cu; shared with weights_io.cu).
 int set_last_error_v(int code, const char *fmt, va_list ap);
 

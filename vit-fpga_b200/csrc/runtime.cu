@@ -1006,31 +1006,9 @@ static int kernel_error(netcuda_net *h)
     return fail(NETCUDA_ERR_KERNEL, "device-side wait timed out in the %s (wait site %d); the CUDA context is poisoned by the trap", where, code);
 }
 
-// Pageable host inputs are staged through pinned slots; one thread moves ~8-10 GB/s, a 1024-image ViT batch is 616 MB: the copy
-// is split over a few threads (the staging copy, not the GPU, sets the pace of net_cuda::launch_forward(std::vector) otherwise).
-static void staging_memcpy(void *dst, const void *src, size_t bytes)
-{
-    constexpr size_t MIN_PER_THREAD = 8u << 20;
-    unsigned hw = std::thread::hardware_concurrency();
-    size_t nt = std::min<size_t>({(size_t)8, hw ? (size_t)(hw + 1) / 2 : (size_t)1, bytes / MIN_PER_THREAD});
-    if (const char *e = getenv("NETCUDA_COPY_THREADS")) nt = std::min<size_t>((size_t)std::max(atoi(e), 1), 64);
-    if (nt <= 1)
-    {
-        memcpy(dst, src, bytes);
-        return;
-    }
-    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
-    std::vector<std::thread> workers;
-    for (size_t i = 1; i < nt; i++)
-    {
-        const size_t lo = i * per;
-        if (lo >= bytes) break;
-        workers.emplace_back([=]() { memcpy((char *)dst + lo, (const char *)src + lo, std::min(per, bytes - lo)); });
-    }
-    memcpy(dst, src, std::min(per, bytes));
-    for (auto &w : workers) w.join();
-}
-
+// Pageable host inputs are staged through page-locked slots by the process-wide copy pool (staging.cpp: all cores the process
+// may use, non-temporal stores).  The staging copy, not the GPU, sets the pace of net_cuda::launch_forward(std::vector) otherwise:
+// a 1024-image ViT-B batch is 616 MB per call.
 static bool is_pinned(const void *p)
 {
     cudaPointerAttributes a;
@@ -1060,7 +1038,8 @@ static int ensure_staging(netcuda_net *h, size_t in_elem, bool need_pin_in)
         h->stage_in_bytes = slot_bytes;
     }
     if (need_pin_in && !h->pin_in[0])
-        for (int i = 0; i < 2; i++) CK(cudaHostAlloc(&h->pin_in[i], h->stage_in_bytes, cudaHostAllocDefault));
+        // write-combined: the CPU only ever writes these slots (with non-temporal stores), the DMA engine only reads them
+        for (int i = 0; i < 2; i++) CK(cudaHostAlloc(&h->pin_in[i], h->stage_in_bytes, cudaHostAllocWriteCombined));
     return NETCUDA_OK;
 }
 
@@ -1133,10 +1112,18 @@ static int submit_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_
         if (!pinned_in)
         {
             if (h->chunk_seq >= 2) CK(cudaEventSynchronize(h->h2d_done[slot])); // pinned slot drained
-            staging_memcpy(h->pin_in[slot], src, bytes);
-            src = (const char *)h->pin_in[slot];
+            // staged and sent in up to four sub-copies: the DMA of one runs while the next is being staged, so a chunk costs
+            // max(staging, H2D) instead of their sum (it matters most for the first chunk of a call, which nothing hides)
+            const size_t sub = std::max<size_t>((bytes / 4 + ((size_t)1 << 21) - 1) & ~(((size_t)1 << 21) - 1), (size_t)8 << 20);
+            for (size_t off = 0; off < bytes; off += sub)
+            {
+                const size_t len = std::min(sub, bytes - off);
+                staging_copy((char *)h->pin_in[slot] + off, src + off, len);
+                CK(cudaMemcpyAsync((char *)h->dev_in[slot] + off, (const char *)h->pin_in[slot] + off, len, cudaMemcpyHostToDevice, h->copy_stream));
+            }
         }
-        CK(cudaMemcpyAsync(h->dev_in[slot], src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        else
+            CK(cudaMemcpyAsync(h->dev_in[slot], src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaEventRecord(h->h2d_done[slot], h->copy_stream));
         CK(cudaStreamWaitEvent(h->stream, h->h2d_done[slot], 0));
         char *dout = (char *)pd.dev_out + done * h->n_out * out_elem;

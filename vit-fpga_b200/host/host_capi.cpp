@@ -201,6 +201,47 @@ long long nch_launch_forward_frame(void *net, const unsigned char *frame, size_t
     }
 }
 
+// filter_image / get_filtered_image through the vtable: push one single-channel frame; pop the oldest (returns the number of
+// pixels written, 0 for an empty ring -- whose header is still reported through h / w -- or -1 on error).
+int nch_filter_image(void *net, const unsigned char *pixels, size_t h, size_t w)
+{
+    try
+    {
+        net::image_set set;
+        set.resized_image_data.assign(pixels, pixels + h * w);
+        set.original_x_pos = set.original_y_pos = 0;
+        set.original_h = h, set.original_w = w;
+        static_cast<net::net_abstract *>(net)->filter_image(set);
+        return 0;
+    }
+    catch (const std::exception &e)
+    {
+        set_err(e.what());
+        return -1;
+    }
+}
+
+long long nch_get_filtered_image(void *net, unsigned char *out, size_t capacity, size_t *h, size_t *w)
+{
+    try
+    {
+        net::image_set img = static_cast<net::net_abstract *>(net)->get_filtered_image();
+        *h = img.original_h, *w = img.original_w;
+        if (img.resized_image_data.size() > capacity)
+        {
+            set_err("output buffer too small");
+            return -1;
+        }
+        if (!img.resized_image_data.empty()) memcpy(out, img.resized_image_data.data(), img.resized_image_data.size());
+        return (long long)img.resized_image_data.size();
+    }
+    catch (const std::exception &e)
+    {
+        set_err(e.what());
+        return -1;
+    }
+}
+
 long nch_forward_us(void *net) { return static_cast<net::net_abstract *>(net)->get_forward_performance(); }
 long nch_gradient_us(void *net) { return static_cast<net::net_abstract *>(net)->get_gradient_performance(); }
 

@@ -38,9 +38,11 @@ namespace cuda
         // ViT host copy
         vit_data vit;
         signed long gradient_performance = 0;
+        netcuda_ring_t *ring = nullptr; // image side channel (filter_image / get_filtered_image), created by the first frame
 
         ~impl()
         {
+            if (ring) netcuda_ring_destroy(ring);
             for (netcuda_t *r : replicas)
                 if (r) netcuda_destroy(r);
             if (h) netcuda_destroy(h);
@@ -504,18 +506,39 @@ namespace cuda
         return (signed long)us;
     }
 
-    // Image-filter side channel: a separate workload with an unknown device kernel (`image_process`,
-    // src/netFPGA.cpp:303) -- out of scope.  filter_image accepts and drops the frame;
-    // get_filtered_image answers like the reference does for an empty ring (:336-365): a 1080p header, no pixels.
-    void net_cuda::filter_image(const net::image_set &set) { (void)set; }
+    // Image side channel (src/netFPGA.cpp:292-365): filter_image enqueues a single-channel frame of original_h * original_w bytes
+    // into a ring of 24 slots (BATCH_SIZE, :12) -- copy, H2D, filter kernel, non-blocking D2H -- and returns at once; a full ring
+    // drops the frame (the reference prints "PILA LLENA", :333).  get_filtered_image waits for the oldest frame (:349).  The ring
+    // (netcuda_ring_*, csrc/frame_ring.cu) is created by the first frame and sized from it, like the reference's
+    // _init_kernel("image_process", set) (:443-458), but at least 1920 x 1080 (IMAGE_WIDTH x IMAGE_HEIGHT, include/netFPGA.h:14-15).
+    void net_cuda::filter_image(const net::image_set &set)
+    {
+        if (!p_) throw std::runtime_error("net_cuda: moved-from net");
+        const std::size_t pixels = set.original_h * set.original_w;
+        if (pixels == 0 || set.resized_image_data.size() < pixels) return; // nothing to filter (the reference would read out of bounds)
+        if (p_->ring == nullptr)
+        {
+            const int rc = netcuda_ring_create(p_->opt.device, NETCUDA_RING_DEPTH, std::max<std::size_t>(pixels, 1920u * 1080u), &p_->ring);
+            if (rc != NETCUDA_OK) throw_last("netcuda_ring_create", rc);
+        }
+        const int rc = netcuda_ring_push(p_->ring, set.resized_image_data.data(), set.original_h, set.original_w);
+        if (rc != NETCUDA_OK && rc != NETCUDA_ERR_RING_FULL) throw_last("netcuda_ring_push", rc); // full: the frame is dropped, as in the reference
+    }
 
     net::image_set net_cuda::get_filtered_image()
     {
+        if (!p_) throw std::runtime_error("net_cuda: moved-from net");
         net::image_set out;
         out.original_x_pos = 0;
         out.original_y_pos = 0;
-        out.original_h = 1080;
+        out.original_h = 1080; // IMAGE_HEIGHT / IMAGE_WIDTH: what the reference answers for an empty ring (:336-365)
         out.original_w = 1920;
+        std::size_t h = 0, w = 0;
+        if (p_->ring == nullptr || netcuda_ring_peek(p_->ring, &h, &w) != NETCUDA_OK) return out; // "PILA VACIA": a header, no pixels
+        out.resized_image_data.resize(h * w);
+        const int rc = netcuda_ring_pop(p_->ring, out.resized_image_data.data(), out.resized_image_data.size(), &h, &w);
+        if (rc != NETCUDA_OK) throw_last("netcuda_ring_pop", rc);
+        out.original_h = h, out.original_w = w;
         return out;
     }
 }

@@ -23,7 +23,8 @@ PREC_FP32, PREC_TF32, PREC_BF16, PREC_INT8 = 0, 1, 2, 3
 ACT_RELU_HIDDEN, ACT_RELU_ALL, ACT_NONE = 0, 1, 2
 OUT_F32, OUT_BF16, OUT_S8, OUT_S32 = 0, 1, 2, 3
 EPI_NONE, EPI_RELU, EPI_GELU, EPI_RESIDUAL, EPI_REQUANT = 0, 1, 2, 3, 4
-OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_KERNEL = 0, 1, 2, 3, 4, 5
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_KERNEL, ERR_RING_FULL, ERR_RING_EMPTY = 0, 1, 2, 3, 4, 5, 6, 7
+RING_DEPTH = 24
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16, "int8": PREC_INT8}
 
 
@@ -76,6 +77,7 @@ hostlib.nch_vit_create.restype = C.c_void_p
 hostlib.nch_load.restype = C.c_void_p
 hostlib.nch_launch_forward.restype = C.c_longlong
 hostlib.nch_launch_forward_frame.restype = C.c_longlong
+hostlib.nch_get_filtered_image.restype = C.c_longlong
 hostlib.nch_forward_us.restype = C.c_long
 hostlib.nch_gradient_us.restype = C.c_long
 
@@ -381,6 +383,52 @@ def op_attention(qkv, out, batch, tokens, heads, device=0, stream=None) -> None:
                                     _stream(stream)))
 
 
+def op_filter3x3(d_in, d_out, h, w, device=0, stream=None) -> None:
+    _check(lib.netcuda_op_filter3x3(C.c_int(device), _ptr(d_in), _ptr(d_out), C.c_int(h), C.c_int(w), _stream(stream)))
+
+
+class FrameRing:
+    """netcuda_ring_*: the image side channel's ring of in-flight frames (src/netFPGA.cpp:292-365)."""
+
+    def __init__(self, max_pixels, depth=RING_DEPTH, device=0):
+        self._r = C.c_void_p(0)
+        _check(lib.netcuda_ring_create(C.c_int(device), C.c_int(depth), C.c_size_t(max_pixels), C.byref(self._r)))
+
+    def push(self, frame) -> None:
+        f = np.ascontiguousarray(frame, dtype=np.uint8)
+        _check(lib.netcuda_ring_push(self._r, _ptr(f), C.c_size_t(f.shape[0]), C.c_size_t(f.shape[1])))
+
+    def pop(self) -> np.ndarray:
+        h, w = C.c_size_t(0), C.c_size_t(0)
+        _check(lib.netcuda_ring_peek(self._r, C.byref(h), C.byref(w)))
+        out = np.empty((h.value, w.value), dtype=np.uint8)
+        _check(lib.netcuda_ring_pop(self._r, _ptr(out), C.c_size_t(out.size), C.byref(h), C.byref(w)))
+        return out
+
+    @property
+    def in_flight(self) -> int:
+        n, d = C.c_int(0), C.c_uint64(0)
+        _check(lib.netcuda_ring_in_flight(self._r, C.byref(n), C.byref(d)))
+        return n.value
+
+    @property
+    def dropped(self) -> int:
+        n, d = C.c_int(0), C.c_uint64(0)
+        _check(lib.netcuda_ring_in_flight(self._r, C.byref(n), C.byref(d)))
+        return d.value
+
+    def close(self) -> None:
+        if self._r:
+            lib.netcuda_ring_destroy(self._r)
+            self._r = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 ATT_KERNEL_MMA_SYNC = 100
 
 
@@ -471,6 +519,21 @@ class HostNet:
         if rc != 0:
             raise RuntimeError(f"get_net_data rc={rc}: " + hostlib.nch_last_error().decode())
         return w, b, n_ins.value, n_layers.value
+
+    def filter_image(self, frame) -> None:
+        """net_abstract::filter_image: enqueue one single-channel u8 frame [h, w] (dropped when 24 frames are in flight)."""
+        f = np.ascontiguousarray(frame, dtype=np.uint8)
+        if hostlib.nch_filter_image(self._h, _ptr(f), C.c_size_t(f.shape[0]), C.c_size_t(f.shape[1])) != 0:
+            raise RuntimeError("filter_image failed: " + hostlib.nch_last_error().decode())
+
+    def get_filtered_image(self, capacity=1920 * 1080):
+        """net_abstract::get_filtered_image: (pixels [h, w] or None for an empty ring, (original_h, original_w))."""
+        out = np.empty(capacity, dtype=np.uint8)
+        h, w = C.c_size_t(0), C.c_size_t(0)
+        n = hostlib.nch_get_filtered_image(self._h, _ptr(out), C.c_size_t(capacity), C.byref(h), C.byref(w))
+        if n < 0:
+            raise RuntimeError("get_filtered_image failed: " + hostlib.nch_last_error().decode())
+        return (out[:n].reshape(h.value, w.value).copy() if n else None), (h.value, w.value)
 
     def forward_us(self) -> int:
         return int(hostlib.nch_forward_us(self._h))
