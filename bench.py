@@ -472,7 +472,8 @@ def bench_c5(nc, torch, dev, local, peaks, threads, with_cpu):
     # e2e of the largest batch through the host-buffer call (int8 in, int32 out)
     xq = np.random.default_rng(5).integers(-128, 128, (16384, n_ins), dtype=np.int8)
     yq_host = np.empty((16384, npl[-1]), dtype=np.int32)
-    net.forward_i8(xq, out=yq_host)  # (first touch of the output pages stays outside the clock)
+    for _ in range(5):  # (first touch of the output pages, and the first use of each of the library's four in-flight output slots, stay outside the clock)
+        net.forward_i8(xq, out=yq_host)
     t0 = time.perf_counter()
     for _ in range(3):
         net.forward_i8(xq, out=yq_host)

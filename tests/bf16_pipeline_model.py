@@ -50,7 +50,9 @@ def vit_forward_bf16_model(cfg: dict, flat: np.ndarray, images: np.ndarray, roun
         q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
         s = (q @ k.transpose(-1, -2)) / float(np.sqrt(D // H))
         pe = torch.exp(s - s.max(-1, keepdim=True).values)
-        o = (r(pe) @ v) / pe.sum(-1, keepdim=True)  # the row sum is taken from the fp32 numerators
+        # the row sum comes out of the tensor core next to P.V (P.1 against a tile of ones, csrc/attention.cu): it is the sum of the
+        # bf16-rounded numerators, the very weights that multiply V
+        o = (r(pe) @ v) / r(pe).sum(-1, keepdim=True)
         x = x + r(o.permute(0, 2, 1, 3).reshape(B, T, D)) @ r(ow).T + ob
         y = r(ln(x, (D,), g2, b2, 1e-6))
         h = r(torch.nn.functional.gelu(y @ r(f1w).T + f1b))

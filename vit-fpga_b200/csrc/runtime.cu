@@ -132,7 +132,8 @@ struct netcuda_net
         bool in_is_i8 = false, out_is_i32 = false;
         uint64_t launches = 0; // kernels inside the graph (for the launch counter)
     };
-    static constexpr int PASS_GRAPHS = 8; // the host API cycles through 2 input slots x up to 4 output buffers
+    static constexpr int PASS_GRAPHS = 40; // the host API cycles through 2 input slots x up to 4 output buffers; a device-resident call of
+                                           // several small passes (NETCUDA_VIT_GRAPH_MULTIPASS) keeps one graph per pass
     PassGraph pass_graphs[PASS_GRAPHS];
     PassGraph graph_candidates[PASS_GRAPHS]; // ViT: a (buffers, batch) combination is captured the second time it shows up
     int graph_candidate_next = 0;
@@ -962,7 +963,8 @@ static int forward_device_impl(netcuda_net *h, const void *d_in, bool in_is_i8, 
             const float *img = in_is_i8 ? nullptr : (const float *)d_in + done * h->n_in;
             const uint8_t *img_u8 = in_is_i8 ? (const uint8_t *)d_in + done * h->n_in : nullptr;
             float *logits = (float *)d_out + done * h->n_out;
-            if (allow_graph && (long long)n * h->T <= vit_graph_max_rows() && batch <= (size_t)h->max_batch && !h->profiling && h->use_graphs)
+            static const bool multipass = getenv("NETCUDA_VIT_GRAPH_MULTIPASS") != nullptr; // (A/B: graphs for every pass of a multi-pass call)
+            if (allow_graph && (long long)n * h->T <= vit_graph_max_rows() && (batch <= (size_t)h->max_batch || multipass) && !h->profiling && h->use_graphs)
                 rc = pass_graphed(h, in_is_i8 ? (const void *)img_u8 : (const void *)img, logits, n, in_is_i8, false, s, true,
                                   [&]() { return vit_pass(h, img, img_u8, n, logits, s); });
             else
