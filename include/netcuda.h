@@ -264,8 +264,9 @@ int netcuda_op_layernorm(int device, const float *d_x, int ldx, const float *d_g
 int netcuda_op_attention(int device, const void *d_qkv, void *d_out, int batch, int tokens, int heads, void *stream);
 /* The same with an explicit kernel choice and output type (tests and A/B measurements):
  *   kernel < 0: the product default;  NETCUDA_ATT_KERNEL_MMA_SYNC: the mma.sync cross-check kernel;
- *   otherwise 10 * POLY + MODE of the short-sequence tcgen05 kernel (csrc/attention.cu: MODE 0 = one polling MMA issuer,
- *   1 = one blocking issuer per query tile, 2 = 1 + exp2 turn-taking; POLY 0..2 = exponentials per four on the FMA pipe).
+ *   otherwise a build variant of the short-sequence tcgen05 kernels (csrc/attention.cu): 0..2 = the 12-warp kernel (0 = one polling
+ *   MMA issuer, 1 = one blocking issuer per query tile, 2 = 1 + exp2 turn-taking); 4 = the 16-softmax-warp kernel (the default),
+ *   14 / 24 / 34 its double-buffered / balanced-split forms, + 100 without turn-taking between the query tiles.
  *   out_f32 != 0: d_out is fp32 [batch*tokens][heads*64] (what a TF32 ViT's output projection reads). */
 #define NETCUDA_ATT_KERNEL_MMA_SYNC 100
 int netcuda_op_attention_ex(int device, const void *d_qkv, void *d_out, int batch, int tokens, int heads, int kernel, int out_f32,

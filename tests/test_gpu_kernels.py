@@ -274,12 +274,13 @@ def test_attention_tcgen05_matches_mma_sync_kernel(netcuda, torch_cuda, monkeypa
     assert err <= 1e-2, err
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 2, 12, 22, 3, 13, 23, 4, 14, 24, 34, 104])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 4, 14, 24, 34, 104])
 @pytest.mark.parametrize("batch,tokens,heads", [(40, 197, 12), (3, 37, 2), (2, 129, 2), (2, 256, 1), (1, 128, 1), (5, 200, 3)])
 def test_attention_kernel_variants_vs_oracle(netcuda, oracle, torch_cuda, kernel, batch, tokens, heads):
-    """Every build variant of the short-sequence tcgen05 kernel (10 * POLY + MODE: polling / per-tile MMA issuers, exp2 turn-taking,
-    exponentials on the FMA pipe), bf16 and fp32 outputs, against the oracle; several items per CTA (40 x 12 heads over 148 SMs),
-    one and two query tiles, ragged last tile.  The polynomial exp2 is within 7.5e-5 of 2^x: far inside P's bf16 rounding."""
+    """Every build variant of the short-sequence tcgen05 kernels (12-warp kernel: polling / per-tile MMA issuers, exp2 turn-taking;
+    16-softmax-warp kernel: key halves per row block, row sums from the N = 80 P.V MMA, single / double-buffered loads, both key
+    splits, with and without tile turn-taking), bf16 and fp32 outputs, against the oracle; several items per CTA (40 x 12 heads over
+    148 SMs), one and two query tiles, ragged last tile, sequences with and without keys for the second half."""
     torch = torch_cuda
     rng = np.random.default_rng(tokens * 7 + heads + kernel)
     qkv = _bf16_round(torch, (rng.standard_normal((batch * tokens, 3 * heads * 64)) * 1.5).astype(np.float32))

@@ -1,4 +1,4 @@
-"""A/B of the short-sequence attention kernel's build variants (10 * POLY + MODE, csrc/attention.cu) on ViT-B / ViT-Tiny shapes:
+"""A/B of the short-sequence attention kernel's build variants (netcuda_op_attention_ex codes, csrc/attention.cu) on ViT-B / ViT-Tiny shapes:
 CUDA-event time per launch (median of 15), all variants in one process on one box."""
 import os, sys
 import torch
@@ -11,7 +11,7 @@ for batch, tokens, heads in ((512, 197, 12), (256, 197, 3)):
     out = torch.empty((batch * tokens, heads * 64), dtype=torch.bfloat16, device="cuda")
     ref = None
     torch.cuda.synchronize()
-    for kernel in (2, 4, 14, 24, 34, 104, 4):
+    for kernel in (0, 1, 2, 4, 14, 24, 34, 104, 4):
         with torch.cuda.stream(s):
             for _ in range(3):
                 nc.op_attention_ex(qkv, out, batch, tokens, heads, kernel=kernel, stream=s)

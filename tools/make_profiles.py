@@ -21,8 +21,8 @@ METRICS = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__grid_siz
            "sm__warps_active.avg.pct_of_peak_sustained_active"]
 
 
-def launch_list():
-    src = os.path.join(G, "launches.csv")
+def launch_list(fname="launches.csv", suffix="", what="`python bench.py --steps 1 --warmup 3 --batch 512 --no-cpu-baseline --no-e2e --no-configs` (weight upload + 4 warm-up + 1 timed + 1 profiled pass of 512 images)"):
+    src = os.path.join(G, fname)
     if not os.path.exists(src):
         return
     rows = list(csv.reader(open(src)))
@@ -40,12 +40,12 @@ def launch_list():
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += ns
-    with open(os.path.join(P, f"{tag}_launches.csv"), "w", newline="") as f:
+    with open(os.path.join(P, f"{tag}_launches{suffix}.csv"), "w", newline="") as f:
         csv.writer(f).writerows(out)
     tot = sum(a[1] for a in agg.values())
-    with open(os.path.join(P, f"{tag}_launch_shares.md"), "w") as f:
-        f.write(f"# Launch list summary ({tag})\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over `python bench.py --steps 1 --warmup 3 --batch 512 "
-                "--no-cpu-baseline --no-e2e` (weight upload + 4 warm-up + 1 timed + 1 profiled pass of 512 images).  Per-launch times are cold-cache and serialised: "
+    with open(os.path.join(P, f"{tag}_launch_shares{suffix}.md"), "w") as f:
+        f.write(f"# Launch list summary ({tag}{suffix})\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over {what}.  "
+                "Per-launch times are cold-cache and serialised: "
                 "compare SHARES with `roofline.per_kernel` of the bench line, not absolutes.\n\n| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {a[0]} | {a[1] / 1e6:.3f} | {a[1] / tot * 100:.1f} % |\n")
@@ -90,6 +90,7 @@ def traffic_json():
 
 
 launch_list()
+launch_list("launches_tiny.csv", "_vit_tiny", "`python bench.py --steps 1 --warmup 3 --workload vit_tiny_16_224_b256 --no-cpu-baseline --no-e2e --no-configs` (ViT-Tiny/16-224, 256 images per pass)")
 full_reports()
 traffic_json()
 print(sorted(os.listdir(P)))

@@ -14,8 +14,8 @@
 //      with the A operand in TMEM and V consumed MN-major straight from its row-major [key][64] tile;
 //      the warpgroup scales O by 1/rowsum and stores its rows with TMA.  S and P never touch smem or HBM.
 //      One MMA-issuing thread per query tile (blocking waits); the two softmax warps of an SM sub-partition
-//      take turns in their exp2 pass (template parameter MODE), part of the exponentials can run on the FMA
-//      pipe (POLY).  Measured alternatives of round 1 (256 x 12 x 197, us per launch): two-pass softmax 126; a
+//      take turns in their exp2 pass (template parameter MODE).  The PRODUCT kernel for these sequence lengths is
+//      attention_tc16_kernel (sixteen softmax warps, further below).  Measured alternatives of round 1 (256 x 12 x 197, us per launch): two-pass softmax 126; a
 //      single-read softmax that keeps the row as fp16 differences in registers 134; P through shared memory
 //      with an SS-mode P.V 171; P.V issued in 64-key groups while the softmax is still running 147.
 //  (2) attention_tc_long_kernel (tokens > 256, e.g. 577 tokens at 384 pixels): the key-blocked variant of the
@@ -300,27 +300,6 @@ __device__ __forceinline__ float fmax3(float a, float b, float c)
     return d;
 }
 
-// 2^x for two arguments x <= 0 on the FMA / ALU pipes instead of the MUFU (which, at 4 results per cycle and SM sub-partition, is
-// the busiest unit of this kernel: one exponential per score against 1/32 of a tensor-core cycle of MMA work for it).
-// Cody-Waite: n = round(x) through the 1.5 * 2^23 magic add, f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial
-// (relative error 7.5e-5; P is rounded to bf16, 2e-3, right after), 2^n by adding n to the exponent field.
-__device__ __forceinline__ void exp2_poly_x2(float xa, float xb, float &ra, float &rb)
-{
-    const float MAGIC = 12582912.0f; // 1.5 * 2^23: as_int(x + MAGIC) = as_int(MAGIC) + round(x), and as_int(MAGIC) << 23 == 0
-    const uint64_t x2 = pack_f32x2(fmaxf(xa, -125.0f), fmaxf(xb, -125.0f));
-    const uint64_t t2 = add_f32x2(x2, pack_f32x2(MAGIC, MAGIC));
-    const uint64_t n2 = add_f32x2(t2, pack_f32x2(-MAGIC, -MAGIC));
-    const uint64_t f2 = fma_f32x2(n2, pack_f32x2(-1.0f, -1.0f), x2);
-    uint64_t p2 = fma_f32x2(pack_f32x2(0.055171459913253784f, 0.055171459913253784f), f2, pack_f32x2(0.2426108568906784f, 0.2426108568906784f));
-    p2 = fma_f32x2(p2, f2, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
-    p2 = fma_f32x2(p2, f2, pack_f32x2(0.9999281167984009f, 0.9999281167984009f));
-    float pa, pb, ta, tb;
-    unpack_f32x2(p2, pa, pb);
-    unpack_f32x2(t2, ta, tb);
-    ra = __uint_as_float(__float_as_uint(pa) + (__float_as_uint(ta) << 23));
-    rb = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(tb) << 23));
-}
-
 // O rows of one softmax warp (lane = row, 64 fp32 columns each, scaled by inv) -> global memory through the warp's 128B-swizzled
 // slab and 3-D TMA stores (rows past the image's last token are clipped by the tensor map): one 64-column bf16 box, or two
 // 32-column fp32 boxes.  Per-lane-row global stores -- 8 x 16 bytes to 32 different lines per instruction -- kept the warp in
@@ -379,19 +358,13 @@ __device__ __forceinline__ void store_o_rows(const uint32_t *o, float inv, uint8
 // MODE 1: one issuing thread per query tile (warps 1 and 3), each in blocking mbarrier waits: no polling round (six test_waits of
 //         ~150 cycles each) between "P is ready" and the P.V issue, or between "O has been read" and the next S.
 // MODE 2: MODE 1 + the two softmax warps of one SM sub-partition (query tile 0 / tile 1, same TMEM lane quarter) take turns in
-//         their exponential pass: a warp alone runs it at the MUFU's pace; two at once both take twice as long, which lengthens
-//         BOTH serial chains (S -> softmax -> P.V -> O).  Turn-taking keeps one warp in exp2 while the other one waits for its
-//         MMAs, reduces the row maximum or stores O.
-// MODE 3: MODE 1 + register re-balancing (setmaxnreg: 232 per softmax thread, 40 for the other warps) that buys a deeper TMEM
-//         load pipeline and a re-ordered exponential pass.  Measured on the MODE 0..2 kernels (tools/attn_timeline.py): the period
-//         of a CTA (~7.5 k cycles per item) IS the serial chain of one query tile -- S issue 0.7 k, max pass 1.35 k, exp2 pass 3.35 k,
-//         P.V 1.45 k, O 0.1 k -- and the two tiles hardly slow each other down.  The max pass was one tcgen05.ld (~80 cycles, all-or-
-//         nothing wait::ld) ahead of 17 FMNMX3; the exp2 pass ran at ~420 cycles per 32 keys where the MUFU needs 256, because
-//         every FADD / F2FP sat two MUFU issues behind the MUFU whose result it consumes (in-order issue stalls on the scoreboard).
-//         Here both passes keep two 32-column loads in flight (four 32-register buffers) and the exp2 pass issues the 32 MUFUs of
-//         a chunk back to back before anything consumes them.
-// POLY: how many of every four exponentials run on the FMA pipe (exp2_poly_x2) instead of the MUFU: 0, 1 or 2.
-template <int POLY, int MODE>
+//         their exponential pass.
+// Measured (512 x 12 x 197, us per launch in isolation): MODE 0 200, MODE 1 194, MODE 2 187.  Tried on top of MODE 1 and dropped
+// (tools/attn_timeline.py shows why): a deeper tcgen05.ld pipeline with setmaxnreg 232 / 40 and the 32 MUFUs of a chunk issued
+// before anything consumes them (193); a quarter or half of the exponentials as a degree-3 Cody-Waite polynomial on the FMA pipe
+// (192 / 200: a polynomial costs ~7 FMA-pipe issue slots of 2 cycles against the MUFU's 8 cycles, and a single warp cannot overlap
+// the two pipes anyway -- see attention_tc16_kernel below, which is the product kernel for these sequence lengths).
+template <int MODE>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
                     const __grid_constant__ CUtensorMap tma_out, const AttnTcParams p)
@@ -456,8 +429,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     griddep_wait(); // the qkv matrix is the previous kernel's output
     if (warp < 4)
     {
-    // MODE 3: whole warpgroups (warps 0-3 | 4-7 | 8-11) re-balance their registers: 128 x 40 + 256 x 232 = 384 x 168
-    if constexpr (MODE == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == ATC_W_PRODUCER)
     {
         // ===================== TMA producer =====================
@@ -600,7 +571,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     }
     else
     {
-    if constexpr (MODE == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     if (((warp - 4) >> 2) < p.n_mtiles && ((warp - 4) >> 2) * 128 + (warp & 3) * 32 < p.tokens)
     {
         // ===================== softmax + output warpgroups (one per query tile) =====================
@@ -655,51 +625,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                         if (j < tail) mx = fmaxf(mx, __uint_as_float(v[j]));
                 }
             };
-            // two 32-column loads (chunks c, c + 1) into x / y; tcgen05.wait::ld is all-or-nothing, so loads travel in pairs
-            // (both loads are unconditional: chunk c + 1 <= 7 stays inside the tile's 256-column region even when it is not a full one)
-            auto ld2 = [&](uint32_t *x, uint32_t *y, int c) {
-                tmem_ld_32x32(region + c * 32, x);
-                tmem_ld_32x32(region + (c + 1) * 32, y);
-            };
-            if constexpr (MODE == 3)
-            {
-                uint32_t a0[32], a1[32], b0[32], b1[32];
-                const int npairs = (nfull + 1) >> 1; // pairs of FULL chunks; the ragged last chunk is reduced on its own below
-                auto red2 = [&](const uint32_t *lo, const uint32_t *hi, int pr) {
-                    reduce(lo, 2 * pr);
-                    if (2 * pr + 1 < nfull) reduce(hi, 2 * pr + 1);
-                };
-                if (npairs > 0)
-                {
-                    ld2(a0, a1, 0);
-                    for (int pr = 0;; pr += 2) // every load dominates its uses on every path (no conditionally written buffers)
-                    {
-                        tmem_ld_wait();
-                        if (pr + 1 >= npairs)
-                        {
-                            red2(a0, a1, pr);
-                            break;
-                        }
-                        ld2(b0, b1, 2 * (pr + 1)); // in flight while the pair pr is reduced
-                        red2(a0, a1, pr);
-                        tmem_ld_wait();
-                        if (pr + 2 >= npairs)
-                        {
-                            red2(b0, b1, pr + 1);
-                            break;
-                        }
-                        ld2(a0, a1, 2 * (pr + 2));
-                        red2(b0, b1, pr + 1);
-                    }
-                }
-                if (tail)
-                {
-                    tmem_ld_32x32(region + nfull * 32, a0);
-                    tmem_ld_wait();
-                    reduce(a0, nfull);
-                }
-            }
-            else
             {
                 // (chunk c + 1 is in flight while c is reduced)
                 uint32_t va[32], vb[32];
@@ -725,82 +650,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             // ---- pass 2: p = 2^((s - max) * scale); P (bf16) overwrites the first half of the S columns it came from ----
             const float msc = mx * sl;
             float sum0 = 0.0f, sum1 = 0.0f;
-            if constexpr (MODE == 3)
-            {
-                // One chunk: every exponent first, then the 32 exponentials back to back (MUFU, or exp2_poly_x2 for POLY of every 4
-                // pairs: FMA-pipe work that fills the issue slots between MUFUs), and only then the sums and the bf16 packing -- no
-                // instruction waits on a MUFU result that was issued a couple of slots earlier.
-                auto expo_full = [&](uint32_t *v, int c) {
-                    uint32_t w[16];
-                    float x[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j++) x[j] = fmaf(__uint_as_float(v[j]), sl, -msc);
-#pragma unroll
-                    for (int j = 0; j < 16; j++)
-                    {
-                        if ((POLY == 1 && (j & 3) == 3) || (POLY == 2 && (j & 1) == 1))
-                            exp2_poly_x2(x[2 * j], x[2 * j + 1], x[2 * j], x[2 * j + 1]);
-                        else
-                            x[2 * j] = ex2_approx(x[2 * j]), x[2 * j + 1] = ex2_approx(x[2 * j + 1]);
-                    }
-                    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f; // four chains of eight adds
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                    {
-                        s0 += x[4 * j], s1 += x[4 * j + 1], s2 += x[4 * j + 2], s3 += x[4 * j + 3];
-                        w[2 * j] = pack_bf16x2(x[4 * j], x[4 * j + 1]);
-                        w[2 * j + 1] = pack_bf16x2(x[4 * j + 2], x[4 * j + 3]);
-                    }
-                    sum0 += s0 + s2, sum1 += s1 + s3;
-                    tmem_st_32x16(region + c * 16, w);
-                };
-                auto expo2 = [&](uint32_t *lo, uint32_t *hi, int pr) {
-                    expo_full(lo, 2 * pr);
-                    if (2 * pr + 1 < nfull) expo_full(hi, 2 * pr + 1);
-                };
-                uint32_t a0[32], a1[32], b0[32], b1[32];
-                const int npairs = (nfull + 1) >> 1;
-                if (npairs > 0)
-                {
-                    ld2(a0, a1, 0);
-                    for (int pr = 0;; pr += 2)
-                    {
-                        tmem_ld_wait();
-                        if (pr + 1 >= npairs)
-                        {
-                            expo2(a0, a1, pr);
-                            break;
-                        }
-                        ld2(b0, b1, 2 * (pr + 1));
-                        expo2(a0, a1, pr);
-                        tmem_ld_wait();
-                        if (pr + 2 >= npairs)
-                        {
-                            expo2(b0, b1, pr + 1);
-                            break;
-                        }
-                        ld2(a0, a1, 2 * (pr + 2));
-                        expo2(b0, b1, pr + 1);
-                    }
-                }
-                if (tail)
-                {
-                    // ragged last chunk: keys beyond the image are written as zeros (they are rows of the next image, or TMA zero fill)
-                    tmem_ld_32x32(region + nfull * 32, a0);
-                    tmem_ld_wait();
-                    uint32_t w[16];
-#pragma unroll
-                    for (int j = 0; j < 16; j++)
-                    {
-                        const float p0 = (2 * j < tail) ? ex2_approx(fmaf(__uint_as_float(a0[2 * j]), sl, -msc)) : 0.0f;
-                        const float p1 = (2 * j + 1 < tail) ? ex2_approx(fmaf(__uint_as_float(a0[2 * j + 1]), sl, -msc)) : 0.0f;
-                        sum0 += p0, sum1 += p1;
-                        w[j] = pack_bf16x2(p0, p1);
-                    }
-                    tmem_st_32x16(region + nfull * 16, w);
-                }
-            }
-            else
             {
                 uint32_t va[32], vb[32];
                 auto expo = [&](const uint32_t *v, int c) {
@@ -810,13 +659,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
 #pragma unroll
                         for (int j = 0; j < 16; j++)
                         {
-                            const float x0 = fmaf(__uint_as_float(v[2 * j]), sl, -msc), x1 = fmaf(__uint_as_float(v[2 * j + 1]), sl, -msc);
-                            float p0, p1;
-                            // POLY of every 4 element PAIRS go to the FMA pipe (1 of 4 / 2 of 4 exponentials)
-                            if ((POLY == 1 && (j & 3) == 3) || (POLY == 2 && (j & 1) == 1))
-                                exp2_poly_x2(x0, x1, p0, p1);
-                            else
-                                p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl, -msc));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl, -msc));
                             sum0 += p0, sum1 += p1;
                             w[j] = pack_bf16x2(p0, p1);
                         }
@@ -1613,17 +1457,17 @@ static cudaError_t launch_attention_tc_long(const void *qkv, void *out, int batc
                       map_kv, map_out, p);
 }
 
-template <int POLY, int MODE>
+template <int MODE>
 static cudaError_t launch_attention_tc_v(const CUtensorMap &map_q, const CUtensorMap &map_kv, const CUtensorMap &map_out, const AttnTcParams &p,
                                          int grid, cudaStream_t stream)
 {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<POLY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
     if (e != cudaSuccess) return e;
-    return launch_pdl(attention_tc_kernel<POLY, MODE>, dim3(grid), dim3(ATC_THREADS), (size_t)ATC_SMEM, stream, 1, map_q, map_kv, map_out, p);
+    return launch_pdl(attention_tc_kernel<MODE>, dim3(grid), dim3(ATC_THREADS), (size_t)ATC_SMEM, stream, 1, map_q, map_kv, map_out, p);
 }
 
-// Kernel variant = 10 * POLY + MODE (see attention_tc_kernel).  The default is the measured best; NETCUDA_ATT_TC_VARIANT (read once)
-// selects another one for A/B runs.
+// Kernel variant: 0..2 = MODE of attention_tc_kernel (12 warps); 4 / 14 / 24 / 34 (+ 100) = attention_tc16_kernel with its A/B switches.
+// The default is the measured best; NETCUDA_ATT_TC_VARIANT (read once) selects another one for A/B runs.
 constexpr int ATT_TC_DEFAULT_VARIANT = 4; // the 16-softmax-warp kernel (177 us per 512 x 12 x 197 launch in isolation; round-1 kernel = variant 0: 200 us)
 static int att_tc_variant()
 {
@@ -1681,14 +1525,9 @@ static cudaError_t launch_attention_tc(const void *qkv, void *out, int batch, in
     }
     switch (variant)
     {
-    case 0: return launch_attention_tc_v<0, 0>(map_q, map_kv, map_out, p, grid, stream);
-    case 1: return launch_attention_tc_v<0, 1>(map_q, map_kv, map_out, p, grid, stream);
-    case 2: return launch_attention_tc_v<0, 2>(map_q, map_kv, map_out, p, grid, stream);
-    case 12: return launch_attention_tc_v<1, 2>(map_q, map_kv, map_out, p, grid, stream);
-    case 22: return launch_attention_tc_v<2, 2>(map_q, map_kv, map_out, p, grid, stream);
-    case 3: return launch_attention_tc_v<0, 3>(map_q, map_kv, map_out, p, grid, stream);
-    case 13: return launch_attention_tc_v<1, 3>(map_q, map_kv, map_out, p, grid, stream);
-    case 23: return launch_attention_tc_v<2, 3>(map_q, map_kv, map_out, p, grid, stream);
+    case 0: return launch_attention_tc_v<0>(map_q, map_kv, map_out, p, grid, stream);
+    case 1: return launch_attention_tc_v<1>(map_q, map_kv, map_out, p, grid, stream);
+    case 2: return launch_attention_tc_v<2>(map_q, map_kv, map_out, p, grid, stream);
     default: return cudaErrorInvalidValue;
     }
 }
