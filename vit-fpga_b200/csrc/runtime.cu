@@ -1055,6 +1055,7 @@ static int finish_pending(netcuda_net *h, netcuda_net::Pending &pd)
     if (rc == NETCUDA_OK && e != cudaSuccess) rc = fail(NETCUDA_ERR_CUDA, "forward failed: %s", cudaGetErrorString(e));
     if (rc == NETCUDA_OK && !pd.pinned_out) memcpy(pd.user_out, pd.pin_out, pd.out_bytes);
     h->last_us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - pd.t0).count();
+    if (getenv("NETCUDA_HOST_TRACE")) fprintf(stderr, "[netcuda] call retired after %.2f ms\n", h->last_us / 1e3);
     pd.status = rc;
     return rc;
 }
@@ -1076,20 +1077,29 @@ static int submit_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_
     pd.pinned_out = is_pinned(out);
     pd.user_out = out, pd.out_bytes = batch * h->n_out * out_elem;
     if (!pd.done) CK(cudaEventCreateWithFlags(&pd.done, cudaEventDisableTiming));
-    if (pd.dev_cap < pd.out_bytes)
-    {
-        if (pd.dev_out) CK(cudaFree(pd.dev_out)); // (cudaFree waits for the device: nothing can still be writing it)
-        pd.dev_out = nullptr, pd.dev_cap = 0;
-        CK(cudaMalloc(&pd.dev_out, pd.out_bytes));
-        pd.dev_cap = pd.out_bytes;
-    }
-    if (!pd.pinned_out && pd.pin_cap < pd.out_bytes)
-    {
-        if (pd.pin_out) CK(cudaFreeHost(pd.pin_out));
-        pd.pin_out = nullptr, pd.pin_cap = 0;
-        CK(cudaHostAlloc(&pd.pin_out, pd.out_bytes, cudaHostAllocDefault));
-        pd.pin_cap = pd.out_bytes;
-    }
+    // Output buffers of the in-flight ring.  When this call needs larger ones, every idle slot of the ring grows with it: the
+    // allocations (milliseconds each, and cudaMalloc / cudaFree synchronise the device) are paid by one call instead of by each of the
+    // next MAX_IN_FLIGHT calls as they come round to their slot.
+    const bool need_pin_out = !pd.pinned_out;
+    if (pd.dev_cap < pd.out_bytes || (need_pin_out && pd.pin_cap < pd.out_bytes))
+        for (auto &q : h->pending)
+        {
+            if (q.active) continue;
+            if (q.dev_cap < pd.out_bytes)
+            {
+                if (q.dev_out) CK(cudaFree(q.dev_out)); // (cudaFree waits for the device: nothing can still be writing it)
+                q.dev_out = nullptr, q.dev_cap = 0;
+                CK(cudaMalloc(&q.dev_out, pd.out_bytes));
+                q.dev_cap = pd.out_bytes;
+            }
+            if (need_pin_out && q.pin_cap < pd.out_bytes)
+            {
+                if (q.pin_out) CK(cudaFreeHost(q.pin_out));
+                q.pin_out = nullptr, q.pin_cap = 0;
+                CK(cudaHostAlloc(&q.pin_out, pd.out_bytes, cudaHostAllocDefault));
+                q.pin_cap = pd.out_bytes;
+            }
+        }
 
     // The first chunk of a call is the only one whose H2D copy nothing hides (the compute stream may be idle): for large ViT batches
     // it is a quarter of a pass, so that the kernels start after a quarter of the copy time (blocking netcuda_forward, ViT-B,
@@ -1124,10 +1134,14 @@ static int submit_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_
         }
         const size_t bytes = n * h->n_in * in_elem;
         const char *src = (const char *)in + done * h->n_in * in_elem;
+        static const bool trace = getenv("NETCUDA_HOST_TRACE") != nullptr; // per-chunk host timeline on stderr (diagnostics)
+        auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - pd.t0).count(); };
+        if (trace) fprintf(stderr, "[netcuda] chunk %zu..%zu (slot %d): start %.2f ms", done, done + n, slot, since());
         if (h->chunk_seq >= 2) CK(cudaStreamWaitEvent(h->copy_stream, h->compute_done[slot], 0)); // device slot free again
         if (!pinned_in)
         {
             if (h->chunk_seq >= 2) CK(cudaEventSynchronize(h->h2d_done[slot])); // pinned slot drained
+            if (trace) fprintf(stderr, ", slot drained %.2f", since());
             // staged and sent in up to four sub-copies: the DMA of one runs while the next is being staged, so a chunk costs
             // max(staging, H2D) instead of their sum (it matters most for the first chunk of a call, which nothing hides)
             const size_t sub = std::max<size_t>((bytes / 4 + ((size_t)1 << 21) - 1) & ~(((size_t)1 << 21) - 1), (size_t)8 << 20);
@@ -1141,11 +1155,13 @@ static int submit_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_
         else
             CK(cudaMemcpyAsync(h->dev_in[slot], src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaEventRecord(h->h2d_done[slot], h->copy_stream));
+        if (trace) fprintf(stderr, ", staged + H2D queued %.2f", since());
         CK(cudaStreamWaitEvent(h->stream, h->h2d_done[slot], 0));
         char *dout = (char *)pd.dev_out + done * h->n_out * out_elem;
         // (a multi-pass batch walks through fresh (input slot, output offset) pairs: nothing a cached graph could be reused for)
         if (int rc = forward_device_impl(h, h->dev_in[slot], in_is_i8, n, dout, out_is_i32, h->stream, batch <= (size_t)h->max_batch)) return rc;
         CK(cudaEventRecord(h->compute_done[slot], h->stream));
+        if (trace) fprintf(stderr, ", kernels queued %.2f\n", since());
     }
     CK(cudaMemcpyAsync(pd.pinned_out ? out : pd.pin_out, pd.dev_out, pd.out_bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaEventRecord(pd.done, h->stream));
