@@ -275,6 +275,47 @@ def test_int8_weight_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl
     np.testing.assert_array_equal(got, oracle.mlp_forward_i8(xq, wq, bq, npl, n_ins))
 
 
+@pytest.mark.parametrize("npl,n_ins", [([272, 48, 10], 1040), ([64, 32], 4080), ([4096, 304, 4096], 4096), ([16], 48), ([4096] * 3, 4096)])
+def test_int8_tcgen05_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl, n_ins, monkeypatch):
+    """64..128 samples of an INT8 net with 16-byte-aligned fan-ins run as ONE persistent tcgen05 kernel (mlp_umma_stream.cu: weights
+    and activations through TMA rings, kind::i8 MMAs of 128 samples x 32 neurons into tensor memory, grid barrier between layers;
+    33..63 samples stay on the split-K GEMM path, which is faster there -- NETCUDA_MLP_UMMA_MIN moves that boundary).
+    Same integers as the oracle for every batch up to 128 (rows past the batch are TMA zero fill), ragged neuron tiles (10, 48, 304
+    neurons), fan-ins that are not a multiple of the 128-byte k-block, all activation modes, repeated launches (the barrier counters
+    reset themselves), and -- with the hand-over point moved to zero -- for the small batches the mma.sync kernel normally serves."""
+    rng = np.random.default_rng(78)
+    wq, bq = _int8_net(rng, npl, n_ins)
+    for act in (0, 1, 2):
+        net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8, activation=act, max_batch=160)
+        net.upload_mlp_i8(wq, bq)
+        for batch in (33, 47, 64, 100, 127, 128, 129):
+            xq = rng.integers(-128, 128, (batch, n_ins), dtype=np.int8)
+            want = oracle.mlp_forward_i8(xq, wq, bq, npl, n_ins, act)
+            np.testing.assert_array_equal(net.forward_i8(xq), want)
+            np.testing.assert_array_equal(net.forward_i8(xq), want)
+            net.profile_enable(True)
+            net.forward_i8(xq)
+            assert ("mlp_umma_stream" in net.profile_read()) == (64 <= batch <= 128)
+            net.profile_enable(False)
+        net.close()
+    monkeypatch.setenv("NETCUDA_MLP_STREAM_SPLIT", "0")  # the tcgen05 kernel for every batch up to 128
+    monkeypatch.setenv("NETCUDA_MLP_UMMA_MIN", "1")
+    net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8, max_batch=64)
+    net.upload_mlp_i8(wq, bq)
+    for batch in (1, 7, 32, 33, 47):
+        xq = rng.integers(-128, 128, (batch, n_ins), dtype=np.int8)
+        net.profile_enable(True)
+        got = net.forward_i8(xq)
+        assert "mlp_umma_stream" in net.profile_read()
+        net.profile_enable(False)
+        np.testing.assert_array_equal(got, oracle.mlp_forward_i8(xq, wq, bq, npl, n_ins))
+    # float API on the same kernel: quantise -> stream -> dequantise
+    x = rng.uniform(-1, 1, (40, n_ins)).astype(np.float32)
+    acc = oracle.mlp_forward_i8(oracle.quantize_q17(x), wq, bq, npl, n_ins)
+    np.testing.assert_array_equal(net.forward(x), acc.astype(np.float32) * np.float32(1.0 / 16384.0))
+    net.close()
+
+
 def test_int8_float_api_quantises_like_oracle(netcuda, oracle, torch_cuda):
     rng = np.random.default_rng(32)
     npl, n_ins = [96, 40], 72

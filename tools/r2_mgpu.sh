@@ -19,4 +19,4 @@ try:
 except Exception as e:
     print("parse failed", e)
 PY
-NETCUDA_DEVICES_LIST="1 $N" timeout 600 python tools/class_multi_gpu_probe.py 2>&1 | tail -4
+timeout 900 python tools/class_multi_gpu_probe.py $((N * 1024)) 2>&1 | tail -5

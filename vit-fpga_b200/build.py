@@ -33,7 +33,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-ccbin", CXX]
 if os.environ.get("NETCUDA_DEBUG_TIMELINE"):  # clock64 timeline hooks for tools/*_timeline.py (never in the shipped build)
     NVCC_FLAGS += ["-DNETCUDA_DEBUG_TIMELINE"]
-CU_SOURCES = ["gemm.cu", "elementwise.cu", "attention.cu", "mlp_stream.cu", "runtime.cu", "weights_io.cu", "frame_ring.cu", "staging.cpp"]
+CU_SOURCES = ["gemm.cu", "elementwise.cu", "attention.cu", "mlp_stream.cu", "mlp_umma_stream.cu", "runtime.cu", "weights_io.cu", "frame_ring.cu", "staging.cpp"]
 CU_HEADERS = ["ptx.cuh", "gemm_tcgen05.cuh", "kernels.h"]
 HOST_SOURCES = ["net_cuda.cpp"]
 HOST_DRIVER_SOURCES = ["host_capi.cpp"]  # ctypes driver for tests/ and bench.py: NOT part of the shipped host library

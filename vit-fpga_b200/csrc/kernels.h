@@ -112,6 +112,10 @@ struct MlpStreamParams
 };
 bool mlp_stream_supported(const MlpStreamParams &p, int grid);
 cudaError_t launch_mlp_i8_stream(const MlpStreamParams &p, int grid, cudaStream_t stream);
+// ---- the same for up to 128 samples on tcgen05 (mlp_umma_stream.cu): activations through shared memory, accumulators in TMEM ----
+constexpr int MLP_UMMA_STREAM_MAX_BATCH = 128;
+bool mlp_umma_stream_supported(const MlpStreamParams &p);
+cudaError_t launch_mlp_i8_umma_stream(const MlpStreamParams &p, int num_sms, cudaStream_t stream);
 
 // y = LayerNorm(x) * gamma + beta; x fp32 rows (pitch ldx), y bf16 rows (pitch ldy) -- or fp32 rows for the tf32 nets.
 cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, const float *beta, void *y, long long ldy,

@@ -119,6 +119,9 @@ struct netcuda_net
     int32_t *splitk_ws = nullptr;          // INT8 small batch: [128][widest layer] int32 partial sums, all zero between layers
     unsigned *stream_bar = nullptr;        // INT8, <= 32 samples: the two counters of the weight-streaming kernel's grid barrier
     bool use_stream = true;                // NETCUDA_MLP_STREAM=0 keeps such batches on the split-K GEMM path
+    int stream_max_batch = MLP_STREAM_MAX_BATCH; // up to here the mma.sync streaming kernel, above it (<= 128) the tcgen05 one
+                                                 // (NETCUDA_MLP_STREAM_SPLIT: A/B of the hand-over point)
+    int umma_min_batch = 64;                     // ... from here on; in between the split-K GEMM path is faster (NETCUDA_MLP_UMMA_MIN)
     void *patches = nullptr, *ybuf = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *cls_ln = nullptr;
     float *x = nullptr;
 
@@ -427,6 +430,8 @@ static int create_impl(const netcuda_desc *desc, netcuda_net *h)
             CK(cudaMalloc((void **)&h->stream_bar, 2 * sizeof(unsigned)));
             CK(cudaMemset(h->stream_bar, 0, 2 * sizeof(unsigned)));
             if (const char *e = getenv("NETCUDA_MLP_STREAM")) h->use_stream = atoi(e) != 0;
+            if (const char *e = getenv("NETCUDA_MLP_STREAM_SPLIT")) h->stream_max_batch = std::min(std::max(atoi(e), 0), MLP_STREAM_MAX_BATCH);
+            if (const char *e = getenv("NETCUDA_MLP_UMMA_MIN")) h->umma_min_batch = std::max(atoi(e), 1);
         }
     }
     else
@@ -648,12 +653,15 @@ static cudaError_t run_gemm(netcuda_net *h, const char *label, int kind, const v
 
 // INT8 nets, up to 32 samples: the whole forward is one persistent weight-streaming kernel (mlp_stream.cu) when every layer's
 // fan-in is a multiple of 16 bytes (no row padding anywhere) and the per-CTA output slices fit its shared memory.
+// (n <= 32: the register-resident mma.sync kernel; 64..128: the tcgen05 kernel of mlp_umma_stream.cu -- same parameter block.  Measured
+//  on config C5, us per forward: tcgen05 stream 105 / 107 / 110 at 33 / 64 / 128 samples, split-K GEMM graph 98 / 108 / 125: the
+//  split-K path keeps 33..63.)
 static bool mlp_stream_params(netcuda_net *h, int n, const int8_t *in, int32_t *out, MlpStreamParams &p)
 {
     if (h->desc.kind != NETCUDA_KIND_MLP || h->desc.precision != NETCUDA_PREC_INT8 || !h->use_stream || h->gemm_variant != 0 || !h->stream_bar)
         return false;
     const int L = (int)h->layers.size();
-    if (n < 1 || n > MLP_STREAM_MAX_BATCH || L > MLP_STREAM_MAX_LAYERS) return false;
+    if (n < 1 || n > MLP_UMMA_STREAM_MAX_BATCH || L > MLP_STREAM_MAX_LAYERS) return false;
     p.n_layers = L, p.batch = n, p.relu_mask = 0, p.max_fan_in = 0;
     for (int l = 0; l < L; l++)
     {
@@ -672,7 +680,8 @@ static bool mlp_stream_params(netcuda_net *h, int n, const int8_t *in, int32_t *
     if (const char *dbg = getenv("NETCUDA_STREAM_DEBUG_PTR")) p.debug = reinterpret_cast<long long *>(strtoull(dbg, nullptr, 0));
     if (const char *dc = getenv("NETCUDA_STREAM_DEBUG_CTA")) p.debug_cta = atoi(dc);
 #endif
-    return mlp_stream_supported(p, h->num_sms);
+    if (n <= h->stream_max_batch) return mlp_stream_supported(p, h->num_sms);
+    return n >= h->umma_min_batch && mlp_umma_stream_supported(p);
 }
 
 namespace nc
@@ -697,7 +706,7 @@ static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, in
     long long cur_ld;
     MlpStreamParams sp;
     // (an int8 input of a streamed pass is read in place: its rows are unpadded)
-    const bool stream_in_place = in_i8 && n <= MLP_STREAM_MAX_BATCH && mlp_stream_params(h, n, in_i8, out_i32 ? out_i32 : h->acc_out, sp);
+    const bool stream_in_place = in_i8 && n <= MLP_UMMA_STREAM_MAX_BATCH && mlp_stream_params(h, n, in_i8, out_i32 ? out_i32 : h->acc_out, sp);
     if (prec == NETCUDA_PREC_FP32)
     {
         cur = in_f32, cur_ld = (long long)h->n_in; // CUDA-core path reads the caller's matrix in place
@@ -721,14 +730,22 @@ static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, in
     }
     int slot = 1;
     bool streamed = false;
-    if (prec == NETCUDA_PREC_INT8 && n <= MLP_STREAM_MAX_BATCH)
+    if (prec == NETCUDA_PREC_INT8 && n <= MLP_UMMA_STREAM_MAX_BATCH)
     {
         if (mlp_stream_params(h, n, (const int8_t *)cur, out_i32 ? out_i32 : h->acc_out, sp))
         {
             double bytes = 0.0, ops = 0.0;
             for (auto &ly : h->layers) bytes += (double)ly.fan_in * ly.fan_out + 4.0 * ly.fan_out, ops += 2.0 * n * (double)ly.fan_in * ly.fan_out;
-            KernelScope scope(h, s, "mlp_stream", ops, bytes);
-            CK(launch_mlp_i8_stream(sp, h->num_sms, s));
+            if (n <= h->stream_max_batch)
+            {
+                KernelScope scope(h, s, "mlp_stream", ops, bytes);
+                CK(launch_mlp_i8_stream(sp, h->num_sms, s));
+            }
+            else
+            {
+                KernelScope scope(h, s, "mlp_umma_stream", ops, bytes);
+                CK(launch_mlp_i8_umma_stream(sp, h->num_sms, s));
+            }
             streamed = true;
         }
     }
