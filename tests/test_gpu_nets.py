@@ -208,6 +208,15 @@ def _int8_net(rng, npl, n_ins):
     return wq, bq
 
 
+def _assert_same_ints(got, want, what):
+    """assert_array_equal with the mismatch pattern (which rows / columns) in the message: it tells a stale tile from a stale row."""
+    bad = got != want
+    if bad.any():
+        rows, cols = np.unique(np.nonzero(bad)[0]), np.unique(np.nonzero(bad)[1])
+        raise AssertionError(f"{what}: {int(bad.sum())} of {bad.size} differ; rows {rows.tolist()[:40]} ({rows.size} rows), columns "
+                             f"{cols.tolist()[:40]} ({cols.size} columns), max |diff| {int(np.abs(got.astype(np.int64) - want)[bad].max())}")
+
+
 def test_int8_small_bit_exact_all_activations(netcuda, oracle, torch_cuda):
     rng = np.random.default_rng(31)
     npl, n_ins = [64, 50, 32], 48
@@ -291,8 +300,8 @@ def test_int8_tcgen05_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, np
         for batch in (33, 47, 64, 100, 127, 128, 129):
             xq = rng.integers(-128, 128, (batch, n_ins), dtype=np.int8)
             want = oracle.mlp_forward_i8(xq, wq, bq, npl, n_ins, act)
-            np.testing.assert_array_equal(net.forward_i8(xq), want)
-            np.testing.assert_array_equal(net.forward_i8(xq), want)
+            _assert_same_ints(net.forward_i8(xq), want, f"act {act} batch {batch} first call")
+            _assert_same_ints(net.forward_i8(xq), want, f"act {act} batch {batch} second call")
             net.profile_enable(True)
             net.forward_i8(xq)
             assert ("mlp_umma_stream" in net.profile_read()) == (64 <= batch <= 128)
@@ -314,6 +323,24 @@ def test_int8_tcgen05_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, np
     acc = oracle.mlp_forward_i8(oracle.quantize_q17(x), wq, bq, npl, n_ins)
     np.testing.assert_array_equal(net.forward(x), acc.astype(np.float32) * np.float32(1.0 / 16384.0))
     net.close()
+
+
+def test_int8_tcgen05_streaming_narrow_layer_does_not_run_ahead(netcuda, oracle, torch_cuda):
+    """Regression (tools/umma_stream_stress.py): 272 -> 48 -> 10 neurons is 9, 2 and 1 output tiles on a 9-CTA grid.  The CTAs without a
+    tile in the 48-neuron layer wait for nothing there; with one barrier arrival per CTA and layer their early arrivals stood in for
+    CTAs still storing the 272-neuron layer, and the first call after an idle gap read stale bytes of its ragged last tile (2 % of the
+    calls).  The barrier now counts finished tiles.  Fresh nets, an oracle run (the idle gap) before every first call."""
+    npl, n_ins = [272, 48, 10], 1040
+    for rep in range(40):
+        rng = np.random.default_rng(500 + rep)
+        wq, bq = _int8_net(rng, npl, n_ins)
+        net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8, max_batch=160)
+        net.upload_mlp_i8(wq, bq)
+        for batch in (100, 127, 128):
+            xq = rng.integers(-128, 128, (batch, n_ins), dtype=np.int8)
+            want = oracle.mlp_forward_i8(xq, wq, bq, npl, n_ins)
+            _assert_same_ints(net.forward_i8(xq), want, f"net {rep} batch {batch}")
+        net.close()
 
 
 def test_int8_float_api_quantises_like_oracle(netcuda, oracle, torch_cuda):

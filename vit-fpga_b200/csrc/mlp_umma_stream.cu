@@ -10,8 +10,9 @@
 //     never waits for activations: it runs ahead across the grid barrier between layers;
 //   * warp 1 loads the activation tiles ([samples x 128 bytes] per k-block: the box holds the batch rounded up to 8 rows; the MMA
 //     reads 128 rows, and whatever stale bytes sit in the rest of the slot only reach accumulator rows that are never stored) of
-//     layer l once every CTA has published its outputs of layer l - 1 (grid barrier: global arrival counter, release /
-//     acquire at GPU scope, reset by the last CTA -- the same protocol as mlp_stream.cu);
+//     layer l once every output tile of layer l - 1 is stored (a global counter of finished TILES, cumulative over the layers,
+//     release / acquire at GPU scope, reset by the last CTA; only the CTAs that load wait, so -- unlike mlp_stream.cu, where every CTA
+//     waits at every layer -- one arrival per CTA would let the CTAs without a tile in a narrow layer run ahead of the count);
 //   * warp 2 issues tcgen05.mma kind::i8, M = 128 (samples) x N = 32 (neurons) x K = 32 per instruction, int32 accumulators in tensor
 //     memory (two stages of 32 columns);
 //   * warps 4-7 (one per TMEM lane quarter, thread = sample): + bias, ReLU, >> 7, clamp -- the integers of EPI_REQUANT[_RELU] and of the
@@ -159,12 +160,13 @@ mlp_i8_umma_stream_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmm
         {
             for (int l = 0; l < p.n_layers; l++) tma_prefetch_desc(&maps.a[l]);
             uint32_t seq = 0;
+            unsigned target = 0; // output tiles of all the layers before this one (the counter starts every launch at zero: reset below)
             for (int l = 0; l < p.n_layers; l++)
             {
                 const int tiles = (p.fan_out[l] + MU_TILE_N - 1) / MU_TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
+                if (l > 0) target += (unsigned)((p.fan_out[l - 1] + MU_TILE_N - 1) / MU_TILE_N);
                 if (l > 0 && cta < tiles)
                 {
-                    const unsigned target = (unsigned)l * (unsigned)grid; // the counter starts every launch at zero (reset below)
                     const long long t0 = clock64();
                     while (mu_ld_acquire_gpu(p.barrier) < target)
                         if (clock64() - t0 > 4000000000LL)
@@ -315,11 +317,16 @@ mlp_i8_umma_stream_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmm
                     }
                 }
             }
-            if (!last)
+            // Publish this CTA's output tiles of the layer.  The counter counts TILES, cumulatively over the layers, and a CTA without a
+            // tile in a layer adds nothing: only a CTA that has passed the wait for layer l (every tile of the layers before it is
+            // stored) can add a tile of layer l, so the count reaches "all tiles up to layer l" only when they all are.  (Counting one
+            // arrival per CTA and layer is wrong here: the CTAs without a tile in a narrow layer arrive for it at once -- they wait for
+            // nothing -- and their early arrivals would stand in for CTAs still storing the layer before.)
+            const int my_tiles = cta < tiles ? (tiles - cta + grid - 1) / grid : 0;
+            if (!last && my_tiles > 0)
             {
-                // publish this CTA's outputs of the layer: the barrier orders every epilogue thread's stores before the release-add
-                named_bar_sync(1, 128);
-                if (threadIdx.x == 128) mu_red_release_gpu_add(p.barrier, 1u);
+                named_bar_sync(1, 128); // orders every epilogue thread's stores before the release-add (cumulativity)
+                if (threadIdx.x == 128) mu_red_release_gpu_add(p.barrier, (unsigned)my_tiles);
                 if (dbg && threadIdx.x == 128) dbg[l * 8 + 4] = clock64(); // outputs published
             }
         }

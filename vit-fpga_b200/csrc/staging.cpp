@@ -71,6 +71,9 @@ void copy_piece(char *dst, const char *src, size_t n)
     }
 #endif
     memcpy(dst, src, n);
+#if defined(__x86_64__)
+    _mm_sfence(); // the destination may be write-combined memory: drain this core's WC buffers before the DMA is queued
+#endif
 }
 
 constexpr size_t PIECE = 1u << 20;
