@@ -253,26 +253,29 @@ def test_int8_split_k_small_batch_bit_exact(netcuda, oracle, torch_cuda, batch):
 @pytest.mark.parametrize("npl,n_ins", [([272, 48, 10], 1040), ([64, 32], 4080), ([4096, 304, 4096], 4096), ([16], 48)])
 def test_int8_weight_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl, n_ins, monkeypatch):
     """Up to 32 samples an INT8 net whose fan-ins are multiples of 16 runs as ONE persistent weight-streaming kernel (mlp_stream.cu:
-    K split over 8 warps, mma.sync int8, per-CTA output slices, grid barrier between layers).  Same integers as the oracle and as the
+    K split over 8 warps, mma.sync int8, per-CTA output slices; hidden activations exchanged as tagged words up to 4 samples, behind a
+    grid barrier above -- and at every batch size with NETCUDA_MLP_STREAM_LL=0).  Same integers as the oracle and as the
     split-K GEMM path, for batches 1..32, ragged output slices (10 or 304 neurons over 148 CTAs), fan-ins that are not a multiple
     of the 32-byte MMA step or leave warps without work, all three activation modes, and across repeated launches (the barrier
-    counters reset themselves)."""
+    counters reset themselves, the tag epoch advances)."""
     rng = np.random.default_rng(77)
     wq, bq = _int8_net(rng, npl, n_ins)
-    for act in (0, 1, 2):
+    for rnd, act in enumerate((0, 1, 2, 0)):
+        if rnd == 3: monkeypatch.setenv("NETCUDA_MLP_STREAM_LL", "0")  # last round: the grid barrier at 1..4 samples too
         net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8, activation=act, max_batch=64)
         net.upload_mlp_i8(wq, bq)
-        for batch in (1, 2, 3, 5, 8, 11, 16, 17, 25, 32, 33):
+        for batch in (1, 2, 3, 4, 5, 8, 11, 16, 17, 25, 32, 33, 2, 1):
             xq = rng.integers(-128, 128, (batch, n_ins), dtype=np.int8)
             want = oracle.mlp_forward_i8(xq, wq, bq, npl, n_ins, act)
-            np.testing.assert_array_equal(net.forward_i8(xq), want)
-            np.testing.assert_array_equal(net.forward_i8(xq), want)
+            _assert_same_ints(net.forward_i8(xq), want, f"round {rnd} act {act} batch {batch} first call")
+            _assert_same_ints(net.forward_i8(xq), want, f"round {rnd} act {act} batch {batch} second call")
             if batch <= 32:  # the kernel really ran (its label shows up in the per-kernel profile)
                 net.profile_enable(True)
                 net.forward_i8(xq)
                 assert "mlp_stream" in net.profile_read()
                 net.profile_enable(False)
         net.close()
+    monkeypatch.delenv("NETCUDA_MLP_STREAM_LL")
     monkeypatch.setenv("NETCUDA_MLP_STREAM", "0")  # the split-K GEMM path on the same net: identical integers
     net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8, max_batch=64)
     net.upload_mlp_i8(wq, bq)

@@ -90,6 +90,7 @@ cudaError_t encode_tma_3d(void *map_out, int dtype_bytes, const void *ptr, long 
 // ---- INT8 MLP forward for 1..32 samples in one persistent weight-streaming kernel (mlp_stream.cu) ----
 constexpr int MLP_STREAM_MAX_LAYERS = 16;
 constexpr int MLP_STREAM_MAX_BATCH = 32;
+constexpr int MLP_STREAM_LL_MAX_BATCH = 4; // ... of which up to here without a grid barrier (tagged words)
 struct MlpStreamLayer
 {
     const int8_t *w;     // [fan_out][fan_in], fan_in a multiple of 16, at most 4096
@@ -105,7 +106,10 @@ struct MlpStreamParams
     const int8_t *in;    // [batch][fan_in of layer 0]
     int8_t *act[2];      // hidden activations: layer l writes act[(l + 1) & 1] with pitch fan_out, layer l + 1 reads it
     int32_t *out;        // [batch][fan_out of the last layer]: raw accumulators (+ bias, ReLU if flagged)
-    unsigned *barrier;   // two zero-initialised counters in device memory (left at zero by every launch)
+    unsigned *barrier;   // four zero-initialised words in device memory: [0], [1] counters (left at zero by every launch), [2] launch epoch
+    void *ll[2] = {nullptr, nullptr}; // tagged-word activation buffers (mlp_stream.cu, <= MLP_STREAM_LL_MAX_BATCH samples):
+                                      // [samples][fan_out / 4] x {4 activations, tag}; zeroed at allocation; null = grid-barrier path
+    int l2_prefetch_tiles = 0;  // mlp_stream.cu: 16-row weight tiles requested into L2 ahead of the shared-memory ring
     long long *debug = nullptr; // optional [n_layers][6] globaltimer stamps of CTA debug_cta (NETCUDA_STREAM_DEBUG_PTR)
     int debug_cta = 0;
     int *error_flag;

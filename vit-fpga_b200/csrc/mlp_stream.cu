@@ -17,7 +17,17 @@
 //   * per layer and CTA the 8 partial sums per (row, sample) meet in shared memory: + bias, ReLU, >> 7 and clamp exactly like the
 //     GEMM epilogue (EPI_REQUANT[_RELU]) -- integer arithmetic, order-independent, bit-identical to the oracle;
 //   * layers are separated by a grid barrier (global arrival counter, release / acquire at GPU scope, reset by the last CTA at kernel
-//     end); the next layer's activations are read with ld.global.cg.
+//     end; activations read with ld.global.cg).  Its cost is the release: `fence.acq_rel.gpu` takes 1.3-1.5 us here (0.5 us once the
+//     weight stream has ended) -- the acknowledgements of the few activation stores queue behind ~112 KB of weight data per layer on
+//     this SM's return path -- out of a ~4.1 us chain per layer (barrier seen 0.4, activations 0.5, two tiles 1.0, partial sums 0.3,
+//     release 1.5-1.8; tools/stream_timeline_all.py) against 2.6 us of pure weight streaming;
+//   * up to 4 samples the hidden activations therefore travel WITHOUT barrier or fence, the way NCCL's LL protocol moves data: every
+//     8-byte store carries 4 activations and a 4-byte tag (launch epoch, layer), a reader polls the words it needs (ld.volatile, 16
+//     bytes = two tagged words) and has the data the moment the tags match.  C5: 36.9 -> 35.4 us per forward at 1-2 samples; from 8
+//     samples on the doubled read volume costs more than the fence (39.6 vs 37.0 us at 8, 58 vs 43 at 9-16): grid barrier there;
+//   * the weights are also prefetched into L2 three tiles ahead of the ring (HBM keeps streaming while the ring is full; 39 -> 37 us)
+//     and read with an L2 evict-first policy (128 MiB of them would otherwise flush the biases out of L2 every launch, and a bias
+//     load that misses L2 waits 2-4 us behind the queued weight reads); biases are requested a layer ahead.
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -52,10 +62,20 @@ enum : int
     KERR_MS_GRID_BARRIER = 23,
 };
 
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+// Weights are read exactly once per launch: L2 evict-first, so that 128 MiB of them do not flush the biases (and whatever else the
+// caller keeps in L2) on their way through.  It matters more than it looks: with ~29 MB of weight reads queued at the memory
+// controllers, a bias load that misses L2 comes back 2-4 us later -- tools/stream_timeline.py showed the finalize of most layers
+// waiting that long for 28 bias values.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-                 "r"(bar)
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ int4 ld_cg_int4(const void *p)
@@ -81,6 +101,19 @@ __device__ __forceinline__ unsigned ld_cg_u32(const void *p)
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint4 ld_volatile_v4(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_v2(void *p, unsigned a, unsigned b)
+{
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+// rows of a layer per CTA: a multiple of 4, so that a tagged word (4 neurons of one sample) never straddles two CTAs
+__host__ __device__ inline int ms_rows_per_cta(int fan_out, int grid) { return (((fan_out + grid - 1) / grid) + 3) & ~3; }
+
 __device__ __forceinline__ void mma_s8_16832(int *d, const unsigned *a, unsigned b0, unsigned b1)
 {
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -88,8 +121,8 @@ __device__ __forceinline__ void mma_s8_16832(int *d, const unsigned *a, unsigned
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// NT: 8-sample groups (1: up to 8 samples, 2: up to 16, 4: up to 32)
-template <int NT>
+// NT: 8-sample groups (1: up to 8 samples, 2: up to 16, 4: up to 32); LL: tagged-word exchange of the hidden activations
+template <int NT, bool LL>
 __global__ void __launch_bounds__(MS_THREADS, 1)
 mlp_i8_stream_kernel(const MlpStreamParams p)
 {
@@ -103,6 +136,15 @@ mlp_i8_stream_kernel(const MlpStreamParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta = blockIdx.x, grid = gridDim.x;
 
+    auto stamp_raw = [&](int row, int slot) { // (timeline of every CTA: kernel entry / exit)
+        if (p.debug && p.debug_cta < 0 && threadIdx.x == 0)
+        {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.debug[cta * 32 * 6 + row * 6 + slot] = (long long)t;
+        }
+    };
+    stamp_raw(24, 0);
     if (threadIdx.x == 0)
     {
         for (int s = 0; s < MS_MAX_SLOTS; s++)
@@ -126,19 +168,43 @@ mlp_i8_stream_kernel(const MlpStreamParams p)
         if (lane == 0)
         {
             uint32_t seq = 0;
+            const uint64_t stream_once = l2_policy_evict_first();
+            // The ring (~1.5 layers of this CTA's rows) is not deep enough to keep HBM busy through the latency chain of a layer
+            // (activation exchange, tiles, partial sums: ~4 us against 2.6 us of streaming), and a ring slot only frees when its
+            // tile has been consumed.  So the rows are also prefetched into L2 -- which holds 7 layers of this net -- a few tiles
+            // ahead of the ring: HBM streams from the first microsecond on, and the ring fills from L2.
+            int pf_l = 0, pf_r = 0, pf_r1 = 0; // prefetch cursor: layer, next row, end of this CTA's rows in that layer
+            auto pf_layer = [&]() {
+                const int rpc = ms_rows_per_cta(p.layers[pf_l].fan_out, grid);
+                pf_r = cta * rpc, pf_r1 = min(p.layers[pf_l].fan_out, pf_r + rpc);
+            };
+            auto prefetch_tile = [&]() {
+                while (pf_l < p.n_layers && pf_r >= pf_r1)
+                    if (++pf_l < p.n_layers) pf_layer();
+                if (pf_l >= p.n_layers) return;
+                const MlpStreamLayer &ly = p.layers[pf_l];
+                const int nrows = min(MS_TILE_ROWS, pf_r1 - pf_r);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ly.w + (long long)pf_r * ly.fan_in),
+                             "r"((uint32_t)nrows * (uint32_t)ly.fan_in)
+                             : "memory"); // (rows of a tile are contiguous in global memory: one request per tile)
+                pf_r += MS_TILE_ROWS;
+            };
+            pf_layer();
+            for (int i = 0; i < p.l2_prefetch_tiles; i++) prefetch_tile();
             for (int l = 0; l < p.n_layers; l++)
             {
                 const MlpStreamLayer &ly = p.layers[l];
-                const int rpc = (ly.fan_out + grid - 1) / grid;
+                const int rpc = ms_rows_per_cta(ly.fan_out, grid);
                 const int r0 = cta * rpc, r1 = min(ly.fan_out, r0 + rpc);
                 for (int r = r0; r < r1; r += MS_TILE_ROWS, seq++)
                 {
                     const int slot = seq % nslots;
+                    if (p.l2_prefetch_tiles > 0) prefetch_tile();
                     mbar_wait(empty_bar(slot), ((seq / nslots) & 1u) ^ 1u, p.error_flag, KERR_MS_PRODUCER);
                     const int nrows = min(MS_TILE_ROWS, r1 - r);
                     mbar_arrive_expect_tx(full_bar(slot), (uint32_t)nrows * (uint32_t)ly.fan_in);
                     for (int i = 0; i < nrows; i++)
-                        bulk_load_1d(base + slot * slot_bytes + i * pitch, ly.w + (long long)(r + i) * ly.fan_in, (uint32_t)ly.fan_in, full_bar(slot));
+                        bulk_load_1d(base + slot * slot_bytes + i * pitch, ly.w + (long long)(r + i) * ly.fan_in, (uint32_t)ly.fan_in, full_bar(slot), stream_once);
                 }
             }
         }
@@ -148,13 +214,39 @@ mlp_i8_stream_kernel(const MlpStreamParams p)
     // ===================== consumers =====================
     const int gid = lane >> 2, tig = lane & 3;
     auto stamp = [&](int l, int slot) { // optional timeline of CTA `debug_cta` (profiling aid): [layer][6] globaltimer ns
-        if (p.debug && cta == p.debug_cta && threadIdx.x == 0)
+        if (p.debug && (cta == p.debug_cta || p.debug_cta < 0) && threadIdx.x == 0) // (debug_cta < 0: every CTA, [cta][32][6])
         {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            p.debug[l * 6 + slot] = (long long)t;
+            p.debug[(p.debug_cta < 0 ? cta * 32 * 6 : 0) + l * 6 + slot] = (long long)t;
         }
     };
+    // tag of the words layer l reads (= what layer l - 1 wrote): (launch epoch, l).  The epoch lives in device memory and is advanced
+    // by the last CTA of every launch, so a replayed CUDA graph still gets fresh tags; the word buffers are zeroed at allocation and
+    // no tag is zero.  (A stale word could only pass for a fresh one after exactly 2^27 launches that never rewrote it.)
+    const unsigned epoch = LL ? ld_cg_u32(p.barrier + 2) : 0u;
+    // Biases: the weight stream keeps ~29 MB of reads queued at the memory controllers (195 KB per SM), so a load that misses L2
+    // -- the biases are 16 KB per layer, flushed out of L2 by every launch's 128 MiB of weights -- comes back after 2-4 us.  Asked for
+    // between the activation load and the tiles (~1 us ahead) it stalled the finalize of most layers; asked for a layer ahead it is free.
+    constexpr int FIN = (MS_MAX_PARTIAL + MS_CONSUMER_WARPS * 32 - 1) / (MS_CONSUMER_WARPS * 32); // plain finalize: values per thread
+    int bias_r_next[FIN], bias4_next[4] = {0, 0, 0, 0};
+    auto fetch_bias = [&](int l) {
+        const MlpStreamLayer &ly = p.layers[l];
+        const int rpc = ms_rows_per_cta(ly.fan_out, grid);
+        const int r0 = cta * rpc, r1 = min(ly.fan_out, r0 + rpc);
+        const int nvals = (r1 - r0) * BTP;
+#pragma unroll
+        for (int j = 0; j < FIN; j++)
+        {
+            const int i = threadIdx.x + j * MS_CONSUMER_WARPS * 32;
+            bias_r_next[j] = (!(LL && l + 1 < p.n_layers) && i < nvals) ? __ldg(ly.bias + r0 + i / BTP) : 0;
+        }
+        // (tagged-word finalize: 4 consecutive neurons of one sample per thread)
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            bias4_next[e] = (LL && l + 1 < p.n_layers && (threadIdx.x / BTP) * 4 < r1 - r0) ? __ldg(ly.bias + r0 + (threadIdx.x / BTP) * 4 + e) : 0;
+    };
+    fetch_bias(0);
     uint32_t seq = 0;
     for (int l = 0; l < p.n_layers; l++)
     {
@@ -163,12 +255,12 @@ mlp_i8_stream_kernel(const MlpStreamParams p)
         const int dsteps = (K + 63) >> 6;                                     // 64-byte K steps per row
         const int dw = (dsteps + MS_CONSUMER_WARPS - 1) / MS_CONSUMER_WARPS; // ... per warp (<= MS_DSTEPS)
         const int ds0 = warp * dw, ds1 = min(dsteps, ds0 + dw);
-        const int rpc = (ly.fan_out + grid - 1) / grid;
+        const int rpc = ms_rows_per_cta(ly.fan_out, grid);
         const int r0 = cta * rpc, r1 = min(ly.fan_out, r0 + rpc);
 
         stamp(l, 0);
         // the previous layer's outputs of every CTA must be visible
-        if (l > 0)
+        if (!LL && l > 0)
         {
             if (threadIdx.x == 0)
             {
@@ -194,30 +286,81 @@ mlp_i8_stream_kernel(const MlpStreamParams p)
         // 16 + tig*4) of the step's first MMA, word 2 / 3 those of its second MMA; the weight rows are read the same way below.
         const int8_t *act = l == 0 ? p.in : p.act[l & 1];
         int4 bf[MS_DSTEPS][NT];
-#pragma unroll
-        for (int s = 0; s < MS_DSTEPS; s++)
+        if (!LL || l == 0)
         {
-            const int k = (ds0 + s) * 64 + tig * 16;
 #pragma unroll
-            for (int nt = 0; nt < NT; nt++)
+            for (int s = 0; s < MS_DSTEPS; s++)
             {
-                const int smp = nt * 8 + gid;
-                const bool ok = ds0 + s < ds1 && smp < p.batch && k < K;
-                bf[s][nt] = ok ? ld_cg_int4(act + (long long)smp * K + k) : make_int4(0, 0, 0, 0);
+                const int k = (ds0 + s) * 64 + tig * 16;
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++)
+                {
+                    const int smp = nt * 8 + gid;
+                    const bool ok = ds0 + s < ds1 && smp < p.batch && k < K;
+                    bf[s][nt] = ok ? ld_cg_int4(act + (long long)smp * K + k) : make_int4(0, 0, 0, 0);
+                }
+            }
+        }
+        else
+        {
+            // Tagged words: 16 bytes of activations are 32 bytes here, {a0..3, tag, a4..7, tag} {a8..11, tag, a12..15, tag}.  Every lane
+            // requests all its units at once and again, only the missing ones, until each carries this layer's tag: the data is in
+            // registers one L2 round trip after the last writer's store lands.  (At <= 4 samples a round is <= 32 KB per CTA next
+            // to 112 KB of weights per layer; polling ONE unit first and fetching the rest after it -- less polling traffic -- costs
+            // a second round trip and measured slower than the grid barrier at every batch size.)
+            const unsigned tag = epoch * 32u + (unsigned)l;
+            const uint8_t *ll = reinterpret_cast<const uint8_t *>(p.ll[l & 1]);
+            const long long t0 = clock64();
+            unsigned pending = 0;
+#pragma unroll
+            for (int s = 0; s < MS_DSTEPS; s++)
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++)
+                {
+                    const int k = (ds0 + s) * 64 + tig * 16, smp = nt * 8 + gid;
+                    if (ds0 + s < ds1 && smp < p.batch && k < K) pending |= 1u << (s * NT + nt);
+                    bf[s][nt] = make_int4(0, 0, 0, 0);
+                }
+            while (pending)
+            {
+                uint4 ra[MS_DSTEPS][NT], rb[MS_DSTEPS][NT];
+#pragma unroll
+                for (int s = 0; s < MS_DSTEPS; s++)
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++)
+                        if (pending >> (s * NT + nt) & 1u)
+                        {
+                            const int k = (ds0 + s) * 64 + tig * 16, smp = nt * 8 + gid;
+                            const uint8_t *u = ll + ((long long)smp * K + k) * 2;
+                            ra[s][nt] = ld_volatile_v4(u), rb[s][nt] = ld_volatile_v4(u + 16);
+                        }
+#pragma unroll
+                for (int s = 0; s < MS_DSTEPS; s++)
+#pragma unroll
+                    for (int nt = 0; nt < NT; nt++)
+                        if ((pending >> (s * NT + nt) & 1u) && ra[s][nt].y == tag && ra[s][nt].w == tag && rb[s][nt].y == tag && rb[s][nt].w == tag)
+                        {
+                            bf[s][nt] = make_int4((int)ra[s][nt].x, (int)ra[s][nt].z, (int)rb[s][nt].x, (int)rb[s][nt].z);
+                            pending &= ~(1u << (s * NT + nt));
+                        }
+                if (pending && clock64() - t0 > 4000000000LL)
+                {
+                    if (p.error_flag) atomicExch(p.error_flag, KERR_MS_GRID_BARRIER);
+                    __threadfence_system();
+                    __trap();
+                }
             }
         }
         if (bf[0][0].x == 0x12345678) stamp(l, 5); // (keeps the loads above ahead of the next stamp)
         stamp(l, 2);
-        // bias of the (up to two) outputs this thread finalises below: fetched now, needed after the last tile
+        // biases of the outputs this thread finalises below: requested one layer AHEAD (see fetch_bias)
         const int nvals = (r1 - r0) * BTP;
-        constexpr int FIN = (MS_MAX_PARTIAL + MS_CONSUMER_WARPS * 32 - 1) / (MS_CONSUMER_WARPS * 32); // values per thread
-        int bias_r[FIN];
+        int bias_r[FIN], bias4[4];
 #pragma unroll
-        for (int j = 0; j < FIN; j++)
-        {
-            const int i = threadIdx.x + j * MS_CONSUMER_WARPS * 32;
-            bias_r[j] = i < nvals ? __ldg(ly.bias + r0 + i / BTP) : 0;
-        }
+        for (int j = 0; j < FIN; j++) bias_r[j] = bias_r_next[j];
+#pragma unroll
+        for (int e = 0; e < 4; e++) bias4[e] = bias4_next[e];
+        if (l + 1 < p.n_layers) fetch_bias(l + 1);
 
         int32_t *my_partial = partial + warp * MS_MAX_PARTIAL;
         for (int r = r0; r < r1; r += MS_TILE_ROWS, seq++)
@@ -272,6 +415,32 @@ mlp_i8_stream_kernel(const MlpStreamParams p)
         stamp(l, 4);
         const bool last = l + 1 == p.n_layers;
         const bool relu = (p.relu_mask >> l) & 1u;
+        if (LL && !last)
+        {
+            // one thread = 4 consecutive neurons of one sample = one tagged word (rows per CTA and hidden widths are multiples of 4)
+            const int i = threadIdx.x, g = i / BTP, b = i - g * BTP;
+            if (g * 4 < r1 - r0 && b < p.batch)
+            {
+                unsigned word = 0;
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                {
+                    const int row = g * 4 + e;
+                    int v = bias4[e];
+#pragma unroll
+                    for (int ww = 0; ww < MS_CONSUMER_WARPS; ww++) v += partial[ww * MS_MAX_PARTIAL + row * BTP + b];
+                    if (relu) v = max(v, 0);
+                    word |= ((unsigned)min(127, max(-128, v >> 7)) & 0xFFu) << (8 * e);
+                }
+                stamp(16 + l, 0);
+                st_volatile_v2(reinterpret_cast<uint8_t *>(p.ll[(l + 1) & 1]) + ((long long)b * ly.fan_out + r0 + g * 4) * 2, word,
+                               epoch * 32u + (unsigned)(l + 1));
+                stamp(16 + l, 1);
+            }
+            named_bar_sync(1, MS_CONSUMER_WARPS * 32); // `partial` is rewritten by the next layer's tiles
+            stamp(l, 5);
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < FIN; j++)
         {
@@ -290,21 +459,30 @@ mlp_i8_stream_kernel(const MlpStreamParams p)
         if (!last)
         {
             // release: the barrier orders every consumer thread's stores before thread 0's release-add (cumulativity)
+            stamp(16 + l, 0);
             named_bar_sync(1, MS_CONSUMER_WARPS * 32);
-            if (threadIdx.x == 0) red_release_gpu_add(p.barrier, 1u);
+            stamp(16 + l, 1);
+            if (threadIdx.x == 0)
+            {
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                stamp(16 + l, 2);
+                asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p.barrier), "r"(1u) : "memory");
+            }
         }
         stamp(l, 5);
     }
     // The last CTA to get here leaves both counters at zero for the next launch: nobody polls `barrier` any more (every CTA is
     // past its last wait), and launches of one handle are stream-ordered.  No host-side state, so the launch can sit in a CUDA graph.
+    stamp_raw(24, 1);
     if (threadIdx.x == 0 && atomicAdd(p.barrier + 1, 1u) == (unsigned)grid - 1u)
     {
         p.barrier[0] = 0u;
         p.barrier[1] = 0u;
+        if (LL) p.barrier[2] = epoch + 1u; // (every CTA read the epoch before it arrived here)
     }
 }
 
-template <int NT>
+template <int NT, bool LL>
 static cudaError_t launch_one(const MlpStreamParams &p, int grid, cudaStream_t stream)
 {
     static bool opted[64] = {};
@@ -312,7 +490,7 @@ static cudaError_t launch_one(const MlpStreamParams &p, int grid, cudaStream_t s
     cudaGetDevice(&dev);
     if (dev < 64 && !opted[dev])
     {
-        cudaError_t e = cudaFuncSetAttribute(mlp_i8_stream_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(mlp_i8_stream_kernel<NT, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM);
         if (e != cudaSuccess) return e;
         opted[dev] = true;
     }
@@ -322,7 +500,7 @@ static cudaError_t launch_one(const MlpStreamParams &p, int grid, cudaStream_t s
     attr[0].id = cudaLaunchAttributeCooperative; // all CTAs co-resident: the grid barrier cannot deadlock
     attr[0].val.cooperative = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, mlp_i8_stream_kernel<NT>, p);
+    return cudaLaunchKernelEx(&cfg, mlp_i8_stream_kernel<NT, LL>, p);
 }
 
 bool mlp_stream_supported(const MlpStreamParams &p, int grid)
@@ -334,7 +512,7 @@ bool mlp_stream_supported(const MlpStreamParams &p, int grid)
     {
         const MlpStreamLayer &ly = p.layers[l];
         if (ly.fan_in < 16 || (ly.fan_in & 15) || ly.fan_in > MS_MAX_K || ly.fan_out < 1) return false;
-        const int rpc = (ly.fan_out + grid - 1) / grid;
+        const int rpc = ms_rows_per_cta(ly.fan_out, grid);
         if (rpc * btp > MS_MAX_PARTIAL) return false;
         if ((reinterpret_cast<uintptr_t>(ly.w) & 15u) != 0) return false;
         max_k = ly.fan_in > max_k ? ly.fan_in : max_k;
@@ -345,7 +523,9 @@ bool mlp_stream_supported(const MlpStreamParams &p, int grid)
 cudaError_t launch_mlp_i8_stream(const MlpStreamParams &p, int grid, cudaStream_t stream)
 {
     if (!mlp_stream_supported(p, grid)) return cudaErrorInvalidValue;
-    return p.batch <= 8 ? launch_one<1>(p, grid, stream) : p.batch <= 16 ? launch_one<2>(p, grid, stream) : launch_one<4>(p, grid, stream);
+    const bool ll = p.ll[0] && p.ll[1] && p.batch <= MLP_STREAM_LL_MAX_BATCH;
+    if (p.batch <= 8) return ll ? launch_one<1, true>(p, grid, stream) : launch_one<1, false>(p, grid, stream);
+    return p.batch <= 16 ? launch_one<2, false>(p, grid, stream) : launch_one<4, false>(p, grid, stream);
 }
 
 } // namespace nc

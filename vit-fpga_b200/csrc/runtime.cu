@@ -117,6 +117,8 @@ struct netcuda_net
     void *act[2] = {nullptr, nullptr};     // MLP ping-pong
     int32_t *acc_out = nullptr;            // INT8 float API: last layer accumulators
     int32_t *splitk_ws = nullptr;          // INT8 small batch: [128][widest layer] int32 partial sums, all zero between layers
+    int stream_pf_tiles = 3;               // ... and how many weight tiles it prefetches into L2 ahead of its ring (NETCUDA_MLP_STREAM_PF)
+    void *stream_ll[2] = {nullptr, nullptr}; // ... and its tagged-word activation buffers (<= 4 samples: no grid barrier)
     unsigned *stream_bar = nullptr;        // INT8, <= 32 samples: the two counters of the weight-streaming kernel's grid barrier
     bool use_stream = true;                // NETCUDA_MLP_STREAM=0 keeps such batches on the split-K GEMM path
     int stream_max_batch = MLP_STREAM_MAX_BATCH; // up to here the mma.sync streaming kernel, above it (<= 128) the tcgen05 one
@@ -315,7 +317,7 @@ extern "C" int netcuda_destroy(netcuda_net *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-    void *dev_ptrs[] = {h->arena, h->act[0], h->act[1], h->acc_out, h->splitk_ws, h->stream_bar, h->patches, h->ybuf, h->qkv, h->att, h->hid, h->cls_ln, h->x,
+    void *dev_ptrs[] = {h->arena, h->act[0], h->act[1], h->acc_out, h->splitk_ws, h->stream_bar, h->stream_ll[0], h->stream_ll[1], h->patches, h->ybuf, h->qkv, h->att, h->hid, h->cls_ln, h->x,
                         h->dev_in[0], h->dev_in[1]};
     for (void *p : dev_ptrs)
         if (p) cudaFree(p);
@@ -427,8 +429,20 @@ static int create_impl(const netcuda_desc *desc, netcuda_net *h)
             for (auto &L : h->layers) widest = std::max(widest, L.fan_out);
             CK(cudaMalloc((void **)&h->splitk_ws, (size_t)SPLITK_MAX_M * widest * 4));
             CK(cudaMemset(h->splitk_ws, 0, (size_t)SPLITK_MAX_M * widest * 4));
-            CK(cudaMalloc((void **)&h->stream_bar, 2 * sizeof(unsigned)));
-            CK(cudaMemset(h->stream_bar, 0, 2 * sizeof(unsigned)));
+            CK(cudaMalloc((void **)&h->stream_bar, 4 * sizeof(unsigned)));
+            CK(cudaMemset(h->stream_bar, 0, 4 * sizeof(unsigned)));
+            // tagged-word activation buffers of the weight-streaming kernel (<= 4 samples): 2 bytes per activation, two layers
+            if (const char *e = getenv("NETCUDA_MLP_STREAM_PF")) h->stream_pf_tiles = std::min(std::max(atoi(e), 0), 64);
+            const char *ll_env = getenv("NETCUDA_MLP_STREAM_LL"); // (=0: grid-barrier exchange at every batch size, for A/B runs)
+            if (widest <= 4096 && !(ll_env && atoi(ll_env) == 0))
+            {
+                const size_t ll_bytes = (size_t)MLP_STREAM_LL_MAX_BATCH * widest * 2;
+                for (int i = 0; i < 2; i++)
+                {
+                    CK(cudaMalloc(&h->stream_ll[i], ll_bytes));
+                    CK(cudaMemset(h->stream_ll[i], 0, ll_bytes));
+                }
+            }
             if (const char *e = getenv("NETCUDA_MLP_STREAM")) h->use_stream = atoi(e) != 0;
             if (const char *e = getenv("NETCUDA_MLP_STREAM_SPLIT")) h->stream_max_batch = std::min(std::max(atoi(e), 0), MLP_STREAM_MAX_BATCH);
             if (const char *e = getenv("NETCUDA_MLP_UMMA_MIN")) h->umma_min_batch = std::max(atoi(e), 1);
@@ -675,6 +689,8 @@ static bool mlp_stream_params(netcuda_net *h, int n, const int8_t *in, int32_t *
     }
     p.in = in, p.act[0] = (int8_t *)h->act[0], p.act[1] = (int8_t *)h->act[1], p.out = out;
     p.barrier = h->stream_bar, p.error_flag = h->d_err;
+    p.ll[0] = h->stream_ll[0], p.ll[1] = h->stream_ll[1];
+    p.l2_prefetch_tiles = h->stream_pf_tiles;
     p.debug = nullptr, p.debug_cta = 0;
 #ifdef NETCUDA_DEBUG_TIMELINE // clock-stamp hooks of tools/*_timeline.py: compiled out of release builds (NETCUDA_DEBUG_TIMELINE=1 python build.py)
     if (const char *dbg = getenv("NETCUDA_STREAM_DEBUG_PTR")) p.debug = reinterpret_cast<long long *>(strtoull(dbg, nullptr, 0));
