@@ -289,12 +289,13 @@ def test_int8_weight_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl
 
 @pytest.mark.parametrize("npl,n_ins", [([272, 48, 10], 1040), ([64, 32], 4080), ([4096, 304, 4096], 4096), ([16], 48), ([4096] * 3, 4096)])
 def test_int8_tcgen05_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl, n_ins, monkeypatch):
-    """64..128 samples of an INT8 net with 16-byte-aligned fan-ins run as ONE persistent tcgen05 kernel (mlp_umma_stream.cu: weights
-    and activations through TMA rings, kind::i8 MMAs of 128 samples x 32 neurons into tensor memory, grid barrier between layers;
-    33..63 samples stay on the split-K GEMM path, which is faster there -- NETCUDA_MLP_UMMA_MIN moves that boundary).
-    Same integers as the oracle for every batch up to 128 (rows past the batch are TMA zero fill), ragged neuron tiles (10, 48, 304
-    neurons), fan-ins that are not a multiple of the 128-byte k-block, all activation modes, repeated launches (the barrier counters
-    reset themselves), and -- with the hand-over point moved to zero -- for the small batches the mma.sync kernel normally serves."""
+    """33..128 samples of an INT8 net with 16-byte-aligned fan-ins run as ONE persistent tcgen05 kernel (mlp_umma_stream.cu: weights
+    and activations through TMA rings, two MMA-issuing threads that split the K range of a tile -- kind::i8 MMAs of 128 samples x 32
+    neurons into an accumulator each in tensor memory -- grid barrier between layers; NETCUDA_MLP_UMMA_MIN moves the hand-over from
+    the mma.sync kernel).  Same integers as the oracle for every batch up to 128 (rows past the batch are TMA zero fill), ragged
+    neuron tiles (10, 48, 304 neurons), fan-ins that are not a multiple of the 128-byte k-block or leave the second issuer without
+    a weight group, all activation modes, repeated launches (the barrier counters reset themselves), and -- with the hand-over point
+    moved to zero -- for the small batches the mma.sync kernel normally serves."""
     rng = np.random.default_rng(78)
     wq, bq = _int8_net(rng, npl, n_ins)
     for act in (0, 1, 2):
@@ -307,7 +308,7 @@ def test_int8_tcgen05_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, np
             _assert_same_ints(net.forward_i8(xq), want, f"act {act} batch {batch} second call")
             net.profile_enable(True)
             net.forward_i8(xq)
-            assert ("mlp_umma_stream" in net.profile_read()) == (64 <= batch <= 128)
+            assert ("mlp_umma_stream" in net.profile_read()) == (33 <= batch <= 128)
             net.profile_enable(False)
         net.close()
     monkeypatch.setenv("NETCUDA_MLP_STREAM_SPLIT", "0")  # the tcgen05 kernel for every batch up to 128

@@ -8,13 +8,14 @@
 //   * cooperative launch, one CTA per SM; CTA c owns the output-neuron tiles c, c + G, ... (32 neurons each) of EVERY layer;
 //   * warp 0 streams this CTA's weight tiles ([32 rows x 128 bytes] per k-block, TMA, 128B swizzle; four k-blocks per ring slot) and
 //     never waits for activations: it runs ahead across the grid barrier between layers;
-//   * warp 1 loads the activation tiles ([samples x 128 bytes] per k-block: the box holds the batch rounded up to 8 rows; the MMA
+//   * warp 1 loads the activation tiles ([samples x 128 bytes] per k-block, one per ring slot: the box holds the batch rounded up to 8 rows; the MMA
 //     reads 128 rows, and whatever stale bytes sit in the rest of the slot only reach accumulator rows that are never stored) of
 //     layer l once every output tile of layer l - 1 is stored (a global counter of finished TILES, cumulative over the layers,
 //     release / acquire at GPU scope, reset by the last CTA; only the CTAs that load wait, so -- unlike mlp_stream.cu, where every CTA
 //     waits at every layer -- one arrival per CTA would let the CTAs without a tile in a narrow layer run ahead of the count);
-//   * warp 2 issues tcgen05.mma kind::i8, M = 128 (samples) x N = 32 (neurons) x K = 32 per instruction, int32 accumulators in tensor
-//     memory (two stages of 32 columns);
+//   * warps 2 and 3 issue tcgen05.mma kind::i8, M = 128 (samples) x N = 32 (neurons) x K = 32 per instruction -- each takes every
+//     other four-k-block weight group of a tile (split K) into its own int32 accumulator in tensor memory (two stages x two
+//     accumulators of 32 columns), from ring slots of its own;
 //   * warps 4-7 (one per TMEM lane quarter, thread = sample): + bias, ReLU, >> 7, clamp -- the integers of EPI_REQUANT[_RELU] and of the
 //     oracle -- 32 bytes of the next layer's activation row per thread (or 32 int32 of the output row after the last layer).
 // Integer arithmetic: order-independent, bit-exact.
@@ -26,19 +27,26 @@
 namespace nc
 {
 
-constexpr int MU_THREADS = 256;
-// Ring slots hold GROUPS of k-blocks (several TMA boxes signalling one mbarrier): a measured timeline of this kernel with one
-// k-block per slot showed the MMA-issuing thread, not the memory system, setting the pace -- 627 cycles per k-block at every batch
-// size: two mbarrier waits (~90 cycles each even when already complete), four tcgen05.mma (~90 each) and two commits.  Weights travel
-// four k-blocks per slot, activations two; depths follow Little's law (weights: ~128 KB per layer and SM, activations up to 512 KB
-// per layer and SM out of L2 at ~1.2 us per load).
-constexpr int MU_W_GROUP = 4, MU_A_GROUP = 2;   // k-blocks per slot
-constexpr int MU_W_SLOTS = 4;                   // weight ring: 4 x [32 rows x 128 B] per slot
+constexpr int MU_ISSUERS = 2;                   // MMA-issuing warps: issuer i takes the weight groups i, i + 2, ... of every tile (split K)
+constexpr int MU_EPI_WARP0 = 4;                 // first epilogue warp (a multiple of 4: TMEM lane quarters)
+constexpr int MU_THREADS = (MU_EPI_WARP0 + 4) * 32;
+// Rings.  A timeline of the first form of this kernel (one issuing thread, one k-block per slot) showed the MMA-issuing thread, not
+// the memory system, setting the pace: ~650 cycles per 128-byte k-block -- mbarrier waits of ~90 cycles each even when already
+// complete, four tcgen05.mma of ~160 cycles issue-to-issue at N = 32 and the commits.  So weights travel four k-blocks per slot, and
+// the K range of a tile is split over two issuing threads with an accumulator each (110 -> 70 us at 128 samples on config C5).
+// Every issuer owns its slots: a slot has ONE producer and ONE consumer, who visits its phases in order.  (A ring shared by both
+// issuers is wrong: a parity wait can only tell a phase from the one before it, and an issuer asking for the phase after next of a
+// slot whose next phase -- the other issuer's -- has not landed yet is told "complete" for the one before.  With four issuers on a
+// shared ring that hung config C5; with two it would have been a rare wrong answer.)
+constexpr int MU_W_GROUP = 4;                   // k-blocks per weight slot
+constexpr int MU_W_SLOTS_PER = 2;               // weight slots per issuer: 2 x 4 x [32 rows x 128 B]
+constexpr int MU_W_SLOTS = MU_ISSUERS * MU_W_SLOTS_PER;
 constexpr int MU_W_TILE_BYTES = 32 * 128;
 constexpr int MU_W_SLOT_BYTES = MU_W_GROUP * MU_W_TILE_BYTES;
-constexpr int MU_A_SLOTS = 5;                   // activation ring: 2 x [128 samples x 128 B] per slot (only the batch's rows are loaded)
+constexpr int MU_A_SLOTS_PER = 5;               // activation slots per issuer: one k-block each, [128 samples x 128 B] (only the batch's rows are loaded)
+constexpr int MU_A_SLOTS = MU_ISSUERS * MU_A_SLOTS_PER;
 constexpr int MU_A_TILE_BYTES = 128 * 128;
-constexpr int MU_A_SLOT_BYTES = MU_A_GROUP * MU_A_TILE_BYTES;
+constexpr int MU_A_SLOT_BYTES = MU_A_TILE_BYTES;
 constexpr int MU_OFF_A = MU_W_SLOTS * MU_W_SLOT_BYTES;                 // 64 KB, 1024-byte aligned
 constexpr int MU_OFF_BARS = MU_OFF_A + MU_A_SLOTS * MU_A_SLOT_BYTES;   // + 160 KB
 constexpr int MU_NUM_BARS = 2 * MU_W_SLOTS + 2 * MU_A_SLOTS + 4;
@@ -46,7 +54,8 @@ constexpr int MU_OFF_TMEM_PTR = MU_OFF_BARS + MU_NUM_BARS * 8;
 constexpr int MU_SMEM = MU_OFF_TMEM_PTR + 16;
 static_assert(MU_SMEM <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 constexpr int MU_TILE_N = 32;
-constexpr uint32_t MU_TMEM_COLS = 64; // two accumulator stages of 32 columns
+constexpr uint32_t MU_TMEM_COLS = 2 * MU_ISSUERS * 32; // two accumulator stages x one 32-column accumulator per issuer
+static_assert((MU_TMEM_COLS & (MU_TMEM_COLS - 1)) == 0 && MU_TMEM_COLS >= 32 && MU_TMEM_COLS <= 512, "TMEM allocations are powers of two");
 
 enum : int
 {
@@ -118,7 +127,7 @@ mlp_i8_umma_stream_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmm
     {
         for (int s = 0; s < MU_W_SLOTS; s++) mbar_init(wfull(s), 1), mbar_init(wempty(s), 1);
         for (int s = 0; s < MU_A_SLOTS; s++) mbar_init(afull(s), 1), mbar_init(aempty(s), 1);
-        for (int a = 0; a < 2; a++) mbar_init(tfull(a), 1), mbar_init(tempty(a), 4); // one arrive per epilogue warp
+        for (int a = 0; a < 2; a++) mbar_init(tfull(a), MU_ISSUERS), mbar_init(tempty(a), 4); // one arrive per issuer / per epilogue warp
         fence_barrier_init();
     }
     if (warp == 3)
@@ -137,15 +146,20 @@ mlp_i8_umma_stream_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmm
         if (lane == 0)
         {
             for (int l = 0; l < p.n_layers; l++) tma_prefetch_desc(&maps.w[l]);
-            uint32_t seq = 0;
+            uint32_t cnt[MU_ISSUERS] = {}; // weight groups handed to each issuer so far: slot and phase of its next one
             for (int l = 0; l < p.n_layers; l++)
             {
                 const int tiles = (p.fan_out[l] + MU_TILE_N - 1) / MU_TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
                 for (int tile = cta; tile < tiles; tile += grid)
-                    for (int kb = 0; kb < nkb; kb += MU_W_GROUP, seq++)
+                    for (int kb = 0, g = 0; kb < nkb; kb += MU_W_GROUP, g++)
                     {
-                        const int s = seq % MU_W_SLOTS, nb = min(MU_W_GROUP, nkb - kb);
-                        mbar_wait(wempty(s), ((seq / MU_W_SLOTS) & 1u) ^ 1u, p.error_flag, KERR_MU_W_PRODUCER);
+                        const int is = g % MU_ISSUERS;
+                        uint32_t c = 0;
+#pragma unroll
+                        for (int i = 0; i < MU_ISSUERS; i++)
+                            if (i == is) c = cnt[i]++;
+                        const int s = is * MU_W_SLOTS_PER + (int)(c % MU_W_SLOTS_PER), nb = min(MU_W_GROUP, nkb - kb);
+                        mbar_wait(wempty(s), ((c / MU_W_SLOTS_PER) & 1u) ^ 1u, p.error_flag, KERR_MU_W_PRODUCER);
                         mbar_arrive_expect_tx(wfull(s), (uint32_t)(nb * MU_W_TILE_BYTES));
                         for (int i = 0; i < nb; i++)
                             tma_load_2d(base + s * MU_W_SLOT_BYTES + i * MU_W_TILE_BYTES, &maps.w[l], wfull(s), (kb + i) * 128, tile * MU_TILE_N);
@@ -159,7 +173,7 @@ mlp_i8_umma_stream_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmm
         if (lane == 0)
         {
             for (int l = 0; l < p.n_layers; l++) tma_prefetch_desc(&maps.a[l]);
-            uint32_t seq = 0;
+            uint32_t cnt[MU_ISSUERS] = {}; // activation k-blocks handed to each issuer so far
             unsigned target = 0; // output tiles of all the layers before this one (the counter starts every launch at zero: reset below)
             for (int l = 0; l < p.n_layers; l++)
             {
@@ -180,57 +194,70 @@ mlp_i8_umma_stream_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmm
                 }
                 if (dbg) dbg[l * 8 + 0] = clock64(); // barrier passed
                 for (int tile = cta; tile < tiles; tile += grid)
-                    for (int kb = 0; kb < nkb; kb += MU_A_GROUP, seq++)
+                    for (int kb = 0; kb < nkb; kb++)
                     {
-                        const int s = seq % MU_A_SLOTS, nb = min(MU_A_GROUP, nkb - kb);
-                        mbar_wait(aempty(s), ((seq / MU_A_SLOTS) & 1u) ^ 1u, p.error_flag, KERR_MU_A_PRODUCER);
-                        mbar_arrive_expect_tx(afull(s), (uint32_t)(nb * ((p.batch + 7) & ~7) * 128));
-                        for (int i = 0; i < nb; i++)
-                            tma_load_2d(base + MU_OFF_A + s * MU_A_SLOT_BYTES + i * MU_A_TILE_BYTES, &maps.a[l], afull(s), (kb + i) * 128, 0);
+                        const int is = (kb / MU_W_GROUP) % MU_ISSUERS; // the issuer of the weight group this k-block belongs to
+                        uint32_t c = 0;
+#pragma unroll
+                        for (int i = 0; i < MU_ISSUERS; i++)
+                            if (i == is) c = cnt[i]++;
+                        const int s = is * MU_A_SLOTS_PER + (int)(c % MU_A_SLOTS_PER);
+                        mbar_wait(aempty(s), ((c / MU_A_SLOTS_PER) & 1u) ^ 1u, p.error_flag, KERR_MU_A_PRODUCER);
+                        mbar_arrive_expect_tx(afull(s), (uint32_t)(((p.batch + 7) & ~7) * 128));
+                        tma_load_2d(base + MU_OFF_A + s * MU_A_SLOT_BYTES, &maps.a[l], afull(s), kb * 128, 0);
                     }
             }
         }
     }
-    else if (warp == 2)
+    else if (warp == 2 || warp == 3)
     {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuers (warp 3 also owns the TMEM allocation) =====================
+        const int issuer = warp - 2;
         if (lane == 0)
         {
             constexpr uint32_t IDESC = KindTraits<KIND_I8>::idesc(128, MU_TILE_N);
-            uint32_t wseq = 0, aseq = 0, tseq = 0;
+            uint32_t wcnt = 0, acnt = 0, tseq = 0; // this issuer's weight groups / activation k-blocks so far; tiles so far
             for (int l = 0; l < p.n_layers; l++)
             {
                 const int tiles = (p.fan_out[l] + MU_TILE_N - 1) / MU_TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
+                const int ngw = (nkb + MU_W_GROUP - 1) / MU_W_GROUP;
                 for (int tile = cta; tile < tiles; tile += grid, tseq++)
                 {
                     const uint32_t acc = tseq & 1u;
                     mbar_wait(tempty(acc), ((tseq >> 1) & 1u) ^ 1u, p.error_flag, KERR_MU_MMA);
                     tcgen05_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * MU_TILE_N;
-                    for (int kb = 0; kb < nkb; kb++)
+                    if (issuer >= ngw) // a short K leaves this issuer without a group: its accumulator is not read either
                     {
-                        // a slot's barrier is waited for at its first k-block and the slot is released after its last one
-                        const int ws = wseq % MU_W_SLOTS, as = aseq % MU_A_SLOTS;
-                        const int wi = kb % MU_W_GROUP, ai = kb % MU_A_GROUP;
-                        if (wi == 0) mbar_wait(wfull(ws), (wseq / MU_W_SLOTS) & 1u, p.error_flag, KERR_MU_MMA);
-                        if (ai == 0) mbar_wait(afull(as), (aseq / MU_A_SLOTS) & 1u, p.error_flag, KERR_MU_MMA);
-                        tcgen05_fence_after();
-                        if (dbg && kb == 0) dbg[l * 8 + 1] = clock64(); // first operands of the layer landed
-                        const uint64_t a_desc = umma_smem_desc_sw128(base + MU_OFF_A + as * MU_A_SLOT_BYTES + ai * MU_A_TILE_BYTES);
-                        const uint64_t b_desc = umma_smem_desc_sw128(base + ws * MU_W_SLOT_BYTES + wi * MU_W_TILE_BYTES);
+                        mbar_arrive(tfull(acc));
+                        continue;
+                    }
+                    const uint32_t d_tmem = tmem_base + (acc * MU_ISSUERS + issuer) * MU_TILE_N;
+                    for (int g = issuer; g < ngw; g += MU_ISSUERS, wcnt++)
+                    {
+                        const int ws = issuer * MU_W_SLOTS_PER + (int)(wcnt % MU_W_SLOTS_PER), kb1 = min(nkb, (g + 1) * MU_W_GROUP);
+                        mbar_wait(wfull(ws), (wcnt / MU_W_SLOTS_PER) & 1u, p.error_flag, KERR_MU_MMA);
+                        for (int kb = g * MU_W_GROUP; kb < kb1; kb++, acnt++)
+                        {
+                            const int as = issuer * MU_A_SLOTS_PER + (int)(acnt % MU_A_SLOTS_PER), wi = kb % MU_W_GROUP;
+                            mbar_wait(afull(as), (acnt / MU_A_SLOTS_PER) & 1u, p.error_flag, KERR_MU_MMA);
+                            tcgen05_fence_after();
+                            if (dbg && issuer == 0 && kb == 0) dbg[l * 8 + 1] = clock64(); // first operands of the layer landed
+                            const uint64_t a_desc = umma_smem_desc_sw128(base + MU_OFF_A + as * MU_A_SLOT_BYTES);
+                            const uint64_t b_desc = umma_smem_desc_sw128(base + ws * MU_W_SLOT_BYTES + wi * MU_W_TILE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) // 4 x 32 bytes of K per k-block
-                            umma_ss<KIND_I8>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, IDESC, (kb != 0 || k != 0) ? 1u : 0u);
-                        if (wi == MU_W_GROUP - 1 || kb == nkb - 1) tcgen05_commit(wempty(ws)), wseq++;
-                        if (ai == MU_A_GROUP - 1 || kb == nkb - 1) tcgen05_commit(aempty(as)), aseq++;
+                            for (int k = 0; k < 4; k++) // 4 x 32 bytes of K per k-block
+                                umma_ss<KIND_I8>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, IDESC, (g != issuer || wi != 0 || k != 0) ? 1u : 0u);
+                            tcgen05_commit(aempty(as));
+                        }
+                        tcgen05_commit(wempty(ws));
                     }
                     tcgen05_commit(tfull(acc));
-                    if (dbg) dbg[l * 8 + 2] = clock64(); // last MMA of the layer issued
+                    if (dbg && issuer == 0) dbg[l * 8 + 2] = clock64(); // this issuer's last MMA of the layer issued
                 }
             }
         }
     }
-    else if (warp >= 4)
+    else if (warp >= MU_EPI_WARP0)
     {
         // ===================== epilogue: thread = sample =====================
         const int q = warp & 3;
@@ -239,6 +266,7 @@ mlp_i8_umma_stream_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmm
         for (int l = 0; l < p.n_layers; l++)
         {
             const int tiles = (p.fan_out[l] + MU_TILE_N - 1) / MU_TILE_N;
+            const int nacc = min(MU_ISSUERS, (((p.fan_in[l] + 127) >> 7) + MU_W_GROUP - 1) / MU_W_GROUP); // accumulators that were written
             const bool last = l + 1 == p.n_layers;
             const bool relu = (p.relu_mask >> l) & 1u;
             for (int tile = cta; tile < tiles; tile += grid, tseq++)
@@ -264,10 +292,20 @@ mlp_i8_umma_stream_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmm
                 }
                 mbar_wait(tfull(acc), (tseq >> 1) & 1u, p.error_flag, KERR_MU_EPILOGUE);
                 tcgen05_fence_after();
-                if (dbg && threadIdx.x == 128) dbg[l * 8 + 3] = clock64(); // accumulator complete
+                if (dbg && threadIdx.x == MU_EPI_WARP0 * 32) dbg[l * 8 + 3] = clock64(); // accumulators complete
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * MU_TILE_N, v);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * MU_ISSUERS * MU_TILE_N, v);
                 tmem_ld_wait();
+#pragma unroll
+                for (int i = 1; i < MU_ISSUERS; i++)
+                    if (i < nacc) // (uniform)
+                    {
+                        uint32_t u[32];
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MU_ISSUERS + i) * MU_TILE_N, u);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] += u[j];
+                    }
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty(acc)); // the accumulator may be overwritten by the tile after next
@@ -326,12 +364,12 @@ mlp_i8_umma_stream_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmm
             if (!last && my_tiles > 0)
             {
                 named_bar_sync(1, 128); // orders every epilogue thread's stores before the release-add (cumulativity)
-                if (threadIdx.x == 128) mu_red_release_gpu_add(p.barrier, (unsigned)my_tiles);
-                if (dbg && threadIdx.x == 128) dbg[l * 8 + 4] = clock64(); // outputs published
+                if (threadIdx.x == MU_EPI_WARP0 * 32) mu_red_release_gpu_add(p.barrier, (unsigned)my_tiles);
+                if (dbg && threadIdx.x == MU_EPI_WARP0 * 32) dbg[l * 8 + 4] = clock64(); // outputs published
             }
         }
         // The last CTA to get here leaves both counters at zero for the next launch (launches of one handle are stream-ordered).
-        if (threadIdx.x == 128 && atomicAdd(p.barrier + 1, 1u) == (unsigned)grid - 1u)
+        if (threadIdx.x == MU_EPI_WARP0 * 32 && atomicAdd(p.barrier + 1, 1u) == (unsigned)grid - 1u)
         {
             p.barrier[0] = 0u;
             p.barrier[1] = 0u;
