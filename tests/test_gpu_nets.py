@@ -252,7 +252,8 @@ def test_int8_split_k_small_batch_bit_exact(netcuda, oracle, torch_cuda, batch):
 
 @pytest.mark.parametrize("npl,n_ins", [([272, 48, 10], 1040), ([64, 32], 4080), ([4096, 304, 4096], 4096), ([16], 48)])
 def test_int8_weight_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl, n_ins, monkeypatch):
-    """Up to 32 samples an INT8 net whose fan-ins are multiples of 16 runs as ONE persistent weight-streaming kernel (mlp_stream.cu:
+    """Up to 16 samples (32 with NETCUDA_MLP_STREAM_SPLIT=32: from 17 on the tcgen05 streaming kernel is faster) an INT8 net whose
+    fan-ins are multiples of 16 runs as ONE persistent weight-streaming kernel (mlp_stream.cu:
     K split over 8 warps, mma.sync int8, per-CTA output slices; hidden activations exchanged as tagged words up to 4 samples, behind a
     grid barrier above -- and at every batch size with NETCUDA_MLP_STREAM_LL=0).  Same integers as the oracle and as the
     split-K GEMM path, for batches 1..32, ragged output slices (10 or 304 neurons over 148 CTAs), fan-ins that are not a multiple
@@ -261,7 +262,9 @@ def test_int8_weight_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl
     rng = np.random.default_rng(77)
     wq, bq = _int8_net(rng, npl, n_ins)
     for rnd, act in enumerate((0, 1, 2, 0)):
-        if rnd == 3: monkeypatch.setenv("NETCUDA_MLP_STREAM_LL", "0")  # last round: the grid barrier at 1..4 samples too
+        if rnd == 3:  # last round: the grid barrier at 1..4 samples too, and this kernel up to 32 samples (default hand-over: 16)
+            monkeypatch.setenv("NETCUDA_MLP_STREAM_LL", "0")
+            monkeypatch.setenv("NETCUDA_MLP_STREAM_SPLIT", "32")
         net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8, activation=act, max_batch=64)
         net.upload_mlp_i8(wq, bq)
         for batch in (1, 2, 3, 4, 5, 8, 11, 16, 17, 25, 32, 33, 2, 1):
@@ -269,13 +272,13 @@ def test_int8_weight_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl
             want = oracle.mlp_forward_i8(xq, wq, bq, npl, n_ins, act)
             _assert_same_ints(net.forward_i8(xq), want, f"round {rnd} act {act} batch {batch} first call")
             _assert_same_ints(net.forward_i8(xq), want, f"round {rnd} act {act} batch {batch} second call")
-            if batch <= 32:  # the kernel really ran (its label shows up in the per-kernel profile)
-                net.profile_enable(True)
-                net.forward_i8(xq)
-                assert "mlp_stream" in net.profile_read()
-                net.profile_enable(False)
+            net.profile_enable(True)  # the kernel really ran (its label shows up in the per-kernel profile)
+            net.forward_i8(xq)
+            assert ("mlp_stream" in net.profile_read()) == (batch <= (32 if rnd == 3 else 16))
+            net.profile_enable(False)
         net.close()
     monkeypatch.delenv("NETCUDA_MLP_STREAM_LL")
+    monkeypatch.delenv("NETCUDA_MLP_STREAM_SPLIT")
     monkeypatch.setenv("NETCUDA_MLP_STREAM", "0")  # the split-K GEMM path on the same net: identical integers
     net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8, max_batch=64)
     net.upload_mlp_i8(wq, bq)
@@ -289,7 +292,7 @@ def test_int8_weight_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl
 
 @pytest.mark.parametrize("npl,n_ins", [([272, 48, 10], 1040), ([64, 32], 4080), ([4096, 304, 4096], 4096), ([16], 48), ([4096] * 3, 4096)])
 def test_int8_tcgen05_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl, n_ins, monkeypatch):
-    """33..128 samples of an INT8 net with 16-byte-aligned fan-ins run as ONE persistent tcgen05 kernel (mlp_umma_stream.cu: weights
+    """17..128 samples of an INT8 net with 16-byte-aligned fan-ins run as ONE persistent tcgen05 kernel (mlp_umma_stream.cu: weights
     and activations through TMA rings, two MMA-issuing threads that split the K range of a tile -- kind::i8 MMAs of 128 samples x 32
     neurons into an accumulator each in tensor memory -- grid barrier between layers; NETCUDA_MLP_UMMA_MIN moves the hand-over from
     the mma.sync kernel).  Same integers as the oracle for every batch up to 128 (rows past the batch are TMA zero fill), ragged
@@ -301,14 +304,14 @@ def test_int8_tcgen05_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, np
     for act in (0, 1, 2):
         net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8, activation=act, max_batch=160)
         net.upload_mlp_i8(wq, bq)
-        for batch in (33, 47, 64, 100, 127, 128, 129):
+        for batch in (17, 24, 33, 47, 64, 100, 127, 128, 129):
             xq = rng.integers(-128, 128, (batch, n_ins), dtype=np.int8)
             want = oracle.mlp_forward_i8(xq, wq, bq, npl, n_ins, act)
             _assert_same_ints(net.forward_i8(xq), want, f"act {act} batch {batch} first call")
             _assert_same_ints(net.forward_i8(xq), want, f"act {act} batch {batch} second call")
             net.profile_enable(True)
             net.forward_i8(xq)
-            assert ("mlp_umma_stream" in net.profile_read()) == (33 <= batch <= 128)
+            assert ("mlp_umma_stream" in net.profile_read()) == (17 <= batch <= 128)
             net.profile_enable(False)
         net.close()
     monkeypatch.setenv("NETCUDA_MLP_STREAM_SPLIT", "0")  # the tcgen05 kernel for every batch up to 128

@@ -121,9 +121,9 @@ struct netcuda_net
     void *stream_ll[2] = {nullptr, nullptr}; // ... and its tagged-word activation buffers (<= 4 samples: no grid barrier)
     unsigned *stream_bar = nullptr;        // INT8, <= 32 samples: the two counters of the weight-streaming kernel's grid barrier
     bool use_stream = true;                // NETCUDA_MLP_STREAM=0 keeps such batches on the split-K GEMM path
-    int stream_max_batch = MLP_STREAM_MAX_BATCH; // up to here the mma.sync streaming kernel, above it (<= 128) the tcgen05 one
+    int stream_max_batch = 16;                   // up to here the mma.sync streaming kernel (it can serve 32: NETCUDA_MLP_STREAM_SPLIT), above it (<= 128) the tcgen05 one
                                                  // (NETCUDA_MLP_STREAM_SPLIT: A/B of the hand-over point)
-    int umma_min_batch = 33;                     // ... from here on (NETCUDA_MLP_UMMA_MIN moves the hand-over, for A/B runs against the split-K path)
+    int umma_min_batch = 17;                     // ... from here on (NETCUDA_MLP_UMMA_MIN moves the hand-over, for A/B runs against the split-K path)
     void *patches = nullptr, *ybuf = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *cls_ln = nullptr;
     float *x = nullptr;
 
@@ -667,9 +667,10 @@ static cudaError_t run_gemm(netcuda_net *h, const char *label, int kind, const v
 
 // INT8 nets, up to 32 samples: the whole forward is one persistent weight-streaming kernel (mlp_stream.cu) when every layer's
 // fan-in is a multiple of 16 bytes (no row padding anywhere) and the per-CTA output slices fit its shared memory.
-// (n <= 32: the register-resident mma.sync kernel; 33..128: the tcgen05 kernel of mlp_umma_stream.cu -- same parameter block.  Measured
-//  on config C5, us per forward at 33 / 64 / 128 samples: tcgen05 stream with two issuing threads 66 / 67 / 70 (one issuing thread:
-//  105 / 107 / 110), split-K GEMM graph 98 / 108 / 125.)
+// (n <= 16: the register-resident mma.sync kernel; 17..128: the tcgen05 kernel of mlp_umma_stream.cu -- same parameter block.  Measured
+//  on config C5, us per forward: mma.sync stream 36 / 37 / 50 / 73 / 83 at 1 / 8 / 16 / 17 / 32 samples; tcgen05 stream with two issuing
+//  threads 66 / 67 / 68 / 70 at 1 / 17 / 64 / 128 (one issuing thread: 105 / 107 / 110 at 33 / 64 / 128); split-K GEMM graph 98 / 108 / 125
+//  at 33 / 64 / 128.)
 static bool mlp_stream_params(netcuda_net *h, int n, const int8_t *in, int32_t *out, MlpStreamParams &p)
 {
     if (h->desc.kind != NETCUDA_KIND_MLP || h->desc.precision != NETCUDA_PREC_INT8 || !h->use_stream || h->gemm_variant != 0 || !h->stream_bar)
