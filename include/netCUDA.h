@@ -51,7 +51,12 @@ namespace cuda
         int activation; // activation_t
         int max_batch;  // samples per internal pass, 0 = library default
         int n_devices;  // GPUs [device, device + n_devices) share every batched forward; -1 = NETCUDA_DEVICES from the environment, else 1
-        net_cuda_options() : precision(-1), device(-1), activation(ACT_RELU_HIDDEN), max_batch(0), n_devices(-1) {}
+        // 1: page-lock the vector a launch_forward(std::vector) call reads, the first time its buffer is seen (up to 8 buffers are
+        // remembered), so that every later call with the same buffer is DMA'd straight from it -- no staging copy.  The caller
+        // promises that such a buffer is not freed or reallocated while the net lives (release_inputs() forgets them earlier).
+        // 0: every call stages its input through the library's pinned slots.  -1 = NETCUDA_PIN_INPUTS from the environment, else 0.
+        int pin_inputs;
+        net_cuda_options() : precision(-1), device(-1), activation(ACT_RELU_HIDDEN), max_batch(0), n_devices(-1), pin_inputs(-1) {}
     };
 
     // Vision-transformer description (net::net_data can only express an MLP, def/defines.h:14-23).
@@ -98,6 +103,8 @@ namespace cuda
         // ---- extensions beyond the abstract interface ----
         // Batched forward on raw host buffers (pinned buffers are DMA'd in place).
         void forward(const DATA_TYPE *inputs, std::size_t batch, DATA_TYPE *outputs);
+        // Forget (and un-page-lock) the input buffers remembered under net_cuda_options::pin_inputs: call it before freeing one.
+        void release_inputs();
         // Vision transformers fed from camera frames, the reference's image carrier (net::image_set, def/defines.h:31-38):
         // resized_image_data holds H x W x 3 interleaved bytes of one frame (original_h / original_w are checked against the
         // net's image size when non-zero).  Normalisation v = (u8 / 255 - mean) / stddev on the GPU; default [-1, 1].

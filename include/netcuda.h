@@ -161,6 +161,14 @@ int netcuda_create_from_file(const char *path, int precision, int device, int ma
  * Replaces the H2D / task / D2H triple at src/netFPGA.cpp:266-277. */
 int netcuda_forward(netcuda_t *h, const float *in, size_t batch, float *out);
 
+/* Page-lock a caller-owned host range (cudaHostRegister, portable across devices) so that netcuda_forward / netcuda_submit DMA
+ * straight from / into it instead of staging through the library's own pinned slots -- the reference keeps its host vectors for
+ * the life of the net (src/netFPGA.cpp:78-107), and a caller that feeds the same buffer again and again pays the page-locking
+ * once.  The range must stay allocated until netcuda_host_unregister(p) (same start address).  Registering a range that already
+ * is page-locked is not an error. */
+int netcuda_host_register(const void *p, size_t bytes);
+int netcuda_host_unregister(const void *p);
+
 /* Asynchronous form of netcuda_forward: the reference chains write -> task -> read with events
  * but then blocks in the read (src/netFPGA.cpp:273-277), so its caller can never overlap two samples.
  * netcuda_submit enqueues the same H2D / kernels / D2H sequence and returns a ticket at once; the H2D copy of call

@@ -188,6 +188,36 @@ def test_cpp_class_shards_over_gpus(netcuda, oracle, torch_cuda, monkeypatch):
     vit1.close()
 
 
+def test_page_locked_caller_buffers(netcuda, torch_cuda, monkeypatch):
+    """netcuda_host_register: a caller-owned buffer that is page-locked is DMA'd from in place (no staging copy) -- same bits as the
+    staged path, registering twice is not an error, the buffer can be unregistered and used again.  And the class does it for its
+    callers under net_cuda_options::pin_inputs / NETCUDA_PIN_INPUTS: the vector a launch_forward call reads is page-locked the first
+    time it is seen, later calls reuse it, a vector that dies is forgotten first (release_inputs)."""
+    g = np.load(os.path.join(GOLDEN, "vit_small.npz"))
+    cfg = dict(zip(("image_size", "patch_size", "dim", "depth", "heads", "mlp_dim", "n_classes"), (int(v) for v in g["cfg"])))
+    n_in = 3 * cfg["image_size"] ** 2
+    batch = max(37, (3 << 20) // (4 * n_in) + 1)  # > 1 MiB of input: below that the class does not bother
+    imgs = np.random.default_rng(4).uniform(-1, 1, (batch, n_in)).astype(np.float32)
+    net = netcuda.Net.vit(cfg, max_batch=8)
+    net.upload_vit(g["flat"])
+    want = net.forward(imgs)
+    netcuda.host_register(imgs)
+    netcuda.host_register(imgs)
+    np.testing.assert_array_equal(net.forward(imgs), want)
+    np.testing.assert_array_equal(net.forward(imgs[5:]), want[5:])  # a pointer inside a registered range
+    netcuda.host_unregister(imgs)
+    np.testing.assert_array_equal(net.forward(imgs), want)
+    net.close()
+    monkeypatch.setenv("NETCUDA_PIN_INPUTS", "1")
+    host = netcuda.HostNet.vit(cfg, g["flat"], max_batch=8)
+    s, got = host.time_launch_forward(imgs, reps=3)  # one vector, five calls: page-locked by the first
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(host.launch_forward(imgs), want)  # a vector per call: registered, used, forgotten
+    np.testing.assert_array_equal(host.launch_forward(imgs[::-1].copy()), want[::-1])
+    np.testing.assert_array_equal(host.launch_forward(imgs[:3]), want[:3])
+    host.close()
+
+
 def test_cpp_class_move_and_copy(netcuda, oracle, torch_cuda):
     npl, n_ins, w, b = c1_net(oracle)
     net = netcuda.HostNet.mlp(npl, n_ins, w, b, precision=-1)  # the reference-shaped 3-argument constructor

@@ -1221,6 +1221,35 @@ static int forward_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size
     return wait_impl(h, tk);
 }
 
+extern "C" int netcuda_host_register(const void *p, size_t bytes)
+{
+    if (!p || bytes == 0) return fail(NETCUDA_ERR_INVALID, "netcuda_host_register: empty range");
+    const cudaError_t e = cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered)
+    {
+        (void)cudaGetLastError();
+        return NETCUDA_OK;
+    }
+    if (e != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        return fail(NETCUDA_ERR_CUDA, "cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+    return NETCUDA_OK;
+}
+
+extern "C" int netcuda_host_unregister(const void *p)
+{
+    if (!p) return NETCUDA_OK;
+    const cudaError_t e = cudaHostUnregister(const_cast<void *>(p));
+    if (e != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        return fail(NETCUDA_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e));
+    }
+    return NETCUDA_OK;
+}
+
 extern "C" int netcuda_submit(netcuda_net *h, const float *in, size_t batch, float *out, uint64_t *ticket)
 {
     if (int rc = check_handle(h)) return rc;

@@ -137,6 +137,8 @@ long long nch_launch_forward(void *net, const float *in, size_t n_in_floats, flo
         net::net_abstract *n = static_cast<net::net_abstract *>(net);
         std::vector<float> x(in, in + n_in_floats);
         std::vector<float> y = n->launch_forward(x);
+        // (x dies with this call: a net that page-locks its inputs -- net_cuda_options::pin_inputs -- must forget it first)
+        if (cuda::net_cuda *c = dynamic_cast<cuda::net_cuda *>(n)) c->release_inputs();
         if (y.size() > out_capacity)
         {
             set_err("output buffer too small");
@@ -165,6 +167,7 @@ double nch_time_launch_forward(void *net, const float *in, size_t n_in_floats, i
         const auto t0 = std::chrono::steady_clock::now();
         for (int i = 0; i < reps; i++) y = n->launch_forward(x);
         const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / (reps > 0 ? reps : 1);
+        if (cuda::net_cuda *c = dynamic_cast<cuda::net_cuda *>(n)) c->release_inputs(); // (x is about to be freed)
         if (last_out && y.size() <= out_capacity) memcpy(last_out, y.data(), y.size() * sizeof(float));
         return s;
     }

@@ -39,9 +39,37 @@ namespace cuda
         vit_data vit;
         signed long gradient_performance = 0;
         netcuda_ring_t *ring = nullptr; // image side channel (filter_image / get_filtered_image), created by the first frame
+        // net_cuda_options::pin_inputs: host buffers page-locked on first sight (start address, bytes), oldest first
+        std::vector<std::pair<const void *, std::size_t>> pinned_inputs;
+
+        void release_inputs()
+        {
+            for (auto &r : pinned_inputs) netcuda_host_unregister(r.first);
+            pinned_inputs.clear();
+        }
+        // Page-lock [p, p + bytes) unless it already is; a buffer that moved or changed size is registered anew.
+        void pin_input(const void *p, std::size_t bytes)
+        {
+            for (std::size_t i = 0; i < pinned_inputs.size(); i++)
+                if (pinned_inputs[i].first == p)
+                {
+                    if (pinned_inputs[i].second == bytes) return;
+                    netcuda_host_unregister(p); // same start, other size: the vector was resized in place
+                    pinned_inputs.erase(pinned_inputs.begin() + (std::ptrdiff_t)i);
+                    break;
+                }
+            if (pinned_inputs.size() >= 8)
+            {
+                netcuda_host_unregister(pinned_inputs.front().first);
+                pinned_inputs.erase(pinned_inputs.begin());
+            }
+            // (a range that cannot be page-locked -- overlapping another registration, locked-memory limit -- is simply staged)
+            if (netcuda_host_register(p, bytes) == NETCUDA_OK) pinned_inputs.emplace_back(p, bytes);
+        }
 
         ~impl()
         {
+            release_inputs();
             if (ring) netcuda_ring_destroy(ring);
             for (netcuda_t *r : replicas)
                 if (r) netcuda_destroy(r);
@@ -88,6 +116,11 @@ namespace cuda
                 if (const char *e = std::getenv("NETCUDA_DEVICES")) o.n_devices = std::atoi(e);
             }
             if (o.n_devices < 1) o.n_devices = 1;
+            if (o.pin_inputs < 0)
+            {
+                o.pin_inputs = 0;
+                if (const char *e = std::getenv("NETCUDA_PIN_INPUTS")) o.pin_inputs = std::atoi(e) != 0;
+            }
             int visible = 0;
             if (o.n_devices > 1 && netcuda_device_count(&visible) == NETCUDA_OK && o.device + o.n_devices > visible)
                 throw std::invalid_argument("net_cuda: n_devices asks for more GPUs than are visible");
@@ -479,8 +512,15 @@ namespace cuda
             throw std::invalid_argument("net_cuda::launch_forward: inputs.size() must be a non-zero multiple of n_ins");
         const std::size_t batch = inputs.size() / ni;
         std::vector<DATA_TYPE> out(batch * no);
+        // (worth it from a few MB on: a small input is staged faster than the driver walks its pages)
+        if (p_->opt.pin_inputs && inputs.size() * sizeof(DATA_TYPE) >= (std::size_t)1 << 20) p_->pin_input(inputs.data(), inputs.size() * sizeof(DATA_TYPE));
         forward(inputs.data(), batch, out.data());
         return out;
+    }
+
+    void net_cuda::release_inputs()
+    {
+        if (p_) p_->release_inputs();
     }
 
     // Training is not implemented by the reference either: init_gradient's body is commented out

@@ -93,6 +93,19 @@ def device_count() -> int:
     return n.value if rc == OK else 0
 
 
+def host_register(a: np.ndarray) -> None:
+    """Page-lock a numpy array's buffer (netcuda_host_register): forward / submit then DMA straight from / into it."""
+    rc = lib.netcuda_host_register(C.c_void_p(a.ctypes.data), C.c_size_t(a.nbytes))
+    if rc != OK:
+        raise NetcudaError(rc, lib.netcuda_last_error().decode())
+
+
+def host_unregister(a: np.ndarray) -> None:
+    rc = lib.netcuda_host_unregister(C.c_void_p(a.ctypes.data))
+    if rc != OK:
+        raise NetcudaError(rc, lib.netcuda_last_error().decode())
+
+
 def _ptr(t) -> C.c_void_p:
     """Device/host pointer of a torch tensor or numpy array."""
     if t is None:
