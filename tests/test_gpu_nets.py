@@ -320,17 +320,37 @@ def test_int8_weight_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl
     np.testing.assert_array_equal(got, oracle.mlp_forward_i8(xq, wq, bq, npl, n_ins))
 
 
-@pytest.mark.parametrize("npl,n_ins", [([272, 48, 10], 1040), ([64, 32], 4080), ([4096, 304, 4096], 4096), ([16], 48), ([4096] * 3, 4096)])
-def test_int8_tcgen05_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl, n_ins, monkeypatch):
+def _umma_kernels(prof):
+    """Which of the two tcgen05 streaming kernels a profile shows: 'pair' (split-K CTA pairs), 'single', or None."""
+    pair, single = "mlp_umma_stream_pair" in prof, "mlp_umma_stream" in prof
+    assert not (pair and single)
+    return "pair" if pair else "single" if single else None
+
+
+@pytest.mark.parametrize("npl,n_ins", [([272, 48, 10], 1040), ([64, 32], 4080), ([4096, 304, 4096], 4096), ([16], 48), ([4096] * 3, 4096),
+                                       ([272, 208, 10], 1040), ([9600, 160], 256)])
+@pytest.mark.parametrize("pair", [1, 2, 3, 0])
+def test_int8_tcgen05_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl, n_ins, pair, monkeypatch):
     """17..128 samples of an INT8 net with 16-byte-aligned fan-ins run as ONE persistent tcgen05 kernel (mlp_umma_stream.cu: weights
     and activations through TMA rings, two MMA-issuing threads that split the K range of a tile -- kind::i8 MMAs of 128 samples x 32
     neurons into an accumulator each in tensor memory -- grid barrier between layers; NETCUDA_MLP_UMMA_MIN moves the hand-over from
     the mma.sync kernel).  Same integers as the oracle for every batch up to 128 (rows past the batch are TMA zero fill), ragged
     neuron tiles (10, 48, 304 neurons), fan-ins that are not a multiple of the 128-byte k-block or leave the second issuer without
     a weight group, all activation modes, repeated launches (the barrier counters reset themselves), and -- with the hand-over point
-    moved to zero -- for the small batches the mma.sync kernel normally serves."""
+    moved to zero -- for the small batches the mma.sync kernel normally serves.
+
+    Nets whose every fan-in exceeds one k-block (128 bytes) run as split-K CTA PAIRS by default (mlp_i8_umma_pair_kernel: a cluster of
+    two CTAs per 64-neuron tile, each with one half of K, partial sums exchanged through distributed shared memory): K halves of
+    unequal length (1040 = 9 k-blocks, 272 = 3), tiles whose second half has no neuron (272, 208, 10 outputs), more tiles than
+    pairs (9600 neurons = 150 tiles on 74 pairs).  pair = 1 (the default): four MMA-issuing threads per CTA, partial sums as st.async stores
+    counted on the peer's barrier; pair = 3: two issuers; pair = 2: two issuers, plain DSMEM stores + release arrive; pair = 0
+    (NETCUDA_MLP_UMMA_PAIR=0) keeps every net on the single-CTA kernel."""
     rng = np.random.default_rng(78)
     wq, bq = _int8_net(rng, npl, n_ins)
+    pair_capable = all(f > 128 for f in [n_ins] + npl[:-1])
+    if pair != 1 and not pair_capable: pytest.skip("this net runs on the single-CTA kernel anyway (covered by pair = 1)")
+    monkeypatch.setenv("NETCUDA_MLP_UMMA_PAIR", str(pair))
+    want_kernel = "pair" if pair and pair_capable else "single"
     for act in (0, 1, 2):
         net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8, activation=act, max_batch=160)
         net.upload_mlp_i8(wq, bq)
@@ -341,7 +361,7 @@ def test_int8_tcgen05_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, np
             _assert_same_ints(net.forward_i8(xq), want, f"act {act} batch {batch} second call")
             net.profile_enable(True)
             net.forward_i8(xq)
-            assert ("mlp_umma_stream" in net.profile_read()) == (17 <= batch <= 128)
+            assert _umma_kernels(net.profile_read()) == (want_kernel if 17 <= batch <= 128 else None)
             net.profile_enable(False)
         net.close()
     monkeypatch.setenv("NETCUDA_MLP_STREAM_SPLIT", "0")  # the tcgen05 kernel for every batch up to 128
@@ -352,7 +372,7 @@ def test_int8_tcgen05_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, np
         xq = rng.integers(-128, 128, (batch, n_ins), dtype=np.int8)
         net.profile_enable(True)
         got = net.forward_i8(xq)
-        assert "mlp_umma_stream" in net.profile_read()
+        assert _umma_kernels(net.profile_read()) == want_kernel
         net.profile_enable(False)
         np.testing.assert_array_equal(got, oracle.mlp_forward_i8(xq, wq, bq, npl, n_ins))
     # float API on the same kernel: quantise -> stream -> dequantise

@@ -120,6 +120,9 @@ cudaError_t launch_mlp_i8_stream(const MlpStreamParams &p, int grid, cudaStream_
 constexpr int MLP_UMMA_STREAM_MAX_BATCH = 128;
 bool mlp_umma_stream_supported(const MlpStreamParams &p);
 cudaError_t launch_mlp_i8_umma_stream(const MlpStreamParams &p, int num_sms, cudaStream_t stream);
+// ... and with a cluster of two CTAs per 64-neuron tile, each streaming one half of K (partial sums meet in distributed shared memory)
+bool mlp_umma_pair_supported(const MlpStreamParams &p, int num_sms);
+cudaError_t launch_mlp_i8_umma_pair(const MlpStreamParams &p, int num_sms, int mode, cudaStream_t stream); // mode: A/B codes, see the launcher
 
 // y = LayerNorm(x) * gamma + beta; x fp32 rows (pitch ldx), y bf16 rows (pitch ldy) -- or fp32 rows for the tf32 nets.
 cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, const float *beta, void *y, long long ldy,

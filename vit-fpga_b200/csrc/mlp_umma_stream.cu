@@ -385,6 +385,389 @@ mlp_i8_umma_stream_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmm
     }
 }
 
+// =====================================================================================================
+// Split-K CTA pairs (mlp_i8_umma_pair_kernel): the same net-in-one-launch kernel, two CTAs per 64-neuron tile
+// =====================================================================================================
+// What bounds the kernel above (measured): at 128 samples every CTA pulls the whole activation matrix of a layer
+// (128 x fan_in bytes, 512 KB on config C5) out of L2 -- 128 CTAs x 512 KB = 64 MB per layer against 16 MB of weights, and the L2 -> SM
+// fabric moves ~6300 B/clk chip-wide (TMA multicast over a cluster of 2..4 saves nothing there: L2 already merges those requests) -- and
+// at 17..64 samples the two MMA-issuing threads (~160 cycles per tcgen05.mma at N = 32, whatever the batch).  Both halve when a
+// CLUSTER OF TWO CTAs shares a tile of 64 neurons and splits K:
+//   * CTA r of the pair streams the weight rows [64 t, 64 t + 64) over ITS half of the k-blocks only (same bytes per CTA as before) and
+//     loads the activations of that K half only (half the bytes); its MMAs are 128 x 64 x 32 (half as many per CTA and layer);
+//   * the partial sums meet in distributed shared memory: every epilogue thread (thread = sample) sends the 32 columns its peer
+//     finalises -- 128 bytes, st.shared::cluster into a double-buffered 16 KB window of the peer, then a release.cluster arrive on the
+//     peer's barrier -- and adds the 32 columns it receives to its own; CTA r then requantises and stores neurons [64 t + 32 r, + 32).
+//     Integer sums: order-independent, still bit-exact.
+//   * everything else is the kernel above: per-issuer rings, the weight producer running ahead across the layers, the cumulative
+//     tile counter as grid barrier (every CTA publishes the tiles of its pair: the target is 2 x tiles).
+// Needs every layer to have at least two k-blocks (fan_in > 128); otherwise the launcher takes the single-CTA kernel.
+constexpr int MP_TILE_N = 64;                    // neurons per pair tile
+constexpr int MP_FIN_N = 32;                     // ... of which each CTA finalises 32
+constexpr int MP_W_TILE_BYTES = MP_TILE_N * 128; // one k-block of a tile's weight rows
+constexpr int MP_X_BYTES = 128 * MP_FIN_N * 4;   // exchange window, 16 KB: [8 column quads][128 samples][4 x int32]
+// NI MMA-issuing threads per CTA (2 or 4), each with weight slots, activation slots and an accumulator of its own.  The rings have the
+// same size either way: 64 KB of weights (NI x 2 slots of 4 / NI k-blocks), 8 activation slots of 16 KB (8 / NI per issuer).  With
+// half the activation bytes per CTA two slots per issuer are enough to cover an L2 round trip, which they were not in the
+// single-CTA kernel (see above): config C5, us per forward at 17 / 64 / 128 samples: NI = 2 57.5 / 58.7 / 61.6.
+template <int NI>
+struct MpLayout
+{
+    static_assert(NI == 2 || NI == 4, "two or four issuers");
+    static constexpr int W_GROUP = 4 / NI;                 // k-blocks per weight slot
+    static constexpr int W_SLOTS_PER = 2;
+    static constexpr int W_SLOTS = NI * W_SLOTS_PER;
+    static constexpr int W_SLOT_BYTES = W_GROUP * MP_W_TILE_BYTES;
+    static constexpr int A_SLOTS_PER = 8 / NI;
+    static constexpr int A_SLOTS = NI * A_SLOTS_PER;
+    static constexpr int OFF_A = W_SLOTS * W_SLOT_BYTES;                // 64 KB
+    static constexpr int OFF_X = OFF_A + A_SLOTS * MU_A_SLOT_BYTES;     // + 128 KB: the two exchange windows
+    static constexpr int OFF_BARS = OFF_X + 2 * MP_X_BYTES;
+    static constexpr int NUM_BARS = 2 * W_SLOTS + 2 * A_SLOTS + 4 + 2;
+    static constexpr int OFF_TMEM_PTR = OFF_BARS + NUM_BARS * 8;
+    static constexpr int SMEM = OFF_TMEM_PTR + 16;
+    static_assert(SMEM <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
+    static constexpr uint32_t TMEM_COLS = 2 * NI * MP_TILE_N;           // two accumulator stages x one 64-column accumulator per issuer
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM allocations are powers of two");
+    static constexpr int THREADS = (MU_EPI_WARP0 + 4 + (NI - 2)) * 32;  // issuers 2 and 3 are warps 8 and 9 (warps 4..7: the TMEM lane quarters)
+};
+
+enum : int
+{
+    KERR_MP_EXCHANGE = 36,
+};
+
+template <bool XASYNC, int NI> // XASYNC: how the partial sums travel -- st.async (bytes counted on the peer's barrier) or plain stores + release arrive
+__global__ void __launch_bounds__(MpLayout<NI>::THREADS, 1)
+mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaParams p)
+{
+    using L = MpLayout<NI>;
+    extern __shared__ __align__(1024) uint8_t mp_smem[];
+    const uint32_t base = smem_u32(mp_smem);
+    if ((base & 1023u) != 0)
+    {
+        if (threadIdx.x == 0 && p.error_flag) atomicExch(p.error_flag, KERR_SMEM_ALIGN);
+        return; // uniform over the grid
+    }
+    const uint32_t bars = base + L::OFF_BARS;
+    auto wfull = [&](int s) { return bars + 8u * s; };
+    auto wempty = [&](int s) { return bars + 8u * (L::W_SLOTS + s); };
+    auto afull = [&](int s) { return bars + 8u * (2 * L::W_SLOTS + s); };
+    auto aempty = [&](int s) { return bars + 8u * (2 * L::W_SLOTS + L::A_SLOTS + s); };
+    auto tfull = [&](int a) { return bars + 8u * (2 * L::W_SLOTS + 2 * L::A_SLOTS + a); };
+    auto tempty = [&](int a) { return bars + 8u * (2 * L::W_SLOTS + 2 * L::A_SLOTS + 2 + a); };
+    auto xfull = [&](int x) { return bars + 8u * (2 * L::W_SLOTS + 2 * L::A_SLOTS + 4 + x); };
+    volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(mp_smem + L::OFF_TMEM_PTR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();                     // which half of K, which half of the tile's neurons
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    // this CTA's k-blocks of a layer: the first ceil(nkb / 2) for rank 0, the rest for rank 1 (never empty: nkb >= 2)
+    auto k_lo = [&](int nkb) { return rank ? (nkb + 1) >> 1 : 0; };
+    auto k_hi = [&](int nkb) { return rank ? nkb : (nkb + 1) >> 1; };
+
+    if (threadIdx.x == 0)
+    {
+        for (int s = 0; s < L::W_SLOTS; s++) mbar_init(wfull(s), 1), mbar_init(wempty(s), 1);
+        for (int s = 0; s < L::A_SLOTS; s++) mbar_init(afull(s), 1), mbar_init(aempty(s), 1);
+        for (int a = 0; a < 2; a++) mbar_init(tfull(a), NI), mbar_init(tempty(a), 4);
+        // XASYNC: one local arrive.expect_tx per tile, the peer's bytes complete the phase; otherwise one remote arrive per peer thread
+        for (int x = 0; x < 2; x++) mbar_init(xfull(x), XASYNC ? 1 : 128);
+        fence_barrier_init();
+    }
+    if (warp == 3)
+    {
+        tmem_alloc(base + L::OFF_TMEM_PTR, L::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    cluster_sync_all(); // the peer's exchange barriers are initialised before anything arrives on them
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0)
+    {
+        // ===================== weight producer: never waits for activations =====================
+        if (lane == 0)
+        {
+            for (int l = 0; l < p.n_layers; l++) tma_prefetch_desc(&maps.w[l]);
+            uint32_t cnt[NI] = {};
+            for (int l = 0; l < p.n_layers; l++)
+            {
+                const int tiles = (p.fan_out[l] + MP_TILE_N - 1) / MP_TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
+                const int lo = k_lo(nkb), hi = k_hi(nkb);
+                for (int tile = pair; tile < tiles; tile += npairs)
+                    for (int kb = lo, g = 0; kb < hi; kb += L::W_GROUP, g++)
+                    {
+                        const int is = g % NI;
+                        uint32_t c = 0;
+#pragma unroll
+                        for (int i = 0; i < NI; i++)
+                            if (i == is) c = cnt[i]++;
+                        const int s = is * L::W_SLOTS_PER + (int)(c % L::W_SLOTS_PER), nb = min(L::W_GROUP, hi - kb);
+                        mbar_wait(wempty(s), ((c / L::W_SLOTS_PER) & 1u) ^ 1u, p.error_flag, KERR_MU_W_PRODUCER);
+                        mbar_arrive_expect_tx(wfull(s), (uint32_t)(nb * MP_W_TILE_BYTES));
+                        for (int i = 0; i < nb; i++)
+                            tma_load_2d(base + s * L::W_SLOT_BYTES + i * MP_W_TILE_BYTES, &maps.w[l], wfull(s), (kb + i) * 128, tile * MP_TILE_N);
+                    }
+            }
+        }
+    }
+    else if (warp == 1)
+    {
+        // ===================== activation producer: this CTA's K half of layer l, after the grid barrier behind layer l - 1 =====================
+        if (lane == 0)
+        {
+            for (int l = 0; l < p.n_layers; l++) tma_prefetch_desc(&maps.a[l]);
+            uint32_t cnt[NI] = {};
+            unsigned target = 0; // both CTAs of a pair publish the pair's tiles: 2 x the output tiles of all the layers before this one
+            for (int l = 0; l < p.n_layers; l++)
+            {
+                const int tiles = (p.fan_out[l] + MP_TILE_N - 1) / MP_TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
+                const int lo = k_lo(nkb), hi = k_hi(nkb);
+                if (l > 0) target += 2u * (unsigned)((p.fan_out[l - 1] + MP_TILE_N - 1) / MP_TILE_N);
+                if (l > 0 && pair < tiles)
+                {
+                    const long long t0 = clock64();
+                    while (mu_ld_acquire_gpu(p.barrier) < target)
+                        if (clock64() - t0 > 4000000000LL)
+                        {
+                            if (p.error_flag) atomicExch(p.error_flag, KERR_MU_GRID_BARRIER);
+                            __threadfence_system();
+                            __trap();
+                        }
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                }
+                for (int tile = pair; tile < tiles; tile += npairs)
+                    for (int kb = lo; kb < hi; kb++)
+                    {
+                        const int is = ((kb - lo) / L::W_GROUP) % NI; // the issuer of the weight group this k-block belongs to
+                        uint32_t c = 0;
+#pragma unroll
+                        for (int i = 0; i < NI; i++)
+                            if (i == is) c = cnt[i]++;
+                        const int s = is * L::A_SLOTS_PER + (int)(c % L::A_SLOTS_PER);
+                        mbar_wait(aempty(s), ((c / L::A_SLOTS_PER) & 1u) ^ 1u, p.error_flag, KERR_MU_A_PRODUCER);
+                        mbar_arrive_expect_tx(afull(s), (uint32_t)(((p.batch + 7) & ~7) * 128));
+                        tma_load_2d(base + L::OFF_A + s * MU_A_SLOT_BYTES, &maps.a[l], afull(s), kb * 128, 0);
+                    }
+            }
+        }
+    }
+    else if (warp == 2 || warp == 3 || warp >= MU_EPI_WARP0 + 4)
+    {
+        // ===================== MMA issuers: 128 samples x 64 neurons x 32 bytes of K per instruction =====================
+        const int issuer = warp < 4 ? warp - 2 : warp - (MU_EPI_WARP0 + 2);
+        if (lane == 0)
+        {
+            constexpr uint32_t IDESC = KindTraits<KIND_I8>::idesc(128, MP_TILE_N);
+            uint32_t wcnt = 0, acnt = 0, tseq = 0;
+            for (int l = 0; l < p.n_layers; l++)
+            {
+                const int tiles = (p.fan_out[l] + MP_TILE_N - 1) / MP_TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
+                const int mykb = k_hi(nkb) - k_lo(nkb);
+                const int ngw = (mykb + L::W_GROUP - 1) / L::W_GROUP;
+                for (int tile = pair; tile < tiles; tile += npairs, tseq++)
+                {
+                    const uint32_t acc = tseq & 1u;
+                    mbar_wait(tempty(acc), ((tseq >> 1) & 1u) ^ 1u, p.error_flag, KERR_MU_MMA);
+                    tcgen05_fence_after();
+                    if (issuer >= ngw) // a short K half leaves this issuer without a group: its accumulator is not read either
+                    {
+                        mbar_arrive(tfull(acc));
+                        continue;
+                    }
+                    const uint32_t d_tmem = tmem_base + (acc * NI + issuer) * MP_TILE_N;
+                    for (int g = issuer; g < ngw; g += NI, wcnt++)
+                    {
+                        const int ws = issuer * L::W_SLOTS_PER + (int)(wcnt % L::W_SLOTS_PER), kr1 = min(mykb, (g + 1) * L::W_GROUP);
+                        mbar_wait(wfull(ws), (wcnt / L::W_SLOTS_PER) & 1u, p.error_flag, KERR_MU_MMA);
+                        for (int kr = g * L::W_GROUP; kr < kr1; kr++, acnt++) // kr: k-block relative to this CTA's first one
+                        {
+                            const int as = issuer * L::A_SLOTS_PER + (int)(acnt % L::A_SLOTS_PER), wi = kr % L::W_GROUP;
+                            mbar_wait(afull(as), (acnt / L::A_SLOTS_PER) & 1u, p.error_flag, KERR_MU_MMA);
+                            tcgen05_fence_after();
+                            const uint64_t a_desc = umma_smem_desc_sw128(base + L::OFF_A + as * MU_A_SLOT_BYTES);
+                            const uint64_t b_desc = umma_smem_desc_sw128(base + ws * L::W_SLOT_BYTES + wi * MP_W_TILE_BYTES);
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                umma_ss<KIND_I8>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, IDESC, (g != issuer || wi != 0 || k != 0) ? 1u : 0u);
+                            tcgen05_commit(aempty(as));
+                        }
+                        tcgen05_commit(wempty(ws));
+                    }
+                    tcgen05_commit(tfull(acc));
+                }
+            }
+        }
+    }
+    else if (warp >= MU_EPI_WARP0 && warp < MU_EPI_WARP0 + 4)
+    {
+        // ===================== epilogue: thread = sample; partial sums of the two K halves meet through DSMEM =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t peer = (uint32_t)(rank ^ 1);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t tseq = 0;
+        for (int l = 0; l < p.n_layers; l++)
+        {
+            const int tiles = (p.fan_out[l] + MP_TILE_N - 1) / MP_TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
+            const int ngw = (k_hi(nkb) - k_lo(nkb) + L::W_GROUP - 1) / L::W_GROUP;
+            const int nacc = min(NI, ngw); // accumulators this CTA's issuers wrote
+            const bool last = l + 1 == p.n_layers;
+            const bool relu = (p.relu_mask >> l) & 1u;
+            for (int tile = pair; tile < tiles; tile += npairs, tseq++)
+            {
+                const uint32_t acc = tseq & 1u, xs = tseq & 1u;
+                const int col0 = tile * MP_TILE_N + rank * MP_FIN_N; // the 32 neurons this CTA finalises
+                int bias[32];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; j4++)
+                {
+                    int4 b4 = make_int4(0, 0, 0, 0);
+                    if (col0 + 4 * j4 + 3 < p.fan_out[l])
+                        b4 = __ldg(reinterpret_cast<const int4 *>(p.bias[l] + col0) + j4);
+                    else
+                    {
+                        int t[4] = {0, 0, 0, 0};
+                        for (int e = 0; e < 4; e++)
+                            if (col0 + 4 * j4 + e < p.fan_out[l]) t[e] = __ldg(p.bias[l] + col0 + 4 * j4 + e);
+                        b4 = make_int4(t[0], t[1], t[2], t[3]);
+                    }
+                    bias[4 * j4] = b4.x, bias[4 * j4 + 1] = b4.y, bias[4 * j4 + 2] = b4.z, bias[4 * j4 + 3] = b4.w;
+                }
+                // (window xs was last waited for two tiles ago by this very thread: its barrier can be armed for this tile)
+                if (XASYNC && threadIdx.x == MU_EPI_WARP0 * 32) mbar_arrive_expect_tx(xfull(xs), MP_X_BYTES);
+                mbar_wait(tfull(acc), (tseq >> 1) & 1u, p.error_flag, KERR_MU_EPILOGUE);
+                tcgen05_fence_after();
+                const uint32_t t_acc = lane_base + acc * NI * MP_TILE_N;
+                // the peer's 32 columns first: they are on their way while this thread reads its own
+                {
+                    uint32_t u[32];
+                    tmem_ld_32x32(t_acc + peer * MP_FIN_N, u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 1; i < NI; i++)
+                        if (i < nacc) // (uniform)
+                        {
+                            uint32_t t[32];
+                            tmem_ld_32x32(t_acc + i * MP_TILE_N + peer * MP_FIN_N, t);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; j++) u[j] += t[j];
+                        }
+                    // Window xs of the peer is free: the peer's threads read their window of tile t - 2 (and used what they read)
+                    // before they sent / arrived for tile t - 1, and this thread has waited for all of that (its own wait of tile t - 1).
+                    const uint32_t dst = mapa_shared(base + L::OFF_X + xs * MP_X_BYTES, peer) + (uint32_t)row * 16u;
+                    const uint32_t peer_bar = mapa_shared(xfull(xs), peer);
+                    if constexpr (XASYNC)
+                    {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; j4++)
+                            st_async_cluster_v4(dst + j4 * 2048u, u[4 * j4], u[4 * j4 + 1], u[4 * j4 + 2], u[4 * j4 + 3], peer_bar);
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; j4++) st_cluster_v4(dst + j4 * 2048u, u[4 * j4], u[4 * j4 + 1], u[4 * j4 + 2], u[4 * j4 + 3]);
+                        mbar_arrive_remote_release(peer_bar);
+                    }
+                }
+                uint32_t v[32];
+                tmem_ld_32x32(t_acc + rank * MP_FIN_N, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 1; i < NI; i++)
+                    if (i < nacc)
+                    {
+                        uint32_t t[32];
+                        tmem_ld_32x32(t_acc + i * MP_TILE_N + rank * MP_FIN_N, t);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] += t[j];
+                    }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty(acc)); // the accumulators may be overwritten by the tile after next
+                mbar_wait_acquire_cluster(xfull(xs), (tseq >> 1) & 1u, p.error_flag, KERR_MP_EXCHANGE);
+                {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(mp_smem + L::OFF_X + xs * MP_X_BYTES) + row;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; j4++)
+                    {
+                        const uint4 r4 = src[j4 * 128];
+                        v[4 * j4] += r4.x, v[4 * j4 + 1] += r4.y, v[4 * j4 + 2] += r4.z, v[4 * j4 + 3] += r4.w;
+                    }
+                }
+                if (row < p.batch && col0 < p.fan_out[l])
+                {
+                    if (last)
+                    {
+                        int32_t *dst = p.out + (long long)row * p.fan_out[l] + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                        {
+                            int a = (int)v[j] + bias[j];
+                            if (relu) a = max(a, 0);
+                            if (col0 + j < p.fan_out[l]) dst[j] = a;
+                        }
+                    }
+                    else
+                    {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; j4++)
+                        {
+                            uint32_t word = 0;
+#pragma unroll
+                            for (int e = 0; e < 4; e++)
+                            {
+                                int a = (int)v[4 * j4 + e] + bias[4 * j4 + e];
+                                if (relu) a = max(a, 0);
+                                a = min(127, max(-128, a >> 7));
+                                word |= ((uint32_t)a & 0xFFu) << (8 * e);
+                            }
+                            w[j4] = word;
+                        }
+                        int8_t *dst = p.act_out[l] + (long long)row * p.ld_out[l] + col0;
+                        if (col0 + MP_FIN_N <= p.fan_out[l])
+                        {
+                            reinterpret_cast<uint4 *>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                            reinterpret_cast<uint4 *>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        }
+                        else
+                        {
+                            for (int j = 0; j < 32; j++)
+                                if (col0 + j < p.fan_out[l]) dst[j] = (int8_t)(w[j >> 2] >> (8 * (j & 3)));
+                        }
+                        // these generic-proxy stores are read by other CTAs' TMA (async proxy) after the grid barrier
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
+                    }
+                }
+            }
+            // publish the pair's tiles of this layer (see the kernel above for why the counter counts tiles, not CTAs)
+            const int my_tiles = pair < tiles ? (tiles - pair + npairs - 1) / npairs : 0;
+            if (!last && my_tiles > 0)
+            {
+                named_bar_sync(1, 128);
+                if (threadIdx.x == MU_EPI_WARP0 * 32) mu_red_release_gpu_add(p.barrier, (unsigned)my_tiles);
+            }
+        }
+        if (threadIdx.x == MU_EPI_WARP0 * 32 && atomicAdd(p.barrier + 1, 1u) == gridDim.x - 1u)
+        {
+            p.barrier[0] = 0u;
+            p.barrier[1] = 0u;
+        }
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all(); // neither CTA exits while its peer may still write into its exchange window or arrive on its barriers
+    if (warp == 3)
+    {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, L::TMEM_COLS);
+    }
+}
+
 bool mlp_umma_stream_supported(const MlpStreamParams &p)
 {
     if (p.n_layers < 1 || p.n_layers > MLP_STREAM_MAX_LAYERS || p.batch < 1 || p.batch > MLP_UMMA_STREAM_MAX_BATCH) return false;
@@ -438,6 +821,65 @@ cudaError_t launch_mlp_i8_umma_stream(const MlpStreamParams &sp, int num_sms, cu
     attr[0].val.cooperative = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, mlp_i8_umma_stream_kernel, maps, p);
+}
+
+bool mlp_umma_pair_supported(const MlpStreamParams &p, int num_sms)
+{
+    if (num_sms < 2 || !mlp_umma_stream_supported(p)) return false;
+    for (int l = 0; l < p.n_layers; l++)
+        if (p.layers[l].fan_in <= 128) return false; // each CTA of a pair needs a k-block of its own
+    return true;
+}
+
+// mode: 1 = four issuers, st.async exchange (the product kernel); 2 = two issuers, plain DSMEM stores + release arrive; 3 = two issuers, st.async
+cudaError_t launch_mlp_i8_umma_pair(const MlpStreamParams &sp, int num_sms, int mode, cudaStream_t stream)
+{
+    if (!mlp_umma_pair_supported(sp, num_sms)) return cudaErrorInvalidValue;
+    static bool opted[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !opted[dev])
+    {
+        cudaError_t e = cudaFuncSetAttribute(mlp_i8_umma_pair_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MpLayout<4>::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_i8_umma_pair_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MpLayout<2>::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_i8_umma_pair_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MpLayout<2>::SMEM);
+        if (e != cudaSuccess) return e;
+        opted[dev] = true;
+    }
+    MlpUmmaMaps maps;
+    MlpUmmaParams p;
+    p.n_layers = sp.n_layers, p.batch = sp.batch, p.relu_mask = sp.relu_mask;
+    p.out = sp.out, p.barrier = sp.barrier, p.error_flag = sp.error_flag;
+    p.debug = nullptr;
+    int max_tiles = 1;
+    for (int l = 0; l < sp.n_layers; l++)
+    {
+        const MlpStreamLayer &ly = sp.layers[l];
+        const bool last = l + 1 == sp.n_layers;
+        p.fan_in[l] = ly.fan_in, p.fan_out[l] = ly.fan_out, p.bias[l] = ly.bias;
+        p.act_out[l] = last ? nullptr : sp.act[(l + 1) & 1];
+        p.ld_out[l] = ly.fan_out;
+        const int8_t *a_src = l == 0 ? sp.in : sp.act[l & 1];
+        cudaError_t e = encode_tma_2d(&maps.a[l], 1, a_src, ly.fan_in, sp.batch, ly.fan_in, 128, (sp.batch + 7) & ~7, true);
+        if (e != cudaSuccess) return e;
+        e = encode_tma_2d(&maps.w[l], 1, ly.w, ly.fan_in, ly.fan_out, ly.fan_in, 128, MP_TILE_N, true);
+        if (e != cudaSuccess) return e;
+        max_tiles = std::max(max_tiles, (ly.fan_out + MP_TILE_N - 1) / MP_TILE_N);
+    }
+    const int npairs = std::min((num_sms > 0 ? num_sms : 148) / 2, max_tiles);
+    cudaLaunchConfig_t cfg = {};
+    const int ni = mode == 1 ? 4 : 2;
+    cfg.gridDim = dim3((unsigned)(2 * npairs)), cfg.blockDim = dim3(ni == 4 ? MpLayout<4>::THREADS : MpLayout<2>::THREADS);
+    cfg.dynamicSmemBytes = ni == 4 ? MpLayout<4>::SMEM : MpLayout<2>::SMEM, cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative; // all CTAs co-resident: the grid barrier cannot deadlock
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2, attr[1].val.clusterDim.y = 1, attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 2;
+    if (mode == 1) return cudaLaunchKernelEx(&cfg, mlp_i8_umma_pair_kernel<true, 4>, maps, p);
+    if (mode == 2) return cudaLaunchKernelEx(&cfg, mlp_i8_umma_pair_kernel<false, 2>, maps, p);
+    return cudaLaunchKernelEx(&cfg, mlp_i8_umma_pair_kernel<true, 2>, maps, p);
 }
 
 } // namespace nc

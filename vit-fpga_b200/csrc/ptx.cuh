@@ -275,6 +275,59 @@ __device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar)
                  : "memory");
 }
 
+// ---- distributed shared memory (any cluster; used by the split-K CTA pairs of mlp_umma_stream.cu) ---------------
+
+// shared::cluster address of `smem_addr` (a shared::cta address of the executing CTA) in the CTA of rank `rank`.
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// The same store as an asynchronous operation that carries its own completion: 16 bytes land in the remote window and are
+// counted (complete_tx) on the remote mbarrier -- the way TMA delivers data -- so the sender needs no fence and no arrive.
+__device__ __forceinline__ void st_async_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t cluster_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_bar)
+                 : "memory");
+}
+// Arrive on a barrier of another CTA of the cluster; the release (cluster scope) orders this thread's earlier
+// st.shared::cluster stores before the arrival.
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_bar)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// Bounded wait with cluster-scope acquire: pairs with mbar_arrive_remote_release (data handed over through DSMEM).
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity, int *err, int code)
+{
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    for (;;)
+    {
+        uint32_t done;
+        asm volatile("{\n\t"
+                     ".reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t"
+                     "}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (done) return;
+        if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 8000000000LL)
+        {
+            if (err) atomicExch(err, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+
 // ---- tcgen05: descriptors and MMA ------------------------------------------------------------
 
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are 128 bytes and which

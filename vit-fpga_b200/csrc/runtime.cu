@@ -124,6 +124,9 @@ struct netcuda_net
     int stream_max_batch = 16;                   // up to here the mma.sync streaming kernel (it can serve 32: NETCUDA_MLP_STREAM_SPLIT), above it (<= 128) the tcgen05 one
                                                  // (NETCUDA_MLP_STREAM_SPLIT: A/B of the hand-over point)
     int umma_min_batch = 17;                     // ... from here on (NETCUDA_MLP_UMMA_MIN moves the hand-over, for A/B runs against the split-K path)
+    int umma_pair = 1;                           // the tcgen05 streaming kernel as split-K CTA pairs where the net allows it: 1 = four issuers, partial sums by
+                                                 // st.async; 2 = two issuers, plain DSMEM stores + release arrive; 3 = two issuers, st.async; 0 = single CTAs
+                                                 // (NETCUDA_MLP_UMMA_PAIR, for A/B runs)
     void *patches = nullptr, *ybuf = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *cls_ln = nullptr;
     float *x = nullptr;
 
@@ -446,6 +449,7 @@ static int create_impl(const netcuda_desc *desc, netcuda_net *h)
             if (const char *e = getenv("NETCUDA_MLP_STREAM")) h->use_stream = atoi(e) != 0;
             if (const char *e = getenv("NETCUDA_MLP_STREAM_SPLIT")) h->stream_max_batch = std::min(std::max(atoi(e), 0), MLP_STREAM_MAX_BATCH);
             if (const char *e = getenv("NETCUDA_MLP_UMMA_MIN")) h->umma_min_batch = std::max(atoi(e), 1);
+            if (const char *e = getenv("NETCUDA_MLP_UMMA_PAIR")) h->umma_pair = std::min(std::max(atoi(e), 0), 3);
         }
     }
     else
@@ -760,8 +764,25 @@ static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, in
             }
             else
             {
-                KernelScope scope(h, s, "mlp_umma_stream", ops, bytes);
-                CK(launch_mlp_i8_umma_stream(sp, h->num_sms, s));
+                bool launched = false;
+                if (h->umma_pair && mlp_umma_pair_supported(sp, h->num_sms))
+                {
+                    KernelScope scope(h, s, "mlp_umma_stream_pair", ops, bytes);
+                    const cudaError_t e = launch_mlp_i8_umma_pair(sp, h->num_sms, h->umma_pair, s);
+                    launched = e == cudaSuccess;
+                    if (!launched)
+                    {
+                        // a driver that refuses cooperative cluster launches: the single-CTA kernel serves this handle from now on
+                        (void)cudaGetLastError();
+                        h->umma_pair = 0;
+                        fprintf(stderr, "[netcuda] split-K pair streaming kernel not launchable (%s); using the single-CTA kernel\n", cudaGetErrorString(e));
+                    }
+                }
+                if (!launched)
+                {
+                    KernelScope scope(h, s, "mlp_umma_stream", ops, bytes);
+                    CK(launch_mlp_i8_umma_stream(sp, h->num_sms, s));
+                }
             }
             streamed = true;
         }
