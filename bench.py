@@ -454,7 +454,7 @@ def bench_c5(nc, torch, dev, local, peaks, threads, with_cpu):
     int8_peak = measure_int8_peak(torch, dev)
     stream = torch.cuda.current_stream()
     sweep = {}
-    for batch in (1, 4, 8, 16, 32, 64, 128, 1024, 16384):  # (kernels: mma.sync stream <= 16, tcgen05 stream 17..128, tcgen05 GEMMs above)
+    for batch in (1, 4, 8, 16, 32, 64, 128, 1024, 16384):  # (kernels: mma.sync stream <= 16, tcgen05 split-K cluster stream 17..128, tcgen05 GEMMs above)
         xq = torch.randint(-128, 128, (batch, n_ins), device=dev, dtype=torch.int32).to(torch.int8)
         yq = torch.empty((batch, npl[-1]), dtype=torch.int32, device=dev)
         steps = 200 if batch <= 1024 else 20

@@ -321,15 +321,15 @@ def test_int8_weight_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl
 
 
 def _umma_kernels(prof):
-    """Which of the two tcgen05 streaming kernels a profile shows: 'pair' (split-K CTA pairs), 'single', or None."""
-    pair, single = "mlp_umma_stream_pair" in prof, "mlp_umma_stream" in prof
-    assert not (pair and single)
-    return "pair" if pair else "single" if single else None
+    """Which of the two tcgen05 streaming kernels a profile shows: 'cluster' (split-K CTA clusters), 'single', or None."""
+    cluster, single = "mlp_umma_stream_cluster" in prof, "mlp_umma_stream" in prof
+    assert not (cluster and single)
+    return "cluster" if cluster else "single" if single else None
 
 
 @pytest.mark.parametrize("npl,n_ins", [([272, 48, 10], 1040), ([64, 32], 4080), ([4096, 304, 4096], 4096), ([16], 48), ([4096] * 3, 4096),
-                                       ([272, 208, 10], 1040), ([9600, 160], 256)])
-@pytest.mark.parametrize("pair", [1, 2, 3, 0])
+                                       ([272, 208, 10], 1040), ([9600, 160], 256), ([400, 1008, 10], 1040), ([9600, 160], 512)])
+@pytest.mark.parametrize("pair", [1, 4, 3, 0])
 def test_int8_tcgen05_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, npl, n_ins, pair, monkeypatch):
     """17..128 samples of an INT8 net with 16-byte-aligned fan-ins run as ONE persistent tcgen05 kernel (mlp_umma_stream.cu: weights
     and activations through TMA rings, two MMA-issuing threads that split the K range of a tile -- kind::i8 MMAs of 128 samples x 32
@@ -339,18 +339,19 @@ def test_int8_tcgen05_streaming_kernel_bit_exact(netcuda, oracle, torch_cuda, np
     a weight group, all activation modes, repeated launches (the barrier counters reset themselves), and -- with the hand-over point
     moved to zero -- for the small batches the mma.sync kernel normally serves.
 
-    Nets whose every fan-in exceeds one k-block (128 bytes) run as split-K CTA PAIRS by default (mlp_i8_umma_pair_kernel: a cluster of
-    two CTAs per 64-neuron tile, each with one half of K, partial sums exchanged through distributed shared memory): K halves of
-    unequal length (1040 = 9 k-blocks, 272 = 3), tiles whose second half has no neuron (272, 208, 10 outputs), more tiles than
-    pairs (9600 neurons = 150 tiles on 74 pairs).  pair = 1 (the default): four MMA-issuing threads per CTA, partial sums as st.async stores
-    counted on the peer's barrier; pair = 3: two issuers; pair = 2: two issuers, plain DSMEM stores + release arrive; pair = 0
-    (NETCUDA_MLP_UMMA_PAIR=0) keeps every net on the single-CTA kernel."""
+    Nets whose every fan-in exceeds one k-block (128 bytes) run as split-K CTA CLUSTERS by default (mlp_i8_umma_cluster_kernel: two
+    CTAs per 64-neuron tile -- four per 128-neuron tile when every fan-in has at least four k-blocks -- each with its part of K, partial
+    sums exchanged through distributed shared memory as st.async stores counted on the receiver's barrier): K ranges of unequal
+    length (1040 = 9 k-blocks, 272 = 3, 400 = 4 with a ragged last one), tiles in which some CTAs have no neuron to finalise (272,
+    208, 400, 1008, 10 outputs), more tiles than clusters (9600 neurons).  pair = 1 (the default): clusters of four up to 88 samples where the net
+    allows them, pairs with four MMA-issuing threads otherwise; pair = 4: clusters of four at every batch; pair = 3: pairs, two issuers;
+    pair = 0 (NETCUDA_MLP_UMMA_PAIR=0): the single-CTA kernel."""
     rng = np.random.default_rng(78)
     wq, bq = _int8_net(rng, npl, n_ins)
     pair_capable = all(f > 128 for f in [n_ins] + npl[:-1])
     if pair != 1 and not pair_capable: pytest.skip("this net runs on the single-CTA kernel anyway (covered by pair = 1)")
     monkeypatch.setenv("NETCUDA_MLP_UMMA_PAIR", str(pair))
-    want_kernel = "pair" if pair and pair_capable else "single"
+    want_kernel = "cluster" if pair and pair_capable else "single"
     for act in (0, 1, 2):
         net = netcuda.Net.mlp(npl, n_ins, precision=netcuda.PREC_INT8, activation=act, max_batch=160)
         net.upload_mlp_i8(wq, bq)

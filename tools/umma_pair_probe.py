@@ -1,5 +1,5 @@
-"""A/B of the two tcgen05 INT8 streaming kernels on config C5 (8 x 4096, device-resident): split-K CTA pairs
-(mlp_i8_umma_pair_kernel; NETCUDA_MLP_UMMA_PAIR = 1: four issuers + st.async, the default; 3: two issuers; 2: two issuers, release arrive)
+"""A/B of the two tcgen05 INT8 streaming kernels on config C5 (8 x 4096, device-resident): split-K CTA clusters
+(mlp_i8_umma_cluster_kernel; NETCUDA_MLP_UMMA_PAIR = 1: the default -- four CTAs per tile up to 88 samples, pairs above; 4: four CTAs per tile; 2: pairs, four issuers; 3: pairs, two issuers)
 against single CTAs (NETCUDA_MLP_UMMA_PAIR=0).  Every timing is preceded by a bit-for-bit
 comparison of the two kernels' outputs with each other (the parity tests compare both with the oracle).
 
@@ -54,7 +54,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--worker":
 import numpy as np
 
 files = {}
-for pair in (1, 3, 2, 0, 1):
+for pair in (1, 4, 2, 3, 0, 1):
     env = dict(os.environ, NETCUDA_MLP_UMMA_PAIR=str(pair))
     f = f"/tmp/umma_pair_{pair}.npz"
     print(f"NETCUDA_MLP_UMMA_PAIR={pair}", flush=True)
@@ -64,4 +64,4 @@ for pair in (1, 3, 2, 0, 1):
         sys.exit(1)
     files[pair] = f
 a, b = np.load(files[1]), np.load(files[0])
-print("every pair mode == single, bit for bit:", all(np.array_equal(np.load(files[m])[k], b[k]) for m in (1, 2, 3) for k in b.files))
+print("every cluster mode == single, bit for bit:", all(np.array_equal(np.load(files[m])[k], b[k]) for m in (1, 2, 3, 4) for k in b.files))

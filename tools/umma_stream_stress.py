@@ -13,7 +13,9 @@ o = Oracle()
 import torch  # the test suite's processes hold torch's CUDA context and allocator next to the library's
 _keep = torch.empty(1 << 20, device="cuda")
 seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
-nets = (([272, 48, 10], 1040), ([64, 32], 4080), ([4096, 304, 4096], 4096))
+# (the first two run on the single-CTA kernel, the others as split-K clusters: pairs for the 304- and 208-byte fan-ins, four CTAs per tile
+#  for the last one -- NETCUDA_MLP_UMMA_PAIR selects, see runtime.cu)
+nets = (([272, 48, 10], 1040), ([64, 32], 4080), ([4096, 304, 4096], 4096), ([272, 208, 10], 1040), ([400, 1008, 10], 1040), ([2048, 2048, 640], 1024))
 t_end = time.time() + seconds
 rounds = calls = nfail = 0
 while time.time() < t_end:
@@ -26,7 +28,7 @@ while time.time() < t_end:
     net = nc.Net.mlp(npl, n_ins, precision=nc.PREC_INT8, activation=act, max_batch=160)
     net.upload_mlp_i8(wq, bq)
     prev = None
-    for batch in (33, 47, 64, 100, 127, 128, 129):
+    for batch in (17, 33, 47, 64, 88, 89, 100, 127, 128, 129):
         xq = rng.integers(-128, 128, (batch, n_ins), dtype=np.int8)
         want = o.mlp_forward_i8(xq, wq, bq, npl, n_ins, act)
         for call in range(3):

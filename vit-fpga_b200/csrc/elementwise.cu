@@ -3,6 +3,8 @@
 // (replacing the host scalar copy loops of src/netFPGA.cpp:266-267,285-289 for batched input).
 // All of them are one pass over their data with 128-bit accesses where alignment allows.
 #include "kernels.h"
+
+#include <algorithm>
 #include "ptx.cuh"
 
 namespace nc
@@ -280,6 +282,38 @@ cudaError_t launch_quantize_rows_q17(const float *in, int8_t *out, long long row
 {
     return launch_convert<int8_t, 2>(in, out, rows, n, ld, stream);
 }
+// INT8 weights W[fan_out][ld] -> the streaming layout of mlp_umma_stream.cu's cluster kernel: blocks of 128 neurons x 128 bytes of K
+// (16 KB, zero-padded at the ragged edges), block (T, kb) at ((T * nkb) + kb) * 16 KB, and inside a block the byte order a TMA load with
+// CU_TENSOR_MAP_SWIZZLE_128B would have produced in shared memory (16-byte chunk c of row r at r * 128 + ((c ^ (r & 7)) * 16)) -- so that
+// a plain 1-D bulk copy of a block (or of its 64-row half) lands ready for tcgen05.mma, and the bytes a CTA streams are contiguous in HBM.
+__global__ void retile_i8_weights_kernel(const int8_t *__restrict__ w, long long ld, int fan_out, int fan_in, int nkb, int8_t *__restrict__ out,
+                                         long long n_chunks)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_chunks; i += (long long)gridDim.x * blockDim.x)
+    {
+        const int cs = (int)(i & 7), r = (int)((i >> 3) & 127); // chunk position and row inside the block
+        const long long blk = i >> 10;
+        const int kb = (int)(blk % nkb);
+        const long long T = blk / nkb;
+        const int c = cs ^ (r & 7); // the logical chunk stored at this position
+        const long long row = T * 128 + r;
+        const int col = kb * 128 + c * 16;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (row < fan_out && col < fan_in) v = *reinterpret_cast<const int4 *>(w + row * ld + col); // (fan_in and ld are multiples of 16)
+        reinterpret_cast<int4 *>(out)[i] = v;
+    }
+}
+
+cudaError_t launch_retile_i8_weights(const int8_t *w, long long ld, int fan_out, int fan_in, int8_t *out, cudaStream_t stream)
+{
+    if ((fan_in & 15) || (ld & 15)) return cudaErrorInvalidValue;
+    const int nkb = (fan_in + 127) / 128;
+    const long long n_chunks = (long long)((fan_out + 127) / 128) * nkb * 1024;
+    const int grid = (int)std::min<long long>((n_chunks + 255) / 256, 148 * 16);
+    retile_i8_weights_kernel<<<grid, 256, 0, stream>>>(w, ld, fan_out, fan_in, nkb, out, n_chunks);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pad_rows_i8(const int8_t *in, int8_t *out, long long rows, int n, int ld, cudaStream_t stream)
 {
     return launch_convert<int8_t, 3>(in, out, rows, n, ld, stream);

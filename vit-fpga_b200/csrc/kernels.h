@@ -94,6 +94,7 @@ constexpr int MLP_STREAM_LL_MAX_BATCH = 4; // ... of which up to here without a 
 struct MlpStreamLayer
 {
     const int8_t *w;     // [fan_out][fan_in], fan_in a multiple of 16, at most 4096
+    const int8_t *w_tiled = nullptr; // the same weights in 16 KB streaming blocks (launch_retile_i8_weights), or null
     const int32_t *bias; // [fan_out]
     int fan_in, fan_out;
 };
@@ -120,9 +121,9 @@ cudaError_t launch_mlp_i8_stream(const MlpStreamParams &p, int grid, cudaStream_
 constexpr int MLP_UMMA_STREAM_MAX_BATCH = 128;
 bool mlp_umma_stream_supported(const MlpStreamParams &p);
 cudaError_t launch_mlp_i8_umma_stream(const MlpStreamParams &p, int num_sms, cudaStream_t stream);
-// ... and with a cluster of two CTAs per 64-neuron tile, each streaming one half of K (partial sums meet in distributed shared memory)
-bool mlp_umma_pair_supported(const MlpStreamParams &p, int num_sms);
-cudaError_t launch_mlp_i8_umma_pair(const MlpStreamParams &p, int num_sms, int mode, cudaStream_t stream); // mode: A/B codes, see the launcher
+// ... and with a cluster of two or four CTAs per neuron tile, each streaming its part of K (partial sums meet in distributed shared memory)
+int mlp_umma_cluster_size(const MlpStreamParams &p, int num_sms); // 4, 2, or 0 = only the single-CTA kernel serves this net
+cudaError_t launch_mlp_i8_umma_cluster(const MlpStreamParams &p, int num_sms, int mode, cudaStream_t stream); // mode: A/B codes, see the launcher
 
 // y = LayerNorm(x) * gamma + beta; x fp32 rows (pitch ldx), y bf16 rows (pitch ldy) -- or fp32 rows for the tf32 nets.
 cudaError_t launch_layernorm(const float *x, long long ldx, const float *gamma, const float *beta, void *y, long long ldy,
@@ -149,6 +150,10 @@ cudaError_t launch_convert_rows_bf16(const float *in, void *out, long long rows,
 cudaError_t launch_convert_rows_f32(const float *in, float *out, long long rows, int n, int ld, cudaStream_t stream);
 cudaError_t launch_quantize_rows_q17(const float *in, int8_t *out, long long rows, int n, int ld, cudaStream_t stream);
 cudaError_t launch_pad_rows_i8(const int8_t *in, int8_t *out, long long rows, int n, int ld, cudaStream_t stream);
+// W[fan_out][ld] int8 -> 16 KB blocks of 128 neurons x 128 bytes of K in shared-memory (128B-swizzled) byte order: the layout the
+// cluster streaming kernel copies with 1-D bulk copies.  `out` holds mlp_tiled_weight_bytes(fan_in, fan_out) bytes.
+cudaError_t launch_retile_i8_weights(const int8_t *w, long long ld, int fan_out, int fan_in, int8_t *out, cudaStream_t stream);
+inline size_t mlp_tiled_weight_bytes(int fan_in, int fan_out) { return (size_t)((fan_out + 127) / 128) * ((fan_in + 127) / 128) * 16384; }
 // Second half of a split-K int8 layer: v = ws + bias (optionally max(v, 0)); out = int8 requantisation (clamp(v >> 7)) or the
 // int32 itself; ws is set back to zero for the next layer.
 cudaError_t launch_splitk_finalize(int32_t *ws, const int32_t *bias, void *out, long long ldo, bool out_is_s8, bool relu, int m, int n,

@@ -62,22 +62,6 @@ enum : int
     KERR_MS_GRID_BARRIER = 23,
 };
 
-// Weights are read exactly once per launch: L2 evict-first, so that 128 MiB of them do not flush the biases (and whatever else the
-// caller keeps in L2) on their way through.  It matters more than it looks: with ~29 MB of weight reads queued at the memory
-// controllers, a bias load that misses L2 comes back 2-4 us later -- tools/stream_timeline.py showed the finalize of most layers
-// waiting that long for 28 bias values.
-__device__ __forceinline__ uint64_t l2_policy_evict_first()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
-                 : "memory");
-}
 __device__ __forceinline__ int4 ld_cg_int4(const void *p)
 {
     int4 v;

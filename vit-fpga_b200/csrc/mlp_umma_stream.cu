@@ -23,6 +23,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace nc
 {
@@ -84,6 +85,8 @@ struct MlpUmmaParams
     unsigned *barrier;                      // two zero-initialised counters in device memory (left at zero by every launch)
     int *error_flag;
     long long *debug;                       // optional [n_layers][8] clock64 stamps of CTA 0 (NETCUDA_DEBUG_TIMELINE builds)
+    const int8_t *w_tiled[MLP_STREAM_MAX_LAYERS]; // cluster kernel: the weights in 16 KB streaming blocks (launch_retile_i8_weights)
+    int a_slot_shift = 14;                  // cluster kernel: log2 of the activation slot size (4, 8 or 16 KB: the batch's rows x 128 bytes, rounded up)
 };
 
 __device__ __forceinline__ void mu_red_release_gpu_add(unsigned *p, unsigned v)
@@ -386,50 +389,59 @@ mlp_i8_umma_stream_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmm
 }
 
 // =====================================================================================================
-// Split-K CTA pairs (mlp_i8_umma_pair_kernel): the same net-in-one-launch kernel, two CTAs per 64-neuron tile
+// Split-K CTA clusters (mlp_i8_umma_cluster_kernel): the same net-in-one-launch kernel, CL = 2 or 4 CTAs per neuron tile
 // =====================================================================================================
-// What bounds the kernel above (measured): at 128 samples every CTA pulls the whole activation matrix of a layer
+// What bounds the kernel above (measured): (1) at 128 samples every CTA pulls the whole activation matrix of a layer
 // (128 x fan_in bytes, 512 KB on config C5) out of L2 -- 128 CTAs x 512 KB = 64 MB per layer against 16 MB of weights, and the L2 -> SM
-// fabric moves ~6300 B/clk chip-wide (TMA multicast over a cluster of 2..4 saves nothing there: L2 already merges those requests) -- and
-// at 17..64 samples the two MMA-issuing threads (~160 cycles per tcgen05.mma at N = 32, whatever the batch).  Both halve when a
-// CLUSTER OF TWO CTAs shares a tile of 64 neurons and splits K:
-//   * CTA r of the pair streams the weight rows [64 t, 64 t + 64) over ITS half of the k-blocks only (same bytes per CTA as before) and
-//     loads the activations of that K half only (half the bytes); its MMAs are 128 x 64 x 32 (half as many per CTA and layer);
-//   * the partial sums meet in distributed shared memory: every epilogue thread (thread = sample) sends the 32 columns its peer
-//     finalises -- 128 bytes, st.shared::cluster into a double-buffered 16 KB window of the peer, then a release.cluster arrive on the
-//     peer's barrier -- and adds the 32 columns it receives to its own; CTA r then requantises and stores neurons [64 t + 32 r, + 32).
-//     Integer sums: order-independent, still bit-exact.
+// fabric moves ~6300 B/clk chip-wide (TMA multicast over a cluster of 2..4 saves nothing there: L2 already merges those requests);
+// (2) at every batch the tensor pipe itself: a kind::i8 MMA of 128 samples x N neurons x 32 bytes costs ~70 cycles for N = 32 and for
+// N = 64 alike (tools/umma_pair_timeline.py: 64 MMAs per layer and CTA in 4.5 k cycles, the same with two or four issuing threads,
+// 17 or 128 samples, with or without the weights prefetched into L2) -- the 4 KB of the 128-row A operand are read from shared memory
+// for every MMA, whatever N is.  Both shrink when a CLUSTER of CL CTAs shares a tile of 32 CL neurons and splits K:
+//   * CTA r of the cluster streams the weight rows [32 CL t, 32 CL (t + 1)) over ITS 1 / CL of the k-blocks (same bytes per CTA as
+//     before) and loads the activations of that K range only (1 / CL of the bytes); its MMAs are 128 x 32 CL x 32 (1 / CL as many);
+//   * the partial sums meet in distributed shared memory: every epilogue thread (thread = sample) sends each peer the 32 columns that
+//     peer finalises -- 128 bytes as eight st.async, which land in a window of the peer's shared memory and are counted on the peer's
+//     mbarrier like TMA bytes: no fence, no arrive (plain st.shared::cluster + a release.cluster arrive cost a MEMBAR.GPU per thread
+//     and tile: 62 -> 57 us) -- and adds the CL - 1 rows of 32 columns it receives to its own; CTA r then requantises and stores
+//     neurons [32 CL t + 32 r, + 32).  Integer sums: order-independent, still bit-exact.  Only the batch's rows travel.
 //   * everything else is the kernel above: per-issuer rings, the weight producer running ahead across the layers, the cumulative
-//     tile counter as grid barrier (every CTA publishes the tiles of its pair: the target is 2 x tiles).
-// Needs every layer to have at least two k-blocks (fan_in > 128); otherwise the launcher takes the single-CTA kernel.
-constexpr int MP_TILE_N = 64;                    // neurons per pair tile
-constexpr int MP_FIN_N = 32;                     // ... of which each CTA finalises 32
-constexpr int MP_W_TILE_BYTES = MP_TILE_N * 128; // one k-block of a tile's weight rows
-constexpr int MP_X_BYTES = 128 * MP_FIN_N * 4;   // exchange window, 16 KB: [8 column quads][128 samples][4 x int32]
-// NI MMA-issuing threads per CTA (2 or 4), each with weight slots, activation slots and an accumulator of its own.  The rings have the
-// same size either way: 64 KB of weights (NI x 2 slots of 4 / NI k-blocks), 8 activation slots of 16 KB (8 / NI per issuer).  With
-// half the activation bytes per CTA two slots per issuer are enough to cover an L2 round trip, which they were not in the
-// single-CTA kernel (see above): config C5, us per forward at 17 / 64 / 128 samples: NI = 2 57.5 / 58.7 / 61.6.
-template <int NI>
+//     tile counter as grid barrier (every CTA publishes the tiles of its cluster: the target is CL x tiles).
+// Needs every layer to have at least CL k-blocks; the launcher picks CL = 4 (fan-ins >= 512), CL = 2 (> 128) or the single-CTA kernel.
+// Config C5, us per forward at 17 / 64 / 128 samples: single CTAs 66.6 / 67.9 / 70.2; pairs 55.5 / 56.2 / 59.6 (two issuers: 57.5 / 58.9 / 61.8).
+constexpr int MP_FIN_N = 32;                     // neurons a CTA finalises per tile
+constexpr int MP_X_BYTES = 128 * MP_FIN_N * 4;   // one exchange window, 16 KB: [8 column quads][128 samples][4 x int32]
+// NI MMA-issuing threads per CTA (2 or 4), each with weight slots, activation slots and an accumulator of its own.
+template <int CL, int NI>
 struct MpLayout
 {
+    static_assert(CL == 2 || CL == 4, "two or four CTAs per tile");
     static_assert(NI == 2 || NI == 4, "two or four issuers");
-    static constexpr int W_GROUP = 4 / NI;                 // k-blocks per weight slot
+    static constexpr int TILE_N = MP_FIN_N * CL;           // neurons per cluster tile = N of the MMAs
+    static constexpr int W_TILE_BYTES = TILE_N * 128;      // one k-block of a tile's weight rows
     static constexpr int W_SLOTS_PER = 2;
     static constexpr int W_SLOTS = NI * W_SLOTS_PER;
-    static constexpr int W_SLOT_BYTES = W_GROUP * MP_W_TILE_BYTES;
-    static constexpr int A_SLOTS_PER = 8 / NI;
+    static constexpr int W_GROUP = 65536 / (W_SLOTS * W_TILE_BYTES); // k-blocks per weight slot: the ring holds 64 KB
+    static_assert(W_GROUP >= 1, "weight ring too small for this tile");
+    static constexpr int W_SLOT_BYTES = W_GROUP * W_TILE_BYTES;
+    // Activations: an equal region per issuer, cut into slots of the batch's size (128 samples: 16 KB, <= 64: 8 KB, <= 32: 4 KB; at
+    // most 8 slots per issuer) -- a small batch gets a deeper ring, i.e. fewer L2 round trips in the critical path of a layer.
+    // 128 KB for pairs; 64 KB for clusters of four (a quarter of K per CTA, and three exchange windows per stage instead of one).
+    static constexpr int A_REGION_LOG = (CL == 2 ? 17 : 16) - (NI == 4 ? 2 : 1);
+    static constexpr int A_SLOTS_PER = 8;                  // barriers per issuer (slots in use: region >> slot shift, capped)
     static constexpr int A_SLOTS = NI * A_SLOTS_PER;
     static constexpr int OFF_A = W_SLOTS * W_SLOT_BYTES;                // 64 KB
-    static constexpr int OFF_X = OFF_A + A_SLOTS * MU_A_SLOT_BYTES;     // + 128 KB: the two exchange windows
-    static constexpr int OFF_BARS = OFF_X + 2 * MP_X_BYTES;
+    static constexpr int OFF_X = OFF_A + (NI << A_REGION_LOG);          // the exchange windows: [2 stages][CL - 1 senders]
+    static constexpr int OFF_BARS = OFF_X + 2 * (CL - 1) * MP_X_BYTES;
     static constexpr int NUM_BARS = 2 * W_SLOTS + 2 * A_SLOTS + 4 + 2;
     static constexpr int OFF_TMEM_PTR = OFF_BARS + NUM_BARS * 8;
     static constexpr int SMEM = OFF_TMEM_PTR + 16;
     static_assert(SMEM <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
-    static constexpr uint32_t TMEM_COLS = 2 * NI * MP_TILE_N;           // two accumulator stages x one 64-column accumulator per issuer
-    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM allocations are powers of two");
-    static constexpr int THREADS = (MU_EPI_WARP0 + 4 + (NI - 2)) * 32;  // issuers 2 and 3 are warps 8 and 9 (warps 4..7: the TMEM lane quarters)
+    static constexpr uint32_t TMEM_COLS = 2 * NI * TILE_N;              // two accumulator stages x one accumulator per issuer
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM allocations are powers of two, at most 512 columns");
+    // warps: 0 weight producer, 1 activation producer, 2 / 3 issuers 0 / 1, 4..7 epilogue (the TMEM lane quarters), 8 / 9 issuers 2 / 3 (NI = 4)
+    static constexpr int W_ISSUER2 = MU_EPI_WARP0 + 4;
+    static constexpr int THREADS = (W_ISSUER2 + NI - 2) * 32;
 };
 
 enum : int
@@ -437,11 +449,11 @@ enum : int
     KERR_MP_EXCHANGE = 36,
 };
 
-template <bool XASYNC, int NI> // XASYNC: how the partial sums travel -- st.async (bytes counted on the peer's barrier) or plain stores + release arrive
-__global__ void __launch_bounds__(MpLayout<NI>::THREADS, 1)
-mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaParams p)
+template <int CL, int NI>
+__global__ void __launch_bounds__((MpLayout<CL, NI>::THREADS), 1)
+mlp_i8_umma_cluster_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaParams p)
 {
-    using L = MpLayout<NI>;
+    using L = MpLayout<CL, NI>;
     extern __shared__ __align__(1024) uint8_t mp_smem[];
     const uint32_t base = smem_u32(mp_smem);
     if ((base & 1023u) != 0)
@@ -459,19 +471,26 @@ mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaP
     auto xfull = [&](int x) { return bars + 8u * (2 * L::W_SLOTS + 2 * L::A_SLOTS + 4 + x); };
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(mp_smem + L::OFF_TMEM_PTR);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rank = (int)cluster_ctarank();                     // which half of K, which half of the tile's neurons
-    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    // this CTA's k-blocks of a layer: the first ceil(nkb / 2) for rank 0, the rest for rank 1 (never empty: nkb >= 2)
-    auto k_lo = [&](int nkb) { return rank ? (nkb + 1) >> 1 : 0; };
-    auto k_hi = [&](int nkb) { return rank ? nkb : (nkb + 1) >> 1; };
+    const int rank = (int)cluster_ctarank();                     // which part of K, which 32 of the tile's neurons
+    const int grp = blockIdx.x / CL, ngrps = gridDim.x / CL;     // cluster index: walks the tiles
+    // this CTA's k-blocks of a layer (never empty: nkb >= CL)
+    auto k_lo = [&](int nkb) { return rank * nkb / CL; };
+    auto k_hi = [&](int nkb) { return (rank + 1) * nkb / CL; };
+    const int a_slots_log = min(3, L::A_REGION_LOG - p.a_slot_shift);  // activation slots per issuer in use (2, 4 or 8)
+    const uint32_t a_mask = (1u << a_slots_log) - 1u;
+    auto a_slot_addr = [&](int issuer, uint32_t slot) { return base + L::OFF_A + ((uint32_t)issuer << L::A_REGION_LOG) + (slot << p.a_slot_shift); };
+#ifdef NETCUDA_DEBUG_TIMELINE
+    long long *const dbg = blockIdx.x == 0 ? p.debug : nullptr; // [n_layers][8] clock64 stamps of CTA 0 (tools/umma_pair_timeline.py)
+#else
+    constexpr long long *dbg = nullptr;
+#endif
 
     if (threadIdx.x == 0)
     {
         for (int s = 0; s < L::W_SLOTS; s++) mbar_init(wfull(s), 1), mbar_init(wempty(s), 1);
         for (int s = 0; s < L::A_SLOTS; s++) mbar_init(afull(s), 1), mbar_init(aempty(s), 1);
         for (int a = 0; a < 2; a++) mbar_init(tfull(a), NI), mbar_init(tempty(a), 4);
-        // XASYNC: one local arrive.expect_tx per tile, the peer's bytes complete the phase; otherwise one remote arrive per peer thread
-        for (int x = 0; x < 2; x++) mbar_init(xfull(x), XASYNC ? 1 : 128);
+        for (int x = 0; x < 2; x++) mbar_init(xfull(x), 1); // one local arrive.expect_tx per tile; the peers' bytes complete the phase
         fence_barrier_init();
     }
     if (warp == 3)
@@ -480,22 +499,30 @@ mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaP
         tmem_relinquish();
     }
     tcgen05_fence_before();
-    cluster_sync_all(); // the peer's exchange barriers are initialised before anything arrives on them
+    cluster_sync_all(); // the peers' exchange barriers are initialised before anything is counted on them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0)
     {
         // ===================== weight producer: never waits for activations =====================
+        // The weights come from the tiled copy (elementwise.cu: 16 KB blocks of 128 neurons x 128 bytes of K, already in the 128B-swizzled
+        // byte order): what a CTA streams is contiguous in HBM -- its K range of a 128-neuron tile is ONE run of bytes, of a 64-neuron tile
+        // 8 KB out of every 16 -- and arrives by 1-D bulk copies.  Out of the row-major matrix a k-block of a tile is 64..128 pieces of
+        // 128 bytes, 4 KB apart: the 2-D TMA loads of that took 2.6-3 k cycles each with every CTA at it (tools/umma_pair_timeline.py),
+        // and the issuers spent a layer waiting for their second pair of weight slots.
         if (lane == 0)
         {
-            for (int l = 0; l < p.n_layers; l++) tma_prefetch_desc(&maps.w[l]);
+            const uint64_t stream_once = l2_policy_evict_first();
             uint32_t cnt[NI] = {};
             for (int l = 0; l < p.n_layers; l++)
             {
-                const int tiles = (p.fan_out[l] + MP_TILE_N - 1) / MP_TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
+                const int tiles = (p.fan_out[l] + L::TILE_N - 1) / L::TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
                 const int lo = k_lo(nkb), hi = k_hi(nkb);
-                for (int tile = pair; tile < tiles; tile += npairs)
+                for (int tile = grp; tile < tiles; tile += ngrps)
+                {
+                    // first k-block of this tile's rows: a whole 16 KB block per k-block (CL = 4), or one 8 KB half of it (CL = 2)
+                    const int8_t *src0 = p.w_tiled[l] + (CL == 4 ? (size_t)tile * nkb * 16384 : ((size_t)(tile >> 1) * nkb * 16384 + (size_t)(tile & 1) * 8192));
                     for (int kb = lo, g = 0; kb < hi; kb += L::W_GROUP, g++)
                     {
                         const int is = g % NI;
@@ -505,27 +532,33 @@ mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaP
                             if (i == is) c = cnt[i]++;
                         const int s = is * L::W_SLOTS_PER + (int)(c % L::W_SLOTS_PER), nb = min(L::W_GROUP, hi - kb);
                         mbar_wait(wempty(s), ((c / L::W_SLOTS_PER) & 1u) ^ 1u, p.error_flag, KERR_MU_W_PRODUCER);
-                        mbar_arrive_expect_tx(wfull(s), (uint32_t)(nb * MP_W_TILE_BYTES));
-                        for (int i = 0; i < nb; i++)
-                            tma_load_2d(base + s * L::W_SLOT_BYTES + i * MP_W_TILE_BYTES, &maps.w[l], wfull(s), (kb + i) * 128, tile * MP_TILE_N);
+                        mbar_arrive_expect_tx(wfull(s), (uint32_t)(nb * L::W_TILE_BYTES));
+                        if constexpr (CL == 4)
+                            bulk_load_1d(base + s * L::W_SLOT_BYTES, src0 + (size_t)kb * 16384, (uint32_t)(nb * L::W_TILE_BYTES), wfull(s), stream_once);
+                        else
+                            for (int i = 0; i < nb; i++)
+                                bulk_load_1d(base + s * L::W_SLOT_BYTES + i * L::W_TILE_BYTES, src0 + (size_t)(kb + i) * 16384, L::W_TILE_BYTES, wfull(s), stream_once);
                     }
+                }
             }
         }
     }
     else if (warp == 1)
     {
-        // ===================== activation producer: this CTA's K half of layer l, after the grid barrier behind layer l - 1 =====================
+        // ===================== activation producer: this CTA's K range of layer l, after the grid barrier behind layer l - 1 =====================
+        // (one producing thread per issuer, and the weights beyond the ring prefetched into L2, were measured: no gain -- the MMA phase
+        // of a layer is paced by the tensor pipe, see the header)
         if (lane == 0)
         {
             for (int l = 0; l < p.n_layers; l++) tma_prefetch_desc(&maps.a[l]);
-            uint32_t cnt[NI] = {};
-            unsigned target = 0; // both CTAs of a pair publish the pair's tiles: 2 x the output tiles of all the layers before this one
+            uint32_t cnt[NI] = {}; // k-blocks handed to each issuer so far
+            unsigned target = 0; // every CTA of a cluster publishes the cluster's tiles: CL x the output tiles of all the layers before this one
             for (int l = 0; l < p.n_layers; l++)
             {
-                const int tiles = (p.fan_out[l] + MP_TILE_N - 1) / MP_TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
+                const int tiles = (p.fan_out[l] + L::TILE_N - 1) / L::TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
                 const int lo = k_lo(nkb), hi = k_hi(nkb);
-                if (l > 0) target += 2u * (unsigned)((p.fan_out[l - 1] + MP_TILE_N - 1) / MP_TILE_N);
-                if (l > 0 && pair < tiles)
+                if (l > 0) target += (unsigned)CL * (unsigned)((p.fan_out[l - 1] + L::TILE_N - 1) / L::TILE_N);
+                if (l > 0 && grp < tiles)
                 {
                     const long long t0 = clock64();
                     while (mu_ld_acquire_gpu(p.barrier) < target)
@@ -537,7 +570,8 @@ mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaP
                         }
                     asm volatile("fence.proxy.async.global;" ::: "memory");
                 }
-                for (int tile = pair; tile < tiles; tile += npairs)
+                if (dbg) dbg[l * 8 + 0] = clock64(); // barrier passed
+                for (int tile = grp; tile < tiles; tile += ngrps)
                     for (int kb = lo; kb < hi; kb++)
                     {
                         const int is = ((kb - lo) / L::W_GROUP) % NI; // the issuer of the weight group this k-block belongs to
@@ -545,49 +579,52 @@ mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaP
 #pragma unroll
                         for (int i = 0; i < NI; i++)
                             if (i == is) c = cnt[i]++;
-                        const int s = is * L::A_SLOTS_PER + (int)(c % L::A_SLOTS_PER);
-                        mbar_wait(aempty(s), ((c / L::A_SLOTS_PER) & 1u) ^ 1u, p.error_flag, KERR_MU_A_PRODUCER);
+                        const int s = is * L::A_SLOTS_PER + (int)(c & a_mask);
+                        mbar_wait(aempty(s), ((c >> a_slots_log) & 1u) ^ 1u, p.error_flag, KERR_MU_A_PRODUCER);
                         mbar_arrive_expect_tx(afull(s), (uint32_t)(((p.batch + 7) & ~7) * 128));
-                        tma_load_2d(base + L::OFF_A + s * MU_A_SLOT_BYTES, &maps.a[l], afull(s), kb * 128, 0);
+                        tma_load_2d(a_slot_addr(is, c & a_mask), &maps.a[l], afull(s), kb * 128, 0);
                     }
             }
         }
     }
-    else if (warp == 2 || warp == 3 || warp >= MU_EPI_WARP0 + 4)
+    else if (warp == 2 || warp == 3 || warp >= L::W_ISSUER2)
     {
-        // ===================== MMA issuers: 128 samples x 64 neurons x 32 bytes of K per instruction =====================
-        const int issuer = warp < 4 ? warp - 2 : warp - (MU_EPI_WARP0 + 2);
+        // ===================== MMA issuers: 128 samples x 32 CL neurons x 32 bytes of K per instruction =====================
+        const int issuer = warp < 4 ? warp - 2 : warp - L::W_ISSUER2 + 2;
         if (lane == 0)
         {
-            constexpr uint32_t IDESC = KindTraits<KIND_I8>::idesc(128, MP_TILE_N);
+            constexpr uint32_t IDESC = KindTraits<KIND_I8>::idesc(128, L::TILE_N);
             uint32_t wcnt = 0, acnt = 0, tseq = 0;
             for (int l = 0; l < p.n_layers; l++)
             {
-                const int tiles = (p.fan_out[l] + MP_TILE_N - 1) / MP_TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
+                const int tiles = (p.fan_out[l] + L::TILE_N - 1) / L::TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
                 const int mykb = k_hi(nkb) - k_lo(nkb);
                 const int ngw = (mykb + L::W_GROUP - 1) / L::W_GROUP;
-                for (int tile = pair; tile < tiles; tile += npairs, tseq++)
+                for (int tile = grp; tile < tiles; tile += ngrps, tseq++)
                 {
                     const uint32_t acc = tseq & 1u;
                     mbar_wait(tempty(acc), ((tseq >> 1) & 1u) ^ 1u, p.error_flag, KERR_MU_MMA);
                     tcgen05_fence_after();
-                    if (issuer >= ngw) // a short K half leaves this issuer without a group: its accumulator is not read either
+                    if (issuer >= ngw) // a short K range leaves this issuer without a group: its accumulator is not read either
                     {
                         mbar_arrive(tfull(acc));
                         continue;
                     }
-                    const uint32_t d_tmem = tmem_base + (acc * NI + issuer) * MP_TILE_N;
+                    const uint32_t d_tmem = tmem_base + (acc * NI + issuer) * L::TILE_N;
                     for (int g = issuer; g < ngw; g += NI, wcnt++)
                     {
                         const int ws = issuer * L::W_SLOTS_PER + (int)(wcnt % L::W_SLOTS_PER), kr1 = min(mykb, (g + 1) * L::W_GROUP);
                         mbar_wait(wfull(ws), (wcnt / L::W_SLOTS_PER) & 1u, p.error_flag, KERR_MU_MMA);
+                        if (dbg && l == 3 && g * L::W_GROUP < 16) dbg[128 + (issuer * 16 + g * L::W_GROUP) * 2] = clock64(); // weights of the group landed
                         for (int kr = g * L::W_GROUP; kr < kr1; kr++, acnt++) // kr: k-block relative to this CTA's first one
                         {
-                            const int as = issuer * L::A_SLOTS_PER + (int)(acnt % L::A_SLOTS_PER), wi = kr % L::W_GROUP;
-                            mbar_wait(afull(as), (acnt / L::A_SLOTS_PER) & 1u, p.error_flag, KERR_MU_MMA);
+                            const int as = issuer * L::A_SLOTS_PER + (int)(acnt & a_mask), wi = kr % L::W_GROUP;
+                            mbar_wait(afull(as), (acnt >> a_slots_log) & 1u, p.error_flag, KERR_MU_MMA);
                             tcgen05_fence_after();
-                            const uint64_t a_desc = umma_smem_desc_sw128(base + L::OFF_A + as * MU_A_SLOT_BYTES);
-                            const uint64_t b_desc = umma_smem_desc_sw128(base + ws * L::W_SLOT_BYTES + wi * MP_W_TILE_BYTES);
+                            if (dbg && l == 3 && kr < 16) dbg[128 + (issuer * 16 + kr) * 2 + 1] = clock64(); // activations of the k-block landed
+                            if (dbg && issuer == 0 && kr == 0) dbg[l * 8 + 1] = clock64(); // first operands of the layer landed
+                            const uint64_t a_desc = umma_smem_desc_sw128(a_slot_addr(issuer, acnt & a_mask));
+                            const uint64_t b_desc = umma_smem_desc_sw128(base + ws * L::W_SLOT_BYTES + wi * L::W_TILE_BYTES);
 #pragma unroll
                             for (int k = 0; k < 4; k++)
                                 umma_ss<KIND_I8>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, IDESC, (g != issuer || wi != 0 || k != 0) ? 1u : 0u);
@@ -596,29 +633,30 @@ mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaP
                         tcgen05_commit(wempty(ws));
                     }
                     tcgen05_commit(tfull(acc));
+                    if (dbg && issuer == 0) dbg[l * 8 + 2] = clock64(); // issuer 0's last MMA of the layer issued
                 }
             }
         }
     }
     else if (warp >= MU_EPI_WARP0 && warp < MU_EPI_WARP0 + 4)
     {
-        // ===================== epilogue: thread = sample; partial sums of the two K halves meet through DSMEM =====================
+        // ===================== epilogue: thread = sample; partial sums of the CL K ranges meet through DSMEM =====================
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const uint32_t peer = (uint32_t)(rank ^ 1);
+        const bool live = row < p.batch; // only the batch's rows are exchanged and stored
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t tseq = 0;
         for (int l = 0; l < p.n_layers; l++)
         {
-            const int tiles = (p.fan_out[l] + MP_TILE_N - 1) / MP_TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
+            const int tiles = (p.fan_out[l] + L::TILE_N - 1) / L::TILE_N, nkb = (p.fan_in[l] + 127) >> 7;
             const int ngw = (k_hi(nkb) - k_lo(nkb) + L::W_GROUP - 1) / L::W_GROUP;
             const int nacc = min(NI, ngw); // accumulators this CTA's issuers wrote
             const bool last = l + 1 == p.n_layers;
             const bool relu = (p.relu_mask >> l) & 1u;
-            for (int tile = pair; tile < tiles; tile += npairs, tseq++)
+            for (int tile = grp; tile < tiles; tile += ngrps, tseq++)
             {
                 const uint32_t acc = tseq & 1u, xs = tseq & 1u;
-                const int col0 = tile * MP_TILE_N + rank * MP_FIN_N; // the 32 neurons this CTA finalises
+                const int col0 = tile * L::TILE_N + rank * MP_FIN_N; // the 32 neurons this CTA finalises
                 int bias[32];
 #pragma unroll
                 for (int j4 = 0; j4 < 8; j4++)
@@ -635,13 +673,17 @@ mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaP
                     }
                     bias[4 * j4] = b4.x, bias[4 * j4 + 1] = b4.y, bias[4 * j4 + 2] = b4.z, bias[4 * j4 + 3] = b4.w;
                 }
-                // (window xs was last waited for two tiles ago by this very thread: its barrier can be armed for this tile)
-                if (XASYNC && threadIdx.x == MU_EPI_WARP0 * 32) mbar_arrive_expect_tx(xfull(xs), MP_X_BYTES);
+                // (window stage xs was last waited for two tiles ago by this very thread: its barrier can be armed for this tile)
+                if (threadIdx.x == MU_EPI_WARP0 * 32) mbar_arrive_expect_tx(xfull(xs), (uint32_t)((CL - 1) * p.batch * 128));
                 mbar_wait(tfull(acc), (tseq >> 1) & 1u, p.error_flag, KERR_MU_EPILOGUE);
                 tcgen05_fence_after();
-                const uint32_t t_acc = lane_base + acc * NI * MP_TILE_N;
-                // the peer's 32 columns first: they are on their way while this thread reads its own
+                if (dbg && threadIdx.x == MU_EPI_WARP0 * 32) dbg[l * 8 + 3] = clock64(); // accumulators complete
+                const uint32_t t_acc = lane_base + acc * NI * L::TILE_N;
+                // the peers' columns first: they are on their way while this thread reads its own
+#pragma unroll
+                for (int d = 1; d < CL; d++)
                 {
+                    const uint32_t peer = (uint32_t)(rank + d) % CL;
                     uint32_t u[32];
                     tmem_ld_32x32(t_acc + peer * MP_FIN_N, u);
                     tmem_ld_wait();
@@ -650,28 +692,25 @@ mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaP
                         if (i < nacc) // (uniform)
                         {
                             uint32_t t[32];
-                            tmem_ld_32x32(t_acc + i * MP_TILE_N + peer * MP_FIN_N, t);
+                            tmem_ld_32x32(t_acc + i * L::TILE_N + peer * MP_FIN_N, t);
                             tmem_ld_wait();
 #pragma unroll
                             for (int j = 0; j < 32; j++) u[j] += t[j];
                         }
-                    // Window xs of the peer is free: the peer's threads read their window of tile t - 2 (and used what they read)
-                    // before they sent / arrived for tile t - 1, and this thread has waited for all of that (its own wait of tile t - 1).
-                    const uint32_t dst = mapa_shared(base + L::OFF_X + xs * MP_X_BYTES, peer) + (uint32_t)row * 16u;
-                    const uint32_t peer_bar = mapa_shared(xfull(xs), peer);
-                    if constexpr (XASYNC)
+                    if (live)
                     {
+                        // Stage xs of the peer's windows is free: the peer's threads read it for tile t - 2 (and used what they read)
+                        // before they sent for tile t - 1, and this thread has waited for all of those bytes (its own wait of tile t - 1).
+                        // A peer keeps one window per sender: this CTA's is number rank (or rank - 1 behind the peer's own rank).
+                        const uint32_t win = (uint32_t)(rank < (int)peer ? rank : rank - 1);
+                        const uint32_t dst = mapa_shared(base + L::OFF_X + (xs * (CL - 1) + win) * MP_X_BYTES, peer) + (uint32_t)row * 16u;
+                        const uint32_t peer_bar = mapa_shared(xfull(xs), peer);
 #pragma unroll
                         for (int j4 = 0; j4 < 8; j4++)
                             st_async_cluster_v4(dst + j4 * 2048u, u[4 * j4], u[4 * j4 + 1], u[4 * j4 + 2], u[4 * j4 + 3], peer_bar);
                     }
-                    else
-                    {
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; j4++) st_cluster_v4(dst + j4 * 2048u, u[4 * j4], u[4 * j4 + 1], u[4 * j4 + 2], u[4 * j4 + 3]);
-                        mbar_arrive_remote_release(peer_bar);
-                    }
                 }
+                if (dbg && threadIdx.x == MU_EPI_WARP0 * 32) dbg[l * 8 + 4] = clock64(); // the peers' columns are on their way
                 uint32_t v[32];
                 tmem_ld_32x32(t_acc + rank * MP_FIN_N, v);
                 tmem_ld_wait();
@@ -680,7 +719,7 @@ mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaP
                     if (i < nacc)
                     {
                         uint32_t t[32];
-                        tmem_ld_32x32(t_acc + i * MP_TILE_N + rank * MP_FIN_N, t);
+                        tmem_ld_32x32(t_acc + i * L::TILE_N + rank * MP_FIN_N, t);
                         tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 32; j++) v[j] += t[j];
@@ -689,17 +728,20 @@ mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaP
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty(acc)); // the accumulators may be overwritten by the tile after next
                 mbar_wait_acquire_cluster(xfull(xs), (tseq >> 1) & 1u, p.error_flag, KERR_MP_EXCHANGE);
+                if (dbg && threadIdx.x == MU_EPI_WARP0 * 32) dbg[l * 8 + 5] = clock64(); // the peers' partial sums are here
+                if (live && col0 < p.fan_out[l])
                 {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(mp_smem + L::OFF_X + xs * MP_X_BYTES) + row;
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; j4++)
+                    for (int w = 0; w < CL - 1; w++)
                     {
-                        const uint4 r4 = src[j4 * 128];
-                        v[4 * j4] += r4.x, v[4 * j4 + 1] += r4.y, v[4 * j4 + 2] += r4.z, v[4 * j4 + 3] += r4.w;
+                        const uint4 *src = reinterpret_cast<const uint4 *>(mp_smem + L::OFF_X + (xs * (CL - 1) + w) * MP_X_BYTES) + row;
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; j4++)
+                        {
+                            const uint4 r4 = src[j4 * 128];
+                            v[4 * j4] += r4.x, v[4 * j4 + 1] += r4.y, v[4 * j4 + 2] += r4.z, v[4 * j4 + 3] += r4.w;
+                        }
                     }
-                }
-                if (row < p.batch && col0 < p.fan_out[l])
-                {
                     if (last)
                     {
                         int32_t *dst = p.out + (long long)row * p.fan_out[l] + col0;
@@ -744,12 +786,14 @@ mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaP
                     }
                 }
             }
-            // publish the pair's tiles of this layer (see the kernel above for why the counter counts tiles, not CTAs)
-            const int my_tiles = pair < tiles ? (tiles - pair + npairs - 1) / npairs : 0;
+            // publish the cluster's tiles of this layer (see the kernel above for why the counter counts tiles, not CTAs)
+            const int my_tiles = grp < tiles ? (tiles - grp + ngrps - 1) / ngrps : 0;
             if (!last && my_tiles > 0)
             {
+                if (dbg && threadIdx.x == MU_EPI_WARP0 * 32) dbg[l * 8 + 6] = clock64(); // outputs stored
                 named_bar_sync(1, 128);
                 if (threadIdx.x == MU_EPI_WARP0 * 32) mu_red_release_gpu_add(p.barrier, (unsigned)my_tiles);
+                if (dbg && threadIdx.x == MU_EPI_WARP0 * 32) dbg[l * 8 + 7] = clock64(); // ... and published
             }
         }
         if (threadIdx.x == MU_EPI_WARP0 * 32 && atomicAdd(p.barrier + 1, 1u) == gridDim.x - 1u)
@@ -760,7 +804,7 @@ mlp_i8_umma_pair_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmmaP
     }
 
     tcgen05_fence_before();
-    cluster_sync_all(); // neither CTA exits while its peer may still write into its exchange window or arrive on its barriers
+    cluster_sync_all(); // no CTA exits while a peer may still write into its exchange windows or count bytes on its barriers
     if (warp == 3)
     {
         tcgen05_fence_after();
@@ -823,26 +867,29 @@ cudaError_t launch_mlp_i8_umma_stream(const MlpStreamParams &sp, int num_sms, cu
     return cudaLaunchKernelEx(&cfg, mlp_i8_umma_stream_kernel, maps, p);
 }
 
-bool mlp_umma_pair_supported(const MlpStreamParams &p, int num_sms)
+// Cluster size the net can run with: 4 (every fan-in has at least four k-blocks), 2 (at least two), 0 = single-CTA kernel only
+int mlp_umma_cluster_size(const MlpStreamParams &p, int num_sms)
 {
-    if (num_sms < 2 || !mlp_umma_stream_supported(p)) return false;
+    if (num_sms < 2 || !mlp_umma_stream_supported(p)) return 0;
+    int min_fan_in = 1 << 30;
     for (int l = 0; l < p.n_layers; l++)
-        if (p.layers[l].fan_in <= 128) return false; // each CTA of a pair needs a k-block of its own
-    return true;
+    {
+        if (!p.layers[l].w_tiled) return 0; // (the runtime builds the tiled copy at upload for the nets this kernel can serve)
+        min_fan_in = std::min(min_fan_in, p.layers[l].fan_in);
+    }
+    return min_fan_in > 384 && num_sms >= 4 ? 4 : min_fan_in > 128 ? 2 : 0;
 }
 
-// mode: 1 = four issuers, st.async exchange (the product kernel); 2 = two issuers, plain DSMEM stores + release arrive; 3 = two issuers, st.async
-cudaError_t launch_mlp_i8_umma_pair(const MlpStreamParams &sp, int num_sms, int mode, cudaStream_t stream)
+template <int CL, int NI>
+static cudaError_t launch_cluster(const MlpStreamParams &sp, int num_sms, cudaStream_t stream)
 {
-    if (!mlp_umma_pair_supported(sp, num_sms)) return cudaErrorInvalidValue;
+    using L = MpLayout<CL, NI>;
     static bool opted[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !opted[dev])
     {
-        cudaError_t e = cudaFuncSetAttribute(mlp_i8_umma_pair_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MpLayout<4>::SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_i8_umma_pair_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MpLayout<2>::SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_i8_umma_pair_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MpLayout<2>::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(mlp_i8_umma_cluster_kernel<CL, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM);
         if (e != cudaSuccess) return e;
         opted[dev] = true;
     }
@@ -850,7 +897,9 @@ cudaError_t launch_mlp_i8_umma_pair(const MlpStreamParams &sp, int num_sms, int 
     MlpUmmaParams p;
     p.n_layers = sp.n_layers, p.batch = sp.batch, p.relu_mask = sp.relu_mask;
     p.out = sp.out, p.barrier = sp.barrier, p.error_flag = sp.error_flag;
-    p.debug = nullptr;
+    p.debug = sp.debug;
+    const int box_bytes = ((sp.batch + 7) & ~7) * 128;
+    p.a_slot_shift = box_bytes <= 4096 ? 12 : box_bytes <= 8192 ? 13 : 14;
     int max_tiles = 1;
     for (int l = 0; l < sp.n_layers; l++)
     {
@@ -862,24 +911,47 @@ cudaError_t launch_mlp_i8_umma_pair(const MlpStreamParams &sp, int num_sms, int 
         const int8_t *a_src = l == 0 ? sp.in : sp.act[l & 1];
         cudaError_t e = encode_tma_2d(&maps.a[l], 1, a_src, ly.fan_in, sp.batch, ly.fan_in, 128, (sp.batch + 7) & ~7, true);
         if (e != cudaSuccess) return e;
-        e = encode_tma_2d(&maps.w[l], 1, ly.w, ly.fan_in, ly.fan_out, ly.fan_in, 128, MP_TILE_N, true);
-        if (e != cudaSuccess) return e;
-        max_tiles = std::max(max_tiles, (ly.fan_out + MP_TILE_N - 1) / MP_TILE_N);
+        p.w_tiled[l] = ly.w_tiled; // (maps.w stays unused: the weights arrive by 1-D bulk copies)
+        max_tiles = std::max(max_tiles, (ly.fan_out + L::TILE_N - 1) / L::TILE_N);
     }
-    const int npairs = std::min((num_sms > 0 ? num_sms : 148) / 2, max_tiles);
     cudaLaunchConfig_t cfg = {};
-    const int ni = mode == 1 ? 4 : 2;
-    cfg.gridDim = dim3((unsigned)(2 * npairs)), cfg.blockDim = dim3(ni == 4 ? MpLayout<4>::THREADS : MpLayout<2>::THREADS);
-    cfg.dynamicSmemBytes = ni == 4 ? MpLayout<4>::SMEM : MpLayout<2>::SMEM, cfg.stream = stream;
+    cfg.blockDim = dim3(L::THREADS), cfg.dynamicSmemBytes = L::SMEM, cfg.stream = stream;
     cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeCooperative; // all CTAs co-resident: the grid barrier cannot deadlock
-    attr[0].val.cooperative = 1;
-    attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = 2, attr[1].val.clusterDim.y = 1, attr[1].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 2;
-    if (mode == 1) return cudaLaunchKernelEx(&cfg, mlp_i8_umma_pair_kernel<true, 4>, maps, p);
-    if (mode == 2) return cudaLaunchKernelEx(&cfg, mlp_i8_umma_pair_kernel<false, 2>, maps, p);
-    return cudaLaunchKernelEx(&cfg, mlp_i8_umma_pair_kernel<true, 2>, maps, p);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative; // all CTAs co-resident: the grid barrier cannot deadlock
+    attr[1].val.cooperative = 1;
+    cfg.attrs = attr;
+    // How many clusters the device holds at once: the SMs of a cluster share a GPC, so it can be fewer than num_sms / CL (a cooperative
+    // launch of more is refused).  Asked once per device.
+    static int max_clusters[64] = {};
+    if (dev >= 64 || max_clusters[dev] == 0)
+    {
+        int n = 0;
+        cfg.gridDim = dim3((unsigned)(CL * ((num_sms > 0 ? num_sms : 148) / CL))), cfg.numAttrs = 1;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, mlp_i8_umma_cluster_kernel<CL, NI>, &cfg);
+        if (e != cudaSuccess) return e;
+        if (n < 1) return cudaErrorCooperativeLaunchTooLarge;
+        if (dev < 64) max_clusters[dev] = n;
+        else max_clusters[0] = n; // (not cached)
+    }
+    const int ngrps = std::min(std::min((num_sms > 0 ? num_sms : 148) / CL, max_clusters[dev < 64 ? dev : 0]), max_tiles);
+    cfg.gridDim = dim3((unsigned)(CL * ngrps)), cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, mlp_i8_umma_cluster_kernel<CL, NI>, maps, p);
+}
+
+// mode (A/B codes): 1 = the product choice -- clusters of four (two issuers) where the net allows them and the batch is at most
+// MLP_UMMA_QUAD_MAX_BATCH, else pairs (four issuers); 2 = pairs, four issuers; 3 = pairs, two issuers; 4 = clusters of four at every batch.
+// Config C5, us per forward at 17 / 64 / 96 / 128 samples: clusters of four 49.7 / 52.9 / 57.5 / 62.0 (three 16 KB windows per CTA
+// travel at 128 samples), pairs 53.6 / 55.6 / 56.8 / 59.5.
+constexpr int MLP_UMMA_QUAD_MAX_BATCH = 88;
+cudaError_t launch_mlp_i8_umma_cluster(const MlpStreamParams &sp, int num_sms, int mode, cudaStream_t stream)
+{
+    const int cl = mlp_umma_cluster_size(sp, num_sms);
+    if (cl == 0) return cudaErrorInvalidValue;
+    if (cl == 4 && ((mode == 1 && sp.batch <= MLP_UMMA_QUAD_MAX_BATCH) || mode == 4)) return launch_cluster<4, 2>(sp, num_sms, stream);
+    if (mode == 3) return launch_cluster<2, 2>(sp, num_sms, stream);
+    return launch_cluster<2, 4>(sp, num_sms, stream);
 }
 
 } // namespace nc

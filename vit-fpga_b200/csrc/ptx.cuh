@@ -117,6 +117,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
                  : "memory");
 }
 
+// Weights are read exactly once per launch: L2 evict-first, so that 128 MiB of them do not flush the biases (and whatever else the
+// caller keeps in L2) on their way through.  It matters more than it looks: with ~29 MB of weight reads queued at the memory
+// controllers, a bias load that misses L2 comes back 2-4 us later -- tools/stream_timeline.py showed the finalize of most layers
+// waiting that long for 28 bias values.
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+                 : "memory");
+}
+
 // 2-D tiled store shared -> global (bulk async-group completion).  Out-of-bounds rows / columns of the
 // box are clipped by the hardware, so ragged tile edges need no predicates.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src_smem, int c0, int c1)
@@ -284,25 +301,15 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-// The same store as an asynchronous operation that carries its own completion: 16 bytes land in the remote window and are
-// counted (complete_tx) on the remote mbarrier -- the way TMA delivers data -- so the sender needs no fence and no arrive.
+// A store into another CTA's shared memory as an asynchronous operation that carries its own completion: 16 bytes land in the
+// remote window and are counted (complete_tx) on the remote mbarrier -- the way TMA delivers data -- so the sender needs no fence and no arrive.
 __device__ __forceinline__ void st_async_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t cluster_bar)
 {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                  ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(cluster_bar)
                  : "memory");
 }
-// Arrive on a barrier of another CTA of the cluster; the release (cluster scope) orders this thread's earlier
-// st.shared::cluster stores before the arrival.
-__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_bar)
-{
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
-}
-// Bounded wait with cluster-scope acquire: pairs with mbar_arrive_remote_release (data handed over through DSMEM).
+// Bounded wait with cluster-scope acquire (data handed over through DSMEM).
 __device__ __forceinline__ void mbar_wait_acquire_cluster(uint32_t bar, uint32_t parity, int *err, int code)
 {
     const long long t0 = clock64();

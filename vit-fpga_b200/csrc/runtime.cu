@@ -72,6 +72,7 @@ struct MlpLayer
     long long ldw;   // elements
     void *w;         // operand type
     void *bias;      // float or int32
+    int8_t *w_tiled = nullptr; // INT8 nets the cluster streaming kernel can serve: the same weights in 16 KB streaming blocks
 };
 
 struct VitBlock
@@ -119,14 +120,15 @@ struct netcuda_net
     int32_t *splitk_ws = nullptr;          // INT8 small batch: [128][widest layer] int32 partial sums, all zero between layers
     int stream_pf_tiles = 3;               // ... and how many weight tiles it prefetches into L2 ahead of its ring (NETCUDA_MLP_STREAM_PF)
     void *stream_ll[2] = {nullptr, nullptr}; // ... and its tagged-word activation buffers (<= 4 samples: no grid barrier)
+    void *w_tiled_base = nullptr;          // INT8: the tiled weight copy of every layer (retile_int8_weights)
     unsigned *stream_bar = nullptr;        // INT8, <= 32 samples: the two counters of the weight-streaming kernel's grid barrier
     bool use_stream = true;                // NETCUDA_MLP_STREAM=0 keeps such batches on the split-K GEMM path
     int stream_max_batch = 16;                   // up to here the mma.sync streaming kernel (it can serve 32: NETCUDA_MLP_STREAM_SPLIT), above it (<= 128) the tcgen05 one
                                                  // (NETCUDA_MLP_STREAM_SPLIT: A/B of the hand-over point)
     int umma_min_batch = 17;                     // ... from here on (NETCUDA_MLP_UMMA_MIN moves the hand-over, for A/B runs against the split-K path)
-    int umma_pair = 1;                           // the tcgen05 streaming kernel as split-K CTA pairs where the net allows it: 1 = four issuers, partial sums by
-                                                 // st.async; 2 = two issuers, plain DSMEM stores + release arrive; 3 = two issuers, st.async; 0 = single CTAs
-                                                 // (NETCUDA_MLP_UMMA_PAIR, for A/B runs)
+    int umma_pair = 1;                           // the tcgen05 streaming kernel as split-K CTA clusters where the net allows it: 1 = clusters of four up to
+                                                 // 88 samples, pairs above; 2 = pairs, four issuers; 3 = pairs, two issuers; 4 = clusters of four at every
+                                                 // batch; 0 = single CTAs (NETCUDA_MLP_UMMA_PAIR, for A/B runs)
     void *patches = nullptr, *ybuf = nullptr, *qkv = nullptr, *att = nullptr, *hid = nullptr, *cls_ln = nullptr;
     float *x = nullptr;
 
@@ -320,7 +322,7 @@ extern "C" int netcuda_destroy(netcuda_net *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-    void *dev_ptrs[] = {h->arena, h->act[0], h->act[1], h->acc_out, h->splitk_ws, h->stream_bar, h->stream_ll[0], h->stream_ll[1], h->patches, h->ybuf, h->qkv, h->att, h->hid, h->cls_ln, h->x,
+    void *dev_ptrs[] = {h->arena, h->act[0], h->act[1], h->acc_out, h->splitk_ws, h->w_tiled_base, h->stream_bar, h->stream_ll[0], h->stream_ll[1], h->patches, h->ybuf, h->qkv, h->att, h->hid, h->cls_ln, h->x,
                         h->dev_in[0], h->dev_in[1]};
     for (void *p : dev_ptrs)
         if (p) cudaFree(p);
@@ -449,7 +451,7 @@ static int create_impl(const netcuda_desc *desc, netcuda_net *h)
             if (const char *e = getenv("NETCUDA_MLP_STREAM")) h->use_stream = atoi(e) != 0;
             if (const char *e = getenv("NETCUDA_MLP_STREAM_SPLIT")) h->stream_max_batch = std::min(std::max(atoi(e), 0), MLP_STREAM_MAX_BATCH);
             if (const char *e = getenv("NETCUDA_MLP_UMMA_MIN")) h->umma_min_batch = std::max(atoi(e), 1);
-            if (const char *e = getenv("NETCUDA_MLP_UMMA_PAIR")) h->umma_pair = std::min(std::max(atoi(e), 0), 3);
+            if (const char *e = getenv("NETCUDA_MLP_UMMA_PAIR")) h->umma_pair = std::min(std::max(atoi(e), 0), 4);
         }
     }
     else
@@ -540,6 +542,30 @@ static int upload_matrix(netcuda_net *h, const float *src, long long rows, int c
     return NETCUDA_OK;
 }
 
+// INT8 nets whose every layer the cluster streaming kernel can serve (fan-ins: multiples of 16 with at least two k-blocks) keep a
+// second copy of their weights in that kernel's streaming layout: +1 byte per weight of HBM (config C5: 128 MiB), for 17..128-sample
+// forwards that read contiguous 8..16 KB runs instead of 128-byte pieces 4 KB apart.  Rebuilt by every upload.
+static int retile_int8_weights(netcuda_net *h)
+{
+    if (h->desc.precision != NETCUDA_PREC_INT8 || !h->use_stream || !h->umma_pair) return NETCUDA_OK;
+    size_t total = 0;
+    for (auto &L : h->layers)
+    {
+        if (L.ldw != L.fan_in || (L.fan_in & 15) || L.fan_in <= 128) return NETCUDA_OK; // the single-CTA kernels serve this net
+        total += mlp_tiled_weight_bytes(L.fan_in, L.fan_out);
+    }
+    if (!h->w_tiled_base) CK(cudaMalloc(&h->w_tiled_base, total));
+    size_t off = 0;
+    for (auto &L : h->layers)
+    {
+        L.w_tiled = (int8_t *)h->w_tiled_base + off;
+        CK(launch_retile_i8_weights((const int8_t *)L.w, L.ldw, L.fan_out, L.fan_in, L.w_tiled, h->stream));
+        off += mlp_tiled_weight_bytes(L.fan_in, L.fan_out);
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return NETCUDA_OK;
+}
+
 extern "C" int netcuda_upload_mlp(netcuda_net *h, const float *w_flat, const float *b_flat)
 {
     if (int rc = check_handle(h)) return rc;
@@ -573,6 +599,7 @@ extern "C" int netcuda_upload_mlp(netcuda_net *h, const float *w_flat, const flo
         b_flat += L.fan_out;
     }
     cudaFree(scratch);
+    if (rc == NETCUDA_OK) rc = retile_int8_weights(h);
     if (rc == NETCUDA_OK) h->weights_loaded = true;
     return rc;
 }
@@ -591,6 +618,7 @@ extern "C" int netcuda_upload_mlp_i8(netcuda_net *h, const int8_t *w_flat, const
         w_flat += (size_t)L.fan_in * L.fan_out;
         b_flat += L.fan_out;
     }
+    if (int rc = retile_int8_weights(h)) return rc;
     h->weights_loaded = true;
     return NETCUDA_OK;
 }
@@ -687,6 +715,7 @@ static bool mlp_stream_params(netcuda_net *h, int n, const int8_t *in, int32_t *
         const MlpLayer &ly = h->layers[l];
         if (ly.ldw != ly.fan_in) return false;
         p.layers[l].w = (const int8_t *)ly.w, p.layers[l].bias = (const int32_t *)ly.bias;
+        p.layers[l].w_tiled = ly.w_tiled;
         p.layers[l].fan_in = ly.fan_in, p.layers[l].fan_out = ly.fan_out;
         p.max_fan_in = std::max(p.max_fan_in, ly.fan_in);
         const bool last = l == L - 1;
@@ -765,17 +794,17 @@ static int mlp_pass(netcuda_net *h, const float *in_f32, const int8_t *in_i8, in
             else
             {
                 bool launched = false;
-                if (h->umma_pair && mlp_umma_pair_supported(sp, h->num_sms))
+                if (h->umma_pair && mlp_umma_cluster_size(sp, h->num_sms) > 0)
                 {
-                    KernelScope scope(h, s, "mlp_umma_stream_pair", ops, bytes);
-                    const cudaError_t e = launch_mlp_i8_umma_pair(sp, h->num_sms, h->umma_pair, s);
+                    KernelScope scope(h, s, "mlp_umma_stream_cluster", ops, bytes);
+                    const cudaError_t e = launch_mlp_i8_umma_cluster(sp, h->num_sms, h->umma_pair, s);
                     launched = e == cudaSuccess;
                     if (!launched)
                     {
                         // a driver that refuses cooperative cluster launches: the single-CTA kernel serves this handle from now on
                         (void)cudaGetLastError();
                         h->umma_pair = 0;
-                        fprintf(stderr, "[netcuda] split-K pair streaming kernel not launchable (%s); using the single-CTA kernel\n", cudaGetErrorString(e));
+                        fprintf(stderr, "[netcuda] split-K cluster streaming kernel not launchable (%s); using the single-CTA kernel\n", cudaGetErrorString(e));
                     }
                 }
                 if (!launched)
