@@ -89,6 +89,7 @@ def traffic_json():
     json.dump(out, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
 
 
+# (every artefact found under gpurun_out/ is summarised under the given tag: clear gpurun_out/ of older captures first)
 launch_list()
 launch_list("launches_tiny.csv", "_vit_tiny", "`python bench.py --steps 1 --warmup 3 --workload vit_tiny_16_224_b256 --no-cpu-baseline --no-e2e --no-configs` (ViT-Tiny/16-224, 256 images per pass)")
 full_reports()

@@ -31,6 +31,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("NETCUDA_CXX", "/usr/bin/g++")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-ccbin", CXX]
+NVCC_FLAGS += os.environ.get("NETCUDA_EXTRA_NVCC_FLAGS", "").split()  # (A/B builds, together with NETCUDA_BUILD_TAG)
 if os.environ.get("NETCUDA_DEBUG_TIMELINE"):  # clock64 timeline hooks for tools/*_timeline.py (never in the shipped build)
     NVCC_FLAGS += ["-DNETCUDA_DEBUG_TIMELINE"]
 CU_SOURCES = ["gemm.cu", "elementwise.cu", "attention.cu", "mlp_stream.cu", "mlp_umma_stream.cu", "runtime.cu", "weights_io.cu", "frame_ring.cu", "staging.cpp"]

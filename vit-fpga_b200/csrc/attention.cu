@@ -386,7 +386,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     auto turn_bar = [&](int t, int q) { return bars + 8u * (12 + t * 4 + q); }; // MODE 2: "tile t's warp of lane quarter q may run its exp2 pass"
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(atc_smem + ATC_OFF_TMEM_PTR);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31; // (uniform: the MMA issuers' descriptors stay in uniform registers, see ptx.cuh)
     const int items = p.batch * p.heads;
     const int D = p.heads * ATT_HD;
 #ifdef NETCUDA_DEBUG_TIMELINE
@@ -789,7 +789,7 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     auto turn_bar = [&](int t, int q) { return bars + 8u * (12 + t * 4 + q); }; // "tile t's warps of lane quarter q may run their exp2 pass"
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(a16_smem + A16_OFF_TMEM_PTR);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31; // (uniform: the MMA issuers' descriptors stay in uniform registers, see ptx.cuh)
     const int items = p.batch * p.heads;
     const int D = p.heads * ATT_HD;
     const int nfull = p.tokens >> 5, tail = p.tokens & 31; // full 32-key chunks, keys in the ragged last chunk
@@ -1173,7 +1173,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid
     auto sfree_bar = [&](int t) { return bars + 8u * (14 + t); };
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(atl_smem + ATL_OFF_TMEM_PTR);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31; // (uniform: the MMA issuers' descriptors stay in uniform registers, see ptx.cuh)
     const int items = p.batch * p.heads * p.n_qpairs;
     const int D = p.heads * ATT_HD;
     const int n_it = blockIdx.x < items ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0; // items of this CTA

@@ -338,7 +338,7 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(smem + L::OFF_TMEM_PTR);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = uniform_warp_idx(); // (uniform: the producer's and the issuer's operands stay in uniform registers, see ptx.cuh)
     const int lane = threadIdx.x & 31;
 
     const int tiles_m = (p.M + TILE_M - 1) / TILE_M;

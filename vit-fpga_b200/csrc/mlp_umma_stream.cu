@@ -118,7 +118,7 @@ mlp_i8_umma_stream_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUmm
     auto tfull = [&](int a) { return bars + 8u * (2 * MU_W_SLOTS + 2 * MU_A_SLOTS + a); };
     auto tempty = [&](int a) { return bars + 8u * (2 * MU_W_SLOTS + 2 * MU_A_SLOTS + 2 + a); };
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(mu_smem + MU_OFF_TMEM_PTR);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31; // (uniform: the issuers' descriptors stay in uniform registers, see ptx.cuh)
     const int cta = blockIdx.x, grid = gridDim.x;
 #ifdef NETCUDA_DEBUG_TIMELINE
     long long *const dbg = cta == 0 ? p.debug : nullptr;
@@ -470,7 +470,7 @@ mlp_i8_umma_cluster_kernel(const __grid_constant__ MlpUmmaMaps maps, const MlpUm
     auto tempty = [&](int a) { return bars + 8u * (2 * L::W_SLOTS + 2 * L::A_SLOTS + 2 + a); };
     auto xfull = [&](int x) { return bars + 8u * (2 * L::W_SLOTS + 2 * L::A_SLOTS + 4 + x); };
     volatile uint32_t *tmem_ptr = reinterpret_cast<volatile uint32_t *>(mp_smem + L::OFF_TMEM_PTR);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31; // (uniform: the issuers' descriptors stay in uniform registers, see ptx.cuh)
     const int rank = (int)cluster_ctarank();                     // which part of K, which 32 of the tile's neurons
     const int grp = blockIdx.x / CL, ngrps = gridDim.x / CL;     // cluster index: walks the tiles
     // this CTA's k-blocks of a layer (never empty: nkb >= CL)

@@ -24,6 +24,20 @@ enum : int
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Warp index as a value the compiler knows to be warp-uniform (a broadcast shuffle).  Everything a warp-specialised role derives
+// from it -- ring slots, shared-memory descriptors, TMEM addresses -- can then live in uniform registers; computed from threadIdx
+// alone those values are per-thread as far as the compiler can tell, and every tcgen05.mma / TMA instruction (which take uniform-
+// register operands) is wrapped in an ELECT + R2UR.BROADCAST waterfall loop: ~160 cycles from one tcgen05.mma to the next in the INT8
+// streaming kernels, where the MMAs are small.  Must be called by all threads of the warp, converged (kernel entry).
+__device__ __forceinline__ int uniform_warp_idx()
+{
+#ifdef NETCUDA_NO_UNIFORM_WARP // A/B builds (NETCUDA_EXTRA_NVCC_FLAGS=-DNETCUDA_NO_UNIFORM_WARP NETCUDA_BUILD_TAG=... python build.py)
+    return (int)(threadIdx.x >> 5);
+#else
+    return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+#endif
+}
+
 // ---- programmatic dependent launch ---------------------------------------------------------------
 // Kernels of a forward pass are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel may start
 // (set up barriers, allocate TMEM, prefetch descriptors) while its predecessor in the stream drains; griddep_wait()

@@ -702,7 +702,7 @@ static cudaError_t run_gemm(netcuda_net *h, const char *label, int kind, const v
 // (n <= 16: the register-resident mma.sync kernel; 17..128: the tcgen05 kernel of mlp_umma_stream.cu -- same parameter block.  Measured
 //  on config C5, us per forward: mma.sync stream 36 / 37 / 50 / 73 / 83 at 1 / 8 / 16 / 17 / 32 samples; tcgen05 stream with two issuing
 //  threads 66 / 67 / 68 / 70 at 1 / 17 / 64 / 128 (one issuing thread: 105 / 107 / 110 at 33 / 64 / 128); split-K GEMM graph 98 / 108 / 125
-//  at 33 / 64 / 128.)
+//  at 33 / 64 / 128; the tcgen05 stream as split-K clusters, mlp_i8_umma_cluster_kernel: 49 / 52 / 59 at 17 / 64 / 128.)
 static bool mlp_stream_params(netcuda_net *h, int n, const int8_t *in, int32_t *out, MlpStreamParams &p)
 {
     if (h->desc.kind != NETCUDA_KIND_MLP || h->desc.precision != NETCUDA_PREC_INT8 || !h->use_stream || h->gemm_variant != 0 || !h->stream_bar)
