@@ -114,6 +114,57 @@ def test_gemm_tf32_vs_oracle(netcuda, oracle, torch_cuda, m, n, k):
     assert _max_rel(out.cpu().numpy(), want) <= 1e-4
 
 
+# (M, N, K, row pitch of A and W, element offset of both base pointers).  The latency-oriented ordered kernel serves every problem with
+# fewer 64 x 64 tiles than SMs: CH = 1 / 2 / 4 neurons per thread by grid size, 16-byte cp.async when pointers and pitches allow it
+# (with a zero-filled partial piece when K is not a multiple of four), 4-byte cp.async otherwise.
+FP32_ORDERED_SHAPES = [
+    (1, 128, 784, 784, 0),     # config C1, first layer, the reference's one sample per call
+    (64, 128, 784, 784, 0),    # ... at batch 64
+    (64, 10, 64, 64, 0),       # C1 last layer: a partly empty neuron group
+    (37, 33, 61, 61, 0),       # nothing aligned: 4-byte copies, ragged k tail
+    (5, 7, 3, 3, 0),           # K smaller than one float4
+    (64, 128, 784, 784, 1),    # base pointers 4 bytes off a 16-byte boundary: 4-byte copies
+    (33, 50, 70, 72, 0),       # K % 4 = 2 under an aligned pitch: partial 16-byte piece
+    (200, 40, 300, 300, 0),    # four sample tiles, the last one ragged; five k chunks (ring wraps)
+    (64, 2000, 100, 100, 0),   # CH = 2
+    (64, 4090, 136, 136, 0),   # CH = 4, ragged neuron tail
+    (130, 1000, 1030, 1032, 0),  # CH = 4 with three sample tiles, 17 k chunks
+]
+
+
+@pytest.mark.parametrize("m,n,k,ld,off", FP32_ORDERED_SHAPES)
+@pytest.mark.parametrize("relu", [0, 1])
+def test_gemm_fp32_ordered_small_problem_kernel_bit_equal(netcuda, oracle, torch_cuda, m, n, k, ld, off, relu):
+    """NETCUDA_PREC_FP32 on problems that do not fill the GPU: the latency-oriented kernel (variant 0) against the oracle's
+    ordered fmaf chain and against the 64 x 64 tile kernel (variant 1), bit for bit."""
+    torch = torch_cuda
+    rng = np.random.default_rng(m * 7 + n * 3 + k + off)
+    a = rng.uniform(-1, 1, (m, k)).astype(np.float32)
+    w = rng.uniform(-1, 1, (n, k)).astype(np.float32)
+    bias = rng.uniform(-1, 1, n).astype(np.float32)
+    da_buf = torch.full((m * ld + 8,), float("nan"), dtype=torch.float32, device="cuda")
+    dw_buf = torch.full((n * ld + 8,), float("nan"), dtype=torch.float32, device="cuda")
+    da = da_buf[off:off + m * ld].view(m, ld)
+    dw = dw_buf[off:off + n * ld].view(n, ld)
+    da[:, :k] = torch.from_numpy(a).cuda()
+    dw[:, :k] = torch.from_numpy(w).cuda()
+    db = torch.from_numpy(bias).cuda()
+    epi = netcuda.EPI_RELU if relu else netcuda.EPI_NONE
+    want = oracle.linear(a, w, bias)
+    if relu:
+        want = np.maximum(want, 0)
+    outs = []
+    for variant in (0, 1):
+        out = torch.full((m, n + 3), -7.0, dtype=torch.float32, device="cuda")  # padded pitch: columns past N stay untouched
+        netcuda.op_gemm(da, dw, db, out, netcuda.PREC_FP32, netcuda.OUT_F32, epilogue=epi, variant=variant, m=m, n=n, k=k, lda=ld, ldw=ld)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        assert (got[:, n:] == -7.0).all()
+        outs.append(got[:, :n])
+    np.testing.assert_array_equal(outs[0], want)
+    np.testing.assert_array_equal(outs[1], want)
+
+
 @pytest.mark.parametrize("m,n,k", [(128, 128, 128), (1, 4096, 4096), (77, 300, 200), (513, 4096, 4096), (16384, 256, 4096)])
 def test_gemm_int8_bit_exact(netcuda, torch_cuda, m, n, k):
     torch = torch_cuda

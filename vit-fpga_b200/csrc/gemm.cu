@@ -74,6 +74,14 @@ constexpr int STAGES_256_PAIR = 6; // CTA pair, BN = 256: 16 KB of A + 16 KB of 
 constexpr int STAGES_256_PAIR_EW16 = 5; // the same with 16 epilogue warps (64 KB of slabs)
 constexpr int STAGES_256_PAIR_DS = 5;   // the same with two output slabs per epilogue warp (64 KB of slabs)
 
+// the latency-oriented ordered fp32 kernel (defined below, next to the 64 x 64 tile kernel)
+constexpr int OS_KC = 64, OS_PITCH = OS_KC + 4, OS_STAGES = 4, OS_ROWS = 64, OS_THREADS = 256;
+__host__ __device__ constexpr int os_smem_bytes(int ch) { return OS_STAGES * (OS_ROWS + 4 * ch) * OS_PITCH * 4; }
+template <int CH>
+__global__ void gemm_fp32_ordered_small_kernel(const float *__restrict__ a, long long lda, const float *__restrict__ w, long long ldw,
+                                               const float *__restrict__ bias, float *__restrict__ out, long long ldc, int relu, int M, int N,
+                                               int K, int vec_ok);
+
 // cudaFuncSetAttribute is per device, so the opt-in runs once for every device that is used.
 cudaError_t gemm_global_init()
 {
@@ -107,6 +115,9 @@ cudaError_t gemm_global_init()
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_EW16, 2, 16>()) != cudaSuccess) return e;
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_DS, 2, 8, 1>()) != cudaSuccess) return e;
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_F32, STAGES_256_PAIR_DS, 2, 8, 1>()) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(gemm_fp32_ordered_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, os_smem_bytes(1))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(gemm_fp32_ordered_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, os_smem_bytes(2))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(gemm_fp32_ordered_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, os_smem_bytes(4))) != cudaSuccess) return e;
     if (dev < 64) done[dev] = true;
     return cudaSuccess;
 }
@@ -373,6 +384,152 @@ gemm_fp32_ordered_kernel(const float *__restrict__ a, long long lda, const float
     }
 }
 
+// The same arithmetic for problems that do not fill the GPU with 64 x 64 tiles (the reference's own contract: ONE sample per
+// launch_forward call, src/netFPGA.cpp:266-289; BASELINE config 1: 784-128-64-10 at 1..64 samples).  There every output is a chain
+// of K dependent FMAs (4 cycles each: 784 + 128 + 64 of them are ~2 us for config 1) and everything else is latency to be hidden:
+//   * a CTA computes 64 samples x 4 CH neurons, one thread = one sample x CH neurons, so a layer of 128 neurons is 32 CTAs
+//     (the 64 x 64 kernel above: 2 CTAs, 49 unpipelined load -> barrier -> 16 FMAs -> barrier rounds, ~60 us);
+//   * operands arrive through a 4-deep cp.async ring of 64-wide k chunks, rows kept k-contiguous at a pitch of 68 words: a
+//     thread reads ITS sample's row as float4 (pitch = 4 mod 32 words: the eight lanes of a quarter warp hit 32 distinct banks) and
+//     the neuron rows as float4 broadcasts -- (1 + CH) LDS.128 per 4 CH FMAs, no transposition on the way in;
+//   * programmatic dependent launch: the next layer's CTAs are resident (and past their set-up) when this layer's last store lands.
+// Same operation sequence per output as the oracle (acc = bias, fmaf in ascending k): bit-equal, tests/test_gpu_nets.py.
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src, int src_bytes) // bytes past src_bytes are zero-filled
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int CH>
+__global__ void __launch_bounds__(OS_THREADS)
+gemm_fp32_ordered_small_kernel(const float *__restrict__ a, long long lda, const float *__restrict__ w, long long ldw,
+                               const float *__restrict__ bias, float *__restrict__ out, long long ldc, int relu, int M, int N, int K,
+                               int vec_ok)
+{
+    extern __shared__ __align__(16) float os_smem[];
+    constexpr int NT = 4 * CH;                                // neurons per CTA
+    constexpr int STAGE_WORDS = (OS_ROWS + NT) * OS_PITCH;    // 64 sample rows, then NT neuron rows
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.y * OS_ROWS, col0 = blockIdx.x * NT;
+    const int mrows = min(OS_ROWS, M - row0), nrows = min(NT, N - col0);
+    const int nchunks = (K + OS_KC - 1) / OS_KC;
+    const uint32_t smem_base = smem_u32(os_smem);
+
+    griddep_launch_dependents(); // the next layer may take its seats; it reads nothing before its own griddep_wait()
+    griddep_wait();              // the previous layer's activations are complete and visible from here on
+
+    auto load_stage = [&](int kc)
+    {
+        const uint32_t st = smem_base + (uint32_t)((kc % OS_STAGES) * STAGE_WORDS * 4);
+        const int k0 = kc * OS_KC, kn = min(OS_KC, K - k0);
+        if (vec_ok) // 16-byte pieces: both base pointers and both row pitches are multiples of 16 bytes
+        {
+            const int total = (mrows + nrows) * (OS_KC / 4);
+            for (int p = tid; p < total; p += OS_THREADS)
+            {
+                const int r = p >> 4, j = p & 15;
+                if (4 * j >= kn) continue;
+                const float *src = r < mrows ? a + (long long)(row0 + r) * lda : w + (long long)(col0 + r - mrows) * ldw;
+                const int srow = r < mrows ? r : OS_ROWS + (r - mrows);
+                cp_async_16(st + (uint32_t)((srow * OS_PITCH + 4 * j) * 4), src + k0 + 4 * j, min(16, 4 * (kn - 4 * j)));
+            }
+        }
+        else
+        {
+            const int total = (mrows + nrows) * OS_KC;
+            for (int p = tid; p < total; p += OS_THREADS)
+            {
+                const int r = p >> 6, kk = p & 63;
+                if (kk >= kn) continue;
+                const float *src = r < mrows ? a + (long long)(row0 + r) * lda : w + (long long)(col0 + r - mrows) * ldw;
+                const int srow = r < mrows ? r : OS_ROWS + (r - mrows);
+                cp_async_4(st + (uint32_t)((srow * OS_PITCH + kk) * 4), src + k0 + kk);
+            }
+        }
+    };
+
+    const int m = tid & (OS_ROWS - 1), ng = tid >> 6; // sample of the tile; group of CH neurons (uniform over a warp)
+    const bool active = m < mrows && ng * CH < nrows;
+    float acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; c++)
+    {
+        const int n = col0 + ng * CH + c;
+        acc[c] = (bias != nullptr && n < N) ? bias[n] : 0.0f;
+    }
+
+    for (int s = 0; s < OS_STAGES - 1; s++)
+    {
+        if (s < nchunks) load_stage(s);
+        cp_async_commit();
+    }
+    for (int kc = 0; kc < nchunks; kc++)
+    {
+        cp_async_wait<OS_STAGES - 2>(); // chunk kc has landed (this thread's pieces) ...
+        __syncthreads();                // ... everybody's; and everybody is done reading the slot refilled below (chunk kc - 1)
+        if (kc + OS_STAGES - 1 < nchunks) load_stage(kc + OS_STAGES - 1);
+        cp_async_commit();
+        if (!active) continue;
+        const float *st = os_smem + (kc % OS_STAGES) * STAGE_WORDS;
+        const float *as = st + m * OS_PITCH;
+        const float *ws = st + (OS_ROWS + ng * CH) * OS_PITCH;
+        const int kn = min(OS_KC, K - kc * OS_KC);
+        int k = 0;
+#pragma unroll 8
+        for (; k + 4 <= kn; k += 4) // strictly ascending k: the oracle's rounding sequence
+        {
+            const float4 av = *reinterpret_cast<const float4 *>(as + k);
+            float4 wv[CH];
+#pragma unroll
+            for (int c = 0; c < CH; c++) wv[c] = *reinterpret_cast<const float4 *>(ws + c * OS_PITCH + k);
+#pragma unroll
+            for (int c = 0; c < CH; c++) acc[c] = fmaf(wv[c].x, av.x, acc[c]);
+#pragma unroll
+            for (int c = 0; c < CH; c++) acc[c] = fmaf(wv[c].y, av.y, acc[c]);
+#pragma unroll
+            for (int c = 0; c < CH; c++) acc[c] = fmaf(wv[c].z, av.z, acc[c]);
+#pragma unroll
+            for (int c = 0; c < CH; c++) acc[c] = fmaf(wv[c].w, av.w, acc[c]);
+        }
+        for (; k < kn; k++)
+        {
+            const float a1 = as[k];
+#pragma unroll
+            for (int c = 0; c < CH; c++) acc[c] = fmaf(ws[c * OS_PITCH + k], a1, acc[c]);
+        }
+    }
+    cp_async_wait<0>();
+    if (!active) return;
+#pragma unroll
+    for (int c = 0; c < CH; c++)
+    {
+        const int n = col0 + ng * CH + c;
+        if (n >= N) continue;
+        float v = acc[c];
+        if (relu && v < 0.0f) v = 0.0f;
+        out[(long long)(row0 + m) * ldc + n] = v;
+    }
+}
+
+template <int CH>
+static cudaError_t launch_fp32_small(const GemmCall &c, cudaStream_t stream)
+{
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(c.a) | reinterpret_cast<uintptr_t>(c.w)) & 15u) == 0 && (c.lda & 3) == 0 && (c.ldw & 3) == 0;
+    const dim3 grid((unsigned)((c.n + 4 * CH - 1) / (4 * CH)), (unsigned)((c.m + OS_ROWS - 1) / OS_ROWS));
+    return launch_pdl(gemm_fp32_ordered_small_kernel<CH>, grid, dim3(OS_THREADS), (size_t)os_smem_bytes(CH), stream, 1, (const float *)c.a, c.lda,
+                      (const float *)c.w, c.ldw, (const float *)c.bias, (float *)c.out, c.ldc, c.epi == EPI_RELU ? 1 : 0, c.m, c.n, c.k, vec_ok);
+}
+
 // ---- dispatcher -------------------------------------------------------------------------------------
 
 cudaError_t launch_gemm(const GemmCall &c, cudaStream_t stream)
@@ -382,6 +539,16 @@ cudaError_t launch_gemm(const GemmCall &c, cudaStream_t stream)
     {
         if (c.out_type != OUT_F32 || (c.epi != EPI_NONE && c.epi != EPI_RELU)) return cudaErrorInvalidValue;
         dim3 grid((c.n + 63) / 64, (c.m + 63) / 64);
+        // fewer 64 x 64 tiles than SMs: the latency-oriented kernel, with as few neurons per CTA as keeps the grid within ~2 CTAs
+        // per SM (variant 1 forces the tile kernel: A/B and cross-check)
+        const int sms = c.num_sms > 0 ? c.num_sms : 148;
+        if (c.variant == 0 && (long long)grid.x * grid.y < sms)
+        {
+            const long long mt = grid.y;
+            if (mt * ((c.n + 3) / 4) <= 2LL * sms) return launch_fp32_small<1>(c, stream);
+            if (mt * ((c.n + 7) / 8) <= 2LL * sms) return launch_fp32_small<2>(c, stream);
+            return launch_fp32_small<4>(c, stream);
+        }
         gemm_fp32_ordered_kernel<<<grid, 256, 0, stream>>>((const float *)c.a, c.lda, (const float *)c.w, c.ldw,
                                                          (const float *)c.bias, (float *)c.out, c.ldc, c.epi == EPI_RELU, c.m,
                                                          c.n, c.k);

@@ -61,6 +61,7 @@ static inline long long round_up(long long v, long long m) { return (v + m - 1) 
 
 // INT8 layers at small batch are weight streaming: up to this many samples a layer is split along K over the whole GPU
 constexpr int SPLITK_MAX_M = 128;
+constexpr size_t SMALL_CALL_BYTES = 256 << 10; // host calls of an MLP whose inputs and outputs are at most this large take the single-stream path
 constexpr int GRAPH_MAX_SAMPLES = 4096;   // MLP passes up to this many samples are launch-latency bound (graph replay, PDL)
 constexpr int VIT_GRAPH_MAX_ROWS = 8192; // ViT passes up to this many token rows are launch-latency bound (graph replay, PDL)
 
@@ -176,6 +177,7 @@ struct netcuda_net
         int status = NETCUDA_OK; // of a retired ticket
         cudaEvent_t done = nullptr;
         void *dev_out = nullptr, *pin_out = nullptr;
+        void *small_in = nullptr; // page-locked input of a small call (SMALL_CALL_BYTES), see submit_host_impl
         size_t dev_cap = 0, pin_cap = 0;
         void *user_out = nullptr;
         size_t out_bytes = 0;
@@ -341,6 +343,7 @@ extern "C" int netcuda_destroy(netcuda_net *h)
         if (pd.done) cudaEventDestroy(pd.done);
         if (pd.dev_out) cudaFree(pd.dev_out);
         if (pd.pin_out) cudaFreeHost(pd.pin_out);
+        if (pd.small_in) cudaFreeHost(pd.small_in);
     }
     for (auto &r : h->prof_recs)
     {
@@ -1155,10 +1158,18 @@ static int submit_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_
     netcuda_net::Pending &pd = h->pending[tk % netcuda_net::MAX_IN_FLIGHT];
     if (pd.active) (void)finish_pending(h, pd); // ring full: the oldest call is retired first (its status stays readable)
     const size_t in_elem = in_is_i8 ? 1 : 4, out_elem = 4;
-    const bool pinned_in = is_pinned(in);
+    // Small call (the reference's own contract is ONE sample per launch_forward, src/netFPGA.cpp:266-289): what the caller waits for is
+    // driver calls, not bytes.  Such a call stays on the compute stream -- input copied into a page-locked slot of this ticket, one H2D,
+    // the kernels, and (fp32 nets, whose last layer is a CUDA-core kernel with plain stores) the outputs written by the kernel straight
+    // into page-locked host memory -- instead of the two-stream pipeline below: no pointer-attribute queries, no copy-stream events,
+    // no D2H copy.  NETCUDA_SMALL_CALL=0 switches it off (A/B).
+    static const bool small_call_on = !getenv("NETCUDA_SMALL_CALL") || atoi(getenv("NETCUDA_SMALL_CALL")) != 0;
+    const bool small_call = small_call_on && h->desc.kind == NETCUDA_KIND_MLP && batch <= (size_t)h->max_batch &&
+                            batch * h->n_in * in_elem <= SMALL_CALL_BYTES && batch * h->n_out * out_elem <= SMALL_CALL_BYTES;
+    const bool pinned_in = small_call ? true : is_pinned(in);
     if (int rc = ensure_staging(h, in_elem, !pinned_in)) return rc;
     pd.t0 = std::chrono::steady_clock::now();
-    pd.pinned_out = is_pinned(out);
+    pd.pinned_out = small_call ? false : is_pinned(out);
     pd.user_out = out, pd.out_bytes = batch * h->n_out * out_elem;
     if (!pd.done) CK(cudaEventCreateWithFlags(&pd.done, cudaEventDisableTiming));
     // Output buffers of the in-flight ring.  When this call needs larger ones, every idle slot of the ring grows with it: the
@@ -1184,6 +1195,27 @@ static int submit_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_
                 q.pin_cap = pd.out_bytes;
             }
         }
+
+    if (small_call)
+    {
+        if (!pd.small_in) CK(cudaHostAlloc(&pd.small_in, SMALL_CALL_BYTES, cudaHostAllocDefault));
+        const int slot = (int)(h->chunk_seq & 1);
+        const size_t bytes = batch * h->n_in * in_elem;
+        memcpy(pd.small_in, in, bytes);
+        // (every kernel that read dev_in[slot] ran on this stream; a copy-stream H2D into it finished before those kernels started)
+        CK(cudaMemcpyAsync(h->dev_in[slot], pd.small_in, bytes, cudaMemcpyHostToDevice, h->stream));
+        // page-locked host memory is device-addressable under unified addressing: the ordered fp32 kernels store into it directly
+        const bool direct_out = h->desc.precision == NETCUDA_PREC_FP32;
+        if (int rc = forward_device_impl(h, h->dev_in[slot], in_is_i8, batch, direct_out ? pd.pin_out : pd.dev_out, out_is_i32, h->stream, true)) return rc;
+        CK(cudaEventRecord(h->compute_done[slot], h->stream)); // (a later pipelined call waits for it before it refills the slot)
+        h->chunk_seq++;
+        if (!direct_out) CK(cudaMemcpyAsync(pd.pin_out, pd.dev_out, pd.out_bytes, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(pd.done, h->stream));
+        pd.ticket = tk, pd.active = true, pd.status = NETCUDA_OK;
+        h->next_ticket++;
+        if (ticket) *ticket = tk;
+        return NETCUDA_OK;
+    }
 
     // The first chunk of a call is the only one whose H2D copy nothing hides (the compute stream may be idle): for large ViT batches
     // it is a quarter of a pass, so that the kernels start after a quarter of the copy time (blocking netcuda_forward, ViT-B,
