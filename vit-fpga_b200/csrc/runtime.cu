@@ -177,7 +177,7 @@ struct netcuda_net
         int status = NETCUDA_OK; // of a retired ticket
         cudaEvent_t done = nullptr;
         void *dev_out = nullptr, *pin_out = nullptr;
-        void *small_in = nullptr; // page-locked input of a small call (SMALL_CALL_BYTES), see submit_host_impl
+        void *small_in = nullptr, *small_dev_in = nullptr; // page-locked / device input of a small call (SMALL_CALL_BYTES), see submit_host_impl
         size_t dev_cap = 0, pin_cap = 0;
         void *user_out = nullptr;
         size_t out_bytes = 0;
@@ -344,6 +344,7 @@ extern "C" int netcuda_destroy(netcuda_net *h)
         if (pd.dev_out) cudaFree(pd.dev_out);
         if (pd.pin_out) cudaFreeHost(pd.pin_out);
         if (pd.small_in) cudaFreeHost(pd.small_in);
+        if (pd.small_dev_in) cudaFree(pd.small_dev_in);
     }
     for (auto &r : h->prof_recs)
     {
@@ -1167,7 +1168,8 @@ static int submit_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_
     const bool small_call = small_call_on && h->desc.kind == NETCUDA_KIND_MLP && batch <= (size_t)h->max_batch &&
                             batch * h->n_in * in_elem <= SMALL_CALL_BYTES && batch * h->n_out * out_elem <= SMALL_CALL_BYTES;
     const bool pinned_in = small_call ? true : is_pinned(in);
-    if (int rc = ensure_staging(h, in_elem, !pinned_in)) return rc;
+    if (!small_call)
+        if (int rc = ensure_staging(h, in_elem, !pinned_in)) return rc;
     pd.t0 = std::chrono::steady_clock::now();
     pd.pinned_out = small_call ? false : is_pinned(out);
     pd.user_out = out, pd.out_bytes = batch * h->n_out * out_elem;
@@ -1198,18 +1200,35 @@ static int submit_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_
 
     if (small_call)
     {
+        // Everything the call touches belongs to its ticket's ring slot (retired before it is reused), so nothing here depends on
+        // the pipeline's input slots or their events.
         if (!pd.small_in) CK(cudaHostAlloc(&pd.small_in, SMALL_CALL_BYTES, cudaHostAllocDefault));
-        const int slot = (int)(h->chunk_seq & 1);
+        if (!pd.small_dev_in) CK(cudaMalloc(&pd.small_dev_in, SMALL_CALL_BYTES));
         const size_t bytes = batch * h->n_in * in_elem;
         memcpy(pd.small_in, in, bytes);
-        // (every kernel that read dev_in[slot] ran on this stream; a copy-stream H2D into it finished before those kernels started)
-        CK(cudaMemcpyAsync(h->dev_in[slot], pd.small_in, bytes, cudaMemcpyHostToDevice, h->stream));
-        // page-locked host memory is device-addressable under unified addressing: the ordered fp32 kernels store into it directly
+        // page-locked host memory is device-addressable under unified addressing:
+        //  * the ordered fp32 kernels store the last layer's outputs into it directly (no D2H copy);
+        //  * a few samples of a tf32 / bf16 net are read from it in place (no H2D copy): the first kernel of such a pass converts the
+        //    inputs, reading them once with plain loads (NETCUDA_SMALL_CALL_ZC_BYTES, default 16 KB; 0 = always copy).  Not for fp32
+        //    nets -- every CTA of the first layer streams all the input rows through its cp.async ring, and over PCIe each ring
+        //    refill is a bus round trip (config C1, one sample per call: 40.7 us in place, 27.3 us with the copy).
+        // Copies and kernels of the call are replayed as ONE graph from the second sight of a (ring slot, batch) on
+        // (NETCUDA_SMALL_CALL_GRAPH=0: plain launches; C1, one sample per call: bf16 37.9 -> 29.7 us, fp32 27.3 -> 26.3 us, tf32 unchanged).
+        static const size_t zc_bytes = getenv("NETCUDA_SMALL_CALL_ZC_BYTES") ? (size_t)atoll(getenv("NETCUDA_SMALL_CALL_ZC_BYTES")) : (size_t)16 << 10;
+        static const bool small_graph = !getenv("NETCUDA_SMALL_CALL_GRAPH") || atoi(getenv("NETCUDA_SMALL_CALL_GRAPH")) != 0;
         const bool direct_out = h->desc.precision == NETCUDA_PREC_FP32;
-        if (int rc = forward_device_impl(h, h->dev_in[slot], in_is_i8, batch, direct_out ? pd.pin_out : pd.dev_out, out_is_i32, h->stream, true)) return rc;
-        CK(cudaEventRecord(h->compute_done[slot], h->stream)); // (a later pipelined call waits for it before it refills the slot)
-        h->chunk_seq++;
-        if (!direct_out) CK(cudaMemcpyAsync(pd.pin_out, pd.dev_out, pd.out_bytes, cudaMemcpyDeviceToHost, h->stream));
+        const bool zc_in = bytes <= zc_bytes && !in_is_i8 && (h->desc.precision == NETCUDA_PREC_TF32 || h->desc.precision == NETCUDA_PREC_BF16);
+        const void *src = zc_in ? pd.small_in : pd.small_dev_in;
+        void *dst = direct_out ? pd.pin_out : pd.dev_out;
+        const bool graphed = small_graph && h->use_graphs && !h->profiling && h->desc.precision != NETCUDA_PREC_INT8;
+        auto body = [&]() -> int
+        {
+            if (!zc_in) CK(cudaMemcpyAsync(pd.small_dev_in, pd.small_in, bytes, cudaMemcpyHostToDevice, h->stream));
+            if (int rc = forward_device_impl(h, src, in_is_i8, batch, dst, out_is_i32, h->stream, !graphed)) return rc;
+            if (!direct_out) CK(cudaMemcpyAsync(pd.pin_out, pd.dev_out, pd.out_bytes, cudaMemcpyDeviceToHost, h->stream));
+            return NETCUDA_OK;
+        };
+        if (int rc = graphed ? pass_graphed(h, pd.small_in, pd.pin_out, (int)batch, in_is_i8, out_is_i32, h->stream, true, body) : body()) return rc;
         CK(cudaEventRecord(pd.done, h->stream));
         pd.ticket = tk, pd.active = true, pd.status = NETCUDA_OK;
         h->next_ticket++;
