@@ -1037,10 +1037,11 @@ static int forward_device_impl(netcuda_net *h, const void *d_in, bool in_is_i8, 
             float *of = out_is_i32 ? nullptr : (float *)d_out + done * h->n_out;
             int32_t *oi = out_is_i32 ? (int32_t *)d_out + done * h->n_out : nullptr;
             // single small pass, not being profiled (the profile brackets individual launches): graph replay
-            // (worth it from about eight kernels up: a 3-layer net was measured faster with plain launches, 71 vs 86 us per call)
+            // (NETCUDA_MLP_GRAPH_MIN_LAYERS: nets with fewer layers take plain launches; A/B)
+            static const size_t graph_min_layers = getenv("NETCUDA_MLP_GRAPH_MIN_LAYERS") ? (size_t)atoi(getenv("NETCUDA_MLP_GRAPH_MIN_LAYERS")) : 2;
             MlpStreamParams sp;
             const bool streamed = mlp_stream_params(h, n, q ? q : (const int8_t *)h->act[0], oi ? oi : h->acc_out, sp); // (three launches at most)
-            if (allow_graph && !streamed && h->layers.size() >= 4 && batch <= (size_t)GRAPH_MAX_SAMPLES && batch <= (size_t)h->max_batch &&
+            if (allow_graph && !streamed && h->layers.size() >= graph_min_layers && batch <= (size_t)GRAPH_MAX_SAMPLES && batch <= (size_t)h->max_batch &&
                 !h->profiling && h->use_graphs)
                 rc = mlp_pass_graphed(h, f, q, n, of, oi, s);
             else
