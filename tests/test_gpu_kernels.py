@@ -126,7 +126,7 @@ FP32_ORDERED_SHAPES = [
     (64, 128, 784, 784, 1),    # base pointers 4 bytes off a 16-byte boundary: 4-byte copies
     (33, 50, 70, 72, 0),       # K % 4 = 2 under an aligned pitch: partial 16-byte piece
     (200, 40, 300, 300, 0),    # four sample tiles, the last one ragged; five k chunks (ring wraps)
-    (64, 2000, 100, 100, 0),   # CH = 2
+    (64, 1000, 100, 100, 0),   # CH = 2
     (64, 4090, 136, 136, 0),   # CH = 4, ragged neuron tail
     (130, 1000, 1030, 1032, 0),  # CH = 4 with three sample tiles, 17 k chunks
 ]

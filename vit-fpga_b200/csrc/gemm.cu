@@ -75,7 +75,7 @@ constexpr int STAGES_256_PAIR_EW16 = 5; // the same with 16 epilogue warps (64 K
 constexpr int STAGES_256_PAIR_DS = 5;   // the same with two output slabs per epilogue warp (64 KB of slabs)
 
 // the latency-oriented ordered fp32 kernel (defined below, next to the 64 x 64 tile kernel)
-constexpr int OS_KC = 64, OS_PITCH = OS_KC + 4, OS_STAGES = 4, OS_ROWS = 64, OS_THREADS = 256;
+constexpr int OS_KC = 64, OS_PITCH = OS_KC + 4, OS_STAGES = 8, OS_ROWS = 64, OS_THREADS = 256;
 __host__ __device__ constexpr int os_smem_bytes(int ch) { return OS_STAGES * (OS_ROWS + 4 * ch) * OS_PITCH * 4; }
 template <int CH>
 __global__ void gemm_fp32_ordered_small_kernel(const float *__restrict__ a, long long lda, const float *__restrict__ w, long long ldw,
@@ -389,7 +389,8 @@ gemm_fp32_ordered_kernel(const float *__restrict__ a, long long lda, const float
 // of K dependent FMAs (4 cycles each: 784 + 128 + 64 of them are ~2 us for config 1) and everything else is latency to be hidden:
 //   * a CTA computes 64 samples x 4 CH neurons, one thread = one sample x CH neurons, so a layer of 128 neurons is 32 CTAs
 //     (the 64 x 64 kernel above: 2 CTAs, 49 unpipelined load -> barrier -> 16 FMAs -> barrier rounds, ~60 us);
-//   * operands arrive through a 4-deep cp.async ring of 64-wide k chunks, rows kept k-contiguous at a pitch of 68 words: a
+//   * operands arrive through an 8-deep cp.async ring of 64-wide k chunks (17 KB each; 4-deep measured the same on config C1:
+//     the ring is not what bounds it), rows kept k-contiguous at a pitch of 68 words: a
 //     thread reads ITS sample's row as float4 (pitch = 4 mod 32 words: the eight lanes of a quarter warp hit 32 distinct banks) and
 //     the neuron rows as float4 broadcasts -- (1 + CH) LDS.128 per 4 CH FMAs, no transposition on the way in;
 //   * programmatic dependent launch: the next layer's CTAs are resident (and past their set-up) when this layer's last store lands.
@@ -539,14 +540,14 @@ cudaError_t launch_gemm(const GemmCall &c, cudaStream_t stream)
     {
         if (c.out_type != OUT_F32 || (c.epi != EPI_NONE && c.epi != EPI_RELU)) return cudaErrorInvalidValue;
         dim3 grid((c.n + 63) / 64, (c.m + 63) / 64);
-        // fewer 64 x 64 tiles than SMs: the latency-oriented kernel, with as few neurons per CTA as keeps the grid within ~2 CTAs
-        // per SM (variant 1 forces the tile kernel: A/B and cross-check)
+        // fewer 64 x 64 tiles than SMs: the latency-oriented kernel, with as few neurons per CTA as keeps the grid within one CTA
+        // per SM (its ring takes 145..170 KB of shared memory; variant 1 forces the tile kernel: A/B and cross-check)
         const int sms = c.num_sms > 0 ? c.num_sms : 148;
         if (c.variant == 0 && (long long)grid.x * grid.y < sms)
         {
             const long long mt = grid.y;
-            if (mt * ((c.n + 3) / 4) <= 2LL * sms) return launch_fp32_small<1>(c, stream);
-            if (mt * ((c.n + 7) / 8) <= 2LL * sms) return launch_fp32_small<2>(c, stream);
+            if (mt * ((c.n + 3) / 4) <= (long long)sms) return launch_fp32_small<1>(c, stream);
+            if (mt * ((c.n + 7) / 8) <= (long long)sms) return launch_fp32_small<2>(c, stream);
             return launch_fp32_small<4>(c, stream);
         }
         gemm_fp32_ordered_kernel<<<grid, 256, 0, stream>>>((const float *)c.a, c.lda, (const float *)c.w, c.ldw,

@@ -1266,6 +1266,10 @@ static int submit_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_
             {
                 ramp = done == 0 ? (size_t)h->max_batch / 8 : ramp * 2;
                 n = std::min(n, std::max(ramp, (size_t)32));
+                // ... and the ramp ends ON a pass-size boundary (64, 128, 320, then full passes of 512 -- not 64, 128, 256, 512, 64: small
+                // passes quantise badly into 256-row tiles, and a ragged one at the end of the call hides nothing)
+                const size_t to_boundary = (size_t)h->max_batch - done % (size_t)h->max_batch;
+                if (n < to_boundary && to_boundary <= 3 * n) n = std::min(to_boundary, batch - done);
             }
         }
         const size_t bytes = n * h->n_in * in_elem;
