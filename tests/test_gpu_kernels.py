@@ -225,7 +225,7 @@ def test_gemm_tensor_core_matches_cuda_core_variant_at_full_size(netcuda, torch_
     assert ((g16.float() - want).abs().max() / want.abs().max()).item() <= 6e-3
 
 
-@pytest.mark.parametrize("rows,dim", [(1, 192), (197, 192), (1000, 768), (333, 1024), (64, 4096)])
+@pytest.mark.parametrize("rows,dim", [(1, 192), (197, 192), (1001, 64), (50, 128), (1000, 768), (333, 1024), (64, 4096)])
 def test_layernorm_vs_oracle(netcuda, oracle, torch_cuda, rows, dim):
     torch = torch_cuda
     rng = np.random.default_rng(rows + dim)

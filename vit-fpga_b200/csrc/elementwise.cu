@@ -5,6 +5,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include "ptx.cuh"
 
 namespace nc
@@ -73,12 +74,81 @@ layernorm_kernel(const float *__restrict__ x, long long ldx, const float *__rest
     }
 }
 
+// Rows of at most 192 elements (ViT-Tiny: D = 192 = 48 float4): one HALF warp per row, three float4 per lane.  With a whole warp per
+// row a third of the lanes' second load is empty and a warp has 768 bytes in flight; here every lane carries three loads (1536 bytes per
+// warp) and there are half as many warps to schedule.  Same two-pass arithmetic; the reductions stay inside the half warp (xor 8..1).
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+layernorm_halfwarp_kernel(const float *__restrict__ x, long long ldx, const float *__restrict__ gamma, const float *__restrict__ beta,
+                          OutT *__restrict__ y, long long ldy, int rows, int dim, float eps)
+{
+    griddep_launch_dependents();
+    griddep_wait();
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int l = threadIdx.x & 15;
+    const bool valid = row < rows; // (the other half of the warp may still hold a row: no early return before the shuffles)
+    const int nv = dim >> 2;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + (long long)(valid ? row : 0) * ldx);
+    float4 v[3];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+        const int idx = i * 16 + l;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && idx < nv)
+        {
+            v[i] = xr[idx];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)dim;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+        const int idx = i * 16 + l;
+        if (valid && idx < nv)
+        {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (!valid) return;
+    const float rstd = rsqrtf(q / (float)dim + eps);
+    const float4 *g4 = reinterpret_cast<const float4 *>(gamma);
+    const float4 *b4 = reinterpret_cast<const float4 *>(beta);
+    OutT *yrow = y + (long long)row * ldy;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+        const int idx = i * 16 + l;
+        if (idx < nv)
+        {
+            const float4 g = g4[idx], b = b4[idx];
+            const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
+            const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
+            if constexpr (sizeof(OutT) == 2)
+                reinterpret_cast<uint2 *>(yrow)[idx] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+            else
+                reinterpret_cast<float4 *>(yrow)[idx] = make_float4(o0, o1, o2, o3);
+        }
+    }
+}
+
 template <typename OutT>
 static cudaError_t launch_layernorm_t(const float *x, long long ldx, const float *gamma, const float *beta, OutT *y, long long ldy, int rows,
                                       int dim, float eps, cudaStream_t stream)
 {
     const int threads = 256, rows_per_block = threads / 32;
     const int grid = (rows + rows_per_block - 1) / rows_per_block;
+    static const bool halfwarp = !getenv("NETCUDA_LN_HALFWARP") || atoi(getenv("NETCUDA_LN_HALFWARP")) != 0; // (=0: a warp per row, A/B)
+    if (dim <= 192 && halfwarp)
+        return launch_pdl(layernorm_halfwarp_kernel<OutT>, dim3((rows + 15) / 16), dim3(threads), 0, stream, 1, x, ldx, gamma, beta, y, ldy, rows, dim, eps);
     if (dim <= 256)
         return launch_pdl(layernorm_kernel<2, OutT>, dim3(grid), dim3(threads), 0, stream, 1, x, ldx, gamma, beta, y, ldy, rows, dim, eps);
     else if (dim <= 1024)
