@@ -225,6 +225,32 @@ def test_gemm_tensor_core_matches_cuda_core_variant_at_full_size(netcuda, torch_
     assert ((g16.float() - want).abs().max() / want.abs().max()).item() <= 6e-3
 
 
+@pytest.mark.parametrize("n,k,out_bf16,epi", [(576, 192, True, "none"), (192, 192, False, "residual"), (768, 192, True, "gelu"), (192, 768, False, "residual"),
+                                              (200, 136, False, "none")])
+def test_gemm_short_k_sixteen_epilogue_warps(netcuda, torch_cuda, n, k, out_bf16, epi):
+    """GEMMs that are all epilogue (K <= 256 or a single column of tiles: the linear layers of ViT-Tiny) run with 16 epilogue warps.
+    Against the CUDA-core kernel with the same operand rounding (1e-4 / bf16 rounding), and bit for bit against the 8-warp
+    configurations (variant 5: one slab per warp, variant 4: two)."""
+    torch = torch_cuda
+    m = 64 * 197  # 50 row blocks of 256: the CTA-pair path
+    g = torch.Generator(device="cuda").manual_seed(n + k)
+    a = torch.randn((m, k), generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn((n, k), generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    b = torch.randn(n, generator=g, device="cuda")
+    base = torch.randn((m, n), generator=g, device="cuda")
+    e = {"none": netcuda.EPI_NONE, "residual": netcuda.EPI_RESIDUAL, "gelu": netcuda.EPI_GELU}[epi]
+    outs = {}
+    for variant in (0, 3, 4, 5, 1):
+        out = base.clone() if not out_bf16 else torch.empty((m, n), dtype=torch.bfloat16, device="cuda")
+        netcuda.op_gemm(a, w, b, out, netcuda.PREC_BF16, netcuda.OUT_BF16 if out_bf16 else netcuda.OUT_F32, epilogue=e, variant=variant)
+        torch.cuda.synchronize()
+        outs[variant] = out.float()
+    for variant in (3, 4, 5):
+        assert torch.equal(outs[0], outs[variant]), variant
+    err = ((outs[0] - outs[1]).abs().max() / outs[1].abs().max()).item()
+    assert err <= (6e-3 if out_bf16 else 1e-4), err
+
+
 @pytest.mark.parametrize("rows,dim", [(1, 192), (197, 192), (1001, 64), (50, 128), (1000, 768), (333, 1024), (64, 4096)])
 def test_layernorm_vs_oracle(netcuda, oracle, torch_cuda, rows, dim):
     torch = torch_cuda

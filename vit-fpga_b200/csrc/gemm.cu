@@ -113,6 +113,7 @@ cudaError_t gemm_global_init()
     NC_OPT(KIND_I8, OUT_S32)
 #undef NC_OPT
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_EW16, 2, 16>()) != cudaSuccess) return e;
+    if ((e = opt_in_smem<KIND_BF16, 256, OUT_F32, STAGES_256_PAIR_EW16, 2, 16>()) != cudaSuccess) return e;
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_DS, 2, 8, 1>()) != cudaSuccess) return e;
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_F32, STAGES_256_PAIR_DS, 2, 8, 1>()) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(gemm_fp32_ordered_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, os_smem_bytes(1))) != cudaSuccess) return e;
@@ -228,8 +229,16 @@ static cudaError_t launch_tc_bn(const GemmCall &c, cudaStream_t stream)
         // variant 3: 16 epilogue warps for the GELU epilogue.  Measured on ViT-B fc1 (ncu, round 1): 212.5 us vs 203.5 us with
         // 8 warps -- the epilogue is bound by MUFU/FMA work per element, not by the number of warps -- so it is not the default.
         // ... but it is the default where K is so short that the GELU epilogue is all there is (ViT-Tiny fc1, K = 192: 40.7 -> 34.7 us).
-        if constexpr (KIND == KIND_BF16 && OUT == OUT_BF16)
-            if (c.epi == EPI_GELU && (c.variant == 3 || (c.variant == 0 && c.k <= 256))) return launch_tc<KIND, 256, OUT, STAGES_256_PAIR_EW16, 2, 16>(c, stream);
+        if constexpr (KIND == KIND_BF16 && (OUT == OUT_BF16 || OUT == OUT_F32))
+        {
+            // ... and of every other GEMM that is all epilogue, K of at most four k-blocks (ViT-Tiny, 256 images, inside the step: qkv
+            // 0.323 -> 0.300 ms, proj 0.322 -> 0.307 ms, step 139.8 k -> 141.8 k images/s; alone, tools/gemm_k192_ab.py: 23.8 -> 22.8 us and
+            // 18.7 -> 16.6 us.  Not for a single column of tiles with a long K -- fc2, N = 192: faster alone, 28.8 -> 27.1 us, no
+            // faster in the step.  NETCUDA_GEMM_EW16=0: A/B)
+            static const bool ew16_short = !getenv("NETCUDA_GEMM_EW16") || atoi(getenv("NETCUDA_GEMM_EW16")) != 0;
+            if (c.variant == 3 || (c.variant == 0 && ((OUT == OUT_BF16 && c.epi == EPI_GELU && c.k <= 256) || (ew16_short && c.k <= 256))))
+                return launch_tc<KIND, 256, OUT, STAGES_256_PAIR_EW16, 2, 16>(c, stream);
+        }
         // Two output slabs per epilogue warp (slab i + 1 is filled while the TMA store of slab i drains) at the price of one
         // pipeline stage: pays where the epilogue or the store path sets the pace -- the GELU epilogue (ViT-B fc1: 10.3 -> 9.9 ms
         // per step) and the short-K residual update that is bound by the L2 reduce-add (proj: 3.95 -> 3.6 ms) -- and costs where the
