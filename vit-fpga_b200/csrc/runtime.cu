@@ -1180,6 +1180,21 @@ static int submit_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_
     // next MAX_IN_FLIGHT calls as they come round to their slot.
     const bool need_pin_out = !pd.pinned_out;
     if (pd.dev_cap < pd.out_bytes || (need_pin_out && pd.pin_cap < pd.out_bytes))
+    {
+        // The graph of a small call holds BOTH output pointers of its ring slot (kernels -> dev_out, copy -> pin_out) but is found by
+        // one of them: once a slot's buffers are replaced such a graph must go, or a later buffer that happens to get the old address
+        // would revive it with the other pointer dangling.
+        for (auto &g : h->pass_graphs)
+            for (auto &q : h->pending)
+                if (g.exec && g.in != nullptr && g.in == q.small_in)
+                {
+                    CK(cudaStreamSynchronize(h->stream)); // (a replay may still be running)
+                    cudaGraphExecDestroy(g.exec);
+                    g = netcuda_net::PassGraph();
+                }
+        for (auto &c : h->graph_candidates)
+            for (auto &q : h->pending)
+                if (c.in != nullptr && c.in == q.small_in) c = netcuda_net::PassGraph();
         for (auto &q : h->pending)
         {
             if (q.active) continue;
@@ -1198,6 +1213,7 @@ static int submit_host_impl(netcuda_net *h, const void *in, bool in_is_i8, size_
                 q.pin_cap = pd.out_bytes;
             }
         }
+    }
 
     if (small_call)
     {
