@@ -251,6 +251,29 @@ def test_gemm_short_k_sixteen_epilogue_warps(netcuda, torch_cuda, n, k, out_bf16
     assert err <= (6e-3 if out_bf16 else 1e-4), err
 
 
+@pytest.mark.parametrize("n,k,epi", [(576, 192, "none"), (192, 192, "residual"), (768, 192, "gelu"), (192, 256, "residual")])
+def test_gemm_tf32_short_k_sixteen_epilogue_warps(netcuda, torch_cuda, n, k, epi):
+    """The same for tf32 operands with fp32 outputs (the linear layers of a TF32 ViT-Tiny): 16 epilogue warps (default at K <= 256)
+    against 8 (variant 5) bit for bit, and against the CUDA-core kernel with tf32-truncated operands."""
+    torch = torch_cuda
+    m = 64 * 197
+    g = torch.Generator(device="cuda").manual_seed(n * 3 + k)
+    a = torch.randn((m, k), generator=g, device="cuda")
+    w = torch.randn((n, k), generator=g, device="cuda") * 0.05
+    b = torch.randn(n, generator=g, device="cuda")
+    base = torch.randn((m, n), generator=g, device="cuda")
+    e = {"none": netcuda.EPI_NONE, "residual": netcuda.EPI_RESIDUAL, "gelu": netcuda.EPI_GELU}[epi]
+    outs = {}
+    for variant in (0, 3, 5, 1):
+        out = base.clone()
+        netcuda.op_gemm(a, w, b, out, netcuda.PREC_TF32, netcuda.OUT_F32, epilogue=e, variant=variant)
+        torch.cuda.synchronize()
+        outs[variant] = out
+    assert torch.equal(outs[0], outs[3]) and torch.equal(outs[0], outs[5])
+    err = ((outs[0] - outs[1]).abs().max() / outs[1].abs().max()).item()
+    assert err <= 1e-4, err
+
+
 @pytest.mark.parametrize("rows,dim", [(1, 192), (197, 192), (1001, 64), (50, 128), (1000, 768), (333, 1024), (64, 4096)])
 def test_layernorm_vs_oracle(netcuda, oracle, torch_cuda, rows, dim):
     torch = torch_cuda

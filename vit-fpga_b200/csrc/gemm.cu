@@ -114,6 +114,8 @@ cudaError_t gemm_global_init()
 #undef NC_OPT
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_EW16, 2, 16>()) != cudaSuccess) return e;
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_F32, STAGES_256_PAIR_EW16, 2, 16>()) != cudaSuccess) return e;
+    if ((e = opt_in_smem<KIND_TF32, 256, OUT_F32, STAGES_256_PAIR_EW16, 2, 16>()) != cudaSuccess) return e;
+    if ((e = opt_in_smem<KIND_TF32, 256, OUT_BF16, STAGES_256_PAIR_EW16, 2, 16>()) != cudaSuccess) return e;
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_BF16, STAGES_256_PAIR_DS, 2, 8, 1>()) != cudaSuccess) return e;
     if ((e = opt_in_smem<KIND_BF16, 256, OUT_F32, STAGES_256_PAIR_DS, 2, 8, 1>()) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(gemm_fp32_ordered_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, os_smem_bytes(1))) != cudaSuccess) return e;
@@ -229,12 +231,13 @@ static cudaError_t launch_tc_bn(const GemmCall &c, cudaStream_t stream)
         // variant 3: 16 epilogue warps for the GELU epilogue.  Measured on ViT-B fc1 (ncu, round 1): 212.5 us vs 203.5 us with
         // 8 warps -- the epilogue is bound by MUFU/FMA work per element, not by the number of warps -- so it is not the default.
         // ... but it is the default where K is so short that the GELU epilogue is all there is (ViT-Tiny fc1, K = 192: 40.7 -> 34.7 us).
-        if constexpr (KIND == KIND_BF16 && (OUT == OUT_BF16 || OUT == OUT_F32))
+        if constexpr ((KIND == KIND_BF16 || KIND == KIND_TF32) && (OUT == OUT_BF16 || OUT == OUT_F32))
         {
             // ... and of every other GEMM that is all epilogue, K of at most four k-blocks (ViT-Tiny, 256 images, inside the step: qkv
             // 0.323 -> 0.300 ms, proj 0.322 -> 0.307 ms, step 139.8 k -> 141.8 k images/s; alone, tools/gemm_k192_ab.py: 23.8 -> 22.8 us and
             // 18.7 -> 16.6 us.  Not for a single column of tiles with a long K -- fc2, N = 192: faster alone, 28.8 -> 27.1 us, no
-            // faster in the step.  NETCUDA_GEMM_EW16=0: A/B)
+            // faster in the step.  tf32 operands alike: TF32 ViT-Tiny step 92.6 k -> 98.7 k images/s, fc1 (fp32-output GELU) 0.88 -> 0.62 ms.
+            // NETCUDA_GEMM_EW16=0: A/B)
             static const bool ew16_short = !getenv("NETCUDA_GEMM_EW16") || atoi(getenv("NETCUDA_GEMM_EW16")) != 0;
             if (c.variant == 3 || (c.variant == 0 && ((OUT == OUT_BF16 && c.epi == EPI_GELU && c.k <= 256) || (ew16_short && c.k <= 256))))
                 return launch_tc<KIND, 256, OUT, STAGES_256_PAIR_EW16, 2, 16>(c, stream);
