@@ -127,6 +127,10 @@ def test_library_contains_blackwell_sass(netcuda):
     assert "sm_100a" in sass
     for mnemonic in ("UTCHMMA", "UTCIMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, mnemonic
+    # every kernel family the runtime dispatches to is in the shipped library (a stale build would miss the newer ones)
+    for kernel in ("gemm_tn_tcgen05_kernel", "attention_tc16_kernel", "attention_tc_long_kernel", "mlp_i8_stream_kernel", "mlp_i8_umma_cluster_kernel",
+                   "gemm_fp32_ordered_kernel", "gemm_fp32_ordered_small_kernel", "layernorm_kernel", "layernorm_halfwarp_kernel", "filter3x3_kernel"):
+        assert kernel in sass, kernel
 
 
 def test_vit_param_count_matches_oracle(netcuda, oracle):
